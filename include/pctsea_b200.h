@@ -1,0 +1,182 @@
+/*
+ * pctsea_b200.h — C ABI of libpctsea_b200.so: the B200 (sm_100a) implementation of PCTSEA's hot path
+ * (per-cell scoring -> ranking -> weighted-KS enrichment + label-permutation null -> norm/p/FDR).
+ *
+ * The reference (proteomicsyates/pctsea-parent) has no FFI/plugin interface for this path: the path is a
+ * set of private methods of pctsea-core's PCTSEA class working on Java object graphs. Each entry point
+ * below names the reference code whose *body* it replaces; a Java host binds them through JNI or Panama
+ * (INTEGRATION.md shows the stubs). Paths are relative to
+ * pctsea-core/src/main/java/edu/scripps/yates/pctsea/ of the reference.
+ *
+ * Conventions: every function returns 0 (PCTSEA_OK) or a negative PCTSEA_E* code; pctsea_last_error(ctx)
+ * returns a message valid until the next call on that ctx. All pointers are HOST pointers unless the
+ * parameter name ends in _dev. Caller allocates every output buffer. No C++ exceptions cross the ABI.
+ * There is NO CPU fallback: without a CUDA device pctsea_create fails with PCTSEA_ECUDA.
+ * A ctx is bound to one device and is not re-entrant; multi-GPU = one ctx (one process) per GPU, each
+ * computing a slice of the permutations (pctsea_null_params.perm_begin/perm_count).
+ */
+#ifndef PCTSEA_B200_H
+#define PCTSEA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCTSEA_ABI_VERSION 1
+
+#define PCTSEA_OK         0
+#define PCTSEA_EINVAL    (-1)
+#define PCTSEA_ECUDA     (-2)
+#define PCTSEA_ENCCL     (-3)  /* reserved: collectives live in the host plumbing (torch.distributed) */
+#define PCTSEA_ETOOFEW   (-4)  /* fewer than min_pass cells pass the score threshold, PCTSEA.java:389-395 */
+#define PCTSEA_EMINGENES (-5)  /* min_genes_cells > list size, model/SingleCell.java:347-352 */
+#define PCTSEA_ENOMEM    (-6)
+
+/* model/ScoringMethod.java:8-23 (only the two methods on the hot path) */
+#define PCTSEA_METHOD_PEARSONS_CORRELATION 0
+#define PCTSEA_METHOD_SIMPLE_SCORE         1
+
+/* zero-variance policy for model/SingleCell.java:433-448 (the reference adds unseeded Math.random()/1e6) */
+#define PCTSEA_JITTER_NAN    0  /* such cells score NaN */
+#define PCTSEA_JITTER_PHILOX 1  /* U[0,1)/1e6 from Philox4x32-10 keyed by (seed, cell, vector, element) */
+
+#define PCTSEA_PERM_REPLAY 0    /* consume uploaded permutation index arrays (validation) */
+#define PCTSEA_PERM_PHILOX 1    /* keyed Feistel bijection with Philox-generated round tables */
+
+#define PCTSEA_KS_EXACT 0       /* sequential fp32/fp64 emulation of EnrichmentWeigthedScoreParallel.run */
+#define PCTSEA_KS_FAST  1       /* fixed-point prefix sums evaluated at hit / pre-hit positions only */
+
+typedef struct pctsea_ctx    pctsea_ctx;
+typedef struct pctsea_matrix pctsea_matrix;
+
+typedef struct pctsea_score_params {
+    int32_t  method;           /* PCTSEA_METHOD_* */
+    int32_t  min_genes_cells;  /* InputParameters.MIN_GENES_CELLS */
+    double   min_corr;         /* InputParameters.MIN_CORRELATION */
+    int32_t  has_min_corr;     /* 0 = null Double (never on the reference's path) */
+    int32_t  jitter_mode;      /* PCTSEA_JITTER_* */
+    uint64_t seed;
+} pctsea_score_params;
+
+typedef struct pctsea_null_params {
+    int32_t  n_perm;           /* P: InputParameters.PERM, total over all ranks */
+    int32_t  perm_begin;       /* first GLOBAL permutation index computed by this call */
+    int32_t  perm_count;       /* permutations computed by this call; 0 = all n_perm */
+    int32_t  perm_mode;        /* PCTSEA_PERM_* */
+    int32_t  ks_mode;          /* PCTSEA_KS_* */
+    int32_t  feistel_rounds;   /* 0 = default (6) */
+    uint64_t seed;
+    int32_t  mean_policy;      /* Maths.mean(TFloatList): 0 = fp32 running sum (default), 1 = fp64 sum */
+    int32_t  min_pass;         /* PCTSEA_ETOOFEW guard; the reference uses 1000 (PCTSEA.java:138) */
+} pctsea_null_params;
+
+/* One per cell type: the fields model/CellTypeClassification.java receives through setEnrichment (:91),
+ * setSizeA/B, setNormalizedEnrichmentScore (:443), setEnrichmentSignificance (:246), setEnrichmentFDR (:447). */
+typedef struct pctsea_type_result {
+    float   ews;        /* observed enrichment score (compensated supremum) */
+    float   dstat;      /* raw supremum * sqrt(sizeA*sizeB/(sizeA+sizeB)) */
+    int32_t supX;       /* 1-based position of the supremum; -1 when NaN */
+    double  norm_supX;  /* supX / Nu; -1 when NaN */
+    int32_t sizeA;      /* cells of the type among the Nu ranked cells */
+    int32_t sizeB;      /* Nu - sizeA */
+    float   raw_sup;    /* supremum before compensation */
+    float   norm_ews;   /* a11 */
+    double  p_emp;      /* a10 */
+    double  fdr;        /* a12 */
+} pctsea_type_result;
+
+/* Per-stage device times (CUDA events on the ctx stream) of the most recent call. */
+typedef struct pctsea_timings {
+    float   setup_ms;     /* list upload + lookup tables */
+    float   score_ms;     /* stage 1 kernel */
+    float   rank_ms;      /* stage 2: compaction + radix sort + gather */
+    float   observed_ms;  /* stage 3 observed (exact) */
+    float   labels_ms;    /* permuted label generation (+ per-type denominators in FAST mode) */
+    float   null_ms;      /* KS over the permuted labels */
+    float   reduce_ms;    /* a10-a12 */
+    float   total_ms;     /* first to last event, includes the copies issued by the call */
+    int64_t n_pass;       /* Np */
+    int64_t n_used;       /* Nu = Np - 1 */
+    int64_t launches;     /* kernels launched by the call */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} pctsea_timings;
+
+int         pctsea_abi_version(void);
+int         pctsea_create(int device_id, pctsea_ctx** out);
+int         pctsea_destroy(pctsea_ctx* ctx);
+const char* pctsea_last_error(pctsea_ctx* ctx);
+int         pctsea_get_timings(pctsea_ctx* ctx, pctsea_timings* out);
+/* cudaStream_t the ctx launches on (so a caller can time or order against it). */
+void*       pctsea_stream(pctsea_ctx* ctx);
+
+/* ---- matrix: loaded once per dataset, device-resident CSR ---------------------------------------
+ * Replaces GeneExpressionsRetriever.getSingleCellExpressionsFromDB (GeneExpressionsRetriever.java:120-274)
+ * + the per-cell sparse vectors of model/SingleCell.java:49-104. Rows are cells in DB order (= tie-break
+ * order), columns are dataset genes. Columns within a row must be unique; storage order of a row is the
+ * canonical order of the Pearson update. */
+int pctsea_matrix_load_csr(pctsea_ctx* ctx, int64_t n_cells, int32_t n_genes, const int64_t* row_ptr,
+                           const int32_t* col_idx, const float* val, pctsea_matrix** out);
+/* Adopt device arrays without copying (they must outlive the matrix). */
+int pctsea_matrix_wrap_device(pctsea_ctx* ctx, int64_t n_cells, int32_t n_genes, const int64_t* row_ptr_dev,
+                              const int32_t* col_idx_dev, const float* val_dev, pctsea_matrix** out);
+/* Cell-type ids per cell in [-1, n_types); -1 = unknown type (model/SingleCell.java:224-229). */
+int pctsea_matrix_set_labels(pctsea_ctx* ctx, pctsea_matrix* m, const int32_t* label, int32_t n_types);
+int pctsea_matrix_free(pctsea_ctx* ctx, pctsea_matrix* m);
+
+/* ---- stage 1: PCTSEA.filterByMinimumNumberOfGenesExpressedInEachCell (PCTSEA.java:544-572) +
+ * calculateScoresToRankSingleCells loop (PCTSEA.java:2305-2343) -> SingleCell.hasMinNumberOfExpressedGenes
+ * (model/SingleCell.java:344-369), calculateCorrelation / calculateSimpleScore (:380-476).
+ * gene_idx[L]: matrix column per list entry (-1 = gene absent from the dataset); entries must be distinct. */
+int pctsea_score(pctsea_ctx* ctx, const pctsea_matrix* m, int32_t L, const int32_t* gene_idx,
+                 const float* abundance, const pctsea_score_params* prm, double* score_out /*[N]*/,
+                 int32_t* n_genes_used_out /*[N] or NULL*/, int32_t* n_nonzero_out /*[N] or NULL*/,
+                 uint8_t* kept_out /*[N] or NULL*/);
+
+/* ---- stage 2: ScoreThreshold.passThreshold / getSingleCellsPassingThresholdSortedByScore
+ * (scoring/ScoreThreshold.java:57-75,98-106), PCTSEAUtils.sortByScoreDescending (utils/PCTSEAUtils.java:44-53).
+ * order_out[0 .. n_pass-2] = KS list (score desc by Double.compare, ties by cell index asc);
+ * order_out[n_pass-1] = the cell dropped by subList(0,size-1) (PCTSEA.java:421-424). */
+int pctsea_rank(pctsea_ctx* ctx, int64_t n_cells, const double* score, const uint8_t* kept /*or NULL*/,
+                double min_score, int32_t* order_out /*[N]*/, int64_t* n_pass_out);
+
+/* ---- stage 3: PCTSEA.calculateEnrichmentScore (PCTSEA.java:2454-2488) ->
+ * EnrichmentWeigthedScoreParallel.run (utils/parallel/EnrichmentWeigthedScoreParallel.java:72-353) for the
+ * observed labels and, per permutation, PCTSEA.calculateSignificanceByCellTypesPermutations
+ * (PCTSEA.java:1380-1549). order[n_used] indexes score/label. replay_perm: [perm_count][n_used] int32 index
+ * arrays (label at rank i = label of rank replay[p][i]) when perm_mode == REPLAY, else NULL.
+ * null_out / nullD_out: [n_types][perm_count] row-major or NULL. When perm_count covers all n_perm the
+ * a10-a12 fields of out[] are filled; otherwise they are NaN and the caller gathers the null slices and
+ * calls pctsea_reduce_null. */
+int pctsea_enrich(pctsea_ctx* ctx, int64_t n_cells, const double* score, int64_t n_used, const int32_t* order,
+                  const int32_t* label, int32_t n_types, const pctsea_null_params* prm,
+                  const int32_t* replay_perm, pctsea_type_result* out /*[n_types]*/, float* null_out,
+                  float* nullD_out);
+
+/* a10-a12 from a supplied null (also the -load_random path, PCTSEA.java:1385-1387): reads out[t].ews,
+ * fills norm_ews, p_emp, fdr. null is [n_types][n_perm]. */
+int pctsea_reduce_null(pctsea_ctx* ctx, int32_t n_types, int32_t n_perm, const float* null_ews,
+                       int32_t mean_policy, pctsea_type_result* inout);
+int pctsea_reduce_null_dev(pctsea_ctx* ctx, int32_t n_types, int32_t n_perm, const float* null_ews_dev,
+                           int32_t mean_policy, pctsea_type_result* inout);
+
+/* ---- the whole path in one call: the body of the per-schema loop PCTSEA.java:348-434 between the list
+ * being known and the CellTypeClassification fields being set. Matrix (and, if label == NULL, its labels)
+ * are resident; list in, per-type results out. Optional outputs may be NULL. */
+int pctsea_analyze(pctsea_ctx* ctx, const pctsea_matrix* m, int32_t L, const int32_t* gene_idx,
+                   const float* abundance, const pctsea_score_params* sprm, double min_score,
+                   const int32_t* label /*[N] or NULL*/, int32_t n_types, const pctsea_null_params* nprm,
+                   const int32_t* replay_perm, pctsea_type_result* out /*[n_types]*/,
+                   float* null_out, float* nullD_out, double* score_out, int32_t* n_genes_used_out,
+                   uint8_t* kept_out, int32_t* order_out, int64_t* n_pass_out);
+/* Device pointers of the null slice left by the last pctsea_analyze / pctsea_enrich on this ctx:
+ * [n_types][perm_count] fp32 each. Valid until the next call on the ctx. For NCCL all-gathers. */
+int pctsea_last_null_dev(pctsea_ctx* ctx, float** null_dev, float** nullD_dev, int32_t* n_types,
+                         int32_t* perm_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCTSEA_B200_H */

@@ -1,0 +1,601 @@
+/*
+ * pctsea_oracle.c — CPU restatement of the PCTSEA hot path. TEST INFRASTRUCTURE ONLY; see the header.
+ * PARITY UNPINNED (no reference golden vectors exist; reference is not runnable here).
+ *
+ * Build: gcc -O2 -std=c99 -ffp-contract=off -fPIC -shared -pthread (oracle/Makefile). No -ffast-math:
+ * every float/double rounding below is part of the restated semantics.
+ *
+ * CORE/ = /root/reference/pctsea-core/src/main/java/edu/scripps/yates/pctsea/
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "pctsea_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ============================================================================================
+ * JDK pieces (bit-exact restatements of OpenJDK 8 library code; used by the reference at
+ * CORE/PCTSEA.java:1405 (Collections.shuffle), :1523-1537 (Arrays.sort / binarySearch),
+ * CORE/utils/PCTSEAUtils.java:44-53 (Double.compare)).
+ * ========================================================================================== */
+
+#define JR_MULT 0x5DEECE66DULL
+#define JR_ADD  0xBULL
+#define JR_MASK ((1ULL << 48) - 1)
+
+void orc_jrandom_init(orc_jrandom* r, int64_t seed) { r->seed = ((uint64_t)seed ^ JR_MULT) & JR_MASK; }
+
+int32_t orc_jrandom_next(orc_jrandom* r, int bits) {
+    r->seed = (r->seed * JR_MULT + JR_ADD) & JR_MASK;
+    /* (int)(seed >>> (48 - bits)) */
+    return (int32_t)(uint32_t)(r->seed >> (48 - bits));
+}
+
+int32_t orc_jrandom_next_int(orc_jrandom* r) { return orc_jrandom_next(r, 32); }
+
+int32_t orc_jrandom_next_int_bound(orc_jrandom* r, int32_t bound) {
+    /* JDK 8 Random.nextInt(int bound) */
+    int32_t rr = orc_jrandom_next(r, 31);
+    int32_t m = bound - 1;
+    if ((bound & m) == 0) {
+        rr = (int32_t)(((int64_t)bound * (int64_t)rr) >> 31);
+    } else {
+        int32_t u = rr;
+        for (;;) {
+            rr = u % bound;
+            /* u - rr + m < 0 with int32 wrap-around */
+            int32_t t = (int32_t)((uint32_t)u - (uint32_t)rr + (uint32_t)m);
+            if (t >= 0) break;
+            u = orc_jrandom_next(r, 31);
+        }
+    }
+    return rr;
+}
+
+double orc_jrandom_next_double(orc_jrandom* r) {
+    int64_t hi = (int64_t)orc_jrandom_next(r, 26);
+    int64_t lo = (int64_t)orc_jrandom_next(r, 27);
+    return (double)((hi << 27) + lo) * (1.0 / (double)(1LL << 53));
+}
+
+void orc_java_shuffle_i32(int32_t* a, int64_t n, orc_jrandom* r) {
+    /* Collections.shuffle: for (int i=size; i>1; i--) swap(list, i-1, rnd.nextInt(i)); */
+    for (int64_t i = n; i > 1; i--) {
+        int32_t j = orc_jrandom_next_int_bound(r, (int32_t)i);
+        int32_t t = a[i - 1];
+        a[i - 1] = a[j];
+        a[j] = t;
+    }
+}
+
+static inline int32_t f32_bits(float f) { int32_t b; memcpy(&b, &f, 4); return b; }
+static inline float bits_f32(int32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static inline int64_t f64_bits(double d) { int64_t b; memcpy(&b, &d, 8); return b; }
+
+/* Float.floatToIntBits: canonical NaN */
+static inline int32_t java_float_to_int_bits(float f) { return isnan(f) ? 0x7fc00000 : f32_bits(f); }
+
+int32_t orc_java_binary_search_f32(const float* a, int32_t n, float key) {
+    /* Arrays.binarySearch0(float[] a, 0, n, key) */
+    int32_t low = 0, high = n - 1;
+    while (low <= high) {
+        int32_t mid = (int32_t)(((uint32_t)low + (uint32_t)high) >> 1);
+        float midVal = a[mid];
+        if (midVal < key) low = mid + 1;
+        else if (midVal > key) high = mid - 1;
+        else {
+            int32_t midBits = java_float_to_int_bits(midVal);
+            int32_t keyBits = java_float_to_int_bits(key);
+            if (midBits == keyBits) return mid;
+            else if (midBits < keyBits) low = mid + 1;
+            else high = mid - 1;
+        }
+    }
+    return -(low + 1);
+}
+
+/* Float.compare total order: -0.0 < 0.0, NaN greater than everything (all NaNs equal). */
+static int java_float_compare(float a, float b) {
+    if (a < b) return -1;
+    if (a > b) return 1;
+    int32_t ab = java_float_to_int_bits(a), bb = java_float_to_int_bits(b);
+    return ab == bb ? 0 : (ab < bb ? -1 : 1);
+}
+static int cmp_f32_java(const void* pa, const void* pb) {
+    return java_float_compare(*(const float*)pa, *(const float*)pb);
+}
+void orc_java_sort_f32(float* a, int64_t n) { qsort(a, (size_t)n, sizeof(float), cmp_f32_java); }
+
+int orc_java_double_compare(double a, double b) {
+    if (a < b) return -1;
+    if (a > b) return 1;
+    int64_t ab = isnan(a) ? 0x7ff8000000000000LL : f64_bits(a);
+    int64_t bb = isnan(b) ? 0x7ff8000000000000LL : f64_bits(b);
+    return ab == bb ? 0 : (ab < bb ? -1 : 1);
+}
+
+/* ============================================================================================
+ * Philox4x32-10 (Salmon et al. 2011) — the repo's own counter-based generator: deterministic
+ * jitter stream and the PHILOX-mode label permutation. Not part of the reference.
+ * ========================================================================================== */
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+double orc_jitter_uniform(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t i) {
+    uint32_t ctr[4] = { i, vec | 0x4A000000u, (uint32_t)cell, (uint32_t)(cell >> 32) };
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t o[4];
+    orc_philox4x32_10(ctr, key, o);
+    uint64_t u = ((uint64_t)(o[0] >> 6) << 27) | (uint64_t)(o[1] >> 5);
+    return (double)u * (1.0 / 9007199254740992.0);
+}
+
+static void feistel_dims(int64_t n, int64_t* a_out, int64_t* b_out) {
+    int64_t a = (int64_t)floor(sqrt((double)n));
+    while (a * a < n) a++;
+    while (a > 1 && (a - 1) * (a - 1) >= n) a--;
+    if (a < 1) a = 1;
+    *a_out = a;
+    *b_out = (n + a - 1) / a;
+}
+
+void orc_feistel_perm(uint64_t seed, uint32_t p, int64_t n, int rounds, int32_t* perm_out) {
+    if (n <= 0) return;
+    int64_t a, b;
+    feistel_dims(n, &a, &b);
+    uint16_t* tab = (uint16_t*)malloc((size_t)rounds * (size_t)a * sizeof(uint16_t));
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int j = 0; j < rounds; j++) {
+        int64_t dom = (j & 1) ? a : b;          /* input half size */
+        uint32_t mod = (uint32_t)((j & 1) ? b : a); /* output half size */
+        for (int64_t v4 = 0; v4 < dom; v4 += 4) {
+            uint32_t ctr[4] = { (uint32_t)(v4 >> 2), (uint32_t)j, p, 0x46454953u };
+            uint32_t o[4];
+            orc_philox4x32_10(ctr, key, o);
+            for (int q = 0; q < 4 && v4 + q < dom; q++)
+                tab[(size_t)j * a + v4 + q] = (uint16_t)(((uint64_t)o[q] * mod) >> 32);
+        }
+    }
+    for (int64_t x = 0; x < n; x++) {
+        uint32_t L = (uint32_t)(x / b), R = (uint32_t)(x % b);
+        int64_t y;
+        do {
+            for (int j = 0; j < rounds; j++) {
+                if (!(j & 1)) { L += tab[(size_t)j * a + R]; if (L >= (uint32_t)a) L -= (uint32_t)a; }
+                else          { R += tab[(size_t)j * a + L]; if (R >= (uint32_t)b) R -= (uint32_t)b; }
+            }
+            y = (int64_t)L * b + R;
+        } while (y >= n);
+        perm_out[x] = (int32_t)y;
+    }
+    free(tab);
+}
+
+/* ============================================================================================
+ * Stage 1 — scoring. CORE/model/SingleCell.java:344-369 (a2), :380-463 (a3).
+ * ========================================================================================== */
+
+/* commons-math3 3.x: PearsonsCorrelation.correlation(xArray, yArray) feeds a SimpleRegression
+ * (with intercept) pair by pair and returns getR(). Restated from the published algorithm
+ * (SimpleRegression.addData / getSlope / getSumSquaredErrors / getRSquare / getR). */
+double orc_pearson(const double* x, const double* y, int32_t n) {
+    if (n < 2) return NAN; /* reference: MathIllegalArgumentException (run aborts) */
+    double sumXX = 0.0, sumYY = 0.0, sumXY = 0.0, xbar = 0.0, ybar = 0.0;
+    int64_t cnt = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (cnt == 0) {
+            xbar = x[i];
+            ybar = y[i];
+        } else {
+            double fact1 = 1.0 + (double)cnt;
+            double fact2 = (double)cnt / (1.0 + (double)cnt);
+            double dx = x[i] - xbar;
+            double dy = y[i] - ybar;
+            sumXX += dx * dx * fact2;
+            sumYY += dy * dy * fact2;
+            sumXY += dx * dy * fact2;
+            xbar += dx / fact1;
+            ybar += dy / fact1;
+        }
+        cnt++;
+    }
+    /* getSlope(): n<2 -> NaN; |sumXX| < 10*Double.MIN_VALUE -> NaN; else sumXY/sumXX */
+    double b1;
+    if (fabs(sumXX) < 10 * 4.9e-324) b1 = NAN; else b1 = sumXY / sumXX;
+    /* getSumSquaredErrors(): FastMath.max(0d, sumYY - sumXY*sumXY/sumXX)  (NaN-propagating max) */
+    double sse_arg = sumYY - sumXY * sumXY / sumXX;
+    double sse;
+    if (isnan(sse_arg)) sse = NAN; else sse = (sse_arg > 0.0) ? sse_arg : 0.0;
+    /* getRSquare(): (ssto - sse)/ssto with ssto = sumYY */
+    double rsq = (sumYY - sse) / sumYY;
+    double result = sqrt(rsq);
+    if (b1 < 0) result = -result;
+    return result;
+}
+
+static int all_equal(const double* v, int32_t n) {
+    /* edu.scripps.yates Maths.var(double[]) is un-vendored; only "== 0" is used
+     * (CORE/model/SingleCell.java:430-441): policy = zero iff every element is equal (n>=1). */
+    if (n < 1) return 0;
+    for (int32_t i = 1; i < n; i++) if (v[i] != v[0]) return 0;
+    return 1;
+}
+
+int orc_score(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const int32_t* col,
+              const float* val, int32_t L, const int32_t* gene_idx, const float* abundance,
+              const orc_score_params* prm, double* score, int32_t* n_genes_used,
+              int32_t* n_nonzero, uint8_t* kept) {
+    if (prm->min_genes_cells > L) return -5; /* SingleCell.java:347-352 */
+    int32_t* slot = (int32_t*)malloc((size_t)n_genes * sizeof(int32_t));
+    for (int32_t g = 0; g < n_genes; g++) slot[g] = -1;
+    for (int32_t l = 0; l < L; l++) if (gene_idx[l] >= 0 && gene_idx[l] < n_genes) slot[gene_idx[l]] = l;
+    double* xs = (double*)malloc((size_t)(L > 0 ? L : 1) * sizeof(double)); /* interactors (abundance) */
+    double* ys = (double*)malloc((size_t)(L > 0 ? L : 1) * sizeof(double)); /* gene expression in cell */
+    for (int64_t c = 0; c < n_cells; c++) {
+        int32_t np = 0, nz = 0;
+        for (int64_t k = row_ptr[c]; k < row_ptr[c + 1]; k++) {
+            int32_t g = col[k];
+            if (g < 0 || g >= n_genes) continue;
+            int32_t l = slot[g];
+            if (l < 0) continue;
+            float x = val[k];
+            float y = abundance[l];
+            if (x > 0.0f && y > 0.0f) { /* SingleCell.java:403 */
+                if (np < L) { xs[np] = (double)y; ys[np] = (double)x; }
+                np++;
+            }
+            if (x != 0.0f) nz++; /* true for NaN, SingleCell.java:409 */
+        }
+        n_genes_used[c] = np;
+        n_nonzero[c] = nz;
+        /* a1: cells with no non-zero doc for any list gene never enter the list
+         * (CORE/GeneExpressionsRetriever.java:213-222); a2: SingleCell.java:344-369 */
+        int k = (nz > 0) && (np >= prm->min_genes_cells);
+        kept[c] = (uint8_t)k;
+        if (!k) { score[c] = NAN; continue; }
+        if (np < 2) { score[c] = NAN; continue; } /* reference would throw inside commons-math */
+        int zx = all_equal(ys, np); /* geneExpressionVariance == 0, checked first (:433) */
+        int zy = all_equal(xs, np); /* interactorsExpressionVariance == 0 (:441) */
+        if ((zx || zy) && prm->jitter_mode == 0) { score[c] = NAN; continue; }
+        if (zx) for (int32_t i = 0; i < np; i++) ys[i] = ys[i] + orc_jitter_uniform(prm->seed, (uint64_t)c, 0u, (uint32_t)i) / 1000000.0;
+        if (zy) for (int32_t i = 0; i < np; i++) xs[i] = xs[i] + orc_jitter_uniform(prm->seed, (uint64_t)c, 1u, (uint32_t)i) / 1000000.0;
+        double r = orc_pearson(xs, ys, np); /* correlation(interactors, genes) :449-450 */
+        if (prm->has_min_corr && r < prm->min_corr) r = NAN;     /* :455-456 */
+        else if (prm->method == 1) r += (double)nz;              /* :457-458 */
+        score[c] = r;
+    }
+    free(slot); free(xs); free(ys);
+    return 0;
+}
+
+/* ============================================================================================
+ * Stage 2 — threshold + rank. CORE/scoring/ScoreThreshold.java:57-75,98-106,
+ * CORE/utils/PCTSEAUtils.java:44-53, CORE/PCTSEA.java:421-424,2497.
+ * ========================================================================================== */
+
+typedef struct { double s; int32_t idx; } rank_item;
+static int cmp_desc(const void* pa, const void* pb) {
+    const rank_item* a = (const rank_item*)pa; const rank_item* b = (const rank_item*)pb;
+    int c = orc_java_double_compare(b->s, a->s);
+    if (c) return c;
+    return (a->idx > b->idx) - (a->idx < b->idx); /* stable merge sort from DB order */
+}
+static int cmp_asc(const void* pa, const void* pb) {
+    const rank_item* a = (const rank_item*)pa; const rank_item* b = (const rank_item*)pb;
+    int c = orc_java_double_compare(a->s, b->s);
+    if (c) return c;
+    return (a->idx > b->idx) - (a->idx < b->idx);
+}
+
+int64_t orc_rank(int64_t n_cells, const double* score, const uint8_t* kept, double min_score,
+                 int32_t* order_out) {
+    rank_item* it = (rank_item*)malloc((size_t)(n_cells > 0 ? n_cells : 1) * sizeof(rank_item));
+    int64_t np = 0;
+    for (int64_t c = 0; c < n_cells; c++) {
+        if (kept && !kept[c]) continue;
+        double s = score[c];
+        int pass = (min_score >= 0.0) ? (s >= min_score) : (s < min_score); /* NaN fails both */
+        if (pass) { it[np].s = s; it[np].idx = (int32_t)c; np++; }
+    }
+    if (min_score >= 0.0) {
+        qsort(it, (size_t)np, sizeof(rank_item), cmp_desc);
+        for (int64_t i = 0; i < np; i++) order_out[i] = it[i].idx;
+    } else {
+        /* ascending stable sort, subList drops the last, then PCTSEA.java:2497 re-sorts descending */
+        qsort(it, (size_t)np, sizeof(rank_item), cmp_asc);
+        if (np > 0) {
+            int32_t dropped = it[np - 1].idx;
+            qsort(it, (size_t)(np - 1), sizeof(rank_item), cmp_desc);
+            for (int64_t i = 0; i < np - 1; i++) order_out[i] = it[i].idx;
+            order_out[np - 1] = dropped;
+        }
+    }
+    free(it);
+    return np;
+}
+
+/* ============================================================================================
+ * Stage 3 — weighted KS. CORE/utils/parallel/EnrichmentWeigthedScoreParallel.java:104-227,315-323,
+ * 492-512.
+ * ========================================================================================== */
+
+static float dstat_of(float sup, int32_t sizea, int32_t sizeb) {
+    /* :203-207 — sizea*sizeb is an int32 multiply (wraps), then widened */
+    int32_t prod = (int32_t)((uint32_t)sizea * (uint32_t)sizeb);
+    int32_t sum = (int32_t)((uint32_t)sizea + (uint32_t)sizeb);
+    float sq = (float)sqrt(((double)prod * 1.0) / (1.0 * (double)sum));
+    return sup * sq;
+}
+
+typedef struct {
+    float sup; int32_t supX; float last_neg_at_sup; int has_neg_at_sup; int32_t nk; int valid;
+} ks_walk;
+
+/* One type, one label vector. observed!=0 also tracks the "last negative difference at 0-based
+ * index < supX" needed by lookForPriorNegativeSupremum (:492-512). */
+static ks_walk ks_one_type(int64_t Nu, const double* s, const int32_t* lab, int32_t t, int observed) {
+    ks_walk w; memset(&w, 0, sizeof w);
+    float denomA = 0.0f, denomB = 0.0f;
+    int32_t nk = 0;
+    for (int64_t i = 0; i < Nu; i++) { /* :110-117 */
+        if (lab[i] == t) { nk++; denomA = (float)((double)denomA + s[i]); }
+        else denomB = (float)((double)denomB + s[i]);
+    }
+    w.nk = nk;
+    if (nk <= 1) { w.valid = 0; return w; } /* :119-127 */
+    float sup = 0.0f, prevA = 0.0f, prevB = 0.0f, numA = 0.0f, numB = 0.0f;
+    int32_t supX = 0;
+    float last_neg = 0.0f; int has_neg = 0;
+    float neg_at_sup = 0.0f; int has_neg_at_sup = 0;
+    for (int64_t i = 0; i < Nu; i++) { /* :140-194 */
+        float a, b;
+        if (lab[i] == t) { numA = (float)((double)numA + s[i]); a = numA / denomA; b = prevB; }
+        else             { numB = (float)((double)numB + s[i]); a = prevA; b = numB / denomB; }
+        float diff = a - b;
+        if (observed && diff < 0) { last_neg = diff; has_neg = 1; }
+        if (fabsf(diff) > fabsf(sup)) {
+            sup = diff; supX = (int32_t)(i + 1);
+            neg_at_sup = last_neg; has_neg_at_sup = has_neg;
+        }
+        prevA = a; prevB = b;
+    }
+    int32_t sizea = nk, sizeb = (int32_t)(Nu - nk);
+    w.sup = sup; w.supX = supX; w.last_neg_at_sup = neg_at_sup; w.has_neg_at_sup = has_neg_at_sup;
+    w.valid = (sizea > 1 && sizeb > 1); /* :195-196 */
+    return w;
+}
+
+void orc_ks_observed(int64_t Nu, const double* s, const int32_t* lab, int32_t T, orc_type_result* out) {
+    for (int32_t t = 0; t < T; t++) {
+        ks_walk w = ks_one_type(Nu, s, lab, t, 1);
+        orc_type_result* r = &out[t];
+        r->sizeA = w.nk; r->sizeB = (int32_t)(Nu - w.nk);
+        r->norm_ews = NAN; r->p_emp = NAN; r->fdr = NAN;
+        if (!w.valid) { /* :120-127, :317-323 */
+            r->ews = NAN; r->dstat = NAN; r->supX = -1; r->norm_supX = -1.0; r->raw_sup = NAN;
+            continue;
+        }
+        float sup = w.sup;
+        r->raw_sup = sup;
+        r->dstat = dstat_of(sup, r->sizeA, r->sizeB);
+        r->supX = w.supX;
+        r->norm_supX = 1.0 * (double)w.supX / (double)Nu; /* :215 */
+        if (w.has_neg_at_sup) sup = sup - fabsf(w.last_neg_at_sup); /* :216-227 */
+        r->ews = sup;
+    }
+}
+
+void orc_ks_null_one(int64_t Nu, const double* s, const int32_t* lab_perm, int32_t T,
+                     float* null_ews, float* null_d) {
+    for (int32_t t = 0; t < T; t++) {
+        ks_walk w = ks_one_type(Nu, s, lab_perm, t, 0);
+        if (!w.valid) { null_ews[t] = NAN; null_d[t] = NAN; continue; }
+        null_ews[t] = w.sup; /* :315 uncompensated */
+        null_d[t] = dstat_of(w.sup, w.nk, (int32_t)(Nu - w.nk));
+    }
+}
+
+/* ---- threads over types, re-created per permutation (CORE/PCTSEA.java:2498-2519) ----------- */
+typedef struct {
+    int64_t Nu; const double* s; const int32_t* lab; int32_t T; int32_t P; int32_t p;
+    float* null_ews; float* null_d; volatile int32_t* next;
+} null_job;
+
+static void* null_worker(void* arg) {
+    null_job* j = (null_job*)arg;
+    for (;;) {
+        int32_t t = __sync_fetch_and_add(j->next, 1);
+        if (t >= j->T) break;
+        ks_walk w = ks_one_type(j->Nu, j->s, j->lab, t, 0);
+        size_t o = (size_t)t * (size_t)j->P + (size_t)j->p;
+        if (!w.valid) { j->null_ews[o] = NAN; j->null_d[o] = NAN; }
+        else { j->null_ews[o] = w.sup; j->null_d[o] = dstat_of(w.sup, w.nk, (int32_t)(j->Nu - w.nk)); }
+    }
+    return NULL;
+}
+
+static void null_one_perm(int64_t Nu, const double* s, const int32_t* labp, int32_t T, int32_t P,
+                          int32_t p, int nthreads, float* null_ews, float* null_d) {
+    volatile int32_t next = 0;
+    null_job job = { Nu, s, labp, T, P, p, null_ews, null_d, &next };
+    if (nthreads <= 1) { null_worker(&job); return; }
+    pthread_t* th = (pthread_t*)malloc((size_t)nthreads * sizeof(pthread_t));
+    for (int k = 0; k < nthreads; k++) pthread_create(&th[k], NULL, null_worker, &job);
+    for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+    free(th);
+}
+
+void orc_null(int64_t Nu, const double* s, const int32_t* lab, int32_t T, int32_t P, int perm_mode,
+              uint64_t seed, int32_t perm_begin, int rounds, int nthreads, int32_t* replay_out,
+              float* null_ews, float* null_d) {
+    int32_t* idx = (int32_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int32_t));
+    int32_t* labp = (int32_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int32_t));
+    orc_jrandom jr; orc_jrandom_init(&jr, (int64_t)seed);
+    for (int32_t p = 0; p < P; p++) {
+        if (perm_mode == 0) {
+            /* CORE/PCTSEA.java:1403-1413: copy, Collections.shuffle, label at rank i = shuffled[i] */
+            for (int64_t i = 0; i < Nu; i++) idx[i] = (int32_t)i;
+            orc_java_shuffle_i32(idx, Nu, &jr);
+        } else {
+            orc_feistel_perm(seed, (uint32_t)(perm_begin + p), Nu, rounds, idx);
+        }
+        if (replay_out) memcpy(replay_out + (size_t)p * (size_t)Nu, idx, (size_t)Nu * sizeof(int32_t));
+        for (int64_t i = 0; i < Nu; i++) labp[i] = lab[idx[i]];
+        null_one_perm(Nu, s, labp, T, P, p, nthreads, null_ews, null_d);
+    }
+    free(idx); free(labp);
+}
+
+void orc_null_replay(int64_t Nu, const double* s, const int32_t* lab, int32_t T, int32_t P,
+                     const int32_t* replay, float* null_ews, float* null_d) {
+    int32_t* labp = (int32_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int32_t));
+    for (int32_t p = 0; p < P; p++) {
+        const int32_t* idx = replay + (size_t)p * (size_t)Nu;
+        for (int64_t i = 0; i < Nu; i++) labp[i] = lab[idx[i]];
+        null_one_perm(Nu, s, labp, T, P, p, 1, null_ews, null_d);
+    }
+    free(labp);
+}
+
+/* ============================================================================================
+ * a10 (CORE/PCTSEA.java:1449-1477,1799-1832), a11 (CORE/model/CellTypeClassification.java:407-441),
+ * a12 (CORE/PCTSEA.java:1479-1549).
+ * ========================================================================================== */
+
+void orc_reduce(int32_t T, int32_t P, const float* null_ews, int mean_policy, orc_type_result* io,
+                float* norm_null_out) {
+    float* norm_null = norm_null_out ? norm_null_out : (float*)malloc((size_t)T * (size_t)(P > 0 ? P : 1) * sizeof(float));
+    /* a10 */
+    for (int32_t t = 0; t < T; t++) {
+        float real = io[t].ews;
+        if (isnan(real)) { io[t].p_emp = NAN; continue; }
+        const float* nl = null_ews + (size_t)t * P;
+        int32_t total = 0, cnt = 0;
+        if (real >= 0.0f) {
+            for (int32_t p = 0; p < P; p++) { float v = nl[p]; if (isnan(v)) continue; if (v <= 0.0f) continue; total++; if (v > real) cnt++; }
+        } else {
+            for (int32_t p = 0; p < P; p++) { float v = nl[p]; if (isnan(v)) continue; if (v >= 0.0f) continue; total++; if (v < real) cnt++; }
+        }
+        io[t].p_emp = 1.0 * (double)cnt / (double)total; /* 0/0 -> NaN */
+    }
+    /* a11 */
+    for (int32_t t = 0; t < T; t++) {
+        float real = io[t].ews;
+        float* nn = norm_null + (size_t)t * P;
+        if (isnan(real)) { io[t].norm_ews = NAN; for (int32_t p = 0; p < P; p++) nn[p] = NAN; continue; }
+        const float* nl = null_ews + (size_t)t * P;
+        /* Maths.mean(TFloatList) is un-vendored: policy 0 = float running sum in list order / size */
+        float fsum_pos = 0.0f, fsum_neg = 0.0f; double dsum_pos = 0.0, dsum_neg = 0.0;
+        int32_t npos = 0, nneg = 0;
+        for (int32_t p = 0; p < P; p++) {
+            float v = nl[p];
+            if (v >= 0.0f) { fsum_pos += v; dsum_pos += (double)v; npos++; }
+            else if (v < 0.0f) { fsum_neg += v; dsum_neg += (double)v; nneg++; }
+        }
+        float mean_pos = mean_policy ? (float)(dsum_pos / (double)npos) : fsum_pos / (float)npos;
+        float mean_neg = mean_policy ? (float)(dsum_neg / (double)nneg) : fsum_neg / (float)nneg;
+        float expct = (real >= 0.0f) ? fabsf(mean_pos) : fabsf(mean_neg);
+        io[t].norm_ews = real / expct;
+        for (int32_t p = 0; p < P; p++) nn[p] = nl[p] / expct;
+    }
+    /* a12 */
+    int32_t nobs = 0; int64_t nnull = 0;
+    float* R = (float*)malloc((size_t)(T > 0 ? T : 1) * sizeof(float));
+    float* Z = (float*)malloc((size_t)T * (size_t)(P > 0 ? P : 1) * sizeof(float) + sizeof(float));
+    for (int32_t t = 0; t < T; t++) {
+        float ne = io[t].norm_ews;
+        if (isnan(ne)) continue;
+        if (!(ne < 0.0f)) R[nobs++] = ne;
+        const float* nn = norm_null + (size_t)t * P;
+        for (int32_t p = 0; p < P; p++) { float v = nn[p]; if (!(v < 0.0f)) Z[nnull++] = v; } /* NaN kept like Java's iterator.remove only on <0 */
+    }
+    orc_java_sort_f32(R, nobs);
+    orc_java_sort_f32(Z, nnull);
+    for (int32_t t = 0; t < T; t++) {
+        float ne = io[t].norm_ews;
+        if (isnan(ne) || ne < 0.0f) { io[t].fdr = NAN; continue; }
+        int32_t i1 = orc_java_binary_search_f32(R, nobs, ne);
+        int32_t i2 = orc_java_binary_search_f32(Z, (int32_t)nnull, ne);
+        int32_t sobs = nobs - (i1 >= 0 ? i1 + 1 : -i1 - 1);
+        int32_t snull = (int32_t)nnull - (i2 >= 0 ? i2 + 1 : -i2 - 1);
+        double fdr;
+        if (snull == 0) fdr = 0.0;
+        else fdr = (1.0 * (double)snull / (double)sobs) * (1.0 * (double)nobs / (double)nnull);
+        io[t].fdr = fdr;
+    }
+    free(R); free(Z);
+    if (!norm_null_out) free(norm_null);
+}
+
+/* ============================================================================================
+ * FAST-mode definition (this repo's own arithmetic, not the reference's): exact fixed-point
+ * prefix sums, supremum evaluated only at hit and pre-hit positions.
+ * ========================================================================================== */
+
+int orc_fast_frac_bits(int64_t Nu, const double* s) {
+    /* |fx| = |rint(s * 2^F)| <= 2^30 for every score: F = 30 - e with maxabs < 2^e */
+    double maxabs = 0.0;
+    for (int64_t i = 0; i < Nu; i++) { double v = fabs(s[i]); if (v > maxabs) maxabs = v; }
+    int e = 0;
+    if (maxabs > 0.0) e = ilogb(maxabs) + 1;
+    int F = 30 - e;
+    if (F > 1000) F = 1000;
+    return F;
+}
+
+static inline int fast_better(float f, float sup) {
+    /* larger |diff| wins; on equal |diff| the positive one wins (order-independent rule) */
+    float af = fabsf(f), as = fabsf(sup);
+    if (af > as) return 1;
+    if (af == as && af > 0.0f && f > 0.0f && sup < 0.0f) return 1;
+    return 0;
+}
+
+void orc_ks_null_fast_one(int64_t Nu, const double* s, const int32_t* lab, int32_t T,
+                          int frac_bits, float* null_ews) {
+    int64_t* fx = (int64_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int64_t));
+    int64_t* S = (int64_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int64_t));
+    int64_t acc = 0;
+    double scale = ldexp(1.0, frac_bits);
+    for (int64_t i = 0; i < Nu; i++) { fx[i] = llrint(s[i] * scale); acc += fx[i]; S[i] = acc; }
+    int64_t Stot = acc;
+    for (int32_t t = 0; t < T; t++) {
+        int64_t dA = 0; int32_t nk = 0;
+        for (int64_t i = 0; i < Nu; i++) if (lab[i] == t) { dA += fx[i]; nk++; }
+        int64_t dB = Stot - dA;
+        if (!(nk > 1 && Nu - nk > 1)) { null_ews[t] = NAN; continue; }
+        if (dA == 0 || dB == 0) { null_ews[t] = 0.0f; continue; }
+        double c1 = 1.0 / (double)dA, c2 = 1.0 / (double)dB;
+        float sup = 0.0f; int64_t numA = 0;
+        for (int64_t i = 0; i < Nu; i++) {
+            if (lab[i] != t) continue;
+            if (i > 0) {
+                double d0 = (double)numA * c1 - (double)(S[i - 1] - numA) * c2;
+                float f0 = (float)d0;
+                if (fast_better(f0, sup)) sup = f0;
+            }
+            numA += fx[i];
+            double d1 = (double)numA * c1 - (double)(S[i] - numA) * c2;
+            float f1 = (float)d1;
+            if (fast_better(f1, sup)) sup = f1;
+        }
+        null_ews[t] = sup;
+    }
+    free(fx); free(S);
+}

@@ -1,0 +1,297 @@
+"""Host-side mirror of pctsea-core's public surface for the accelerated path.
+
+Names, argument meaning and error behaviour follow the reference classes (paths under
+pctsea-core/src/main/java/edu/scripps/yates/pctsea/):
+  model/InputParameters.java:13-227, model/ScoringMethod.java:8-23, model/ScoringSchema.java:14-57,
+  scoring/ScoreThreshold.java, model/CellTypeClassification.java (getters), model/PCTSEAResult.java:17-64,
+  PCTSEA.java:174-217 (constructors), :257-534 (run), :2692-2818 (setters).
+The MongoDB repositories of the reference constructor are replaced by a SingleCellDataset: the matrix and the
+cell-type labels loaded once into device-resident CSR. Everything numeric goes through the C ABI
+(include/pctsea_b200.h); there is no CPU path here.
+"""
+from __future__ import annotations
+
+import dataclasses
+import enum
+import math
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, PctseaError
+
+
+class ScoringMethod(enum.Enum):
+    # model/ScoringMethod.java:8-23 — (scoreName)
+    SIMPLE_SCORE = "SimpleScore"
+    PEARSONS_CORRELATION = "correlation"
+    DOT_PRODUCT = "Dot-product"
+    QUICK_SCORE = "Quick_score"
+    REGRESSION = "Linear Regression"
+
+    def getScoreName(self) -> str:
+        return self.value
+
+
+class ScoreThreshold:
+    """scoring/ScoreThreshold.java: >= threshold when threshold >= 0, else < threshold."""
+
+    def __init__(self, threshold: float):
+        self.threshold = float(threshold)
+
+    def getThresholdValue(self) -> float:
+        return self.threshold
+
+    def __str__(self):
+        return ("<" if self.threshold < 0.0 else ">") + " " + str(self.threshold)
+
+
+@dataclasses.dataclass
+class ScoringSchema:
+    scoringMethod: ScoringMethod
+    scoringThreshold: ScoreThreshold
+    minGenesCells: int
+
+    def getScoringMethod(self):
+        return self.scoringMethod
+
+    def getScoringThreshold(self):
+        return self.scoringThreshold
+
+    def getMinGenesCells(self):
+        return self.minGenesCells
+
+
+class InputParameters:
+    # model/InputParameters.java:14-17, :49-64
+    DEFAULT_MIN_SCORE_SIMPLE_SCORE = 0.0
+    DEFAULT_MIN_SCORE_PEARSON = 0.2
+    DEFAULT_MIN_GENES_CELLS_SIMPLE_SCORE = 10
+    DEFAULT_MIN_GENES_CELLS_PEARSON = 100
+    EMAIL, OUT, PERM, EEF = "email", "out", "perm", "eef"
+    MIN_SCORE, MIN_GENES_CELLS = "min_score", "min_genes_cells"
+    CELL_TYPES_CLASSIFICATION, LOAD_RANDOM = "cell_types_classification", "load_random"
+    PLOT_NEGATIVE_ENRICHED, DATASETS, WRITE_SCORES = "plot_negative_enriched", "datasets", "write_scores"
+    UNIPROT_RELEASE, SCORING_METHOD, INPUT_DATA_TYPE = "uniprot_release", "scoring_method", "input_data_type"
+    MINIMUM_CORRELATION, CREATE_ZIP_FILE = "min_corr", "create_zip"
+
+    def __init__(self):
+        self.inputDataFile: Optional[str] = None
+        self.outputPrefix: Optional[str] = None
+        self.loadRandom = False
+        self.numPermutations = 10            # PCTSEACommandLine.java:213
+        self.minCorr: Optional[float] = -1.0  # PCTSEACommandLine.java:273
+        self.scoringSchemas: List[ScoringSchema] = []
+        # new, optional knobs (defaults keep the reference's behaviour; SURVEY.md §5 "Config / flags")
+        self.permutationMode = "PHILOX"      # or "REPLAY"
+        self.ksMode = "FAST"                 # or "EXACT"
+        self.seed = 0
+
+    def addScoringSchema(self, scoringMethod: ScoringMethod, minScore: float, minGenesCells: int):
+        self.scoringSchemas.append(ScoringSchema(scoringMethod, ScoreThreshold(minScore), minGenesCells))
+
+    def setInputDataFile(self, f):
+        self.inputDataFile = f
+
+    def setNumPermutations(self, n):
+        self.numPermutations = int(n)
+
+    def setMinCorr(self, v):
+        self.minCorr = v
+
+    def setOutputPrefix(self, p):
+        self.outputPrefix = p
+
+    def setLoadRandom(self, b):
+        self.loadRandom = bool(b)
+
+
+def read_experimental_expressions_file(path: str):
+    """GeneExpressionsRetriever.readExperimentalExpressionsFile (GeneExpressionsRetriever.java:358-409):
+    skip blank lines, skip the first non-blank line, TAB-separated, gene = col0 upper-cased,
+    abundance = Float.valueOf(col1); ids in file order."""
+    genes, ab = [], []
+    num_line = 0
+    with open(path, "r") as fh:
+        for line in fh:
+            line = line.rstrip("\n").rstrip("\r")
+            if line.strip() == "":
+                continue
+            num_line += 1
+            if num_line == 1:
+                continue
+            if "\t" not in line:
+                raise IOError(f"Error reading input file at line {num_line}: At least 2 columns separated by TAB are needed")
+            sp = line.split("\t")
+            if len(sp) < 2:
+                raise IOError(f"Error reading input file at line {num_line}: At least 2 columns separated by TAB are needed")
+            genes.append(sp[0].upper())
+            ab.append(np.float32(sp[1]))
+    return genes, np.asarray(ab, dtype=np.float32)
+
+
+class SingleCellDataset:
+    """The dataset the reference keeps in MongoDB (db/Expression.java, db/SingleCell.java), held as
+    device-resident CSR: rows = cells in DB order, columns = upper-cased gene names."""
+
+    def __init__(self, ctx: Context, row_ptr, col, val, gene_names: Sequence[str], cell_types: Sequence[str],
+                 cell_names: Optional[Sequence[str]] = None):
+        self.ctx = ctx
+        self.gene_names = [g.upper() for g in gene_names]
+        self.gene_index: Dict[str, int] = {g: i for i, g in enumerate(self.gene_names)}
+        self.cell_names = list(cell_names) if cell_names is not None else None
+        # model/CellTypes.getCellTypeID: string -> int id registry; empty / None = unknown (-1)
+        self.type_names: List[str] = sorted({t for t in cell_types if t})
+        tid = {t: i for i, t in enumerate(self.type_names)}
+        self.label = np.asarray([tid.get(t, -1) if t else -1 for t in cell_types], dtype=np.int32)
+        self.matrix = ctx.load_csr(row_ptr, col, val, len(self.gene_names))
+        self.matrix.set_labels(self.label, len(self.type_names))
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, row_ptr, col, val, n_genes: int, label: np.ndarray, n_types: int):
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.gene_names = [f"G{i}" for i in range(n_genes)]
+        self.gene_index = None
+        self.cell_names = None
+        self.type_names = [f"type{i}" for i in range(n_types)]
+        self.label = np.asarray(label, dtype=np.int32)
+        self.matrix = ctx.load_csr(row_ptr, col, val, n_genes)
+        self.matrix.set_labels(self.label, n_types)
+        return self
+
+    def map_list(self, genes: Sequence[str]) -> np.ndarray:
+        if self.gene_index is None:
+            return np.asarray([int(g[1:]) if g.startswith("G") else -1 for g in genes], dtype=np.int32)
+        return np.asarray([self.gene_index.get(g.upper(), -1) for g in genes], dtype=np.int32)
+
+
+class CellTypeClassification:
+    """model/CellTypeClassification.java — the fields the hot path sets, with the reference's getter names."""
+
+    def __init__(self, name: str, cellTypeID: int, r):
+        self.name, self.cellTypeID = name, cellTypeID
+        self.enrichmentScore = float(r["ews"])
+        self.dStatistic = float(r["dstat"])
+        self.supremumX = int(r["supX"])
+        self.normalizedSupremumX = float(r["norm_supX"])
+        self.sizeA, self.sizeB = int(r["sizeA"]), int(r["sizeB"])
+        self.normalizedEnrichmentScore = float(r["norm_ews"])
+        self.enrichmentSignificance = float(r["p_emp"])
+        self.enrichmentFDR = float(r["fdr"])
+        self.randomEnrichmentScores: Optional[np.ndarray] = None
+        self.randomKSTestStatistics: Optional[np.ndarray] = None
+
+    def getName(self): return self.name
+    def getCellTypeID(self): return self.cellTypeID
+    def getEnrichmentScore(self): return self.enrichmentScore
+    def getKSTestDStatistic(self): return self.dStatistic
+    def getSupremumX(self): return self.supremumX
+    def getNormalizedSupremumX(self): return self.normalizedSupremumX
+    def getSizeA(self): return self.sizeA
+    def getSizeB(self): return self.sizeB
+    def getNormalizedEnrichmentScore(self): return self.normalizedEnrichmentScore
+    def getEnrichmentSignificance(self): return self.enrichmentSignificance
+    def getEnrichmentFDR(self): return self.enrichmentFDR
+    def getRandomEnrichmentScores(self): return self.randomEnrichmentScores
+
+
+class PCTSEAResult:
+    def __init__(self):
+        self.significantTypes: List[CellTypeClassification] = []
+        self.cellTypesPerRound: List[List[CellTypeClassification]] = []
+        self.timings: List[dict] = []
+
+    def getSignificantTypes(self):
+        return self.significantTypes
+
+
+class PCTSEA:
+    MIN_CELLS_PASSING_SCORE_TRESHOLD = 1000       # PCTSEA.java:138
+    CELL_TYPE_FDR_SIGNIFICANCE_THRESHOLD = 0.05   # PCTSEA.java:167
+
+    def __init__(self, inputParameters: Optional[InputParameters], dataset: SingleCellDataset):
+        self.dataset = dataset
+        self.ctx = dataset.ctx
+        self.sequentialScoringSchemas: List[ScoringSchema] = []
+        self.maxIterations = 10
+        self.minCorr: Optional[float] = -1.0
+        self.experimentExpressionFile: Optional[str] = None
+        self.statusListener: Optional[Callable[[str], None]] = None
+        self.permutationMode, self.ksMode, self.seed = "PHILOX", "FAST", 0
+        self.inputGenes: Optional[Sequence[str]] = None
+        self.inputAbundance: Optional[np.ndarray] = None
+        self.keepNull = False
+        if inputParameters is not None:
+            self.sequentialScoringSchemas = list(inputParameters.scoringSchemas)
+            self.experimentExpressionFile = inputParameters.inputDataFile
+            self.maxIterations = inputParameters.numPermutations
+            self.minCorr = inputParameters.minCorr
+            self.permutationMode = inputParameters.permutationMode
+            self.ksMode = inputParameters.ksMode
+            self.seed = inputParameters.seed
+
+    # setters, PCTSEA.java:2692-2818
+    def setExperimentExpressionFile(self, f): self.experimentExpressionFile = f
+    def addScoreSchema(self, s: ScoringSchema): self.sequentialScoringSchemas.append(s)
+    def setMaxIterations(self, n): self.maxIterations = int(n)
+    def setMinimumCorrelation(self, v): self.minCorr = v
+    def setStatusListener(self, cb): self.statusListener = cb
+    def setInputList(self, genes: Sequence[str], abundance): self.inputGenes, self.inputAbundance = genes, np.asarray(abundance, np.float32)
+
+    def logStatus(self, msg: str):
+        if self.statusListener:
+            self.statusListener(msg)
+
+    def run(self) -> PCTSEAResult:
+        """PCTSEA.run (PCTSEA.java:257-534), the per-schema loop :348-475 with the bodies of a2-a12 on the GPU."""
+        if self.inputGenes is None:
+            if self.experimentExpressionFile is None:
+                raise ValueError("no input list")
+            self.inputGenes, self.inputAbundance = read_experimental_expressions_file(self.experimentExpressionFile)
+        gene_idx = self.dataset.map_list(self.inputGenes)
+        result = PCTSEAResult()
+        if self.minCorr is None:
+            # AnalyzeView.java:659-662 can hand a null Double; PCTSEA.java:379-381 unboxes it
+            raise TypeError("minCorr is null (NullPointerException on unboxing in the reference)")
+        for schema in self.sequentialScoringSchemas:
+            method = schema.getScoringMethod()
+            if method not in (ScoringMethod.PEARSONS_CORRELATION, ScoringMethod.SIMPLE_SCORE):
+                raise ValueError("Method " + method.getScoreName() + " still not supported.")
+            self.logStatus("Calculating " + method.getScoreName() + "...")
+            sprm = _lib.ScoreParams(
+                _lib.METHOD_PEARSONS_CORRELATION if method == ScoringMethod.PEARSONS_CORRELATION else _lib.METHOD_SIMPLE_SCORE,
+                schema.getMinGenesCells(), float(self.minCorr), 1, _lib.JITTER_PHILOX, self.seed)
+            nprm = Context.null_params(
+                self.maxIterations,
+                perm_mode=_lib.PERM_PHILOX if self.permutationMode == "PHILOX" else _lib.PERM_REPLAY,
+                ks_mode=_lib.KS_FAST if self.ksMode == "FAST" else _lib.KS_EXACT,
+                seed=self.seed, min_pass=self.MIN_CELLS_PASSING_SCORE_TRESHOLD)
+            try:
+                out = self.ctx.analyze(self.dataset.matrix, gene_idx, self.inputAbundance, sprm,
+                                       schema.getScoringThreshold().getThresholdValue(),
+                                       self.dataset.matrix.n_types, nprm, want_null=self.keepNull)
+            except PctseaError as e:
+                if e.code in (_lib.PCTSEA_ETOOFEW, _lib.PCTSEA_EMINGENES):
+                    raise ValueError(e.msg) from e  # IllegalArgumentException in the reference
+                raise
+            result.timings.append(self.ctx.timings())
+            types = []
+            for t, name in enumerate(self.dataset.type_names):
+                ct = CellTypeClassification(name, t, out["results"][t])
+                if self.keepNull:
+                    ct.randomEnrichmentScores = out["null"][t]
+                    ct.randomKSTestStatistics = out["nullD"][t]
+                types.append(ct)
+            # PCTSEA.java:2476-2482: sorted by enrichment score, descending (Double.compare: NaN first)
+            types.sort(key=lambda c: (0 if math.isnan(c.enrichmentScore) else 1, -c.enrichmentScore if not math.isnan(c.enrichmentScore) else 0.0))
+            result.cellTypesPerRound.append(types)
+        # getIntersection (PCTSEA.java:574-604): significant in every round, FDR <= 0.05
+        sig = None
+        for types in result.cellTypesPerRound:
+            names = {c.name for c in types if not math.isnan(c.enrichmentFDR) and c.enrichmentFDR <= self.CELL_TYPE_FDR_SIGNIFICANCE_THRESHOLD}
+            sig = names if sig is None else (sig & names)
+        last = result.cellTypesPerRound[-1] if result.cellTypesPerRound else []
+        result.significantTypes = [c for c in last if sig and c.name in sig]
+        return result

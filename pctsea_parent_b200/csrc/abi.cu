@@ -1,0 +1,532 @@
+// abi.cu — the extern "C" boundary of libpctsea_b200.so (see include/pctsea_b200.h).
+// Host-side sequencing only: uploads, stage launches on one stream, per-stage CUDA events, downloads.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+using namespace pctsea;
+
+namespace {
+
+struct EvTimer {
+    // per-chunk events for the null loop
+    std::vector<cudaEvent_t> ev;
+    ~EvTimer() { for (auto e : ev) cudaEventDestroy(e); }
+    cudaEvent_t mark(cudaStream_t s) {
+        cudaEvent_t e;
+        PCT_CUDA(cudaEventCreate(&e));
+        ev.push_back(e);
+        PCT_CUDA(cudaEventRecord(e, s));
+        return e;
+    }
+};
+
+void rec(pctsea_ctx* c, int which) {
+    PCT_CUDA(cudaEventRecord(c->ev[which], c->stream));
+    c->ev_rec[which] = true;
+}
+
+float between(pctsea_ctx* c, int a, int b) {
+    if (!c->ev_rec[a] || !c->ev_rec[b]) return 0.0f;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; }
+    return ms;
+}
+
+void begin_call(pctsea_ctx* c) {
+    PCT_CUDA(cudaSetDevice(c->device));
+    c->err.clear();
+    memset(&c->tm, 0, sizeof c->tm);
+    for (int i = 0; i < EV_COUNT; i++) c->ev_rec[i] = false;
+    c->launches = 0;
+}
+
+template <typename F>
+int guarded(pctsea_ctx* c, F&& f) {
+    if (!c) return PCTSEA_EINVAL;
+    try {
+        begin_call(c);
+        f();
+        return PCTSEA_OK;
+    } catch (const Error& e) {
+        c->err = e.what();
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        c->err = "host allocation failed";
+        return PCTSEA_ENOMEM;
+    } catch (const std::exception& e) {
+        c->err = e.what();
+        return PCTSEA_EINVAL;
+    } catch (...) {
+        c->err = "unknown error";
+        return PCTSEA_EINVAL;
+    }
+}
+
+void h2d(pctsea_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    PCT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->tm.h2d_bytes += (int64_t)bytes;
+}
+void d2h(pctsea_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    PCT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->tm.d2h_bytes += (int64_t)bytes;
+}
+
+void validate_score_params(const pctsea_score_params* p, int32_t L) {
+    PCT_REQUIRE(p != nullptr, "score params are NULL");
+    PCT_REQUIRE(p->method == PCTSEA_METHOD_PEARSONS_CORRELATION || p->method == PCTSEA_METHOD_SIMPLE_SCORE,
+                "scoring method not on the accelerated path (only PEARSONS_CORRELATION and SIMPLE_SCORE)");
+    PCT_REQUIRE(p->jitter_mode == PCTSEA_JITTER_NAN || p->jitter_mode == PCTSEA_JITTER_PHILOX, "bad jitter_mode");
+    if (p->min_genes_cells > L) {
+        // model/SingleCell.java:347-352
+        throw Error(PCTSEA_EMINGENES, "Minimum number of genes to be expressed in the cell lines (" +
+                                          std::to_string(p->min_genes_cells) +
+                                          ") is higher than the actual number of genes in the experimental input data (" +
+                                          std::to_string(L) + ")");
+    }
+}
+
+void upload_list(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_t* gene_idx, const float* abundance) {
+    PCT_REQUIRE(L >= 0, "negative list length");
+    PCT_REQUIRE(L == 0 || (gene_idx && abundance), "gene_idx / abundance are NULL");
+    PCT_REQUIRE(L <= 32767, "list longer than the reference's short gene ids allow (32767)");
+    // list entries must map to distinct columns (one matrix column per list entry)
+    std::vector<int32_t> tmp;
+    tmp.reserve(L);
+    for (int32_t l = 0; l < L; l++) {
+        PCT_REQUIRE(gene_idx[l] >= -1 && gene_idx[l] < m->n_genes, "gene_idx out of range");
+        if (gene_idx[l] >= 0) tmp.push_back(gene_idx[l]);
+    }
+    std::sort(tmp.begin(), tmp.end());
+    PCT_REQUIRE(std::adjacent_find(tmp.begin(), tmp.end()) == tmp.end(), "duplicate matrix column in gene_idx");
+    c->list_gene.reserve((size_t)std::max(L, 1) * 4);
+    c->list_abund.reserve((size_t)std::max(L, 1) * 4);
+    c->pin_in.reserve((size_t)std::max(L, 1) * 8);
+    memcpy(c->pin_in.p, gene_idx, (size_t)L * 4);
+    memcpy(c->pin_in.as<unsigned char>() + (size_t)L * 4, abundance, (size_t)L * 4);
+    h2d(c, c->list_gene.p, c->pin_in.p, (size_t)L * 4);
+    h2d(c, c->list_abund.p, c->pin_in.as<unsigned char>() + (size_t)L * 4, (size_t)L * 4);
+}
+
+struct NullPlan {
+    int32_t P = 0, begin = 0, count = 0;
+    bool full = false;
+    int rounds = 6;
+};
+
+NullPlan validate_null_params(const pctsea_null_params* p) {
+    PCT_REQUIRE(p != nullptr, "null params are NULL");
+    PCT_REQUIRE(p->n_perm >= 0, "negative n_perm");
+    PCT_REQUIRE(p->perm_mode == PCTSEA_PERM_REPLAY || p->perm_mode == PCTSEA_PERM_PHILOX, "bad perm_mode");
+    PCT_REQUIRE(p->ks_mode == PCTSEA_KS_EXACT || p->ks_mode == PCTSEA_KS_FAST, "bad ks_mode");
+    NullPlan np;
+    np.P = p->n_perm;
+    np.begin = p->perm_begin;
+    np.count = p->perm_count == 0 ? (p->n_perm - p->perm_begin) : p->perm_count;
+    PCT_REQUIRE(np.begin >= 0 && np.count >= 0 && np.begin + np.count <= np.P, "permutation slice out of range");
+    np.full = (np.begin == 0 && np.count == np.P);
+    np.rounds = p->feistel_rounds == 0 ? 6 : p->feistel_rounds;
+    PCT_REQUIRE(np.rounds >= 2 && np.rounds <= 32, "feistel_rounds out of range [2,32]");
+    return np;
+}
+
+// Stage 3 on device-resident score / label / order. Leaves results in c->results, the null slice in
+// c->null_ews / c->null_d ([T][count]).
+void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int32_t* label_dev,
+                   const int32_t* order_dev, int64_t Nu, int32_t T, const pctsea_null_params* prm, const NullPlan& np,
+                   const int32_t* replay_host, EvTimer& et, float* labels_ms, float* null_ms,
+                   std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& lab_spans,
+                   std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& null_spans) {
+    (void)labels_ms; (void)null_ms;
+    PCT_REQUIRE(T >= 0 && T <= 65534, "n_types out of range");
+    PCT_REQUIRE(Nu >= 1, "no ranked cells");
+    PCT_REQUIRE(Nu < (int64_t)1 << 31, "too many ranked cells");
+    EnrichGeom g;
+    g.Nu = Nu;
+    g.T = T;
+    const bool fast = prm->ks_mode == PCTSEA_KS_FAST;
+    launch_prepare_ranked(c, N, score_dev, label_dev, order_dev, g, fast);
+    rec(c, EV_RANK);
+    launch_ks_observed(c, g);
+    rec(c, EV_OBS);
+
+    const int32_t Pc_all = np.count;
+    c->null_ews.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
+    c->null_d.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
+    c->last_T = T;
+    c->last_Pc = Pc_all;
+    if (Pc_all > 0 && T > 0) {
+        if (prm->perm_mode == PCTSEA_PERM_REPLAY) PCT_REQUIRE(replay_host != nullptr, "REPLAY mode needs replay_perm");
+        // chunk the permutations so the label matrix stays within half of the free device memory
+        size_t free_b = 0, total_b = 0;
+        PCT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_perm = (size_t)g.Nu_pad * g.lab_bytes +
+                                (prm->perm_mode == PCTSEA_PERM_REPLAY ? (size_t)g.Nu * 4 : 0);
+        size_t budget = std::max<size_t>(free_b / 2 + c->labels.cap + c->replay.cap, (size_t)64 << 20);
+        int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)Pc_all, budget / std::max<size_t>(per_perm, 1)));
+        c->labels.reserve((size_t)chunk * g.Nu_pad * g.lab_bytes + 64);
+        for (int32_t p0 = 0; p0 < Pc_all; p0 += chunk) {
+            const int32_t pc = std::min(chunk, Pc_all - p0);
+            FastPlan fp = plan_fast(g, pc);
+            cudaEvent_t e0 = et.mark(c->stream);
+            if (prm->perm_mode == PCTSEA_PERM_REPLAY) {
+                c->replay.reserve((size_t)pc * g.Nu * 4 + 64);
+                h2d(c, c->replay.p, replay_host + (size_t)p0 * g.Nu, (size_t)pc * g.Nu * 4);
+                launch_labels_replay(c, g, c->replay.as<int32_t>(), pc);
+                if (fast) throw Error(PCTSEA_EINVAL, "REPLAY permutations are a validation mode: use ks_mode EXACT");
+            } else {
+                launch_labels_philox(c, g, prm->seed, np.begin + p0, pc, np.rounds, fast, fp);
+            }
+            cudaEvent_t e1 = et.mark(c->stream);
+            if (fast) launch_ks_fast_null(c, g, pc, fp, Pc_all, p0);
+            else launch_ks_exact_null(c, g, pc, Pc_all, p0);
+            cudaEvent_t e2 = et.mark(c->stream);
+            lab_spans.push_back({ e0, e1 });
+            null_spans.push_back({ e1, e2 });
+        }
+    }
+    rec(c, EV_NULL);
+    if (np.full && T > 0) launch_reduce(c, T, np.P, c->null_ews.as<float>(), prm->mean_policy,
+                                        c->results.as<pctsea_type_result>());
+    rec(c, EV_REDUCE);
+}
+
+void finish_timings(pctsea_ctx* c, const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& lab_spans,
+                    const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& null_spans) {
+    PCT_CUDA(cudaStreamSynchronize(c->stream));
+    c->tm.setup_ms = between(c, EV_BEGIN, EV_SETUP);
+    c->tm.score_ms = between(c, EV_SETUP, EV_SCORE);
+    c->tm.rank_ms = between(c, EV_SCORE, EV_RANK);
+    c->tm.observed_ms = between(c, EV_RANK, EV_OBS);
+    c->tm.reduce_ms = between(c, EV_NULL, EV_REDUCE);
+    c->tm.total_ms = between(c, EV_BEGIN, EV_END);
+    float lm = 0, nm = 0;
+    for (auto& s : lab_spans) { float ms = 0; if (cudaEventElapsedTime(&ms, s.first, s.second) == cudaSuccess) lm += ms; }
+    for (auto& s : null_spans) { float ms = 0; if (cudaEventElapsedTime(&ms, s.first, s.second) == cudaSuccess) nm += ms; }
+    c->tm.labels_ms = lm;
+    c->tm.null_ms = nm;
+    c->tm.launches = c->launches;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pctsea_abi_version(void) { return PCTSEA_ABI_VERSION; }
+
+int pctsea_create(int device_id, pctsea_ctx** out) {
+    if (!out) return PCTSEA_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n) {
+        cudaGetLastError();
+        return PCTSEA_ECUDA;  // no CPU fallback
+    }
+    pctsea_ctx* c = new (std::nothrow) pctsea_ctx();
+    if (!c) return PCTSEA_ENOMEM;
+    c->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return PCTSEA_ECUDA;
+    }
+    for (int i = 0; i < EV_COUNT; i++) {
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { cudaGetLastError(); delete c; return PCTSEA_ECUDA; }
+        c->ev_rec[i] = false;
+    }
+    memset(&c->tm, 0, sizeof c->tm);
+    *out = c;
+    return PCTSEA_OK;
+}
+
+int pctsea_destroy(pctsea_ctx* c) {
+    if (!c) return PCTSEA_EINVAL;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->score, &c->nused, &c->nnzc, &c->kept,
+                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
+                       &c->order, &c->label_tmp, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
+                       &c->replay, &c->segsum, &c->coef, &c->supkey, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
+                       &c->red_keys, &c->red_keys2, &c->red_vals, &c->red_vals2, &c->red_misc };
+    for (DevBuf* b : bufs) b->release();
+    c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
+    for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return PCTSEA_OK;
+}
+
+const char* pctsea_last_error(pctsea_ctx* c) { return c ? c->err.c_str() : "NULL ctx"; }
+
+int pctsea_get_timings(pctsea_ctx* c, pctsea_timings* out) {
+    if (!c || !out) return PCTSEA_EINVAL;
+    *out = c->tm;
+    return PCTSEA_OK;
+}
+
+void* pctsea_stream(pctsea_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int pctsea_matrix_load_csr(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, const int64_t* row_ptr,
+                           const int32_t* col_idx, const float* val, pctsea_matrix** out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(out != nullptr, "out is NULL");
+        *out = nullptr;
+        PCT_REQUIRE(n_cells >= 0 && n_cells < ((int64_t)1 << 31), "n_cells out of range");
+        PCT_REQUIRE(n_genes >= 0, "n_genes out of range");
+        PCT_REQUIRE(row_ptr != nullptr, "row_ptr is NULL");
+        PCT_REQUIRE(row_ptr[0] == 0, "row_ptr[0] must be 0");
+        for (int64_t i = 0; i < n_cells; i++) PCT_REQUIRE(row_ptr[i + 1] >= row_ptr[i], "row_ptr must be non-decreasing");
+        const int64_t nnz = row_ptr[n_cells];
+        PCT_REQUIRE(nnz == 0 || (col_idx && val), "col_idx / val are NULL");
+        pctsea_matrix* m = new pctsea_matrix();
+        m->n_cells = n_cells; m->n_genes = n_genes; m->nnz = nnz; m->owned = true;
+        void *rp = nullptr, *ci = nullptr, *vv = nullptr;
+        try {
+            PCT_CUDA(cudaMalloc(&rp, (size_t)(n_cells + 1) * 8));
+            PCT_CUDA(cudaMalloc(&ci, (size_t)std::max<int64_t>(nnz, 1) * 4));
+            PCT_CUDA(cudaMalloc(&vv, (size_t)std::max<int64_t>(nnz, 1) * 4));
+            PCT_CUDA(cudaMemcpyAsync(rp, row_ptr, (size_t)(n_cells + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+            if (nnz) {
+                PCT_CUDA(cudaMemcpyAsync(ci, col_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+                PCT_CUDA(cudaMemcpyAsync(vv, val, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+            }
+            PCT_CUDA(cudaStreamSynchronize(c->stream));
+        } catch (...) {
+            if (rp) cudaFree(rp);
+            if (ci) cudaFree(ci);
+            if (vv) cudaFree(vv);
+            delete m;
+            throw;
+        }
+        m->row_ptr = (const int64_t*)rp; m->col = (const int32_t*)ci; m->val = (const float*)vv;
+        *out = m;
+    });
+}
+
+int pctsea_matrix_wrap_device(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, const int64_t* row_ptr_dev,
+                              const int32_t* col_idx_dev, const float* val_dev, pctsea_matrix** out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(out != nullptr, "out is NULL");
+        *out = nullptr;
+        PCT_REQUIRE(n_cells >= 0 && n_cells < ((int64_t)1 << 31) && n_genes >= 0, "shape out of range");
+        PCT_REQUIRE(row_ptr_dev != nullptr, "row_ptr_dev is NULL");
+        int64_t nnz = 0;
+        PCT_CUDA(cudaMemcpy(&nnz, row_ptr_dev + n_cells, 8, cudaMemcpyDeviceToHost));
+        pctsea_matrix* m = new pctsea_matrix();
+        m->n_cells = n_cells; m->n_genes = n_genes; m->nnz = nnz; m->owned = false;
+        m->row_ptr = row_ptr_dev; m->col = col_idx_dev; m->val = val_dev;
+        *out = m;
+    });
+}
+
+int pctsea_matrix_set_labels(pctsea_ctx* c, pctsea_matrix* m, const int32_t* label, int32_t n_types) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(m != nullptr && label != nullptr, "matrix / label are NULL");
+        PCT_REQUIRE(n_types >= 0 && n_types <= 65534, "n_types out of range");
+        if (!m->label) { void* p = nullptr; PCT_CUDA(cudaMalloc(&p, (size_t)std::max<int64_t>(m->n_cells, 1) * 4)); m->label = (int32_t*)p; }
+        PCT_CUDA(cudaMemcpy(m->label, label, (size_t)m->n_cells * 4, cudaMemcpyHostToDevice));
+        m->n_types = n_types;
+    });
+}
+
+int pctsea_matrix_free(pctsea_ctx* c, pctsea_matrix* m) {
+    if (!m) return PCTSEA_EINVAL;
+    if (c) cudaSetDevice(c->device);
+    if (m->owned) { cudaFree((void*)m->row_ptr); cudaFree((void*)m->col); cudaFree((void*)m->val); }
+    if (m->label) cudaFree(m->label);
+    delete m;
+    return PCTSEA_OK;
+}
+
+int pctsea_score(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_t* gene_idx, const float* abundance,
+                 const pctsea_score_params* prm, double* score_out, int32_t* n_genes_used_out, int32_t* n_nonzero_out,
+                 uint8_t* kept_out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(m != nullptr, "matrix is NULL");
+        PCT_REQUIRE(score_out != nullptr, "score_out is NULL");
+        rec(c, EV_BEGIN);
+        upload_list(c, m, L, gene_idx, abundance);
+        validate_score_params(prm, L);
+        rec(c, EV_SETUP);
+        ScoreArgs sa{ m, L, c->list_gene.as<int32_t>(), c->list_abund.as<float>(), *prm };
+        launch_score(c, sa);
+        rec(c, EV_SCORE);
+        const int64_t N = m->n_cells;
+        d2h(c, score_out, c->score.p, (size_t)N * 8);
+        if (n_genes_used_out) d2h(c, n_genes_used_out, c->nused.p, (size_t)N * 4);
+        if (n_nonzero_out) d2h(c, n_nonzero_out, c->nnzc.p, (size_t)N * 4);
+        if (kept_out) d2h(c, kept_out, c->kept.p, (size_t)N);
+        rec(c, EV_END);
+        finish_timings(c, {}, {});
+    });
+}
+
+int pctsea_rank(pctsea_ctx* c, int64_t n_cells, const double* score, const uint8_t* kept, double min_score,
+                int32_t* order_out, int64_t* n_pass_out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(n_cells >= 0 && n_cells < ((int64_t)1 << 31), "n_cells out of range");
+        PCT_REQUIRE(n_cells == 0 || score != nullptr, "score is NULL");
+        PCT_REQUIRE(order_out != nullptr && n_pass_out != nullptr, "outputs are NULL");
+        PCT_REQUIRE(min_score == min_score, "min_score is NaN");
+        rec(c, EV_BEGIN);
+        c->score.reserve((size_t)std::max<int64_t>(n_cells, 1) * 8);
+        c->kept.reserve((size_t)std::max<int64_t>(n_cells, 1));
+        h2d(c, c->score.p, score, (size_t)n_cells * 8);
+        if (kept) h2d(c, c->kept.p, kept, (size_t)n_cells);
+        rec(c, EV_SETUP);
+        rec(c, EV_SCORE);
+        int64_t np = launch_rank(c, n_cells, c->score.as<double>(), kept ? c->kept.as<uint8_t>() : nullptr, min_score);
+        rec(c, EV_RANK);
+        d2h(c, order_out, c->order.p, (size_t)np * 4);
+        rec(c, EV_END);
+        finish_timings(c, {}, {});
+        *n_pass_out = np;
+        c->tm.n_pass = np;
+        c->tm.n_used = np > 0 ? np - 1 : 0;
+    });
+}
+
+int pctsea_enrich(pctsea_ctx* c, int64_t n_cells, const double* score, int64_t n_used, const int32_t* order,
+                  const int32_t* label, int32_t n_types, const pctsea_null_params* prm, const int32_t* replay_perm,
+                  pctsea_type_result* out, float* null_out, float* nullD_out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(score && order && label && out, "score / order / label / out are NULL");
+        PCT_REQUIRE(n_cells >= 1 && n_cells < ((int64_t)1 << 31), "n_cells out of range");
+        PCT_REQUIRE(n_used >= 1 && n_used <= n_cells, "n_used out of range");
+        for (int64_t i = 0; i < n_used; i++) PCT_REQUIRE(order[i] >= 0 && order[i] < n_cells, "order entry out of range");
+        NullPlan np = validate_null_params(prm);
+        rec(c, EV_BEGIN);
+        c->score.reserve((size_t)n_cells * 8);
+        c->label_tmp.reserve((size_t)n_cells * 4);
+        c->order.reserve((size_t)n_cells * 4);
+        h2d(c, c->score.p, score, (size_t)n_cells * 8);
+        h2d(c, c->label_tmp.p, label, (size_t)n_cells * 4);
+        h2d(c, c->order.p, order, (size_t)n_used * 4);
+        rec(c, EV_SETUP);
+        rec(c, EV_SCORE);
+        EvTimer et;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ls, ns;
+        float lm = 0, nm = 0;
+        enrich_device(c, n_cells, c->score.as<double>(), c->label_tmp.as<int32_t>(), c->order.as<int32_t>(), n_used,
+                      n_types, prm, np, replay_perm, et, &lm, &nm, ls, ns);
+        d2h(c, out, c->results.p, (size_t)n_types * sizeof(pctsea_type_result));
+        if (null_out) d2h(c, null_out, c->null_ews.p, (size_t)n_types * np.count * 4);
+        if (nullD_out) d2h(c, nullD_out, c->null_d.p, (size_t)n_types * np.count * 4);
+        rec(c, EV_END);
+        finish_timings(c, ls, ns);
+        c->tm.n_used = n_used;
+        c->tm.n_pass = n_used + 1;
+    });
+}
+
+static void reduce_common(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, int32_t mean_policy,
+                          pctsea_type_result* inout) {
+    c->results.reserve((size_t)std::max(T, 1) * sizeof(pctsea_type_result));
+    h2d(c, c->results.p, inout, (size_t)T * sizeof(pctsea_type_result));
+    rec(c, EV_NULL);
+    launch_reduce(c, T, P, null_dev, mean_policy, c->results.as<pctsea_type_result>());
+    rec(c, EV_REDUCE);
+    d2h(c, inout, c->results.p, (size_t)T * sizeof(pctsea_type_result));
+    rec(c, EV_END);
+    finish_timings(c, {}, {});
+}
+
+int pctsea_reduce_null(pctsea_ctx* c, int32_t n_types, int32_t n_perm, const float* null_ews, int32_t mean_policy,
+                       pctsea_type_result* inout) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(n_types >= 0 && n_perm >= 0 && inout != nullptr, "bad arguments");
+        PCT_REQUIRE((int64_t)n_types * n_perm == 0 || null_ews != nullptr, "null_ews is NULL");
+        rec(c, EV_BEGIN);
+        // keep it apart from the ctx's own null slice
+        c->red_tmp.reserve((size_t)std::max<int64_t>((int64_t)n_types * n_perm, 1) * 4);
+        h2d(c, c->red_tmp.p, null_ews, (size_t)n_types * n_perm * 4);
+        reduce_common(c, n_types, n_perm, c->red_tmp.as<float>(), mean_policy, inout);
+    });
+}
+
+int pctsea_reduce_null_dev(pctsea_ctx* c, int32_t n_types, int32_t n_perm, const float* null_ews_dev,
+                           int32_t mean_policy, pctsea_type_result* inout) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(n_types >= 0 && n_perm >= 0 && inout != nullptr, "bad arguments");
+        PCT_REQUIRE((int64_t)n_types * n_perm == 0 || null_ews_dev != nullptr, "null_ews_dev is NULL");
+        rec(c, EV_BEGIN);
+        reduce_common(c, n_types, n_perm, null_ews_dev, mean_policy, inout);
+    });
+}
+
+int pctsea_analyze(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_t* gene_idx, const float* abundance,
+                   const pctsea_score_params* sprm, double min_score, const int32_t* label, int32_t n_types,
+                   const pctsea_null_params* nprm, const int32_t* replay_perm, pctsea_type_result* out,
+                   float* null_out, float* nullD_out, double* score_out, int32_t* n_genes_used_out, uint8_t* kept_out,
+                   int32_t* order_out, int64_t* n_pass_out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(m != nullptr && out != nullptr, "matrix / out are NULL");
+        PCT_REQUIRE(min_score == min_score, "min_score is NaN");
+        const int64_t N = m->n_cells;
+        PCT_REQUIRE(N >= 1, "empty matrix");
+        if (!label) {
+            PCT_REQUIRE(m->label != nullptr, "no labels: pass label[] or call pctsea_matrix_set_labels");
+            PCT_REQUIRE(n_types == m->n_types, "n_types differs from the matrix's resident labels");
+        }
+        NullPlan np = validate_null_params(nprm);
+        rec(c, EV_BEGIN);
+        upload_list(c, m, L, gene_idx, abundance);
+        validate_score_params(sprm, L);
+        const int32_t* label_dev = m->label;
+        if (label) {
+            c->label_tmp.reserve((size_t)N * 4);
+            h2d(c, c->label_tmp.p, label, (size_t)N * 4);
+            label_dev = c->label_tmp.as<int32_t>();
+        }
+        rec(c, EV_SETUP);
+        ScoreArgs sa{ m, L, c->list_gene.as<int32_t>(), c->list_abund.as<float>(), *sprm };
+        launch_score(c, sa);
+        rec(c, EV_SCORE);
+        const int64_t Np = launch_rank(c, N, c->score.as<double>(), c->kept.as<uint8_t>(), min_score);
+        if (n_pass_out) *n_pass_out = Np;
+        c->tm.n_pass = Np;
+        c->tm.n_used = Np > 0 ? Np - 1 : 0;
+        if (score_out) d2h(c, score_out, c->score.p, (size_t)N * 8);
+        if (n_genes_used_out) d2h(c, n_genes_used_out, c->nused.p, (size_t)N * 4);
+        if (kept_out) d2h(c, kept_out, c->kept.p, (size_t)N);
+        if (order_out) d2h(c, order_out, c->order.p, (size_t)Np * 4);
+        if (Np < (int64_t)nprm->min_pass || Np < 2) {
+            PCT_CUDA(cudaStreamSynchronize(c->stream));
+            // PCTSEA.java:389-395
+            throw Error(PCTSEA_ETOOFEW, "There is not enough cells passing the threshold (only " + std::to_string(Np) +
+                                            " pass the threshold and the minimum is " +
+                                            std::to_string(std::max(nprm->min_pass, 2)) + ")");
+        }
+        const int64_t Nu = Np - 1;
+        EvTimer et;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ls, ns;
+        float lm = 0, nm = 0;
+        enrich_device(c, N, c->score.as<double>(), label_dev, c->order.as<int32_t>(), Nu, n_types, nprm, np, replay_perm,
+                      et, &lm, &nm, ls, ns);
+        d2h(c, out, c->results.p, (size_t)n_types * sizeof(pctsea_type_result));
+        if (null_out) d2h(c, null_out, c->null_ews.p, (size_t)n_types * np.count * 4);
+        if (nullD_out) d2h(c, nullD_out, c->null_d.p, (size_t)n_types * np.count * 4);
+        rec(c, EV_END);
+        finish_timings(c, ls, ns);
+        c->tm.n_pass = Np;
+        c->tm.n_used = Nu;
+    });
+}
+
+int pctsea_last_null_dev(pctsea_ctx* c, float** null_dev, float** nullD_dev, int32_t* n_types, int32_t* perm_count) {
+    if (!c) return PCTSEA_EINVAL;
+    if (null_dev) *null_dev = c->null_ews.as<float>();
+    if (nullD_dev) *nullD_dev = c->null_d.as<float>();
+    if (n_types) *n_types = c->last_T;
+    if (perm_count) *perm_count = c->last_Pc;
+    return PCTSEA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+// common.cuh — shared internals of libpctsea_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <cstdio>
+#include <cmath>
+
+#include "../../include/pctsea_b200.h"
+
+namespace pctsea {
+
+constexpr int kNumSMs = 148;  // B200
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PCT_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            char _b[512];                                                                           \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),         \
+                     __FILE__, __LINE__);                                                           \
+            throw ::pctsea::Error(PCTSEA_ECUDA, _b);                                                \
+        }                                                                                           \
+    } while (0)
+
+#define PCT_REQUIRE(cond, msg)                                                                      \
+    do {                                                                                            \
+        if (!(cond)) throw ::pctsea::Error(PCTSEA_EINVAL, std::string(msg));                        \
+    } while (0)
+
+// Grow-only device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(PCTSEA_ENOMEM, std::string("cudaMalloc of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+        }
+        cap = want;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        PCT_CUDA(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+enum Ev { EV_BEGIN = 0, EV_SETUP, EV_SCORE, EV_RANK, EV_OBS, EV_LABELS, EV_NULL, EV_REDUCE, EV_END, EV_COUNT };
+
+}  // namespace pctsea
+
+struct pctsea_matrix {
+    int64_t n_cells = 0;
+    int32_t n_genes = 0;
+    int64_t nnz = 0;
+    const int64_t* row_ptr = nullptr;  // device
+    const int32_t* col = nullptr;      // device
+    const float* val = nullptr;        // device
+    bool owned = false;
+    int32_t* label = nullptr;  // device, [n_cells], owned
+    int32_t n_types = 0;
+};
+
+struct pctsea_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    cudaEvent_t ev[pctsea::EV_COUNT];
+    bool ev_rec[pctsea::EV_COUNT];
+    pctsea_timings tm;
+    int64_t launches = 0;
+
+    // workspaces (grow-only)
+    pctsea::DevBuf list_gene, list_abund, ybg, bitmap;          // stage 1 lookup
+    pctsea::DevBuf score, nused, nnzc, kept;                    // stage 1 outputs [N]
+    pctsea::DevBuf keysA, keysB, valsA, valsB, hist, tile_hist, scan_tmp, counters;  // radix sort
+    pctsea::DevBuf order;                                       // [N] int32
+    pctsea::DevBuf label_tmp;                                   // [N] int32 (when labels passed per call)
+    pctsea::DevBuf s_rank, lab_rank, fx, Sfx, class_cnt;        // ranked arrays [Nu]
+    pctsea::DevBuf labels;                                      // [Pc][Nu_pad] permuted labels
+    pctsea::DevBuf replay;                                      // [Pc][Nu] int32
+    pctsea::DevBuf segsum, coef, supkey;                        // FAST mode
+    pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
+    pctsea::DevBuf results;                                     // [T] pctsea_type_result
+    pctsea::DevBuf red_tmp, red_keys, red_keys2, red_vals, red_vals2, red_misc;  // reduce
+    pctsea::PinnedBuf pin_in, pin_out, pin_small;
+    int32_t last_T = 0, last_Pc = 0;
+};
+
+namespace pctsea {
+
+// ---- Philox4x32-10 (device + host) ------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Feistel geometry shared by host and device: a = ceil(sqrt(n)), b = ceil(n / a).
+inline void feistel_dims(int64_t n, uint32_t* a_out, uint32_t* b_out) {
+    int64_t a = (int64_t)std::floor(std::sqrt((double)n));
+    while (a * a < n) a++;
+    while (a > 1 && (a - 1) * (a - 1) >= n) a--;
+    if (a < 1) a = 1;
+    *a_out = (uint32_t)a;
+    *b_out = (uint32_t)((n + a - 1) / a);
+}
+
+inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return div_up(a, b) * b; }
+
+// ---- stage launchers (implemented in the per-stage .cu files) ----------------------------------
+struct ScoreArgs {
+    const pctsea_matrix* m;
+    int32_t L;
+    const int32_t* gene_idx_dev;
+    const float* abund_dev;
+    pctsea_score_params prm;
+};
+void launch_score(pctsea_ctx* c, const ScoreArgs& a);
+
+// Threshold + stable radix sort; writes c->order ([Np]); returns Np (syncs the stream once).
+int64_t launch_rank(pctsea_ctx* c, int64_t N, const double* score_dev, const uint8_t* kept_dev, double min_score);
+
+// Generic stable LSD radix sort of (u64 key, u32 value) pairs; result lands in keys_out/vals_out
+// (which of the two supplied buffers that is, is returned through the pointers).
+void radix_sort_pairs(pctsea_ctx* c, int64_t n, uint64_t** keys, uint64_t** keys_alt, uint32_t** vals,
+                      uint32_t** vals_alt, int key_bits);
+
+struct EnrichGeom {
+    int64_t Nu = 0;
+    int64_t Nu_pad = 0;  // label row stride in elements (multiple of 128)
+    int32_t T = 0;       // cell types
+    int32_t Tc = 0;      // classes = T + 1 (sentinel class T = unknown type)
+    int lab_bytes = 1;   // 1 (u8) or 2 (u16)
+    int frac_bits = 0;
+};
+// Gather ranked arrays (s_rank, lab_rank), class counts, fixed-point prefix (fx, Sfx).
+void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, const int32_t* label_dev,
+                           const int32_t* order_dev, EnrichGeom& g, bool want_fixed);
+void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g);
+void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* replay_dev, int32_t Pc);
+struct FastPlan { int64_t seg = 0; int32_t K = 0; };
+FastPlan plan_fast(const EnrichGeom& g, int32_t Pc);
+void launch_labels_philox(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc,
+                          int rounds, bool want_sums, const FastPlan& fp);
+void launch_ks_exact_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, int32_t P_stride, int32_t p_off);
+void launch_ks_fast_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, const FastPlan& fp, int32_t P_stride,
+                         int32_t p_off);
+void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, int mean_policy,
+                   pctsea_type_result* results_dev);
+
+inline void count_launch(pctsea_ctx* c, int n = 1) { c->launches += n; }
+
+}  // namespace pctsea

@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): scores <= 1e-9 relative (here: bit-exact, canonical pair order), ranking and
+observed enrichment bit-exact, REPLAY null bit-exact, PHILOX null bit-exact against the oracle's restatement
+of the same keyed permutation, FAST arithmetic within a stated tolerance of EXACT, p/FDR exact given the null.
+"""
+import numpy as np
+import pytest
+
+import pctsea_parent_b200 as P
+from pctsea_parent_b200 import synth
+from tests.helpers import (OBSERVED_FIELDS, assert_bits_equal_f32, assert_bits_equal_f64, assert_results_equal)
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(ctx, d):
+    m = ctx.load_csr(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes)
+    m.set_labels(d["label"], d["cfg"].n_types)
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 1
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("jitter", [0, 1])
+def test_score_bit_exact(ctx, oracle, tiny, method, jitter):
+    d = tiny
+    m = _load(ctx, d)
+    kw = dict(method=method, min_genes_cells=4, min_corr=0.2 if method == 0 else -1.0, has_min_corr=True,
+              jitter_mode=jitter, seed=1234)
+    g = ctx.score(m, d["gene_idx"], d["abundance"], **kw)
+    o = oracle.score(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes, d["gene_idx"], d["abundance"], **kw)
+    assert np.array_equal(g[1], o[1]), "n_genes_used"
+    assert np.array_equal(g[2], o[2]), "n_nonzero"
+    assert np.array_equal(g[3], o[3]), "kept"
+    assert_bits_equal_f64(g[0], o[0], "score")
+    # north_star tolerance, stated: 1e-9 relative (bit-exactness above is stronger)
+    ok = ~np.isnan(o[0])
+    assert ok.sum() > 100
+    assert np.all(np.abs(g[0][ok] - o[0][ok]) <= 1e-9 * np.maximum(1.0, np.abs(o[0][ok])))
+    m.free()
+
+
+def test_score_edge_cases(ctx, oracle):
+    # empty rows, a row with NaN / zero / negative values, list genes absent from the matrix (-1),
+    # non-positive abundance, zero-variance cells, a cell with exactly min_genes pairs
+    G = 50
+    rows = [
+        [],                                                        # empty cell
+        [(1, 1.0), (2, 1.0), (3, 1.0), (4, 1.0)],                 # zero variance in the cell
+        [(1, 2.0), (2, 5.0), (3, 1.0), (4, 7.0), (9, 3.0)],       # regular
+        [(1, float("nan")), (2, 5.0), (3, 0.0), (4, -2.0), (5, 1.0), (6, 2.0), (7, 9.0)],
+        [(1, 3.0), (2, 1.0)],                                      # fewer than min_genes pairs
+        [(10, 4.0), (11, 4.0), (12, 2.0), (13, 8.0)],             # list genes 10..13 share one abundance
+        [(40, 1.0), (41, 2.0)],                                    # no list gene at all
+    ]
+    row_ptr = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64)
+    col = np.array([c for r in rows for c, _ in r], np.int32)
+    val = np.array([v for r in rows for _, v in r], np.float32)
+    gene_idx = np.array([1, 2, 3, 4, 5, 6, 7, 9, -1, 10, 11, 12, 13, 20], np.int32)
+    abundance = np.array([3, 1, 4, 1.5, 9, 2, 6, 5, 7, 2, 2, 2, 2, 0.0], np.float32)
+    m = ctx.load_csr(row_ptr, col, val, G)
+    for method in (0, 1):
+        for jitter in (0, 1):
+            kw = dict(method=method, min_genes_cells=3, min_corr=-1.0, has_min_corr=True, jitter_mode=jitter, seed=7)
+            g = ctx.score(m, gene_idx, abundance, **kw)
+            o = oracle.score(row_ptr, col, val, G, gene_idx, abundance, **kw)
+            assert np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2]) and np.array_equal(g[3], o[3])
+            assert_bits_equal_f64(g[0], o[0], f"score m{method} j{jitter}")
+    # min_genes_cells > L raises like model/SingleCell.java:347-352
+    with pytest.raises(P.PctseaError) as e:
+        ctx.score(m, gene_idx, abundance, min_genes_cells=gene_idx.size + 1)
+    assert e.value.code == -5
+    # duplicate matrix column in the list is rejected
+    with pytest.raises(P.PctseaError):
+        ctx.score(m, np.array([1, 1, 2, 3], np.int32), np.ones(4, np.float32), min_genes_cells=1)
+    m.free()
+
+
+def test_score_long_list_small_buffer(ctx, oracle):
+    # dense cells against a long list: forces the flush-and-rescan path of the pair buffer
+    rng = np.random.default_rng(5)
+    N, G, L = 300, 3000, 2500
+    dense = rng.random((N, G)) < 0.6
+    vals = rng.integers(1, 9, size=(N, G)).astype(np.float32) * dense
+    row_ptr = np.zeros(N + 1, np.int64)
+    row_ptr[1:] = np.cumsum(dense.sum(1))
+    r, c = np.nonzero(dense)
+    col, val = c.astype(np.int32), vals[r, c]
+    gene_idx = rng.permutation(G)[:L].astype(np.int32)
+    abundance = rng.integers(1, 50, L).astype(np.float32)
+    m = ctx.load_csr(row_ptr, col, val, G)
+    g = ctx.score(m, gene_idx, abundance, min_genes_cells=10, min_corr=-1.0)
+    o = oracle.score(row_ptr, col, val, G, gene_idx, abundance, min_genes_cells=10, min_corr=-1.0)
+    assert np.array_equal(g[1], o[1])
+    assert_bits_equal_f64(g[0], o[0], "score")
+    m.free()
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 2
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("thr", [0.0, 0.2, 0.5, -0.1])
+def test_rank_exact(ctx, oracle, thr):
+    rng = np.random.default_rng(11)
+    n = 50_000
+    s = np.round(rng.uniform(-1, 1, n), 3)  # heavy ties
+    s[rng.random(n) < 0.05] = np.nan
+    s[:7] = [0.0, -0.0, 0.0, -0.0, 0.5, 0.5, 0.2]
+    kept = (rng.random(n) < 0.9).astype(np.uint8)
+    go, gn = ctx.rank(s, kept, thr)
+    oo, on = oracle.rank(s, kept, thr)
+    assert gn == on
+    assert np.array_equal(go, oo)
+
+
+def test_rank_edge_cases(ctx, oracle):
+    for s in (np.array([]), np.array([np.nan, np.nan]), np.array([0.3]), np.full(5000, 0.25),
+              np.array([1e-300, 5e-324, 0.0, -0.0, 1e300, np.inf])):
+        go, gn = ctx.rank(s, None, 0.0)
+        oo, on = oracle.rank(s, None, 0.0)
+        assert gn == on and np.array_equal(go, oo)
+
+
+def test_rank_sortedness_large(ctx):
+    # size-independent property at a BASELINE-scale N: order is a permutation of the passing cells and
+    # (score desc, index asc)
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    s = rng.uniform(0, 1, n)
+    s[rng.random(n) < 0.3] = np.nan
+    o, npass = ctx.rank(s, None, 0.2)
+    assert npass == int(np.count_nonzero(s >= 0.2))
+    so = s[o]
+    assert np.all(so[:-1] >= so[1:])
+    tie = so[:-1] == so[1:]
+    assert np.all(o[:-1][tie] < o[1:][tie])
+    assert np.unique(o).size == npass
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 3
+# ---------------------------------------------------------------------------------------------------
+def _ranked(n_used, T, seed=0, simple=False):
+    s, lab = synth.synthetic_ranked(n_used, T, seed, simple)
+    order = np.arange(n_used, dtype=np.int32)
+    return s, lab, order
+
+
+@pytest.mark.parametrize("n_used,T", [(5000, 12), (20_000, 40), (3000, 300), (64, 3)])
+def test_observed_bit_exact(ctx, oracle, n_used, T):
+    s, lab, order = _ranked(n_used, T, seed=n_used)
+    prm = ctx.null_params(0, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT)
+    res, _, _ = ctx.enrich(s, order, lab, T, prm)
+    ores = oracle.ks_observed(s, lab, T)
+    assert_results_equal(res, ores, OBSERVED_FIELDS, "observed")
+
+
+def test_observed_survey_micro_vector(ctx):
+    # SURVEY.md Appendix B.1 (hand-derived bit patterns)
+    s = np.array([0.9, 0.85, 0.8, 0.75, 0.7, 0.65, 0.6, 0.55, 0.5, 0.45])
+    lab = np.array([1, 0, 0, 0, 1, 1, 1, 1, 1, 1], np.int32)
+    res, _, _ = ctx.enrich(s, np.arange(10, dtype=np.int32), lab, 2, ctx.null_params(0, ks_mode=P.KS_EXACT))
+    f = lambda x: np.float32(x).view(np.uint32)
+    assert f(res["raw_sup"][0]) == 0x3F4B08D4 and res["supX"][0] == 4
+    assert f(res["ews"][0]) == 0x3F1611A8 and f(res["dstat"][0]) == 0x3F931CCA
+    assert f(res["ews"][1]) == 0xBFCB08D4 and f(res["dstat"][1]) == 0xBF931CCA
+    assert (res["sizeA"][0], res["sizeB"][0]) == (3, 7)
+
+
+def test_observed_int32_overflow_dstat(ctx, oracle):
+    # sizeA*sizeB >= 2^31 wraps negative in the reference -> sqrt(negative) = NaN dStat (a8 step 4)
+    n_used, T = 100_000, 2
+    rng = np.random.default_rng(1)
+    s = np.sort(rng.uniform(0.2, 1, n_used))[::-1].copy()
+    lab = (rng.random(n_used) < 0.5).astype(np.int32)
+    res, _, _ = ctx.enrich(s, np.arange(n_used, dtype=np.int32), lab, T, ctx.null_params(0, ks_mode=P.KS_EXACT))
+    ores = oracle.ks_observed(s, lab, T)
+    assert np.isnan(ores["dstat"]).all()
+    assert_results_equal(res, ores, OBSERVED_FIELDS, "overflow")
+
+
+@pytest.mark.parametrize("n_used,T,Pn", [(4000, 12, 24), (1500, 300, 6)])
+def test_null_replay_bit_exact(ctx, oracle, n_used, T, Pn):
+    s, lab, order = _ranked(n_used, T, seed=1)
+    one, ond, rep = oracle.null(s, lab, T, Pn, perm_mode=0, seed=42, want_replay=True)
+    prm = ctx.null_params(Pn, perm_mode=P.PERM_REPLAY, ks_mode=P.KS_EXACT)
+    res, ne, nd = ctx.enrich(s, order, lab, T, prm, replay=rep)
+    assert_bits_equal_f32(ne, one, "null ews")
+    assert_bits_equal_f32(nd, ond, "null dstat")
+    ored = oracle.reduce(oracle.ks_observed(s, lab, T), one)
+    assert_results_equal(res, ored, None, "replay end-to-end")
+
+
+@pytest.mark.parametrize("n_used,T,Pn", [(5000, 12, 16), (2500, 300, 5), (777, 5, 9)])
+def test_null_philox_exact_bit_exact(ctx, oracle, n_used, T, Pn):
+    s, lab, order = _ranked(n_used, T, seed=2)
+    one, ond = oracle.null(s, lab, T, Pn, perm_mode=1, seed=99, rounds=6)
+    prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=99)
+    res, ne, nd = ctx.enrich(s, order, lab, T, prm)
+    assert_bits_equal_f32(ne, one, "null ews")
+    assert_bits_equal_f32(nd, ond, "null dstat")
+
+
+@pytest.mark.parametrize("n_used,T,Pn,simple", [(5000, 12, 16, False), (2500, 300, 5, False), (9000, 40, 8, True),
+                                                 (140_000, 20, 3, False)])
+def test_null_philox_fast_matches_oracle_fast(ctx, oracle, n_used, T, Pn, simple):
+    s, lab, order = _ranked(n_used, T, seed=3, simple=simple)
+    prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=5)
+    res, ne, nd = ctx.enrich(s, order, lab, T, prm)
+    F = oracle.fast_frac_bits(s)
+    for p in range(Pn):
+        perm = oracle.feistel_perm(5, p, n_used, 6)
+        exp = oracle.ks_null_fast_one(s, lab[perm], T, F)
+        assert_bits_equal_f32(ne[:, p], exp, f"fast null perm {p}")
+
+
+def test_fast_vs_exact_tolerance(ctx):
+    # FAST (exact prefix sums) vs EXACT (the reference's fp32 running sums) on identical labels.
+    # Stated tolerance: |dES| <= 2e-4 absolute (ES in [-1,1]); the fp32 accumulators of the reference
+    # drift by ~1e-5 relative over 1e5 steps, the FAST value is the exactly-rounded one.
+    n_used, T, Pn = 60_000, 40, 12
+    s, lab, order = _ranked(n_used, T, seed=4)
+    a = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=8))[1]
+    b = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=8))[1]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a)
+    assert np.max(np.abs(a[ok] - b[ok])) <= 2e-4
+    assert np.mean(np.sign(a[ok]) == np.sign(b[ok])) > 0.999
+
+
+def test_null_slices_concatenate(ctx):
+    # permutation index is global: slices computed separately equal the one-shot null (multi-GPU invariance)
+    n_used, T, Pn = 6000, 15, 20
+    s, lab, order = _ranked(n_used, T, seed=6)
+    for ks in (P.KS_EXACT, P.KS_FAST):
+        full = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=ks, seed=3))[1]
+        parts = []
+        for b, c in ((0, 7), (7, 6), (13, 7)):
+            r, ne, _ = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=ks, seed=3, perm_begin=b, perm_count=c))
+            assert np.isnan(r["p_emp"]).all()  # slices do not reduce
+            parts.append(ne)
+        assert_bits_equal_f32(np.concatenate(parts, axis=1), full, "sliced null")
+
+
+@pytest.mark.parametrize("T,Pn", [(12, 50), (300, 7), (40, 1000)])
+def test_reduce_exact(ctx, oracle, T, Pn):
+    rng = np.random.default_rng(T + Pn)
+    null = rng.normal(0.1, 0.3, (T, Pn)).astype(np.float32)
+    null[rng.random((T, Pn)) < 0.02] = 0.0
+    null = np.round(null, 2)  # duplicates: exercises the binarySearch landing index
+    res = np.zeros(T, P.TYPE_RESULT_DTYPE)
+    res["ews"] = np.round(rng.normal(0.2, 0.4, T), 2).astype(np.float32)
+    res["ews"][0] = np.nan
+    null[0, :] = np.nan
+    if T > 3:
+        null[2, :] = -np.abs(null[2, :]) - 0.01  # no positive null at all -> NaN p-value / norm
+        res["ews"][3] = 0.0
+    for pol in (0, 1):
+        g = ctx.reduce_null(res, null, pol)
+        o = oracle.reduce(res, null, pol)
+        assert_results_equal(g, o, ("norm_ews", "p_emp", "fdr"), f"reduce policy {pol}")
+
+
+def test_analyze_end_to_end_vs_oracle(ctx, oracle, small):
+    d = small
+    cfg = d["cfg"]
+    m = _load(ctx, d)
+    sprm = P.ScoreParams(0, 4, 0.2, 1, P.JITTER_PHILOX, 77)
+    Pn = 12
+    nprm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=123, min_pass=100)
+    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, 0.0, cfg.n_types, nprm, want_null=True,
+                      want_scores=True, want_order=True)
+    sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["gene_idx"], d["abundance"],
+                                      method=0, min_genes_cells=4, min_corr=0.2, jitter_mode=1, seed=77)
+    assert_bits_equal_f64(out["score"], sc, "score")
+    order, npass = oracle.rank(sc, kept, 0.0)
+    assert out["n_pass"] == npass and np.array_equal(out["order"], order)
+    nu = npass - 1
+    s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
+    ores = oracle.ks_observed(s_r, lab_r, cfg.n_types)
+    one, ond = oracle.null(s_r, lab_r, cfg.n_types, Pn, perm_mode=1, seed=123)
+    ores = oracle.reduce(ores, one)
+    assert_bits_equal_f32(out["null"], one, "null")
+    assert_results_equal(out["results"], ores, None, "analyze")
+    # too few passing cells -> the reference's IllegalArgumentException (PCTSEA.java:389-395)
+    with pytest.raises(P.PctseaError) as e:
+        ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, 0.0, cfg.n_types,
+                    ctx.null_params(2, min_pass=10**9))
+    assert e.value.code == -4
+    m.free()
+
+
+def test_host_api_mirror(ctx, small):
+    d = small
+    cfg = d["cfg"]
+    ds = P.SingleCellDataset.from_arrays(ctx, d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["label"], cfg.n_types)
+    ip = P.InputParameters()
+    ip.addScoringSchema(P.ScoringMethod.PEARSONS_CORRELATION, 0.0, 4)
+    ip.setNumPermutations(20)
+    ip.setMinCorr(0.2)
+    p = P.PCTSEA(ip, ds)
+    p.MIN_CELLS_PASSING_SCORE_TRESHOLD = 100
+    p.setInputList([f"G{g}" for g in d["gene_idx"]], d["abundance"])
+    r = p.run()
+    types = r.cellTypesPerRound[0]
+    assert len(types) == cfg.n_types
+    es = [c.getEnrichmentScore() for c in types if not np.isnan(c.getEnrichmentScore())]
+    assert es == sorted(es, reverse=True)
+    assert all(c.getEnrichmentFDR() <= 0.05 for c in r.getSignificantTypes())
