@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — cells x permutations KS-scored per second on the BASELINE.json workload.
+
+One step = one full PCTSEA analysis (score -> rank -> observed KS -> permutation null -> p/norm/FDR) of one input
+list against the resident matrix. N=1 runs BASELINE configs[1] ("B": 600k cells x 25k genes ~5 %, 100 cell
+types, 1000-protein list, -perm 1000). Under torchrun each rank owns one GPU with a replica of the matrix and
+computes a slice of the permutations (weak scaling: 1000 permutations per GPU, i.e. B -> C as N grows); the
+null slices are all-gathered over NCCL and reduced.
+
+  value  : Nu * P_total / (device time of the step's stages, inputs resident in HBM), max over ranks
+  e2e    : the same through the C ABI with HOST buffers (list in, per-type results out), wall clock around the
+           K steps bracketed by barrier + synchronize, max over ranks
+  --impl reference : the CPU restatement of the reference's algorithm (oracle/), all host threads, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_UNIT = 10.0  # 8 B fp64 score + 2 B label per (ranked cell x permutation)
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+class _DevPtr:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def workload_config(name: str, world: int):
+    from pctsea_parent_b200 import synth
+    cfg = synth.CONFIGS[name]
+    return cfg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pctsea_parent_b200 as P
+    from pctsea_parent_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; pctsea_parent_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = workload_config(args.config, world)
+    P_per_gpu = args.perm if args.perm else cfg.n_perm
+    P_total = P_per_gpu * world
+    ks_mode = P.KS_EXACT if args.ks == "exact" else P.KS_FAST
+
+    t0 = time.time()
+    ds = synth.make_dataset(cfg, dev)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    ctx = P.Context(local)
+    m = ctx.wrap_device_csr(ds.row_ptr.data_ptr(), ds.col.data_ptr(), ds.val.data_ptr(), cfg.n_cells, cfg.n_genes,
+                            keepalive=ds)
+    label_host = ds.label.cpu().numpy()
+    m.set_labels(label_host, cfg.n_types)
+    gene_idx = ds.gene_idx.cpu().numpy()
+    abundance = ds.abundance.cpu().numpy()
+    sprm = P.ScoreParams(cfg.method, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 1)
+    nprm = ctx.null_params(P_total, perm_mode=P.PERM_PHILOX, ks_mode=ks_mode, seed=20261019,
+                           perm_begin=rank * P_per_gpu, perm_count=P_per_gpu, min_pass=1000)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        out = ctx.analyze(m, gene_idx, abundance, sprm, cfg.min_score, cfg.n_types, nprm)
+        tm = ctx.timings()
+        res = out["results"]
+        if world > 1:
+            nptr, _, T, Pc = ctx.last_null_dev()
+            loc = torch.as_tensor(_DevPtr(nptr, (T, Pc)), device=dev)
+            parts = [torch.empty_like(loc) for _ in range(world)]
+            dist.all_gather(parts, loc)
+            full = torch.cat(parts, dim=1).contiguous()
+            torch.cuda.synchronize()
+            res = ctx.reduce_null_dev(res, full.data_ptr(), T, P_total, 0)
+            tm2 = ctx.timings()
+            tm["reduce_ms"] += tm2["reduce_ms"]
+            tm["launches"] += tm2["launches"]
+            tm["h2d_bytes"] += tm2["h2d_bytes"]
+            tm["d2h_bytes"] += tm2["d2h_bytes"]
+        return res, tm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        flush.zero_()
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    stage_ms = []
+    tms = []
+    t_begin = time.perf_counter()
+    flush_s = 0.0
+    for _ in range(args.steps):
+        tf = time.perf_counter()
+        flush.zero_()          # L2 flush between timed iterations (excluded from the step time below)
+        torch.cuda.synchronize()
+        flush_s += time.perf_counter() - tf
+        res, tm = step()
+        tms.append(tm)
+        stage_ms.append(tm["score_ms"] + tm["rank_ms"] + tm["observed_ms"] + tm["labels_ms"] + tm["null_ms"] + tm["reduce_ms"])
+    barrier()
+    wall_s = time.perf_counter() - t_begin - flush_s
+    clocks = sampler.stop()
+
+    nu = tms[-1]["n_used"]
+    dev_ms = float(np.mean(stage_ms))
+    e2e_ms = wall_s * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+    units = float(nu) * float(P_total)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        mean = lambda k: float(np.mean([t[k] for t in tms]))
+        lab_ms, null_ms = mean("labels_ms"), mean("null_ms")
+        dom_name, dom_ms = ("k_labels_philox", lab_ms) if lab_ms >= null_ms else ("k_ks_fast" if ks_mode == P.KS_FAST else "k_ks_exact", null_ms)
+        units_gpu = float(nu) * float(P_per_gpu)
+        ach = ALGO_BYTES_PER_UNIT * units_gpu / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        stage_ach = ALGO_BYTES_PER_UNIT * units_gpu / ((lab_ms + null_ms) * 1e-3) / 1e9 if lab_ms + null_ms > 0 else 0.0
+        nnz = ds.nnz
+        score_bytes = 8.0 * nnz + 16.0 * cfg.n_cells + 17.0 * cfg.n_cells + 8.0 * cfg.list_len
+        score_ms = mean("score_ms")
+        line = {
+            "metric": "cells x permutations KS-scored per second", "value": units / (dev_ms * 1e-3),
+            "unit": "cell-permutations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": e2e_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 scores / int64 fixed-point prefix sums / f32 enrichment" if ks_mode == P.KS_FAST else "f64 scores / f32 running sums",
+            "data": "synthetic",
+            "config": {"workload": f"{cfg.name}: {cfg.n_cells} cells x {cfg.n_genes} genes (~{cfg.density:.0%}), "
+                                   f"{cfg.n_types} cell types, {cfg.list_len}-protein list, "
+                                   f"{'PEARSONS_CORRELATION' if cfg.method == 0 else 'SIMPLE_SCORE'}, -perm {P_per_gpu} per GPU "
+                                   f"({P_total} total), min_genes_cells {cfg.min_genes_cells}, min_corr {cfg.min_corr}",
+                       "nnz": nnz, "Np": int(tms[-1]["n_pass"]), "Nu": int(nu), "n_perm_total": P_total,
+                       "perm_mode": "PHILOX", "ks_mode": args.ks.upper(), "parallelism": f"perm-shard x{world}",
+                       "l2": "256 MiB flush between timed steps; CSR inputs (>= 6 GB) exceed the 126 MB L2"},
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "cell-permutations/s",
+                    "h2d_bytes_per_step": int(mean("h2d_bytes")), "d2h_bytes_per_step": int(mean("d2h_bytes")),
+                    "analysis_seconds": e2e_ms * 1e-3},
+            "gpu_launches": int(sum(t["launches"] for t in tms)),
+            "stage_ms": {k: mean(k) for k in ("setup_ms", "score_ms", "rank_ms", "observed_ms", "labels_ms", "null_ms", "reduce_ms", "total_ms")},
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "null_stage_achieved": stage_ach, "null_stage_frac": stage_ach / peak,
+                         "score_kernel_achieved": score_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else None,
+                         "score_kernel_frac": score_bytes / (score_ms * 1e-3) / 1e9 / peak if score_ms > 0 else None},
+            "clocks": clocks,
+            "setup": {"generate_s": gen_s},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(ctx, m, ds, cfg, sprm, gene_idx, abundance, label_host, args)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    m.free()
+    ctx.close()
+
+
+def cpu_baseline(ctx, m, ds, cfg, sprm, gene_idx, abundance, label_host, args, p_cpu=None):
+    """C restatement of the reference CPU algorithm (oracle/), timed on this box's host cores: per permutation
+    one Fisher-Yates shuffle + per-type two-pass weighted-KS walk, threads over types re-created per permutation
+    like PCTSEA.java:2501-2519. Bounded sample: p_cpu permutations of the same ranked list (the loop is exactly
+    linear in P, PCTSEA.java:1398-1429)."""
+    import pctsea_parent_b200 as P
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    nprm0 = ctx.null_params(0, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, min_pass=1000)
+    out = ctx.analyze(m, gene_idx, abundance, sprm, cfg.min_score, cfg.n_types, nprm0, want_scores=True, want_order=True)
+    nu = out["n_pass"] - 1
+    order = out["order"][:nu]
+    s_r = out["score"][order]
+    lab_r = label_host[order]
+    # calibrate, then aim at ~15 s of CPU work
+    t0 = time.perf_counter()
+    O.null(s_r, lab_r, cfg.n_types, 2, perm_mode=0, seed=1, nthreads=cores)
+    per = (time.perf_counter() - t0) / 2
+    p_cpu = p_cpu or int(max(4, min(50, 15.0 / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    O.null(s_r, lab_r, cfg.n_types, p_cpu, perm_mode=0, seed=1, nthreads=cores)
+    dt = time.perf_counter() - t0
+    # stage 1 on a sample of cells (single thread, like PCTSEA.java:2305-2343)
+    ns = min(cfg.n_cells, 20000)
+    rp = ds.row_ptr[: ns + 1].cpu().numpy()
+    nn = int(rp[-1])
+    col = ds.col[:nn].cpu().numpy()
+    val = ds.val[:nn].cpu().numpy()
+    t0 = time.perf_counter()
+    O.score(rp, col, val, cfg.n_genes, gene_idx, abundance, method=cfg.method, min_genes_cells=cfg.min_genes_cells,
+            min_corr=cfg.min_corr, jitter_mode=1, seed=1)
+    ds_ = time.perf_counter() - t0
+    return {"value": nu * p_cpu / dt, "unit": "cell-permutations/s", "cores": cores, "kind": "port",
+            "sample": f"{p_cpu} JDK-shuffle permutations of the same {nu}-cell ranked list, {cfg.n_types} types, "
+                      f"{cores} threads over types re-created per permutation; C restatement of the reference CPU "
+                      f"algorithm (not Java)",
+            "null_seconds_per_perm": dt / p_cpu,
+            "score_cells_per_s_1thread": ns / ds_}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path cannot run here (Java + MongoDB, no JDK): this arm
+    times the oracle port on the host cores, on the same workload config. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    import pctsea_parent_b200 as P
+    from oracle import oracle as O
+    from pctsea_parent_b200 import synth
+
+    cfg = workload_config(args.config, 1)
+    P_total = (args.perm if args.perm else cfg.n_perm) * int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    ds = synth.make_dataset(cfg, dev)  # data generation only; nothing of the measured path runs on the GPU
+    d = ds.numpy()
+    del ds
+    N = cfg.n_cells
+    # fixed part, measured once: stage 1 on a cell sample (single thread, as the reference), rank, observed KS
+    ns = min(N, 60000)
+    rp = d["row_ptr"][: ns + 1]
+    t0 = time.perf_counter()
+    O.score(rp, d["col"][: rp[-1]], d["val"][: rp[-1]], cfg.n_genes, d["gene_idx"], d["abundance"], method=cfg.method,
+            min_genes_cells=cfg.min_genes_cells, min_corr=cfg.min_corr, jitter_mode=1, seed=1)
+    t_score_sample = time.perf_counter() - t0
+    t_score_full = t_score_sample * N / ns
+    sc, used, nz, kept = O.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["gene_idx"], d["abundance"],
+                                 method=cfg.method, min_genes_cells=cfg.min_genes_cells, min_corr=cfg.min_corr,
+                                 jitter_mode=1, seed=1)
+    t0 = time.perf_counter()
+    order, npass = O.rank(sc, kept, cfg.min_score)
+    t_rank = time.perf_counter() - t0
+    nu = npass - 1
+    s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
+    t0 = time.perf_counter()
+    O.ks_observed(s_r, lab_r, cfg.n_types)
+    t_obs = time.perf_counter() - t0
+    # calibrate the per-step permutation count to ~10 s
+    t0 = time.perf_counter()
+    O.null(s_r, lab_r, cfg.n_types, 2, perm_mode=0, seed=1, nthreads=cores)
+    per = (time.perf_counter() - t0) / 2
+    p_cpu = int(max(2, min(50, 10.0 / max(per, 1e-6))))
+    for _ in range(min(args.warmup, 1)):
+        O.null(s_r, lab_r, cfg.n_types, 2, perm_mode=0, seed=1, nthreads=cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        O.null(s_r, lab_r, cfg.n_types, p_cpu, perm_mode=0, seed=k, nthreads=cores)
+    t_perm = (time.perf_counter() - t0) / (args.steps * p_cpu)
+    t_job = t_score_full + t_rank + t_obs + P_total * t_perm
+    value = nu * P_total / t_job
+    line = {
+        "impl": "reference", "metric": "cells x permutations KS-scored per second", "value": value,
+        "unit": "cell-permutations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_job * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 scores / f32 running sums", "data": "synthetic",
+        "config": {"workload": f"{cfg.name}: {cfg.n_cells} cells x {cfg.n_genes} genes (~{cfg.density:.0%}), "
+                               f"{cfg.n_types} cell types, {cfg.list_len}-protein list, -perm {P_total}",
+                   "Np": int(npass), "Nu": int(nu), "n_perm_total": P_total},
+        "cpu_baseline": {"value": value, "unit": "cell-permutations/s", "cores": cores, "kind": "port",
+                         "sample": f"each step = {p_cpu} JDK-shuffle permutations on the full {nu}-cell ranked list with "
+                                   f"{cores} threads over types; job time = score({ns}-cell sample x{N / ns:.1f}, 1 thread) "
+                                   f"+ rank + observed + {P_total} x per-permutation time (linear in P, PCTSEA.java:1398-1429); "
+                                   f"C restatement of the reference CPU algorithm, not Java"},
+        "e2e": {"value": value, "unit": "cell-permutations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "parts_s": {"score_full_extrapolated": t_score_full, "rank": t_rank, "observed": t_obs, "per_perm": t_perm},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="B", help="workload from pctsea_parent_b200.synth.CONFIGS (default B)")
+    ap.add_argument("--perm", type=int, default=0, help="permutations per GPU (default: the config's)")
+    ap.add_argument("--ks", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
