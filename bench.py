@@ -92,11 +92,6 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-class _DevPtr:
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
-
-
 def workload_config(name: str, world: int):
     from pctsea_parent_b200 import synth
     cfg = synth.CONFIGS[name]
@@ -108,6 +103,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import pctsea_parent_b200 as P
+    from pctsea_parent_b200 import dist as pdist
     from pctsea_parent_b200 import synth
 
     rank = int(os.environ.get("RANK", "0"))
@@ -147,10 +143,8 @@ def run_ours(args):
         res = out["results"]
         if world > 1:
             nptr, _, T, Pc = ctx.last_null_dev()
-            loc = torch.as_tensor(_DevPtr(nptr, (T, Pc)), device=dev)
-            parts = [torch.empty_like(loc) for _ in range(world)]
-            dist.all_gather(parts, loc)
-            full = torch.cat(parts, dim=1).contiguous()
+            loc = torch.as_tensor(pdist.DevicePointer(nptr, (T, Pc)), device=dev)
+            full = pdist.all_gather_null(loc, P_total)
             torch.cuda.synchronize()
             res = ctx.reduce_null_dev(res, full.data_ptr(), T, P_total, 0)
             tm2 = ctx.timings()

@@ -1,0 +1,43 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), permutations sharded by GLOBAL index.
+
+The path has exactly one exchange step: the per-rank null slices [T][P_r] are all-gathered (<= 12 MB in total,
+latency-bound over NVLink/NVSwitch) so that every rank can run a10-a12 on the complete null in canonical
+permutation order (SURVEY.md §8 e). Works on NCCL (device tensors) and gloo (CPU tensors, used by the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def perm_slice(n_perm: int, rank: int, world: int) -> Tuple[int, int]:
+    """(perm_begin, perm_count) of `rank`: contiguous, sizes differ by at most one, covers [0, n_perm)."""
+    base, rem = divmod(n_perm, world)
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+def all_gather_null(local: torch.Tensor, n_perm: int) -> torch.Tensor:
+    """local: [T][P_rank] fp32 slice of this rank -> [T][n_perm] on every rank, permutations in global order."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        assert local.shape[1] == n_perm
+        return local.contiguous()
+    world = dist.get_world_size()
+    T = local.shape[0]
+    counts = [perm_slice(n_perm, r, world)[1] for r in range(world)]
+    width = max(counts)
+    padded = torch.zeros((T, width), dtype=local.dtype, device=local.device)
+    padded[:, : local.shape[1]] = local
+    parts: List[torch.Tensor] = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[:, :c] for p, c in zip(parts, counts)], dim=1).contiguous()
+
+
+class DevicePointer:
+    """Zero-copy view of a raw device pointer (the ABI's pctsea_last_null_dev) for torch.as_tensor."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
