@@ -269,7 +269,7 @@ def cpu_baseline(ctx, m, ds, cfg, sprm, gene_idx, abundance, label_host, args, p
     val = ds.val[:nn].cpu().numpy()
     t0 = time.perf_counter()
     O.score(rp, col, val, cfg.n_genes, gene_idx, abundance, method=cfg.method, min_genes_cells=cfg.min_genes_cells,
-            min_corr=cfg.min_corr, jitter_mode=1, seed=1)
+            min_corr=cfg.min_corr, jitter_mode=1, seed=1, canonical=False)
     ds_ = time.perf_counter() - t0
     return {"value": nu * p_cpu / dt, "unit": "cell-permutations/s", "cores": cores, "kind": "port",
             "sample": f"{p_cpu} JDK-shuffle permutations of the same {nu}-cell ranked list, {cfg.n_types} types, "
@@ -304,7 +304,7 @@ def run_reference(args):
     rp = d["row_ptr"][: ns + 1]
     t0 = time.perf_counter()
     O.score(rp, d["col"][: rp[-1]], d["val"][: rp[-1]], cfg.n_genes, d["gene_idx"], d["abundance"], method=cfg.method,
-            min_genes_cells=cfg.min_genes_cells, min_corr=cfg.min_corr, jitter_mode=1, seed=1)
+            min_genes_cells=cfg.min_genes_cells, min_corr=cfg.min_corr, jitter_mode=1, seed=1, canonical=False)
     t_score_sample = time.perf_counter() - t0
     t_score_full = t_score_sample * N / ns
     sc, used, nz, kept = O.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["gene_idx"], d["abundance"],

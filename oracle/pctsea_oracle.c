@@ -229,6 +229,71 @@ double orc_pearson(const double* x, const double* y, int32_t n) {
     return result;
 }
 
+/* The accelerated path's canonical reduction order (this repo's choice, not the reference's): pair k of
+ * the cell (CSR order) goes to sub-stream k % 32; each sub-stream runs the same SimpleRegression update as
+ * above; the 32 partial states are merged pairwise with the standard parallel (Chan et al.) formulas in a
+ * fixed tree (offsets 16, 8, 4, 2, 1; lower slot is the left operand). The reference's own pair order is a
+ * Trove hash order (GeneExpressionsRetriever.java:142,266), so no order is "the" reference order; results
+ * agree with orc_pearson to ~1e-15 relative and the GPU is bit-identical to this function. */
+typedef struct { int32_t n; double xbar, ybar, sxx, syy, sxy; } reg_state;
+
+static void reg_add(reg_state* s, double x, double y) {
+    if (s->n == 0) { s->xbar = x; s->ybar = y; }
+    else {
+        double nd = (double)s->n;
+        double fact1 = 1.0 + nd;
+        double fact2 = nd / (1.0 + nd);
+        double dx = x - s->xbar, dy = y - s->ybar;
+        s->sxx += dx * dx * fact2;
+        s->syy += dy * dy * fact2;
+        s->sxy += dx * dy * fact2;
+        s->xbar += dx / fact1;
+        s->ybar += dy / fact1;
+    }
+    s->n++;
+}
+
+static reg_state reg_merge(reg_state a, reg_state b) {
+    if (b.n == 0) return a;
+    if (a.n == 0) return b;
+    reg_state r;
+    double na = (double)a.n, nb = (double)b.n;
+    double n = na + nb;
+    double dx = b.xbar - a.xbar, dy = b.ybar - a.ybar;
+    double w = (na * nb) / n;
+    r.sxx = (a.sxx + b.sxx) + (dx * dx) * w;
+    r.syy = (a.syy + b.syy) + (dy * dy) * w;
+    r.sxy = (a.sxy + b.sxy) + (dx * dy) * w;
+    double f = nb / n;
+    r.xbar = a.xbar + dx * f;
+    r.ybar = a.ybar + dy * f;
+    r.n = a.n + b.n;
+    return r;
+}
+
+static double reg_finish(const reg_state* s) {
+    double sumXX = s->sxx, sumYY = s->syy, sumXY = s->sxy;
+    double b1;
+    if (fabs(sumXX) < 10 * 4.9e-324) b1 = NAN; else b1 = sumXY / sumXX;
+    double sse_arg = sumYY - sumXY * sumXY / sumXX;
+    double sse;
+    if (isnan(sse_arg)) sse = NAN; else sse = (sse_arg > 0.0) ? sse_arg : 0.0;
+    double rsq = (sumYY - sse) / sumYY;
+    double result = sqrt(rsq);
+    if (b1 < 0) result = -result;
+    return result;
+}
+
+double orc_pearson_strided32(const double* x, const double* y, int32_t n) {
+    if (n < 2) return NAN;
+    reg_state st[32];
+    memset(st, 0, sizeof st);
+    for (int32_t k = 0; k < n; k++) reg_add(&st[k & 31], x[k], y[k]);
+    for (int o = 16; o >= 1; o >>= 1)
+        for (int l = 0; l < o; l++) st[l] = reg_merge(st[l], st[l + o]);
+    return reg_finish(&st[0]);
+}
+
 static int all_equal(const double* v, int32_t n) {
     /* edu.scripps.yates Maths.var(double[]) is un-vendored; only "== 0" is used
      * (CORE/model/SingleCell.java:430-441): policy = zero iff every element is equal (n>=1). */
@@ -237,10 +302,10 @@ static int all_equal(const double* v, int32_t n) {
     return 1;
 }
 
-int orc_score(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const int32_t* col,
-              const float* val, int32_t L, const int32_t* gene_idx, const float* abundance,
-              const orc_score_params* prm, double* score, int32_t* n_genes_used,
-              int32_t* n_nonzero, uint8_t* kept) {
+int orc_score2(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const int32_t* col,
+               const float* val, int32_t L, const int32_t* gene_idx, const float* abundance,
+               const orc_score_params* prm, int canonical, double* score, int32_t* n_genes_used,
+               int32_t* n_nonzero, uint8_t* kept) {
     if (prm->min_genes_cells > L) return -5; /* SingleCell.java:347-352 */
     int32_t* slot = (int32_t*)malloc((size_t)n_genes * sizeof(int32_t));
     for (int32_t g = 0; g < n_genes; g++) slot[g] = -1;
@@ -275,13 +340,22 @@ int orc_score(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const in
         if ((zx || zy) && prm->jitter_mode == 0) { score[c] = NAN; continue; }
         if (zx) for (int32_t i = 0; i < np; i++) ys[i] = ys[i] + orc_jitter_uniform(prm->seed, (uint64_t)c, 0u, (uint32_t)i) / 1000000.0;
         if (zy) for (int32_t i = 0; i < np; i++) xs[i] = xs[i] + orc_jitter_uniform(prm->seed, (uint64_t)c, 1u, (uint32_t)i) / 1000000.0;
-        double r = orc_pearson(xs, ys, np); /* correlation(interactors, genes) :449-450 */
+        /* correlation(interactors, genes) :449-450 */
+        double r = canonical ? orc_pearson_strided32(xs, ys, np) : orc_pearson(xs, ys, np);
         if (prm->has_min_corr && r < prm->min_corr) r = NAN;     /* :455-456 */
         else if (prm->method == 1) r += (double)nz;              /* :457-458 */
         score[c] = r;
     }
     free(slot); free(xs); free(ys);
     return 0;
+}
+
+int orc_score(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const int32_t* col,
+              const float* val, int32_t L, const int32_t* gene_idx, const float* abundance,
+              const orc_score_params* prm, double* score, int32_t* n_genes_used,
+              int32_t* n_nonzero, uint8_t* kept) {
+    return orc_score2(n_cells, n_genes, row_ptr, col, val, L, gene_idx, abundance, prm, 0, score,
+                      n_genes_used, n_nonzero, kept);
 }
 
 /* ============================================================================================

@@ -68,8 +68,18 @@ int orc_score(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const in
               const orc_score_params* prm, double* score, int32_t* n_genes_used,
               int32_t* n_nonzero, uint8_t* kept);
 
-/* commons-math3 PearsonsCorrelation.correlation(x, y) via SimpleRegression (restated). */
+/* Same with canonical != 0: the accelerated path's canonical reduction order (orc_pearson_strided32). */
+int orc_score2(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const int32_t* col,
+               const float* val, int32_t L, const int32_t* gene_idx, const float* abundance,
+               const orc_score_params* prm, int canonical, double* score, int32_t* n_genes_used,
+               int32_t* n_nonzero, uint8_t* kept);
+
+/* commons-math3 PearsonsCorrelation.correlation(x, y) via SimpleRegression (restated; sequential,
+ * reference-faithful). */
 double orc_pearson(const double* x, const double* y, int32_t n);
+/* Canonical order of the accelerated path: 32 strided sub-streams (pair k -> k % 32), each updated with
+ * the SimpleRegression recurrence, merged pairwise (Chan et al.) in a fixed tree. */
+double orc_pearson_strided32(const double* x, const double* y, int32_t n);
 
 /* ---- stage 2: threshold + rank (a4, a5, a7) ------------------------------------------------ */
 /* order_out[n_pass]: the first n_pass-1 entries are the KS list in its final order (score desc by

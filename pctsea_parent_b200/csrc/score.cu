@@ -5,12 +5,14 @@
 //   a3  model/SingleCell.java:380-463  calculateCorrelation / calculateSimpleScore (driver PCTSEA.java:2305-2343)
 //       with commons-math3 PearsonsCorrelation -> SimpleRegression restated (un-vendored dependency).
 //
-// Layout: one warp owns a batch of 32 consecutive cells. For each cell the warp streams the CSR row with
-// coalesced loads, tests list membership against a shared-memory bitmap, and compacts the matched
-// (abundance, expression) pairs in CSR order into a per-warp shared-memory buffer (ballot + popc).
-// When the buffer is full or the batch is done, lane c runs cell c's SimpleRegression update sequentially
-// in fp64 with explicit round-to-nearest intrinsics (no FMA contraction), so the score is bit-identical to
-// the CPU oracle's, which walks the same pairs in the same order.
+// Layout: one warp per cell. The warp streams the CSR row with coalesced loads, tests list membership
+// against a shared-memory bitmap and compacts the matched (abundance, expression) pairs in CSR order into a
+// per-warp shared-memory buffer (ballot + popc). Pair k then belongs to lane k % 32: every lane runs the
+// SimpleRegression recurrence over its strided sub-stream in fp64, and the 32 partial states are merged with
+// a fixed xor-shuffle tree (Chan et al. parallel update; lower lane = left operand). All arithmetic uses
+// explicit round-to-nearest intrinsics (no FMA contraction), so the score is bit-identical to the CPU
+// oracle's orc_pearson_strided32, which walks the same sub-streams and the same tree, and within ~1e-13
+// relative of the reference's sequential update (whose own pair order is a hash-set order).
 //
 // Roofline: HBM. Algorithmic bytes = 8 B * nnz (col + val) + 16 B * N (row_ptr) + 17 B * N outputs.
 #include "common.cuh"
@@ -35,34 +37,56 @@ __device__ __forceinline__ double jitter_uniform(uint64_t seed, uint64_t cell, u
     return __dmul_rn((double)u, 1.0 / 9007199254740992.0);
 }
 
-// commons-math3 SimpleRegression.addData + getR, restated; pairs are (x = abundance, y = expression).
-__device__ double pearson_sequential(const float2* __restrict__ pr, int np, bool jit_cell, bool jit_list,
-                                     uint64_t seed, uint64_t cell) {
-    double sumXX = 0.0, sumYY = 0.0, sumXY = 0.0, xbar = 0.0, ybar = 0.0;
-    for (int i = 0; i < np; i++) {
-        float2 v = pr[i];
-        double x = (double)v.x, y = (double)v.y;
-        if (jit_cell) y = __dadd_rn(y, __ddiv_rn(jitter_uniform(seed, cell, 0u, (uint32_t)i), 1000000.0));
-        if (jit_list) x = __dadd_rn(x, __ddiv_rn(jitter_uniform(seed, cell, 1u, (uint32_t)i), 1000000.0));
-        if (i == 0) {
-            xbar = x; ybar = y;
-        } else {
-            double nd = (double)i;
-            double fact1 = __dadd_rn(1.0, nd);
-            double fact2 = __ddiv_rn(nd, __dadd_rn(1.0, nd));
-            double dx = __dsub_rn(x, xbar), dy = __dsub_rn(y, ybar);
-            sumXX = __dadd_rn(sumXX, __dmul_rn(__dmul_rn(dx, dx), fact2));
-            sumYY = __dadd_rn(sumYY, __dmul_rn(__dmul_rn(dy, dy), fact2));
-            sumXY = __dadd_rn(sumXY, __dmul_rn(__dmul_rn(dx, dy), fact2));
-            xbar = __dadd_rn(xbar, __ddiv_rn(dx, fact1));
-            ybar = __dadd_rn(ybar, __ddiv_rn(dy, fact1));
-        }
+struct RegState {
+    int n;
+    double xbar, ybar, sxx, syy, sxy;
+};
+
+// commons-math3 SimpleRegression.addData, restated (x = abundance, y = expression).
+__device__ __forceinline__ void reg_add(RegState& s, double x, double y) {
+    if (s.n == 0) {
+        s.xbar = x; s.ybar = y;
+    } else {
+        const double nd = (double)s.n;
+        const double fact1 = __dadd_rn(1.0, nd);
+        const double fact2 = __ddiv_rn(nd, __dadd_rn(1.0, nd));
+        const double dx = __dsub_rn(x, s.xbar), dy = __dsub_rn(y, s.ybar);
+        s.sxx = __dadd_rn(s.sxx, __dmul_rn(__dmul_rn(dx, dx), fact2));
+        s.syy = __dadd_rn(s.syy, __dmul_rn(__dmul_rn(dy, dy), fact2));
+        s.sxy = __dadd_rn(s.sxy, __dmul_rn(__dmul_rn(dx, dy), fact2));
+        s.xbar = __dadd_rn(s.xbar, __ddiv_rn(dx, fact1));
+        s.ybar = __dadd_rn(s.ybar, __ddiv_rn(dy, fact1));
     }
+    s.n++;
+}
+
+// Parallel update of two partial states (a = left operand).
+__device__ __forceinline__ RegState reg_merge(const RegState& a, const RegState& b) {
+    if (b.n == 0) return a;
+    if (a.n == 0) return b;
+    RegState r;
+    const double na = (double)a.n, nb = (double)b.n;
+    const double n = __dadd_rn(na, nb);
+    const double dx = __dsub_rn(b.xbar, a.xbar), dy = __dsub_rn(b.ybar, a.ybar);
+    const double w = __ddiv_rn(__dmul_rn(na, nb), n);
+    r.sxx = __dadd_rn(__dadd_rn(a.sxx, b.sxx), __dmul_rn(__dmul_rn(dx, dx), w));
+    r.syy = __dadd_rn(__dadd_rn(a.syy, b.syy), __dmul_rn(__dmul_rn(dy, dy), w));
+    r.sxy = __dadd_rn(__dadd_rn(a.sxy, b.sxy), __dmul_rn(__dmul_rn(dx, dy), w));
+    const double f = __ddiv_rn(nb, n);
+    r.xbar = __dadd_rn(a.xbar, __dmul_rn(dx, f));
+    r.ybar = __dadd_rn(a.ybar, __dmul_rn(dy, f));
+    r.n = a.n + b.n;
+    return r;
+}
+
+// SimpleRegression.getR(): sign(slope) * sqrt(RSquare)
+__device__ __forceinline__ double reg_finish(const RegState& s) {
+    const double sumXX = s.sxx, sumYY = s.syy, sumXY = s.sxy;
     const double ten_min = __longlong_as_double(10LL);  // 10 * Double.MIN_VALUE
-    double b1 = (fabs(sumXX) < ten_min) ? __longlong_as_double(0x7ff8000000000000LL) : __ddiv_rn(sumXY, sumXX);
-    double sse_arg = __dsub_rn(sumYY, __ddiv_rn(__dmul_rn(sumXY, sumXY), sumXX));
-    double sse = (sse_arg != sse_arg) ? sse_arg : (sse_arg > 0.0 ? sse_arg : 0.0);
-    double rsq = __ddiv_rn(__dsub_rn(sumYY, sse), sumYY);
+    const double b1 = (fabs(sumXX) < ten_min) ? __longlong_as_double(0x7ff8000000000000LL) : __ddiv_rn(sumXY, sumXX);
+    const double sse_arg = __dsub_rn(sumYY, __ddiv_rn(__dmul_rn(sumXY, sumXY), sumXX));
+    const double sse = (sse_arg != sse_arg) ? sse_arg : (sse_arg > 0.0 ? sse_arg : 0.0);
+    const double rsq = __ddiv_rn(__dsub_rn(sumYY, sse), sumYY);
     double r = __dsqrt_rn(rsq);
     if (b1 < 0.0) r = -r;
     return r;
@@ -100,96 +124,91 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
 
     const unsigned lt_mask = (1u << lane) - 1u;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    const int64_t n_batches = (a.N + 31) / 32;
     const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * WARPS;
 
-    for (int64_t batch = warp_global; batch < n_batches; batch += warp_stride) {
-        const int64_t cell0 = batch * 32;
-        const int64_t my_cell = cell0 + lane;
-        int64_t rp_lo = 0, rp_hi = 0;
-        if (my_cell < a.N) { rp_lo = a.row_ptr[my_cell]; rp_hi = a.row_ptr[my_cell + 1]; }
-        const int ncell = (int)min((int64_t)32, a.N - cell0);
-
-        int my_off = 0, my_np = 0, my_nz = 0;
-        int used = 0, sub_start = 0, c = 0;
-
-        // Flush: lanes sub_start..last run their cell's regression from the compacted pairs.
-        auto flush = [&](int first, int last) {
-            __syncwarp();
-            if (lane >= first && lane <= last) {
-                const int np = my_np, nz = my_nz;
-                const bool keep = (nz > 0) && (np >= a.min_genes);
-                double sc = qnan;
-                if (keep && np >= 2) {
-                    const float2* pr = pairs + my_off;
-                    bool eq_cell = true, eq_list = true;  // zero variance <=> all elements equal
-                    const float2 v0 = pr[0];
-                    for (int i = 1; i < np; i++) {
-                        float2 v = pr[i];
-                        eq_list = eq_list && (v.x == v0.x);
-                        eq_cell = eq_cell && (v.y == v0.y);
-                    }
-                    if (!((eq_cell || eq_list) && a.jitter_mode == PCTSEA_JITTER_NAN)) {
-                        double r = pearson_sequential(pr, np, eq_cell, eq_list, a.seed, (uint64_t)my_cell);
-                        if (a.has_min_corr && r < a.min_corr) r = qnan;
-                        else if (a.method == PCTSEA_METHOD_SIMPLE_SCORE) r = __dadd_rn(r, (double)nz);
-                        sc = r;
-                    }
-                }
-                a.score[my_cell] = sc;
-                a.nused[my_cell] = np;
-                a.nnzc[my_cell] = nz;
-                a.kept[my_cell] = keep ? 1 : 0;
-            }
-            __syncwarp();
-        };
-
-        while (c < ncell) {
-            const int64_t beg = __shfl_sync(0xffffffffu, rp_lo, c);
-            const int64_t end = __shfl_sync(0xffffffffu, rp_hi, c);
-            int cnt = 0, cnt_nz = 0;
-            for (int64_t k0 = beg; k0 < end; k0 += 128) {
-                int32_t g[4];
-                float x[4];
+    for (int64_t cell = warp_global; cell < a.N; cell += warp_stride) {
+        const int64_t beg = a.row_ptr[cell], end = a.row_ptr[cell + 1];
+        const int32_t* colp = a.col + beg;
+        const float* valp = a.val + beg;
+        const int len = (int)(end - beg);
+        int cnt = 0, cnt_nz = 0;
+        for (int j0 = 0; j0 < len; j0 += 128) {
+            int32_t g[4];
+            float x[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    int64_t k = k0 + u * 32 + lane;
-                    bool ok = k < end;
-                    g[u] = ok ? __ldcs(a.col + k) : -1;
-                    x[u] = ok ? __ldcs(a.val + k) : 0.0f;
-                }
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + u * 32 + lane;
+                const bool ok = j < len;
+                g[u] = ok ? __ldcs(colp + j) : -1;
+                x[u] = ok ? __ldcs(valp + j) : 0.0f;
+            }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    bool inlist = false;
-                    if (g[u] >= 0 && g[u] < a.G) inlist = (bm[g[u] >> 5] >> (g[u] & 31)) & 1u;
-                    float y = inlist ? __ldg(a.ybg + g[u]) : 0.0f;
-                    bool ispair = inlist && (x[u] > 0.0f) && (y > 0.0f);
-                    bool isnz = inlist && (x[u] != 0.0f);  // true for NaN
-                    unsigned pm = __ballot_sync(0xffffffffu, ispair);
-                    unsigned zm = __ballot_sync(0xffffffffu, isnz);
-                    if (ispair) {
-                        int pos = used + cnt + __popc(pm & lt_mask);
-                        if (pos < a.cap) pairs[pos] = make_float2(y, x[u]);
-                    }
-                    cnt += __popc(pm);
-                    cnt_nz += __popc(zm);
+            for (int u = 0; u < 4; u++) {
+                bool inlist = false;
+                if ((unsigned)g[u] < (unsigned)a.G) inlist = (bm[g[u] >> 5] >> (g[u] & 31)) & 1u;
+                const float y = inlist ? __ldg(a.ybg + g[u]) : 0.0f;
+                const bool ispair = inlist && (x[u] > 0.0f) && (y > 0.0f);
+                const bool isnz = inlist && (x[u] != 0.0f);  // true for NaN
+                const unsigned pm = __ballot_sync(0xffffffffu, ispair);
+                const unsigned zm = __ballot_sync(0xffffffffu, isnz);
+                if (ispair) {
+                    const int pos = cnt + __popc(pm & lt_mask);
+                    if (pos < a.cap) pairs[pos] = make_float2(y, x[u]);
                 }
+                cnt += __popc(pm);
+                cnt_nz += __popc(zm);
             }
-            if (used == 0 && cnt > a.cap) cnt = a.cap;  // only with duplicate columns in a row (unsupported input)
-            if (used + cnt > a.cap) {
-                // does not fit behind the cells already buffered: score those, then rescan this cell
-                // (cnt <= L <= cap, so after the flush it always fits; the row is still in L2)
-                flush(sub_start, c - 1);
-                used = 0;
-                sub_start = c;
-                continue;
-            }
-            if (lane == c) { my_off = used; my_np = cnt; my_nz = cnt_nz; }
-            used += cnt;
-            c++;
         }
-        flush(sub_start, ncell - 1);
+        __syncwarp();
+        const int np = min(cnt, a.cap);  // cnt > cap only with duplicate columns in a row (unsupported input)
+        const bool keep = (cnt_nz > 0) && (cnt >= a.min_genes);
+        double sc = qnan;
+        if (keep && np >= 2) {
+            // zero variance <=> all elements equal (Maths.var == 0, model/SingleCell.java:430-441)
+            const float2 v0 = pairs[0];
+            bool eq_list = true, eq_cell = true;
+            for (int k = lane; k < np; k += 32) {
+                const float2 v = pairs[k];
+                eq_list = eq_list && (v.x == v0.x);
+                eq_cell = eq_cell && (v.y == v0.y);
+            }
+            eq_list = __all_sync(0xffffffffu, eq_list);
+            eq_cell = __all_sync(0xffffffffu, eq_cell);
+            if (!((eq_cell || eq_list) && a.jitter_mode == PCTSEA_JITTER_NAN)) {
+                RegState st;
+                st.n = 0; st.xbar = 0.0; st.ybar = 0.0; st.sxx = 0.0; st.syy = 0.0; st.sxy = 0.0;
+                for (int k = lane; k < np; k += 32) {
+                    const float2 v = pairs[k];
+                    double x = (double)v.x, y = (double)v.y;
+                    if (eq_cell) y = __dadd_rn(y, __ddiv_rn(jitter_uniform(a.seed, (uint64_t)cell, 0u, (uint32_t)k), 1000000.0));
+                    if (eq_list) x = __dadd_rn(x, __ddiv_rn(jitter_uniform(a.seed, (uint64_t)cell, 1u, (uint32_t)k), 1000000.0));
+                    reg_add(st, x, y);
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    RegState pt;
+                    pt.n = __shfl_xor_sync(0xffffffffu, st.n, o);
+                    pt.xbar = __shfl_xor_sync(0xffffffffu, st.xbar, o);
+                    pt.ybar = __shfl_xor_sync(0xffffffffu, st.ybar, o);
+                    pt.sxx = __shfl_xor_sync(0xffffffffu, st.sxx, o);
+                    pt.syy = __shfl_xor_sync(0xffffffffu, st.syy, o);
+                    pt.sxy = __shfl_xor_sync(0xffffffffu, st.sxy, o);
+                    st = (lane & o) ? reg_merge(pt, st) : reg_merge(st, pt);
+                }
+                double r = reg_finish(st);
+                if (a.has_min_corr && r < a.min_corr) r = qnan;
+                else if (a.method == PCTSEA_METHOD_SIMPLE_SCORE) r = __dadd_rn(r, (double)cnt_nz);
+                sc = r;
+            }
+        }
+        if (lane == 0) {
+            a.score[cell] = sc;
+            a.nused[cell] = cnt;
+            a.nnzc[cell] = cnt_nz;
+            a.kept[cell] = keep ? 1 : 0;
+        }
+        __syncwarp();
     }
 }
 
@@ -221,19 +240,18 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     ka.score = c->score.as<double>(); ka.nused = c->nused.as<int32_t>(); ka.nnzc = c->nnzc.as<int32_t>();
     ka.kept = c->kept.as<uint8_t>();
 
-    // Pair buffer: >= L pairs per warp so any single cell fits; sized so that 2-3 CTAs share an SM.
+    // Pair buffer: >= L pairs per warp so any cell fits; as many warps per SM as shared memory allows.
     const int bm_bytes = ((bm_words * 4 + 15) / 16) * 16;
-    int cap = (int)round_up(std::max(sa.L, 1024), 32);
-    const size_t smem_limit = 200 * 1024;
+    int cap = (int)round_up(std::max(sa.L, 32), 32);
+    const size_t smem_limit = 220 * 1024;
     int warps = 8;
     while (warps > 1 && (size_t)bm_bytes + (size_t)warps * cap * 8 > smem_limit) warps >>= 1;
     size_t smem = (size_t)bm_bytes + (size_t)warps * cap * 8;
     if (smem > 227 * 1024)
         throw Error(PCTSEA_EINVAL, "input list too long for the on-chip pair buffer (L=" + std::to_string(sa.L) + ")");
     ka.cap = cap;
-    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
-    int64_t n_batches = (N + 31) / 32;
-    int grid = (int)std::min<int64_t>((int64_t)kNumSMs * ctas_per_sm, div_up(n_batches, warps));
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(64 / warps, (224 * 1024) / (smem + 1024)));
+    int grid = (int)std::min<int64_t>((int64_t)kNumSMs * ctas_per_sm, div_up(N, warps));
     if (grid < 1) grid = 1;
 #define PCT_LAUNCH_SCORE(W)                                                                                   \
     do {                                                                                                      \
