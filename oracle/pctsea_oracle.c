@@ -229,50 +229,22 @@ double orc_pearson(const double* x, const double* y, int32_t n) {
     return result;
 }
 
-/* The accelerated path's canonical reduction order (this repo's choice, not the reference's): pair k of
- * the cell (CSR order) goes to sub-stream k % 32; each sub-stream runs the same SimpleRegression update as
- * above; the 32 partial states are merged pairwise with the standard parallel (Chan et al.) formulas in a
- * fixed tree (offsets 16, 8, 4, 2, 1; lower slot is the left operand). The reference's own pair order is a
- * Trove hash order (GeneExpressionsRetriever.java:142,266), so no order is "the" reference order; results
- * agree with orc_pearson to ~1e-15 relative and the GPU is bit-identical to this function. */
-typedef struct { int32_t n; double xbar, ybar, sxx, syy, sxy; } reg_state;
-
-static void reg_add(reg_state* s, double x, double y) {
-    if (s->n == 0) { s->xbar = x; s->ybar = y; }
-    else {
-        double nd = (double)s->n;
-        double fact1 = 1.0 + nd;
-        double fact2 = nd / (1.0 + nd);
-        double dx = x - s->xbar, dy = y - s->ybar;
-        s->sxx += dx * dx * fact2;
-        s->syy += dy * dy * fact2;
-        s->sxy += dx * dy * fact2;
-        s->xbar += dx / fact1;
-        s->ybar += dy / fact1;
-    }
-    s->n++;
+/* The accelerated path's canonical Pearson (this repo's choice, not the reference's): the textbook
+ * two-pass centred sums, reduced the way a warp does it. Pair k of the cell (CSR order) goes to
+ * sub-stream k % 32; pass 1 sums x and y per sub-stream (in k order) and adds the 32 partials pairwise
+ * (offsets 16, 8, 4, 2, 1) to get the means; pass 2 does the same for (x-xbar)^2, (y-ybar)^2 and
+ * (x-xbar)(y-ybar); the result goes through the same getR() formula as SimpleRegression. The reference's own
+ * pair order is a Trove hash-set order (GeneExpressionsRetriever.java:142,266), so no summation order is
+ * "the" reference order; this function agrees with orc_pearson to ~1e-14 relative (tested) and the GPU
+ * kernel is bit-identical to it. */
+static double tree32(double* v) {
+    for (int o = 16; o >= 1; o >>= 1)
+        for (int l = 0; l < o; l++) v[l] = v[l] + v[l + o];
+    return v[0];
 }
 
-static reg_state reg_merge(reg_state a, reg_state b) {
-    if (b.n == 0) return a;
-    if (a.n == 0) return b;
-    reg_state r;
-    double na = (double)a.n, nb = (double)b.n;
-    double n = na + nb;
-    double dx = b.xbar - a.xbar, dy = b.ybar - a.ybar;
-    double w = (na * nb) / n;
-    r.sxx = (a.sxx + b.sxx) + (dx * dx) * w;
-    r.syy = (a.syy + b.syy) + (dy * dy) * w;
-    r.sxy = (a.sxy + b.sxy) + (dx * dy) * w;
-    double f = nb / n;
-    r.xbar = a.xbar + dx * f;
-    r.ybar = a.ybar + dy * f;
-    r.n = a.n + b.n;
-    return r;
-}
-
-static double reg_finish(const reg_state* s) {
-    double sumXX = s->sxx, sumYY = s->syy, sumXY = s->sxy;
+static double pearson_finish(double sumXX, double sumYY, double sumXY) {
+    /* SimpleRegression.getSlope / getSumSquaredErrors / getRSquare / getR */
     double b1;
     if (fabs(sumXX) < 10 * 4.9e-324) b1 = NAN; else b1 = sumXY / sumXX;
     double sse_arg = sumYY - sumXY * sumXY / sumXX;
@@ -286,12 +258,18 @@ static double reg_finish(const reg_state* s) {
 
 double orc_pearson_strided32(const double* x, const double* y, int32_t n) {
     if (n < 2) return NAN;
-    reg_state st[32];
-    memset(st, 0, sizeof st);
-    for (int32_t k = 0; k < n; k++) reg_add(&st[k & 31], x[k], y[k]);
-    for (int o = 16; o >= 1; o >>= 1)
-        for (int l = 0; l < o; l++) st[l] = reg_merge(st[l], st[l + o]);
-    return reg_finish(&st[0]);
+    double sx[32], sy[32], sxx[32], syy[32], sxy[32];
+    for (int l = 0; l < 32; l++) { sx[l] = 0.0; sy[l] = 0.0; sxx[l] = 0.0; syy[l] = 0.0; sxy[l] = 0.0; }
+    for (int32_t k = 0; k < n; k++) { sx[k & 31] += x[k]; sy[k & 31] += y[k]; }
+    double xbar = tree32(sx) / (double)n, ybar = tree32(sy) / (double)n;
+    for (int32_t k = 0; k < n; k++) {
+        double dx = x[k] - xbar, dy = y[k] - ybar;
+        sxx[k & 31] += dx * dx;
+        syy[k & 31] += dy * dy;
+        sxy[k & 31] += dx * dy;
+    }
+    double SXX = tree32(sxx), SYY = tree32(syy), SXY = tree32(sxy);
+    return pearson_finish(SXX, SYY, SXY);
 }
 
 static int all_equal(const double* v, int32_t n) {
@@ -623,12 +601,12 @@ void orc_reduce(int32_t T, int32_t P, const float* null_ews, int mean_policy, or
  * ========================================================================================== */
 
 int orc_fast_frac_bits(int64_t Nu, const double* s) {
-    /* |fx| = |rint(s * 2^F)| <= 2^30 for every score: F = 30 - e with maxabs < 2^e */
+    /* |fx| = |rint(s * 2^F)| <= 2^25 for every score: F = 25 - e with maxabs < 2^e */
     double maxabs = 0.0;
     for (int64_t i = 0; i < Nu; i++) { double v = fabs(s[i]); if (v > maxabs) maxabs = v; }
     int e = 0;
     if (maxabs > 0.0) e = ilogb(maxabs) + 1;
-    int F = 30 - e;
+    int F = 25 - e;
     if (F > 1000) F = 1000;
     return F;
 }

@@ -77,8 +77,8 @@ int orc_score2(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const i
 /* commons-math3 PearsonsCorrelation.correlation(x, y) via SimpleRegression (restated; sequential,
  * reference-faithful). */
 double orc_pearson(const double* x, const double* y, int32_t n);
-/* Canonical order of the accelerated path: 32 strided sub-streams (pair k -> k % 32), each updated with
- * the SimpleRegression recurrence, merged pairwise (Chan et al.) in a fixed tree. */
+/* Canonical Pearson of the accelerated path: two-pass centred sums over 32 strided sub-streams
+ * (pair k -> k % 32) added pairwise in a fixed tree, then SimpleRegression's getR() formula. */
 double orc_pearson_strided32(const double* x, const double* y, int32_t n);
 
 /* ---- stage 2: threshold + rank (a4, a5, a7) ------------------------------------------------ */

@@ -5,14 +5,15 @@
 //   a3  model/SingleCell.java:380-463  calculateCorrelation / calculateSimpleScore (driver PCTSEA.java:2305-2343)
 //       with commons-math3 PearsonsCorrelation -> SimpleRegression restated (un-vendored dependency).
 //
-// Layout: one warp per cell. The warp streams the CSR row with coalesced loads, tests list membership
-// against a shared-memory bitmap and compacts the matched (abundance, expression) pairs in CSR order into a
-// per-warp shared-memory buffer (ballot + popc). Pair k then belongs to lane k % 32: every lane runs the
-// SimpleRegression recurrence over its strided sub-stream in fp64, and the 32 partial states are merged with
-// a fixed xor-shuffle tree (Chan et al. parallel update; lower lane = left operand). All arithmetic uses
-// explicit round-to-nearest intrinsics (no FMA contraction), so the score is bit-identical to the CPU
-// oracle's orc_pearson_strided32, which walks the same sub-streams and the same tree, and within ~1e-13
-// relative of the reference's sequential update (whose own pair order is a hash-set order).
+// Layout: one warp per cell. The warp streams the CSR row with 128-bit coalesced loads (each lane takes 4
+// consecutive non-zeros), tests list membership against a shared-memory bitmap and compacts the matched
+// (abundance, expression) pairs in CSR order into a per-warp shared-memory buffer (ballot + popc). Pair k then
+// belongs to lane k % 32. Pearson is the two-pass centred form: pass 1 sums x and y per lane and adds the 32
+// partials with an xor-shuffle tree to get the means, pass 2 does the same for the centred squares and cross
+// products, and the result goes through commons-math's getR() formula. All fp64 arithmetic uses explicit
+// round-to-nearest intrinsics (no FMA contraction), so the score is bit-identical to the CPU oracle's
+// orc_pearson_strided32 (same sub-streams, same tree) and within ~1e-12 relative of the reference's
+// sequential SimpleRegression update on non-degenerate cells (its own pair order is a hash-set order).
 //
 // Roofline: HBM. Algorithmic bytes = 8 B * nnz (col + val) + 16 B * N (row_ptr) + 17 B * N outputs.
 #include "common.cuh"
@@ -37,51 +38,15 @@ __device__ __forceinline__ double jitter_uniform(uint64_t seed, uint64_t cell, u
     return __dmul_rn((double)u, 1.0 / 9007199254740992.0);
 }
 
-struct RegState {
-    int n;
-    double xbar, ybar, sxx, syy, sxy;
-};
-
-// commons-math3 SimpleRegression.addData, restated (x = abundance, y = expression).
-__device__ __forceinline__ void reg_add(RegState& s, double x, double y) {
-    if (s.n == 0) {
-        s.xbar = x; s.ybar = y;
-    } else {
-        const double nd = (double)s.n;
-        const double fact1 = __dadd_rn(1.0, nd);
-        const double fact2 = __ddiv_rn(nd, __dadd_rn(1.0, nd));
-        const double dx = __dsub_rn(x, s.xbar), dy = __dsub_rn(y, s.ybar);
-        s.sxx = __dadd_rn(s.sxx, __dmul_rn(__dmul_rn(dx, dx), fact2));
-        s.syy = __dadd_rn(s.syy, __dmul_rn(__dmul_rn(dy, dy), fact2));
-        s.sxy = __dadd_rn(s.sxy, __dmul_rn(__dmul_rn(dx, dy), fact2));
-        s.xbar = __dadd_rn(s.xbar, __ddiv_rn(dx, fact1));
-        s.ybar = __dadd_rn(s.ybar, __ddiv_rn(dy, fact1));
-    }
-    s.n++;
-}
-
-// Parallel update of two partial states (a = left operand).
-__device__ __forceinline__ RegState reg_merge(const RegState& a, const RegState& b) {
-    if (b.n == 0) return a;
-    if (a.n == 0) return b;
-    RegState r;
-    const double na = (double)a.n, nb = (double)b.n;
-    const double n = __dadd_rn(na, nb);
-    const double dx = __dsub_rn(b.xbar, a.xbar), dy = __dsub_rn(b.ybar, a.ybar);
-    const double w = __ddiv_rn(__dmul_rn(na, nb), n);
-    r.sxx = __dadd_rn(__dadd_rn(a.sxx, b.sxx), __dmul_rn(__dmul_rn(dx, dx), w));
-    r.syy = __dadd_rn(__dadd_rn(a.syy, b.syy), __dmul_rn(__dmul_rn(dy, dy), w));
-    r.sxy = __dadd_rn(__dadd_rn(a.sxy, b.sxy), __dmul_rn(__dmul_rn(dx, dy), w));
-    const double f = __ddiv_rn(nb, n);
-    r.xbar = __dadd_rn(a.xbar, __dmul_rn(dx, f));
-    r.ybar = __dadd_rn(a.ybar, __dmul_rn(dy, f));
-    r.n = a.n + b.n;
-    return r;
+__device__ __forceinline__ double warp_sum_tree(double v) {
+    // offsets 16, 8, 4, 2, 1: lane l ends with the same value as the oracle's tree32 slot 0 (fp add commutes)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
 // SimpleRegression.getR(): sign(slope) * sqrt(RSquare)
-__device__ __forceinline__ double reg_finish(const RegState& s) {
-    const double sumXX = s.sxx, sumYY = s.syy, sumXY = s.sxy;
+__device__ __forceinline__ double pearson_finish(double sumXX, double sumYY, double sumXY) {
     const double ten_min = __longlong_as_double(10LL);  // 10 * Double.MIN_VALUE
     const double b1 = (fabs(sumXX) < ten_min) ? __longlong_as_double(0x7ff8000000000000LL) : __ddiv_rn(sumXY, sumXX);
     const double sse_arg = __dsub_rn(sumYY, __ddiv_rn(__dmul_rn(sumXY, sumXY), sumXX));
@@ -129,36 +94,52 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
 
     for (int64_t cell = warp_global; cell < a.N; cell += warp_stride) {
         const int64_t beg = a.row_ptr[cell], end = a.row_ptr[cell + 1];
-        const int32_t* colp = a.col + beg;
-        const float* valp = a.val + beg;
-        const int len = (int)(end - beg);
         int cnt = 0, cnt_nz = 0;
-        for (int j0 = 0; j0 < len; j0 += 128) {
-            int32_t g[4];
-            float x[4];
+        // 128 non-zeros per warp step, starting at the 16-byte boundary at or below the row start
+        for (int64_t k0 = beg & ~(int64_t)3; k0 < end; k0 += 128) {
+            const int64_t kk = k0 + 4 * lane;
+            int32_t g[4] = { -1, -1, -1, -1 };
+            float x[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+            if (kk < end) {
+                if (kk >= beg && kk + 4 <= end) {
+                    const int4 gv = __ldcs(reinterpret_cast<const int4*>(a.col + kk));
+                    const float4 xv = __ldcs(reinterpret_cast<const float4*>(a.val + kk));
+                    g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+                    x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+                } else {  // row head / tail: element-wise, only inside [beg, end)
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int j = j0 + u * 32 + lane;
-                const bool ok = j < len;
-                g[u] = ok ? __ldcs(colp + j) : -1;
-                x[u] = ok ? __ldcs(valp + j) : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                bool inlist = false;
-                if ((unsigned)g[u] < (unsigned)a.G) inlist = (bm[g[u] >> 5] >> (g[u] & 31)) & 1u;
-                const float y = inlist ? __ldg(a.ybg + g[u]) : 0.0f;
-                const bool ispair = inlist && (x[u] > 0.0f) && (y > 0.0f);
-                const bool isnz = inlist && (x[u] != 0.0f);  // true for NaN
-                const unsigned pm = __ballot_sync(0xffffffffu, ispair);
-                const unsigned zm = __ballot_sync(0xffffffffu, isnz);
-                if (ispair) {
-                    const int pos = cnt + __popc(pm & lt_mask);
-                    if (pos < a.cap) pairs[pos] = make_float2(y, x[u]);
+                    for (int q = 0; q < 4; q++) {
+                        const int64_t k = kk + q;
+                        if (k >= beg && k < end) { g[q] = __ldcs(a.col + k); x[q] = __ldcs(a.val + k); }
+                    }
                 }
-                cnt += __popc(pm);
-                cnt_nz += __popc(zm);
             }
+            bool ispair[4];
+            float y[4];
+            unsigned pm[4];
+            int below = 0, total = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                bool inlist = false;
+                if ((unsigned)g[q] < (unsigned)a.G) inlist = (bm[g[q] >> 5] >> (g[q] & 31)) & 1u;
+                y[q] = inlist ? __ldg(a.ybg + g[q]) : 0.0f;
+                ispair[q] = inlist && (x[q] > 0.0f) && (y[q] > 0.0f);
+                const bool isnz = inlist && (x[q] != 0.0f);  // true for NaN
+                pm[q] = __ballot_sync(0xffffffffu, ispair[q]);
+                cnt_nz += __popc(__ballot_sync(0xffffffffu, isnz));
+                below += __popc(pm[q] & lt_mask);
+                total += __popc(pm[q]);
+            }
+            // CSR order inside the step is (lane, q): lower lanes first, then my own earlier elements
+            int pos = cnt + below;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (ispair[q]) {
+                    if (pos < a.cap) pairs[pos] = make_float2(y[q], x[q]);
+                    pos++;
+                }
+            }
+            cnt += total;
         }
         __syncwarp();
         const int np = min(cnt, a.cap);  // cnt > cap only with duplicate columns in a row (unsupported input)
@@ -176,27 +157,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
             eq_list = __all_sync(0xffffffffu, eq_list);
             eq_cell = __all_sync(0xffffffffu, eq_cell);
             if (!((eq_cell || eq_list) && a.jitter_mode == PCTSEA_JITTER_NAN)) {
-                RegState st;
-                st.n = 0; st.xbar = 0.0; st.ybar = 0.0; st.sxx = 0.0; st.syy = 0.0; st.sxy = 0.0;
+                double sx = 0.0, sy = 0.0;
                 for (int k = lane; k < np; k += 32) {
                     const float2 v = pairs[k];
                     double x = (double)v.x, y = (double)v.y;
                     if (eq_cell) y = __dadd_rn(y, __ddiv_rn(jitter_uniform(a.seed, (uint64_t)cell, 0u, (uint32_t)k), 1000000.0));
                     if (eq_list) x = __dadd_rn(x, __ddiv_rn(jitter_uniform(a.seed, (uint64_t)cell, 1u, (uint32_t)k), 1000000.0));
-                    reg_add(st, x, y);
+                    sx = __dadd_rn(sx, x);
+                    sy = __dadd_rn(sy, y);
                 }
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) {
-                    RegState pt;
-                    pt.n = __shfl_xor_sync(0xffffffffu, st.n, o);
-                    pt.xbar = __shfl_xor_sync(0xffffffffu, st.xbar, o);
-                    pt.ybar = __shfl_xor_sync(0xffffffffu, st.ybar, o);
-                    pt.sxx = __shfl_xor_sync(0xffffffffu, st.sxx, o);
-                    pt.syy = __shfl_xor_sync(0xffffffffu, st.syy, o);
-                    pt.sxy = __shfl_xor_sync(0xffffffffu, st.sxy, o);
-                    st = (lane & o) ? reg_merge(pt, st) : reg_merge(st, pt);
+                const double xbar = __ddiv_rn(warp_sum_tree(sx), (double)np);
+                const double ybar = __ddiv_rn(warp_sum_tree(sy), (double)np);
+                double sxx = 0.0, syy = 0.0, sxy = 0.0;
+                for (int k = lane; k < np; k += 32) {
+                    const float2 v = pairs[k];
+                    double x = (double)v.x, y = (double)v.y;
+                    if (eq_cell) y = __dadd_rn(y, __ddiv_rn(jitter_uniform(a.seed, (uint64_t)cell, 0u, (uint32_t)k), 1000000.0));
+                    if (eq_list) x = __dadd_rn(x, __ddiv_rn(jitter_uniform(a.seed, (uint64_t)cell, 1u, (uint32_t)k), 1000000.0));
+                    const double dx = __dsub_rn(x, xbar), dy = __dsub_rn(y, ybar);
+                    sxx = __dadd_rn(sxx, __dmul_rn(dx, dx));
+                    syy = __dadd_rn(syy, __dmul_rn(dy, dy));
+                    sxy = __dadd_rn(sxy, __dmul_rn(dx, dy));
                 }
-                double r = reg_finish(st);
+                sxx = warp_sum_tree(sxx);
+                syy = warp_sum_tree(syy);
+                sxy = warp_sum_tree(sxy);
+                double r = pearson_finish(sxx, syy, sxy);
                 if (a.has_min_corr && r < a.min_corr) r = qnan;
                 else if (a.method == PCTSEA_METHOD_SIMPLE_SCORE) r = __dadd_rn(r, (double)cnt_nz);
                 sc = r;

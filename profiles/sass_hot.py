@@ -25,7 +25,7 @@ for r in data:
     ops[op] += n; samp_ops[op] += s; tot_inst += n; tot_samp += s
     try:
         wf += int(r[ix["L1 Wavefronts Shared"]] or 0); wf_ideal += int(r[ix["L1 Wavefronts Shared Ideal"]] or 0)
-    except ValueError:
+    except (ValueError, KeyError):
         pass
     recs.append((n, s, src))
 print(f"total warp-instructions {tot_inst:,}  samples {tot_samp:,}  smem wavefronts {wf:,} (ideal {wf_ideal:,})")
