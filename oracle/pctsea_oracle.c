@@ -633,17 +633,19 @@ void orc_ks_null_fast_one(int64_t Nu, const double* s, const int32_t* lab, int32
         int64_t dB = Stot - dA;
         if (!(nk > 1 && Nu - nk > 1)) { null_ews[t] = NAN; continue; }
         if (dA == 0 || dB == 0) { null_ews[t] = 0.0f; continue; }
-        double c1 = 1.0 / (double)dA, c2 = 1.0 / (double)dB;
+        /* diff = numA/dA - (S - numA)/dB = numA * (1/dA + 1/dB) - S * (1/dB), one fused multiply-add */
+        double c2 = 1.0 / (double)dB;
+        double c12 = 1.0 / (double)dA + c2;
         float sup = 0.0f; int64_t numA = 0;
         for (int64_t i = 0; i < Nu; i++) {
             if (lab[i] != t) continue;
             if (i > 0) {
-                double d0 = (double)numA * c1 - (double)(S[i - 1] - numA) * c2;
+                double d0 = fma((double)numA, c12, -((double)S[i - 1] * c2));
                 float f0 = (float)d0;
                 if (fast_better(f0, sup)) sup = f0;
             }
             numA += fx[i];
-            double d1 = (double)numA * c1 - (double)(S[i] - numA) * c2;
+            double d1 = fma((double)numA, c12, -((double)S[i] * c2));
             float f1 = (float)d1;
             if (fast_better(f1, sup)) sup = f1;
         }

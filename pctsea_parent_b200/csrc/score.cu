@@ -21,13 +21,17 @@
 namespace pctsea {
 
 __global__ void k_list_lookup(const int32_t* __restrict__ gene_idx, const float* __restrict__ abund, int L, int G,
-                              float* __restrict__ ybg, uint32_t* __restrict__ bitmap) {
+                              float* __restrict__ ybg, uint32_t* __restrict__ bitmap, int bm_words) {
+    // bitmap[0 .. bm_words)          : gene is in the list (counts towards "non-zero list genes")
+    // bitmap[bm_words .. 2*bm_words) : gene is in the list with abundance > 0 (can form a pair)
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
     int g = gene_idx[l];
     if (g < 0 || g >= G) return;
-    ybg[g] = abund[l];
+    const float y = abund[l];
+    ybg[g] = y;
     atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+    if (y > 0.0f) atomicOr(&bitmap[bm_words + (g >> 5)], 1u << (g & 31));
 }
 
 __device__ __forceinline__ double jitter_uniform(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t i) {
@@ -76,15 +80,46 @@ struct ScoreKernelArgs {
     uint8_t* kept;
 };
 
+struct RowChunk {
+    int32_t g[4];
+    float x[4];
+};
+
+// 4 consecutive non-zeros of the row per lane (one 128-bit load each for col and val when the quad lies
+// inside the row; element-wise at the row's head and tail). Elements outside [beg, end) come back as g = -1.
+__device__ __forceinline__ RowChunk load_chunk(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                               int64_t kk, int64_t beg, int64_t end) {
+    RowChunk c;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { c.g[q] = -1; c.x[q] = 0.0f; }
+    if (kk < end) {
+        if (kk >= beg && kk + 4 <= end) {
+            const int4 gv = __ldcs(reinterpret_cast<const int4*>(col + kk));
+            const float4 xv = __ldcs(reinterpret_cast<const float4*>(val + kk));
+            c.g[0] = gv.x; c.g[1] = gv.y; c.g[2] = gv.z; c.g[3] = gv.w;
+            c.x[0] = xv.x; c.x[1] = xv.y; c.x[2] = xv.z; c.x[3] = xv.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int64_t k = kk + q;
+                if (k >= beg && k < end) { c.g[q] = __ldcs(col + k); c.x[q] = __ldcs(val + k); }
+            }
+        }
+    }
+    return c;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);
-    const int bm_bytes = ((a.bm_words * 4 + 15) / 16) * 16;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);          // in list
+    uint32_t* bmp = bm + a.bm_words;                                // in list with abundance > 0
+    const int bm_bytes = ((a.bm_words * 8 + 15) / 16) * 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // pair buffer: .x = matrix column (int bits) until the abundances are gathered, then the abundance
     float2* pairs = reinterpret_cast<float2*>(smem_raw + bm_bytes) + (size_t)warp * a.cap;
 
-    for (int i = threadIdx.x; i < a.bm_words; i += WARPS * 32) bm[i] = a.bitmap[i];
+    for (int i = threadIdx.x; i < 2 * a.bm_words; i += WARPS * 32) bm[i] = a.bitmap[i];
     __syncthreads();
 
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -92,60 +127,60 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
     const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * WARPS;
 
-    for (int64_t cell = warp_global; cell < a.N; cell += warp_stride) {
-        const int64_t beg = a.row_ptr[cell], end = a.row_ptr[cell + 1];
+    int64_t cell = warp_global;
+    if (cell >= a.N) return;
+    int64_t beg = a.row_ptr[cell], end = a.row_ptr[cell + 1];
+    RowChunk cur = load_chunk(a.col, a.val, (beg & ~(int64_t)3) + 4 * lane, beg, end);
+    while (cell < a.N) {
+        // row bounds of the warp's next cell, fetched while this one is scanned
+        const int64_t ncell = cell + warp_stride;
+        int64_t nbeg = 0, nend = 0;
+        if (ncell < a.N) { nbeg = a.row_ptr[ncell]; nend = a.row_ptr[ncell + 1]; }
         int cnt = 0, cnt_nz = 0;
-        // 128 non-zeros per warp step, starting at the 16-byte boundary at or below the row start
         for (int64_t k0 = beg & ~(int64_t)3; k0 < end; k0 += 128) {
-            const int64_t kk = k0 + 4 * lane;
-            int32_t g[4] = { -1, -1, -1, -1 };
-            float x[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-            if (kk < end) {
-                if (kk >= beg && kk + 4 <= end) {
-                    const int4 gv = __ldcs(reinterpret_cast<const int4*>(a.col + kk));
-                    const float4 xv = __ldcs(reinterpret_cast<const float4*>(a.val + kk));
-                    g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
-                    x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
-                } else {  // row head / tail: element-wise, only inside [beg, end)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int64_t k = kk + q;
-                        if (k >= beg && k < end) { g[q] = __ldcs(a.col + k); x[q] = __ldcs(a.val + k); }
-                    }
-                }
-            }
+            // software pipeline: the next 128 non-zeros (or the first 128 of the next cell) are in flight
+            // while this step is compacted
+            RowChunk nxt;
+            if (k0 + 128 < end) nxt = load_chunk(a.col, a.val, k0 + 128 + 4 * lane, beg, end);
+            else nxt = load_chunk(a.col, a.val, (nbeg & ~(int64_t)3) + 4 * lane, nbeg, nend);
             bool ispair[4];
-            float y[4];
-            unsigned pm[4];
             int below = 0, total = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                bool inlist = false;
-                if ((unsigned)g[q] < (unsigned)a.G) inlist = (bm[g[q] >> 5] >> (g[q] & 31)) & 1u;
-                y[q] = inlist ? __ldg(a.ybg + g[q]) : 0.0f;
-                ispair[q] = inlist && (x[q] > 0.0f) && (y[q] > 0.0f);
-                const bool isnz = inlist && (x[q] != 0.0f);  // true for NaN
-                pm[q] = __ballot_sync(0xffffffffu, ispair[q]);
+                const int g = cur.g[q];
+                bool inlist = false, pairable = false;
+                if ((unsigned)g < (unsigned)a.G) {
+                    inlist = (bm[g >> 5] >> (g & 31)) & 1u;
+                    pairable = (bmp[g >> 5] >> (g & 31)) & 1u;
+                }
+                ispair[q] = pairable && (cur.x[q] > 0.0f);
+                const bool isnz = inlist && (cur.x[q] != 0.0f);  // true for NaN
+                const unsigned pm = __ballot_sync(0xffffffffu, ispair[q]);
                 cnt_nz += __popc(__ballot_sync(0xffffffffu, isnz));
-                below += __popc(pm[q] & lt_mask);
-                total += __popc(pm[q]);
+                below += __popc(pm & lt_mask);
+                total += __popc(pm);
             }
             // CSR order inside the step is (lane, q): lower lanes first, then my own earlier elements
             int pos = cnt + below;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (ispair[q]) {
-                    if (pos < a.cap) pairs[pos] = make_float2(y[q], x[q]);
+                    if (pos < a.cap) pairs[pos] = make_float2(__int_as_float(cur.g[q]), cur.x[q]);
                     pos++;
                 }
             }
             cnt += total;
+            cur = nxt;
         }
+        if (beg == end) cur = load_chunk(a.col, a.val, (nbeg & ~(int64_t)3) + 4 * lane, nbeg, nend);  // empty row
         __syncwarp();
         const int np = min(cnt, a.cap);  // cnt > cap only with duplicate columns in a row (unsupported input)
         const bool keep = (cnt_nz > 0) && (cnt >= a.min_genes);
         double sc = qnan;
         if (keep && np >= 2) {
+            // gather the abundances of the matched genes (L1/L2-resident table)
+            for (int k = lane; k < np; k += 32) pairs[k].x = __ldg(a.ybg + __float_as_int(pairs[k].x));
+            __syncwarp();
             // zero variance <=> all elements equal (Maths.var == 0, model/SingleCell.java:430-441)
             const float2 v0 = pairs[0];
             bool eq_list = true, eq_cell = true;
@@ -195,6 +230,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
             a.kept[cell] = keep ? 1 : 0;
         }
         __syncwarp();
+        cell = ncell; beg = nbeg; end = nend;
     }
 }
 
@@ -204,16 +240,16 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     const int32_t G = m->n_genes;
     const int32_t bm_words = (G + 31) / 32;
     c->ybg.reserve((size_t)G * 4 + 16);
-    c->bitmap.reserve((size_t)bm_words * 4 + 16);
+    c->bitmap.reserve((size_t)bm_words * 8 + 16);
     c->score.reserve((size_t)N * 8 + 16);
     c->nused.reserve((size_t)N * 4 + 16);
     c->nnzc.reserve((size_t)N * 4 + 16);
     c->kept.reserve((size_t)N + 16);
     PCT_CUDA(cudaMemsetAsync(c->ybg.p, 0, (size_t)G * 4, c->stream));
-    PCT_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (size_t)bm_words * 4, c->stream));
+    PCT_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (size_t)bm_words * 8, c->stream));
     if (sa.L > 0) {
         k_list_lookup<<<(sa.L + 255) / 256, 256, 0, c->stream>>>(sa.gene_idx_dev, sa.abund_dev, sa.L, G,
-                                                                  c->ybg.as<float>(), c->bitmap.as<uint32_t>());
+                                                                  c->ybg.as<float>(), c->bitmap.as<uint32_t>(), bm_words);
         count_launch(c);
     }
     if (N == 0) return;
@@ -227,7 +263,7 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     ka.kept = c->kept.as<uint8_t>();
 
     // Pair buffer: >= L pairs per warp so any cell fits; as many warps per SM as shared memory allows.
-    const int bm_bytes = ((bm_words * 4 + 15) / 16) * 16;
+    const int bm_bytes = ((bm_words * 8 + 15) / 16) * 16;
     int cap = (int)round_up(std::max(sa.L, 32), 32);
     const size_t smem_limit = 220 * 1024;
     int warps = 8;

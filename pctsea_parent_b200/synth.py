@@ -76,14 +76,13 @@ def make_list(cfg: Config, device="cpu", list_seed: int = 0):
     abundance = round(LogNormal(2, 1)) + 1."""
     g = _gen("cpu", cfg.config_id, 100, list_seed)
     top = min(5000, cfg.n_genes)
-    n_top = min(int(round(cfg.list_len * 0.8)), top)
-    n_rest = cfg.list_len - n_top
-    a = torch.randperm(top, generator=g)[:n_top]
-    if n_rest > 0 and cfg.n_genes > top:
-        b = top + torch.randperm(cfg.n_genes - top, generator=g)[:n_rest]
-    else:
-        b = torch.randperm(cfg.n_genes, generator=g)[:0]
-    genes = torch.cat([a, b])
+    if cfg.n_genes - top >= cfg.list_len:
+        n_top = min(int(round(cfg.list_len * 0.8)), top)
+        a = torch.randperm(top, generator=g)[:n_top]
+        b = top + torch.randperm(cfg.n_genes - top, generator=g)[:cfg.list_len - n_top]
+        genes = torch.cat([a, b])
+    else:  # small test matrices: the whole gene range is "popular"
+        genes = torch.randperm(cfg.n_genes, generator=g)[:cfg.list_len]
     genes = genes[torch.randperm(genes.numel(), generator=g)]
     ab = torch.round(torch.exp(2.0 + torch.randn(genes.numel(), generator=g))) + 1.0
     return genes.to(torch.int32).to(device), ab.to(torch.float32).to(device)

@@ -322,3 +322,56 @@ def test_host_api_mirror(ctx, small):
     es = [c.getEnrichmentScore() for c in types if not np.isnan(c.getEnrichmentScore())]
     assert es == sorted(es, reverse=True)
     assert all(c.getEnrichmentFDR() <= 0.05 for c in r.getSignificantTypes())
+
+
+def test_against_committed_golden_fixture(ctx, tiny):
+    # tests/golden/golden.json "regression": produced by the oracle with tests/golden/make_golden.py
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))["regression"]
+    d, cfg = tiny, tiny["cfg"]
+    m = _load(ctx, d)
+    sprm = P.ScoreParams(0, 4, 0.2, 1, P.JITTER_PHILOX, 1)
+    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, 0.0, cfg.n_types,
+                      ctx.null_params(8, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=42, min_pass=100),
+                      want_null=True, want_scores=True, want_order=True)
+    sc = out["score"]
+    assert out["n_pass"] == g["n_pass"] and int(out["kept"].sum()) == g["kept_sum"]
+    assert sc[~np.isnan(sc)][:32].view(np.uint64).tolist() == g["score_bits_first32_nonnan"]
+    assert out["order"][:32].tolist() == g["order_first32"]
+    r = out["results"]
+    assert r["ews"].view(np.uint32).tolist() == g["ews_bits"] and r["supX"].tolist() == g["supX"]
+    assert out["null"].view(np.uint32).ravel().tolist() == g["null_feistel_seed42_bits"]
+    assert r["norm_ews"].view(np.uint32).tolist() == g["norm_ews_bits"]
+    assert r["p_emp"].view(np.uint64).tolist() == g["p_emp_bits"] and r["fdr"].view(np.uint64).tolist() == g["fdr_bits"]
+    fast = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, 0.0, cfg.n_types,
+                       ctx.null_params(8, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=42, min_pass=100),
+                       want_null=True)
+    assert fast["null"][:, 0].view(np.uint32).tolist() == g["fast_null_p0_bits"]
+    m.free()
+
+
+def test_full_size_properties(ctx):
+    """BASELINE-scale stage 3 (600k ranked cells, 100 types): size-independent properties instead of an oracle run.
+    (1) slices of the permutation range concatenate to the one-shot null; (2) the label permutation preserves type
+    counts, so a type is NaN in the null iff it is NaN observed; (3) |ES| <= 1 and dStat = ES*sqrt(nA*nB/(nA+nB));
+    (4) FAST stays within the stated tolerance of EXACT on the same permutations."""
+    n_used, T, Pn = 600_000, 100, 6
+    s, lab = synth.synthetic_ranked(n_used, T, seed=9)
+    order = np.arange(n_used, dtype=np.int32)
+    fast, nf, df = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=1))
+    exact, ne, de = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_EXACT, seed=1))
+    nan_obs = np.isnan(exact["ews"])
+    assert np.array_equal(np.isnan(ne).all(axis=1), nan_obs) and np.array_equal(np.isnan(nf), np.isnan(ne))
+    ok = ~np.isnan(ne)
+    assert np.all(np.abs(ne[ok]) <= 1.0) and np.max(np.abs(ne[ok] - nf[ok])) <= 2e-4
+    a = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=1, perm_begin=0, perm_count=2))[1]
+    b = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=1, perm_begin=2, perm_count=4))[1]
+    assert_bits_equal_f32(np.concatenate([a, b], axis=1), nf, "sliced FAST null at full size")
+    nA = exact["sizeA"].astype(np.int64)
+    nB = exact["sizeB"].astype(np.int64)
+    for t in np.flatnonzero(~nan_obs)[:10]:
+        prod = int(np.array([(nA[t] * nB[t]) & 0xFFFFFFFF], dtype=np.uint32).view(np.int32)[0])  # int32 wrap
+        with np.errstate(invalid="ignore"):
+            exp = np.float32(np.sqrt(np.float64(prod) / np.float64(nA[t] + nB[t]))) * ne[t]
+        assert_bits_equal_f32(de[t], exp.astype(np.float32), "dStat")

@@ -1,0 +1,367 @@
+"""CPU tests (no GPU): the oracle against published known answers, the SURVEY's hand-derived vectors and the
+committed regression fixtures; properties of the restated algorithms; host-side logic; ABI surface."""
+import ctypes
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pctsea_parent_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+
+
+def f32(bits):
+    return np.asarray(bits, np.uint32).view(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# published known answers
+# ---------------------------------------------------------------------------------------------------
+def test_java_random_known_answers(oracle):
+    g = GOLD["published"]
+    r = oracle.JRandom(42)
+    assert [r.next_int(), r.next_int()] == g["java_random_42_nextInt"]
+    assert [oracle.JRandom(0).next_int()] == g["java_random_0_nextInt"]
+    r = oracle.JRandom(42)
+    assert [r.next_int(10) for _ in range(10)] == g["java_random_42_nextInt10"]
+    # power-of-two bound takes the multiply-shift path, others the rejection loop: both stay in range
+    r = oracle.JRandom(7)
+    for bound in (1, 2, 3, 64, 1000, 2**31 - 1):
+        v = [r.next_int(bound) for _ in range(200)]
+        assert min(v) >= 0 and max(v) < bound
+    d = [oracle.JRandom(5).next_double() for _ in range(3)]
+    assert all(0.0 <= x < 1.0 for x in d)
+
+
+def test_philox_known_answers(oracle):
+    for kat in GOLD["published"]["philox4x32_10"]:
+        assert oracle.philox4x32_10(kat["ctr"], kat["key"]) == kat["out"]
+
+
+def test_java_shuffle(oracle):
+    assert oracle.JRandom(42).shuffle(np.arange(10)).tolist() == GOLD["survey"]["shuffle_random42_identity10"]
+    a = oracle.JRandom(1).shuffle(np.arange(1000))
+    assert sorted(a.tolist()) == list(range(1000))
+    assert oracle.JRandom(1).shuffle(np.arange(0)).size == 0
+    assert oracle.JRandom(1).shuffle(np.arange(1)).tolist() == [0]
+
+
+def test_java_sort_and_binary_search(oracle):
+    a = np.array([0.0, -0.0, 1.5, np.nan, -3.0, 1.5, np.inf, -np.inf], np.float32)
+    s = oracle.java_sort_f32(a)
+    assert np.isnan(s[-1]) and s[0] == -np.inf and s[-2] == np.inf
+    z = s[2:4]  # -0.0 sorts before 0.0
+    assert np.signbit(z[0]) and not np.signbit(z[1])
+    srt = np.array([0.1, 0.2, 0.2, 0.2, 0.5, 0.9], np.float32)
+    assert oracle.binary_search_f32(srt, np.float32(0.5)) == 4
+    assert oracle.binary_search_f32(srt, np.float32(0.2)) == 2      # the probe lands on the middle duplicate
+    assert oracle.binary_search_f32(srt, np.float32(0.3)) == -5     # -(insertion point) - 1
+    assert oracle.binary_search_f32(srt, np.float32(2.0)) == -7
+    assert oracle.binary_search_f32(np.array([], np.float32), np.float32(1.0)) == -1
+    assert oracle.double_compare(0.0, -0.0) == 1 and oracle.double_compare(float("nan"), 1e308) == 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# SURVEY Appendix B.1
+# ---------------------------------------------------------------------------------------------------
+def test_survey_micro_vector(oracle):
+    b1 = GOLD["survey"]["b1"]
+    res = oracle.ks_observed(np.array(b1["s"]), np.array(b1["lab"], np.int32), 2)
+    for t, key in ((0, "type0"), (1, "type1")):
+        e = b1[key]
+        assert np.float32(res["raw_sup"][t]).view(np.uint32) == e["raw_sup"]
+        assert np.float32(res["ews"][t]).view(np.uint32) == e["ews"]
+        assert np.float32(res["dstat"][t]).view(np.uint32) == e["dstat"]
+        assert (res["supX"][t], res["sizeA"][t], res["sizeB"][t]) == (e["supX"], e["sizeA"], e["sizeB"])
+    assert res["norm_supX"][0] == 0.4
+
+
+# ---------------------------------------------------------------------------------------------------
+# committed regression fixtures (tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------
+def test_regression_fixture(oracle, tiny):
+    g = GOLD["regression"]
+    d, cfg = tiny, tiny["cfg"]
+    sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["gene_idx"], d["abundance"],
+                                      method=0, min_genes_cells=4, min_corr=0.2, jitter_mode=1, seed=1)
+    assert int(kept.sum()) == g["kept_sum"] and int(used.sum()) == g["n_used_sum"]
+    assert sc[~np.isnan(sc)][:32].view(np.uint64).tolist() == g["score_bits_first32_nonnan"]
+    order, npass = oracle.rank(sc, kept, 0.0)
+    assert npass == g["n_pass"] and order[:32].tolist() == g["order_first32"]
+    nu = npass - 1
+    s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
+    res = oracle.ks_observed(s_r, lab_r, cfg.n_types)
+    assert res["ews"].view(np.uint32).tolist() == g["ews_bits"]
+    assert res["dstat"].view(np.uint32).tolist() == g["dstat_bits"]
+    assert res["supX"].tolist() == g["supX"]
+    ne_j, _ = oracle.null(s_r, lab_r, cfg.n_types, 8, perm_mode=0, seed=42)
+    ne_f, _ = oracle.null(s_r, lab_r, cfg.n_types, 8, perm_mode=1, seed=42)
+    assert ne_j.view(np.uint32).ravel().tolist() == g["null_jdk_seed42_bits"]
+    assert ne_f.view(np.uint32).ravel().tolist() == g["null_feistel_seed42_bits"]
+    red = oracle.reduce(res, ne_f)
+    assert red["norm_ews"].view(np.uint32).tolist() == g["norm_ews_bits"]
+    assert red["p_emp"].view(np.uint64).tolist() == g["p_emp_bits"]
+    assert red["fdr"].view(np.uint64).tolist() == g["fdr_bits"]
+    assert oracle.feistel_perm(42, 0, nu, 6)[:16].tolist() == g["feistel_perm_seed42_p0_first16"]
+    assert oracle.fast_frac_bits(s_r) == g["fast_frac_bits"]
+    fast0 = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(42, 0, nu, 6)], cfg.n_types, g["fast_frac_bits"])
+    assert fast0.view(np.uint32).tolist() == g["fast_null_p0_bits"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 1 properties
+# ---------------------------------------------------------------------------------------------------
+def test_pearson_against_numpy_and_canonical(oracle):
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 7, 31, 32, 33, 64, 257, 1000):
+        x = rng.integers(1, 60, n).astype(float)
+        y = rng.geometric(0.45, n).astype(float)
+        if len(set(x)) == 1 or len(set(y)) == 1:
+            continue
+        r = oracle.pearson(x, y)
+        assert abs(r - np.corrcoef(x, y)[0, 1]) < 1e-12
+        assert abs(r - oracle.pearson_strided32(x, y)) <= 1e-12 * max(1.0, abs(r))
+    assert math.isnan(oracle.pearson([1.0], [2.0]))
+    assert math.isnan(oracle.pearson([1.0, 1.0, 1.0], [2.0, 3.0, 4.0]))  # zero variance in x: slope NaN
+    assert oracle.pearson([1.0, 2.0, 3.0], [2.0, 4.0, 6.0]) == 1.0
+    assert oracle.pearson([1.0, 2.0, 3.0], [6.0, 4.0, 2.0]) == -1.0
+
+
+def test_score_semantics(oracle):
+    # cell 0: regular; cell 1: zero variance; cell 2: below min_genes; cell 3: no list gene; cell 4: NaN value
+    rows = [[(1, 2.0), (2, 5.0), (3, 1.0), (4, 7.0)], [(1, 1.0), (2, 1.0), (3, 1.0), (4, 1.0)],
+            [(1, 3.0), (2, 1.0)], [(9, 1.0)], [(1, float("nan")), (2, 2.0), (3, 4.0), (4, 1.0), (5, 6.0)]]
+    row_ptr = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64)
+    col = np.array([c for r in rows for c, _ in r], np.int32)
+    val = np.array([v for r in rows for _, v in r], np.float32)
+    gi, ab = np.array([1, 2, 3, 4, 5], np.int32), np.array([3, 1, 4, 1.5, 9], np.float32)
+    sc, used, nz, kept = oracle.score(row_ptr, col, val, 10, gi, ab, method=0, min_genes_cells=3, min_corr=-1.0,
+                                      jitter_mode=0, canonical=False)
+    assert kept.tolist() == [1, 1, 0, 0, 1] and used.tolist() == [4, 4, 2, 0, 4] and nz.tolist() == [4, 4, 2, 0, 5]
+    assert abs(sc[0] - np.corrcoef([3, 1, 4, 1.5], [2, 5, 1, 7])[0, 1]) < 1e-12
+    assert np.isnan(sc[1]) and np.isnan(sc[2]) and np.isnan(sc[3])
+    # SIMPLE_SCORE adds the number of non-zero list genes (NaN counts), model/SingleCell.java:409-411,457-458
+    ss = oracle.score(row_ptr, col, val, 10, gi, ab, method=1, min_genes_cells=3, min_corr=-1.0, jitter_mode=0,
+                      canonical=False)[0]
+    assert ss[0] == sc[0] + 4 and ss[4] == sc[4] + 5
+    # min_corr turns low correlations into NaN (:455-456)
+    hi = oracle.score(row_ptr, col, val, 10, gi, ab, method=0, min_genes_cells=3, min_corr=0.99, jitter_mode=0)[0]
+    assert np.isnan(hi).all()
+    # Philox jitter is a pure function of (seed, cell, vector, element): same seed -> same score
+    j1 = oracle.score(row_ptr, col, val, 10, gi, ab, method=0, min_genes_cells=3, min_corr=-1.0, jitter_mode=1, seed=5)[0]
+    j2 = oracle.score(row_ptr, col, val, 10, gi, ab, method=0, min_genes_cells=3, min_corr=-1.0, jitter_mode=1, seed=5)[0]
+    j3 = oracle.score(row_ptr, col, val, 10, gi, ab, method=0, min_genes_cells=3, min_corr=-1.0, jitter_mode=1, seed=6)[0]
+    assert not np.isnan(j1[1]) and j1[1] == j2[1] and j1[1] != j3[1] and -1.0 <= j1[1] <= 1.0
+    with pytest.raises(ValueError):  # min_genes_cells > L, model/SingleCell.java:347-352
+        oracle.score(row_ptr, col, val, 10, gi, ab, min_genes_cells=6)
+    u = [oracle.jitter_uniform(1, c, 0, i) for c in range(3) for i in range(50)]
+    assert all(0.0 <= x < 1.0 for x in u) and len(set(u)) == len(u)
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 2 properties
+# ---------------------------------------------------------------------------------------------------
+def test_rank_semantics(oracle):
+    s = np.array([0.5, np.nan, 0.9, 0.5, 0.1, 0.9, -0.0, 0.0, 0.2])
+    order, npass = oracle.rank(s, None, 0.2)
+    assert npass == 5 and order.tolist() == [2, 5, 0, 3, 8]          # ties keep index order; last one is dropped later
+    order, npass = oracle.rank(s, np.array([1, 1, 0, 1, 1, 1, 1, 1, 1], np.uint8), 0.0)
+    assert order.tolist() == [5, 0, 3, 8, 4, 7, 6]                    # 0.0 before -0.0 (Double.compare)
+    # negative threshold: score < thr, the highest passing score (largest index among its ties) is the dropped cell
+    s2 = np.array([-0.5, -0.3, -0.9, -0.3, 0.4, -0.2])
+    order, npass = oracle.rank(s2, None, -0.25)
+    assert npass == 4 and order.tolist() == [1, 0, 2, 3]
+    assert oracle.rank(np.array([np.nan]), None, 0.0)[1] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 3 properties
+# ---------------------------------------------------------------------------------------------------
+def test_ks_properties(oracle):
+    s, lab = synth.synthetic_ranked(3000, 9, seed=1)
+    T = 9
+    res = oracle.ks_observed(s, lab, T)
+    for t in range(T):
+        nk = int((lab == t).sum())
+        assert (res["sizeA"][t], res["sizeB"][t]) == (nk, s.size - nk)
+        if nk > 1:
+            assert -1.0 <= res["raw_sup"][t] <= 1.0 and 1 <= res["supX"][t] <= s.size
+            # compensation only ever lowers a positive supremum and doubles a negative one (a8 step 5)
+            if res["raw_sup"][t] < 0:
+                assert res["ews"][t] == np.float32(2) * res["raw_sup"][t]
+            else:
+                assert res["ews"][t] <= res["raw_sup"][t]
+    # a type with <= 1 hit is NaN with supX -1
+    lab2 = lab.copy()
+    lab2[lab2 == 3] = 4
+    lab2[10] = 3
+    r2 = oracle.ks_observed(s, lab2, T)
+    assert np.isnan(r2["ews"][3]) and r2["supX"][3] == -1 and r2["norm_supX"][3] == -1.0
+    # null: label counts are invariant under the shuffle -> same NaN pattern; replay reproduces the JDK stream
+    ne, nd, rep = oracle.null(s, lab2, T, 6, perm_mode=0, seed=3, want_replay=True)
+    assert np.isnan(ne[3]).all() and not np.isnan(ne[0]).any()
+    ne2, nd2 = oracle.null_replay(s, lab2, T, rep)
+    assert np.array_equal(ne.view(np.uint32), ne2.view(np.uint32)) and np.array_equal(nd.view(np.uint32), nd2.view(np.uint32))
+    for p in range(6):
+        assert sorted(rep[p].tolist()) == list(range(s.size))
+    # threads over types give the same null as one thread
+    ne3, _ = oracle.null(s, lab2, T, 6, perm_mode=0, seed=3, nthreads=4)
+    assert np.array_equal(ne.view(np.uint32), ne3.view(np.uint32))
+
+
+def test_feistel_permutation_is_a_bijection_and_global_indexed(oracle):
+    for n in (1, 2, 3, 17, 1000, 4097, 50_000):
+        p = oracle.feistel_perm(9, 3, n, 6)
+        assert np.array_equal(np.sort(p), np.arange(n))
+    a, b = oracle.feistel_perm(9, 3, 5000, 6), oracle.feistel_perm(9, 4, 5000, 6)
+    assert not np.array_equal(a, b)
+    s, lab = synth.synthetic_ranked(2000, 6, seed=2)
+    full, _ = oracle.null(s, lab, 6, 10, perm_mode=1, seed=11)
+    part, _ = oracle.null(s, lab, 6, 4, perm_mode=1, seed=11, perm_begin=3)
+    assert np.array_equal(full[:, 3:7].view(np.uint32), part.view(np.uint32))
+
+
+def test_feistel_null_is_statistically_equivalent_to_jdk_shuffle(oracle):
+    """north_star: PHILOX-mode nulls within a stated statistical tolerance of the reference's shuffle —
+    per-type two-sample KS test at alpha = 0.001 with Bonferroni over the types, and p-values within
+    4*sqrt(p(1-p)/P) (SURVEY.md §8 c)."""
+    from scipy import stats
+    s, lab = synth.synthetic_ranked(4000, 8, seed=5)
+    T, Pn = 8, 600
+    a, _ = oracle.null(s, lab, T, Pn, perm_mode=0, seed=1)
+    b, _ = oracle.null(s, lab, T, Pn, perm_mode=1, seed=1)
+    for t in range(T):
+        assert stats.ks_2samp(a[t], b[t]).pvalue > 0.001 / T, f"type {t}"
+    obs = oracle.ks_observed(s, lab, T)
+    pa, pb = oracle.reduce(obs, a)["p_emp"], oracle.reduce(obs, b)["p_emp"]
+    for t in range(T):
+        if np.isnan(pa[t]):
+            continue
+        p = 0.5 * (pa[t] + pb[t])
+        assert abs(pa[t] - pb[t]) <= 4 * math.sqrt(max(p * (1 - p), 1.0 / Pn) / Pn) * math.sqrt(2)
+
+
+def test_fast_definition_close_to_exact(oracle):
+    # FAST = exact prefix sums at hit / pre-hit positions; EXACT = the reference's fp32 running sums
+    s, lab = synth.synthetic_ranked(20_000, 12, seed=7)
+    F = oracle.fast_frac_bits(s)
+    assert F == 25  # max score in [0.5, 1)
+    for p in range(3):
+        lp = lab[oracle.feistel_perm(1, p, s.size, 6)]
+        e, _ = oracle.ks_null_one(s, lp, 12)
+        f = oracle.ks_null_fast_one(s, lp, 12, F)
+        ok = ~np.isnan(e)
+        assert np.array_equal(np.isnan(e), np.isnan(f)) and np.max(np.abs(e[ok] - f[ok])) < 2e-4
+
+
+def test_reduce_semantics(oracle):
+    T, Pn = 4, 8
+    null = np.array([[0.1, 0.2, 0.3, 0.4, -0.1, -0.2, 0.0, 0.5],
+                     [0.1] * 8,
+                     [-0.3, -0.2, -0.1, -0.4, 0.1, 0.2, 0.0, -0.5],
+                     [np.nan] * 8], np.float32)
+    res = np.zeros(T, oracle.TYPE_RESULT_DTYPE)
+    res["ews"] = np.array([0.3, 0.1, -0.3, np.nan], np.float32)
+    r, nn = oracle.reduce(res, null, want_norm_null=True)
+    # a10: positives only, strict, zeros excluded: {0.1,0.2,0.3,0.4,0.5} -> 2 of 5 are > 0.3
+    assert r["p_emp"][0] == 2 / 5
+    assert r["p_emp"][1] == 0.0                 # nothing is strictly greater than 0.1
+    assert r["p_emp"][2] == 2 / 5               # negatives strictly below -0.3: {-0.4,-0.5} of 5
+    assert np.isnan(r["p_emp"][3]) and np.isnan(r["norm_ews"][3]) and np.isnan(r["fdr"][3])
+    # a11: zeros count with the positives: mean of {0.1,0.2,0.3,0.4,0.0,0.5} in float, sequential
+    m = np.float32(0)
+    for v in (0.1, 0.2, 0.3, 0.4, 0.0, 0.5):
+        m = np.float32(m + np.float32(v))
+    m = np.float32(m / np.float32(6))
+    assert r["norm_ews"][0] == np.float32(np.float32(0.3) / m)
+    assert np.array_equal(nn[0], (null[0] / m).astype(np.float32))
+    assert np.isnan(r["fdr"][2])                # negative normalised score -> NaN (PCTSEA.java:1530-1533)
+    assert r["fdr"][0] >= 0.0
+    # fp64 mean policy changes only the normalisation
+    r1 = oracle.reduce(res, null, mean_policy=1)
+    assert r1["p_emp"][0] == r["p_emp"][0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# host side + ABI surface
+# ---------------------------------------------------------------------------------------------------
+def test_read_input_file(tmp_path):
+    from pctsea_parent_b200 import read_experimental_expressions_file
+    f = tmp_path / "in.txt"
+    f.write_text("\nacc\tspc\tgene\n\nnme2\t4\tx\nSumf2\t1.5\n\n")
+    genes, ab = read_experimental_expressions_file(str(f))
+    assert genes == ["NME2", "SUMF2"] and ab.tolist() == [4.0, 1.5]
+    f.write_text("header\nnocolumns\n")
+    with pytest.raises(IOError):
+        read_experimental_expressions_file(str(f))
+
+
+def test_input_parameters_mirror():
+    import pctsea_parent_b200 as P
+    ip = P.InputParameters()
+    assert (ip.DEFAULT_MIN_SCORE_PEARSON, ip.DEFAULT_MIN_GENES_CELLS_PEARSON, ip.PERM, ip.MINIMUM_CORRELATION) == (0.2, 100, "perm", "min_corr")
+    ip.addScoringSchema(P.ScoringMethod.SIMPLE_SCORE, 0.0, 10)
+    ip.addScoringSchema(P.ScoringMethod.PEARSONS_CORRELATION, 0.2, 100)
+    assert [s.getScoringMethod().getScoreName() for s in ip.scoringSchemas] == ["SimpleScore", "correlation"]
+    assert str(P.ScoreThreshold(-0.5)).startswith("<") and str(P.ScoreThreshold(0.2)).startswith(">")
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports every function include/pctsea_b200.h declares."""
+    from pctsea_parent_b200 import build as B
+    from pctsea_parent_b200 import _lib
+    B.build()
+    lib = ctypes.CDLL(_lib.SO_PATH)
+    hdr = open(os.path.join(ROOT, "include", "pctsea_b200.h")).read()
+    declared = set(re.findall(r"\b(pctsea_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert lib.pctsea_abi_version() == 1
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import pctsea_parent_b200 as P
+    with pytest.raises(P.PctseaError) as e:
+        P.Context(0)
+    assert e.value.code == -2
+
+
+def test_struct_layouts_match_header():
+    from pctsea_parent_b200 import _lib
+    assert ctypes.sizeof(_lib.TypeResult) == 56 and ctypes.sizeof(_lib.ScoreParams) == 32
+    assert ctypes.sizeof(_lib.NullParams) == 40 and ctypes.sizeof(_lib.Timings) == 72
+    assert _lib.TYPE_RESULT_DTYPE.fields["norm_supX"][1] == 16 and _lib.TYPE_RESULT_DTYPE.fields["fdr"][1] == 48
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pctsea_parent_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in src.replace("the CPU oracle", "").replace("CPU oracle's", "").replace("oracle's", "").replace("(same rule as the oracle)", "").replace("as the oracle", "").replace("the oracle", ""), f"{fn} references oracle/"
+
+
+def test_synthetic_generator_shapes():
+    cfg = synth.CONFIGS["tiny"]
+    ds = synth.make_dataset(cfg, "cpu")
+    assert ds.row_ptr.numel() == cfg.n_cells + 1 and int(ds.row_ptr[-1]) == ds.nnz
+    dens = ds.nnz / (cfg.n_cells * cfg.n_genes)
+    assert 0.03 < dens < 0.09
+    lab = ds.label.numpy()
+    assert lab.min() == -1 and lab.max() == cfg.n_types - 1 and 0.002 < (lab == -1).mean() < 0.03
+    assert np.unique(ds.gene_idx.numpy()).size == cfg.list_len
+    rp, col = ds.row_ptr.numpy(), ds.col.numpy()
+    for c in (0, 17, cfg.n_cells - 1):
+        row = col[rp[c]:rp[c + 1]]
+        assert np.all(np.diff(row) > 0)  # sorted, unique columns
