@@ -165,11 +165,11 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
         // chunk the permutations so the label matrix stays within half of the free device memory
         size_t free_b = 0, total_b = 0;
         PCT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_perm = (size_t)g.Nu_pad * g.lab_bytes +
-                                (prm->perm_mode == PCTSEA_PERM_REPLAY ? (size_t)g.Nu * 4 : 0);
+        const size_t row_bytes = plan_fast(g, Pc_all).label_row_bytes;  // layout-dependent (row-major or lane layout)
+        const size_t per_perm = row_bytes + (prm->perm_mode == PCTSEA_PERM_REPLAY ? (size_t)g.Nu * 4 : 0);
         size_t budget = std::max<size_t>(free_b / 2 + c->labels.cap + c->replay.cap, (size_t)64 << 20);
         int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)Pc_all, budget / std::max<size_t>(per_perm, 1)));
-        c->labels.reserve((size_t)chunk * g.Nu_pad * g.lab_bytes + 64);
+        c->labels.reserve((size_t)chunk * row_bytes + 64);
         for (int32_t p0 = 0; p0 < Pc_all; p0 += chunk) {
             const int32_t pc = std::min(chunk, Pc_all - p0);
             FastPlan fp = plan_fast(g, pc);
@@ -253,7 +253,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->score, &c->nused, &c->nnzc, &c->kept,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
                        &c->order, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
-                       &c->replay, &c->segsum, &c->coef, &c->supkey, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
+                       &c->replay, &c->segsum, &c->coef, &c->supkey, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
                        &c->red_keys, &c->red_keys2, &c->red_vals, &c->red_vals2, &c->red_misc };
     for (DevBuf* b : bufs) b->release();
     c->pin_in.release(); c->pin_out.release(); c->pin_small.release();

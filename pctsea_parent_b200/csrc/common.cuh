@@ -105,7 +105,7 @@ struct pctsea_ctx {
     pctsea::DevBuf obs_chain, obs_misc;                         // observed KS: accumulator history [Nu][Tpad]
     pctsea::DevBuf labels;                                      // [Pc][Nu_pad] permuted labels
     pctsea::DevBuf replay;                                      // [Pc][Nu] int32
-    pctsea::DevBuf segsum, coef, supkey;                        // FAST mode
+    pctsea::DevBuf segsum, coef, supkey, fxT;                   // FAST mode
     pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
     pctsea::DevBuf results;                                     // [T] pctsea_type_result
     pctsea::DevBuf red_tmp, red_keys, red_keys2, red_vals, red_vals2, red_misc;  // reduce
@@ -178,7 +178,14 @@ void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, co
                            const int32_t* order_dev, EnrichGeom& g, bool want_fixed);
 void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g);
 void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* replay_dev, int32_t Pc);
-struct FastPlan { int64_t seg = 0; int32_t K = 0; };
+struct FastPlan {
+    int64_t seg = 0;            // cooperative / label kernels: positions per warp task
+    int32_t K = 0;              // ... and tasks per permutation
+    bool lane_path = false;     // FAST lane kernel: one thread per segment
+    int32_t Kp = 0;             // threads (segments) per permutation
+    int32_t lane_seg = 0;       // positions per thread (multiple of 4)
+    size_t label_row_bytes = 0; // bytes of permuted labels per permutation in the chosen layout
+};
 FastPlan plan_fast(const EnrichGeom& g, int32_t Pc);
 void launch_labels_philox(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc,
                           int rounds, bool want_sums, const FastPlan& fp);

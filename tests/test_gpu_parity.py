@@ -379,3 +379,29 @@ def test_full_size_properties(ctx):
         with np.errstate(invalid="ignore"):
             exp = np.float32(np.sqrt(np.float64(prod) / np.float64(nA[t] + nB[t]))) * ne[t]
         assert_bits_equal_f32(de[t], exp.astype(np.float32), "dStat")
+
+
+def test_fast_lane_and_cooperative_kernels_agree(ctx, oracle):
+    """The FAST null has two kernels (one thread per segment for small type counts, a warp-cooperative one
+    otherwise); both carry the same exact integer arithmetic, so they must agree bit for bit — and with the
+    oracle's restatement of the FAST definition."""
+    import os
+    n_used, T, Pn = 50_000, 30, 7
+    s, lab, order = _ranked(n_used, T, seed=12)
+    prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=21)
+    old = os.environ.get("PCTSEA_FAST_PATH")
+    try:
+        os.environ["PCTSEA_FAST_PATH"] = "coop"
+        coop = ctx.enrich(s, order, lab, T, prm)[1]
+        os.environ["PCTSEA_FAST_PATH"] = "lane"
+        lane = ctx.enrich(s, order, lab, T, prm)[1]
+    finally:
+        if old is None:
+            os.environ.pop("PCTSEA_FAST_PATH", None)
+        else:
+            os.environ["PCTSEA_FAST_PATH"] = old
+    assert_bits_equal_f32(lane, coop, "lane vs cooperative FAST kernel")
+    F = oracle.fast_frac_bits(s)
+    for p in (0, Pn - 1):
+        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(21, p, n_used, 6)], T, F)
+        assert_bits_equal_f32(lane[:, p], exp, f"lane kernel vs oracle, perm {p}")
