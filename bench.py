@@ -226,6 +226,7 @@ def run_ours(args):
                          "score_kernel_achieved": score_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else None,
                          "score_kernel_frac": score_bytes / (score_ms * 1e-3) / 1e9 / peak if score_ms > 0 else None},
             "clocks": clocks,
+            "per_step_total_ms": [round(t["total_ms"], 3) for t in tms],
             "setup": {"generate_s": gen_s},
         }
         if not args.no_cpu_baseline and world == 1:
