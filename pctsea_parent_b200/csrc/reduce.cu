@@ -23,31 +23,43 @@ __device__ __forceinline__ uint32_t java_orderable_f32(float f) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__global__ void __launch_bounds__(128) k_red_type(const float* __restrict__ null_ews, int32_t T, int32_t P,
-                                                  int mean_policy, pctsea_type_result* __restrict__ res,
-                                                  float* __restrict__ expct_out) {
-    int t = blockIdx.x * 128 + threadIdx.x;
-    if (t >= T) return;
+// One warp per type. Counts are warp-parallel (ballots); the fp32 / fp64 running sums of a11 keep the
+// permutation order (the Maths.mean policy) by replaying each coalesced 32-value chunk lane by lane.
+__global__ void __launch_bounds__(32) k_red_type(const float* __restrict__ null_ews, int32_t T, int32_t P,
+                                                 int mean_policy, pctsea_type_result* __restrict__ res,
+                                                 float* __restrict__ expct_out) {
+    const int t = blockIdx.x, lane = threadIdx.x;
     const float real = res[t].ews;
     const double dnan = __longlong_as_double(0x7ff8000000000000LL);
     const float fnan = __int_as_float(0x7fc00000);
-    if (real != real) { res[t].p_emp = dnan; res[t].norm_ews = fnan; res[t].fdr = dnan; expct_out[t] = fnan; return; }
+    if (real != real) {
+        if (lane == 0) { res[t].p_emp = dnan; res[t].norm_ews = fnan; res[t].fdr = dnan; expct_out[t] = fnan; }
+        return;
+    }
     const float* nl = null_ews + (size_t)t * P;
     int32_t total = 0, cnt = 0, npos = 0, nneg = 0;
     float fsum_pos = 0.0f, fsum_neg = 0.0f;
     double dsum_pos = 0.0, dsum_neg = 0.0;
     const bool pos_side = real >= 0.0f;
-    for (int32_t p = 0; p < P; p++) {
-        float v = nl[p];
+    for (int32_t p0 = 0; p0 < P; p0 += 32) {
+        const int32_t p = p0 + lane;
+        const bool in = p < P;
+        const float v = in ? nl[p] : fnan;
         // a10: NaNs dropped, zeros excluded, strict comparisons
-        if (v == v) {
-            if (pos_side) { if (!(v <= 0.0f)) { total++; if (v > real) cnt++; } }
-            else          { if (!(v >= 0.0f)) { total++; if (v < real) cnt++; } }
-        }
+        const bool side = in && (v == v) && (pos_side ? !(v <= 0.0f) : !(v >= 0.0f));
+        total += __popc(__ballot_sync(0xffffffffu, side));
+        cnt += __popc(__ballot_sync(0xffffffffu, side && (pos_side ? (v > real) : (v < real))));
         // a11: zeros go with the positives
-        if (v >= 0.0f) { fsum_pos = __fadd_rn(fsum_pos, v); dsum_pos = __dadd_rn(dsum_pos, (double)v); npos++; }
-        else if (v < 0.0f) { fsum_neg = __fadd_rn(fsum_neg, v); dsum_neg = __dadd_rn(dsum_neg, (double)v); nneg++; }
+        npos += __popc(__ballot_sync(0xffffffffu, in && v >= 0.0f));
+        nneg += __popc(__ballot_sync(0xffffffffu, in && v < 0.0f));
+        const int n = min(32, P - p0);
+        for (int j = 0; j < n; j++) {
+            const float vj = __shfl_sync(0xffffffffu, v, j);
+            if (vj >= 0.0f) { fsum_pos = __fadd_rn(fsum_pos, vj); dsum_pos = __dadd_rn(dsum_pos, (double)vj); }
+            else if (vj < 0.0f) { fsum_neg = __fadd_rn(fsum_neg, vj); dsum_neg = __dadd_rn(dsum_neg, (double)vj); }
+        }
     }
+    if (lane != 0) return;
     res[t].p_emp = __ddiv_rn(__dmul_rn(1.0, (double)cnt), (double)total);  // 0/0 -> NaN
     float mean_pos = mean_policy ? __double2float_rn(__ddiv_rn(dsum_pos, (double)npos)) : __fdiv_rn(fsum_pos, (float)npos);
     float mean_neg = mean_policy ? __double2float_rn(__ddiv_rn(dsum_neg, (double)nneg)) : __fdiv_rn(fsum_neg, (float)nneg);
@@ -169,7 +181,7 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
     PCT_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
     unsigned long long* count = c->counters.as<unsigned long long>() + 4;
 
-    k_red_type<<<(unsigned)div_up(T, 128), 128, 0, c->stream>>>(null_dev, T, P, mean_policy, results_dev, expct);
+    k_red_type<<<(unsigned)T, 32, 0, c->stream>>>(null_dev, T, P, mean_policy, results_dev, expct);
     count_launch(c);
     uint64_t *k = c->red_keys.as<uint64_t>(), *k2 = c->red_keys2.as<uint64_t>();
     uint32_t *v = c->red_vals.as<uint32_t>(), *v2 = c->red_vals2.as<uint32_t>();

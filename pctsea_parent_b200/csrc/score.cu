@@ -21,17 +21,16 @@
 namespace pctsea {
 
 __global__ void k_list_lookup(const int32_t* __restrict__ gene_idx, const float* __restrict__ abund, int L, int G,
-                              float* __restrict__ ybg, uint32_t* __restrict__ bitmap, int bm_words) {
-    // bitmap[0 .. bm_words)          : gene is in the list (counts towards "non-zero list genes")
-    // bitmap[bm_words .. 2*bm_words) : gene is in the list with abundance > 0 (can form a pair)
+                              float* __restrict__ ybg, uint32_t* __restrict__ bitmap) {
+    // two bits per gene, 16 genes per word: bit 0 = gene is in the list (counts towards "non-zero list
+    // genes"), bit 1 = in the list with abundance > 0 (can form a pair)
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
     int g = gene_idx[l];
     if (g < 0 || g >= G) return;
     const float y = abund[l];
     ybg[g] = y;
-    atomicOr(&bitmap[g >> 5], 1u << (g & 31));
-    if (y > 0.0f) atomicOr(&bitmap[bm_words + (g >> 5)], 1u << (g & 31));
+    atomicOr(&bitmap[g >> 4], (y > 0.0f ? 3u : 1u) << ((g & 15) * 2));
 }
 
 __device__ __forceinline__ double jitter_uniform(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t i) {
@@ -112,20 +111,20 @@ __device__ __forceinline__ RowChunk load_chunk(const int32_t* __restrict__ col, 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);          // in list
-    uint32_t* bmp = bm + a.bm_words;                                // in list with abundance > 0
-    const int bm_bytes = ((a.bm_words * 8 + 15) / 16) * 16;
+    uint32_t* bm = reinterpret_cast<uint32_t*>(smem_raw);          // 2 bits per gene (in list, pairable)
+    const int bm_bytes = ((a.bm_words * 4 + 15) / 16) * 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // pair buffer: .x = matrix column (int bits) until the abundances are gathered, then the abundance
     float2* pairs = reinterpret_cast<float2*>(smem_raw + bm_bytes) + (size_t)warp * a.cap;
 
-    for (int i = threadIdx.x; i < 2 * a.bm_words; i += WARPS * 32) bm[i] = a.bitmap[i];
+    for (int i = threadIdx.x; i < a.bm_words; i += WARPS * 32) bm[i] = a.bitmap[i];
     __syncthreads();
 
     const unsigned lt_mask = (1u << lane) - 1u;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * WARPS;
+    const unsigned Gu = (unsigned)a.G;  // bm has a zero entry for index G: out-of-range / padding slots
 
     int64_t cell = warp_global;
     if (cell >= a.N) return;
@@ -136,7 +135,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
         const int64_t ncell = cell + warp_stride;
         int64_t nbeg = 0, nend = 0;
         if (ncell < a.N) { nbeg = a.row_ptr[ncell]; nend = a.row_ptr[ncell + 1]; }
-        int cnt = 0, cnt_nz = 0;
+        int cnt = 0, my_nz = 0;
         for (int64_t k0 = beg & ~(int64_t)3; k0 < end; k0 += 128) {
             // software pipeline: the next 128 non-zeros (or the first 128 of the next cell) are in flight
             // while this step is compacted
@@ -144,24 +143,21 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
             if (k0 + 128 < end) nxt = load_chunk(a.col, a.val, k0 + 128 + 4 * lane, beg, end);
             else nxt = load_chunk(a.col, a.val, (nbeg & ~(int64_t)3) + 4 * lane, nbeg, nend);
             bool ispair[4];
-            int below = 0, total = 0;
+            int mine = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int g = cur.g[q];
-                bool inlist = false, pairable = false;
-                if ((unsigned)g < (unsigned)a.G) {
-                    inlist = (bm[g >> 5] >> (g & 31)) & 1u;
-                    pairable = (bmp[g >> 5] >> (g & 31)) & 1u;
-                }
-                ispair[q] = pairable && (cur.x[q] > 0.0f);
-                const bool isnz = inlist && (cur.x[q] != 0.0f);  // true for NaN
-                const unsigned pm = __ballot_sync(0xffffffffu, ispair[q]);
-                cnt_nz += __popc(__ballot_sync(0xffffffffu, isnz));
-                below += __popc(pm & lt_mask);
-                total += __popc(pm);
+                const unsigned g = min((unsigned)cur.g[q], Gu);   // -1 (padding) and bad columns -> the zero entry
+                const unsigned bits = (bm[g >> 4] >> ((g & 15u) * 2u)) & 3u;
+                ispair[q] = (bits & 2u) && (cur.x[q] > 0.0f);
+                my_nz += ((bits & 1u) && (cur.x[q] != 0.0f)) ? 1 : 0;  // true for NaN
+                mine += ispair[q] ? 1 : 0;
             }
+            // exclusive prefix over lanes of `mine` (0..4) from the ballots of its three bit planes;
             // CSR order inside the step is (lane, q): lower lanes first, then my own earlier elements
-            int pos = cnt + below;
+            const unsigned p0 = __ballot_sync(0xffffffffu, mine & 1), p1 = __ballot_sync(0xffffffffu, mine & 2),
+                           p2 = __ballot_sync(0xffffffffu, mine & 4);
+            int pos = cnt + __popc(p0 & lt_mask) + 2 * __popc(p1 & lt_mask) + 4 * __popc(p2 & lt_mask);
+            cnt += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (ispair[q]) {
@@ -169,9 +165,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
                     pos++;
                 }
             }
-            cnt += total;
             cur = nxt;
         }
+        int cnt_nz = my_nz;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) cnt_nz += __shfl_xor_sync(0xffffffffu, cnt_nz, o);
         if (beg == end) cur = load_chunk(a.col, a.val, (nbeg & ~(int64_t)3) + 4 * lane, nbeg, nend);  // empty row
         __syncwarp();
         const int np = min(cnt, a.cap);  // cnt > cap only with duplicate columns in a row (unsupported input)
@@ -238,18 +236,18 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     const pctsea_matrix* m = sa.m;
     const int64_t N = m->n_cells;
     const int32_t G = m->n_genes;
-    const int32_t bm_words = (G + 31) / 32;
+    const int32_t bm_words = (G + 1 + 15) / 16;  // 2 bits per gene, plus the always-zero entry G
     c->ybg.reserve((size_t)G * 4 + 16);
-    c->bitmap.reserve((size_t)bm_words * 8 + 16);
+    c->bitmap.reserve((size_t)bm_words * 4 + 16);
     c->score.reserve((size_t)N * 8 + 16);
     c->nused.reserve((size_t)N * 4 + 16);
     c->nnzc.reserve((size_t)N * 4 + 16);
     c->kept.reserve((size_t)N + 16);
     PCT_CUDA(cudaMemsetAsync(c->ybg.p, 0, (size_t)G * 4, c->stream));
-    PCT_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (size_t)bm_words * 8, c->stream));
+    PCT_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (size_t)bm_words * 4, c->stream));
     if (sa.L > 0) {
         k_list_lookup<<<(sa.L + 255) / 256, 256, 0, c->stream>>>(sa.gene_idx_dev, sa.abund_dev, sa.L, G,
-                                                                  c->ybg.as<float>(), c->bitmap.as<uint32_t>(), bm_words);
+                                                                  c->ybg.as<float>(), c->bitmap.as<uint32_t>());
         count_launch(c);
     }
     if (N == 0) return;
@@ -263,7 +261,7 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     ka.kept = c->kept.as<uint8_t>();
 
     // Pair buffer: >= L pairs per warp so any cell fits; as many warps per SM as shared memory allows.
-    const int bm_bytes = ((bm_words * 8 + 15) / 16) * 16;
+    const int bm_bytes = ((bm_words * 4 + 15) / 16) * 16;
     int cap = (int)round_up(std::max(sa.L, 32), 32);
     const size_t smem_limit = 220 * 1024;
     int warps = 8;
