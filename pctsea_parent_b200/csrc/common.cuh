@@ -89,6 +89,7 @@ struct pctsea_matrix {
 struct pctsea_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_aux = nullptr;  // label generation runs here, one sub-chunk ahead of the KS kernels
     std::string err;
     cudaEvent_t ev[pctsea::EV_COUNT];
     bool ev_rec[pctsea::EV_COUNT];
@@ -187,11 +188,14 @@ struct FastPlan {
     size_t label_row_bytes = 0; // bytes of permuted labels per permutation in the chosen layout
 };
 FastPlan plan_fast(const EnrichGeom& g, int32_t Pc);
+// `st`: stream to launch on; `label_off`: byte offset of this sub-chunk inside c->labels
 void launch_labels_philox(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc,
-                          int rounds, bool want_sums, const FastPlan& fp);
-void launch_ks_exact_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, int32_t P_stride, int32_t p_off);
+                          int rounds, bool want_sums, const FastPlan& fp, cudaStream_t st, size_t label_off);
+void launch_ks_exact_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, int32_t P_stride, int32_t p_off,
+                          size_t label_off);
+void launch_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const FastPlan& fp);
 void launch_ks_fast_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, const FastPlan& fp, int32_t P_stride,
-                         int32_t p_off);
+                         int32_t p_off, size_t label_off);
 void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, int mean_policy,
                    pctsea_type_result* results_dev);
 
