@@ -131,6 +131,59 @@ def read_experimental_expressions_file(path: str):
     return genes, np.asarray(ab, dtype=np.float32)
 
 
+def _java_float_str(v) -> str:
+    """What `"" + (double) floatValue` prints closely enough for Float.valueOf to read it back exactly."""
+    v = float(v)
+    if math.isnan(v):
+        return "NaN"
+    if math.isinf(v):
+        return "Infinity" if v > 0 else "-Infinity"
+    return repr(v)
+
+
+def get_random_scores_file_name(prefix: str, scoring_method: "ScoringMethod", max_iterations: int) -> str:
+    """PCTSEA.getRandomScoresFile (PCTSEA.java:1911-1914), without the time-stamp folder."""
+    return f"{prefix}_{scoring_method.getScoreName()}_{max_iterations}_random_scores.txt"
+
+
+def print_to_random_distribution_file(path: str, cell_types: Sequence["CellTypeClassification"]):
+    """PCTSEA.printToRandomDistributionFile (PCTSEA.java:1877-1909): one row per type, sorted by name:
+    type, real score, diff, mean, std, then (score, dStat) per permutation."""
+    with open(path, "w") as fh:
+        fh.write("cell type\treal score\tdiff\tavg random score\tstd random score\trandom scores\n")
+        for ct in sorted(cell_types, key=lambda c: c.getName()):
+            real = np.float32(ct.getEnrichmentScore())
+            rnd = np.asarray(ct.randomEnrichmentScores, dtype=np.float32)
+            dst = np.asarray(ct.randomKSTestStatistics, dtype=np.float32)
+            mean = np.float32(0)
+            for v in rnd:                      # Maths.mean(TFloatList): float running sum / size
+                mean = np.float32(mean + v)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                mean = np.float32(mean / np.float32(rnd.size)) if rnd.size else np.float32("nan")
+                std = float(np.std(rnd.astype(np.float64), ddof=1)) if rnd.size > 1 else float("nan")
+            diff = float(real) - float(mean)
+            fh.write(f"{ct.getName()}\t{_java_float_str(real)}\t{_java_float_str(diff)}\t{_java_float_str(mean)}\t{_java_float_str(std)}")
+            for sc, d in zip(rnd, dst):
+                fh.write(f"\t{_java_float_str(sc)}\t{_java_float_str(d)}")
+            fh.write("\n")
+
+
+def read_random_distribution_file(path: str):
+    """PCTSEA.readRandomDistributionFile (PCTSEA.java:1834-1869): skip the header; columns 5.. are
+    (score, dStat) pairs parsed as float. Returns {type name: (scores fp32[P], dstats fp32[P])}."""
+    out = {}
+    with open(path, "r") as fh:
+        for num, line in enumerate(fh, start=1):
+            if num == 1:
+                continue
+            sp = line.rstrip("\n").split("\t")
+            if len(sp) < 5:
+                continue
+            vals = [np.float32(x) for x in sp[5:]]
+            out[sp[0]] = (np.asarray(vals[0::2], np.float32), np.asarray(vals[1::2], np.float32))
+    return out
+
+
 class SingleCellDataset:
     """The dataset the reference keeps in MongoDB (db/Expression.java, db/SingleCell.java), held as
     device-resident CSR: rows = cells in DB order, columns = upper-cased gene names."""
@@ -223,6 +276,9 @@ class PCTSEA:
         self.inputGenes: Optional[Sequence[str]] = None
         self.inputAbundance: Optional[np.ndarray] = None
         self.keepNull = False
+        self.loadRandomDistributionsIfExist = False
+        self.prefix: Optional[str] = None
+        self.outputFolder = "."
         if inputParameters is not None:
             self.sequentialScoringSchemas = list(inputParameters.scoringSchemas)
             self.experimentExpressionFile = inputParameters.inputDataFile
@@ -231,12 +287,16 @@ class PCTSEA:
             self.permutationMode = inputParameters.permutationMode
             self.ksMode = inputParameters.ksMode
             self.seed = inputParameters.seed
+            self.loadRandomDistributionsIfExist = inputParameters.loadRandom
+            self.prefix = inputParameters.outputPrefix
 
     # setters, PCTSEA.java:2692-2818
     def setExperimentExpressionFile(self, f): self.experimentExpressionFile = f
     def addScoreSchema(self, s: ScoringSchema): self.sequentialScoringSchemas.append(s)
     def setMaxIterations(self, n): self.maxIterations = int(n)
     def setMinimumCorrelation(self, v): self.minCorr = v
+    def setLoadRandomDistributionsIfExist(self, b): self.loadRandomDistributionsIfExist = bool(b)
+    def setPrefix(self, p): self.prefix = p
     def setStatusListener(self, cb): self.statusListener = cb
     def setInputList(self, genes: Sequence[str], abundance): self.inputGenes, self.inputAbundance = genes, np.asarray(abundance, np.float32)
 
@@ -268,10 +328,34 @@ class PCTSEA:
                 perm_mode=_lib.PERM_PHILOX if self.permutationMode == "PHILOX" else _lib.PERM_REPLAY,
                 ks_mode=_lib.KS_FAST if self.ksMode == "FAST" else _lib.KS_EXACT,
                 seed=self.seed, min_pass=self.MIN_CELLS_PASSING_SCORE_TRESHOLD)
+            import os
+            rnd_file = None
+            if self.prefix is not None:
+                rnd_file = os.path.join(self.outputFolder, get_random_scores_file_name(self.prefix, method, self.maxIterations))
+            loaded = None
+            if self.loadRandomDistributionsIfExist and rnd_file and os.path.exists(rnd_file) and os.path.getsize(rnd_file) > 0:
+                loaded = read_random_distribution_file(rnd_file)     # PCTSEA.java:1385-1387
             try:
-                out = self.ctx.analyze(self.dataset.matrix, gene_idx, self.inputAbundance, sprm,
-                                       schema.getScoringThreshold().getThresholdValue(),
-                                       self.dataset.matrix.n_types, nprm, want_null=self.keepNull)
+                if loaded is None:
+                    out = self.ctx.analyze(self.dataset.matrix, gene_idx, self.inputAbundance, sprm,
+                                           schema.getScoringThreshold().getThresholdValue(),
+                                           self.dataset.matrix.n_types, nprm,
+                                           want_null=self.keepNull or rnd_file is not None)
+                else:
+                    # observed scores on the GPU, null from the file, a10-a12 on the GPU (pctsea_reduce_null)
+                    nprm0 = Context.null_params(0, min_pass=self.MIN_CELLS_PASSING_SCORE_TRESHOLD)
+                    out = self.ctx.analyze(self.dataset.matrix, gene_idx, self.inputAbundance, sprm,
+                                           schema.getScoringThreshold().getThresholdValue(),
+                                           self.dataset.matrix.n_types, nprm0)
+                    T = self.dataset.matrix.n_types
+                    Pn = max((v[0].size for v in loaded.values()), default=0)
+                    null = np.full((T, Pn), np.nan, np.float32)
+                    nullD = np.full((T, Pn), np.nan, np.float32)
+                    for t, name in enumerate(self.dataset.type_names):
+                        if name in loaded and loaded[name][0].size == Pn:
+                            null[t], nullD[t] = loaded[name]
+                    out["results"] = self.ctx.reduce_null(out["results"], null, 0)
+                    out["null"], out["nullD"] = null, nullD
             except PctseaError as e:
                 if e.code in (_lib.PCTSEA_ETOOFEW, _lib.PCTSEA_EMINGENES):
                     raise ValueError(e.msg) from e  # IllegalArgumentException in the reference
@@ -280,10 +364,12 @@ class PCTSEA:
             types = []
             for t, name in enumerate(self.dataset.type_names):
                 ct = CellTypeClassification(name, t, out["results"][t])
-                if self.keepNull:
+                if "null" in out:
                     ct.randomEnrichmentScores = out["null"][t]
                     ct.randomKSTestStatistics = out["nullD"][t]
                 types.append(ct)
+            if rnd_file is not None and loaded is None:
+                print_to_random_distribution_file(rnd_file, types)   # PCTSEA.java:1431
             # PCTSEA.java:2476-2482: sorted by enrichment score, descending (Double.compare: NaN first)
             types.sort(key=lambda c: (0 if math.isnan(c.enrichmentScore) else 1, -c.enrichmentScore if not math.isnan(c.enrichmentScore) else 0.0))
             result.cellTypesPerRound.append(types)

@@ -405,3 +405,38 @@ def test_fast_lane_and_cooperative_kernels_agree(ctx, oracle):
     for p in (0, Pn - 1):
         exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(21, p, n_used, 6)], T, F)
         assert_bits_equal_f32(lane[:, p], exp, f"lane kernel vs oracle, perm {p}")
+
+
+def test_load_random_checkpoint(ctx, small, tmp_path):
+    """-load_random (PCTSEA.java:1385-1387): a second run that finds the null-distribution file reads it instead
+    of permuting, and reproduces the first run's normalised scores, p-values and FDR exactly."""
+    d, cfg = small, small["cfg"]
+    ds = P.SingleCellDataset.from_arrays(ctx, d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["label"], cfg.n_types)
+
+    def run(load):
+        ip = P.InputParameters()
+        ip.addScoringSchema(P.ScoringMethod.PEARSONS_CORRELATION, 0.0, 4)
+        ip.setNumPermutations(25)
+        ip.setMinCorr(0.2)
+        ip.setOutputPrefix("chk")
+        ip.setLoadRandom(load)
+        p = P.PCTSEA(ip, ds)
+        p.outputFolder = str(tmp_path)
+        p.MIN_CELLS_PASSING_SCORE_TRESHOLD = 100
+        p.setInputList([f"G{g}" for g in d["gene_idx"]], d["abundance"])
+        return {c.getName(): c for c in p.run().cellTypesPerRound[0]}
+
+    first = run(False)
+    import os
+    f = os.path.join(str(tmp_path), "chk_correlation_25_random_scores.txt")
+    assert os.path.exists(f)
+    # poison the generator path: if the second run permuted again with another seed the numbers would move
+    second = run(True)
+    for name, a in first.items():
+        b = second[name]
+        for get in ("getEnrichmentScore", "getNormalizedEnrichmentScore", "getEnrichmentSignificance", "getEnrichmentFDR"):
+            x, y = getattr(a, get)(), getattr(b, get)()
+            assert (np.isnan(x) and np.isnan(y)) or x == y, (name, get, x, y)
+        if a.randomEnrichmentScores is not None and not np.isnan(a.getEnrichmentScore()):
+            assert np.array_equal(np.asarray(a.randomEnrichmentScores).view(np.uint32),
+                                  np.asarray(b.randomEnrichmentScores).view(np.uint32))

@@ -365,3 +365,35 @@ def test_synthetic_generator_shapes():
     for c in (0, 17, cfg.n_cells - 1):
         row = col[rp[c]:rp[c + 1]]
         assert np.all(np.diff(row) > 0)  # sorted, unique columns
+
+
+def test_random_distribution_file_round_trip(tmp_path):
+    """-load_random checkpoint (PCTSEA.java:1834-1909): what print writes, read parses back bit for bit,
+    including NaN rows; rows are sorted by type name and the first five columns are informational."""
+    import pctsea_parent_b200.api as A
+
+    class CT:
+        def __init__(self, n, e, r, d):
+            self.n, self.e, self.randomEnrichmentScores, self.randomKSTestStatistics = n, e, r, d
+
+        def getName(self):
+            return self.n
+
+        def getEnrichmentScore(self):
+            return self.e
+
+    rng = np.random.default_rng(0)
+    a = CT("b cell", 0.3, rng.normal(0, 0.1, 9).astype(np.float32), rng.normal(0, 3, 9).astype(np.float32))
+    b = CT("a cell", float("nan"), np.full(9, np.nan, np.float32), np.full(9, np.nan, np.float32))
+    c = CT("c cell", -1e-7, np.array([1e-8, -3e7, 0.0] * 3, np.float32), np.array([np.inf, -0.0, 1.0] * 3, np.float32))
+    f = str(tmp_path / A.get_random_scores_file_name("run1", A.ScoringMethod.PEARSONS_CORRELATION, 9))
+    assert f.endswith("run1_correlation_9_random_scores.txt")
+    A.print_to_random_distribution_file(f, [a, b, c])
+    lines = open(f).read().splitlines()
+    assert lines[0].startswith("cell type\treal score\tdiff") and [l.split("\t")[0] for l in lines[1:]] == ["a cell", "b cell", "c cell"]
+    assert "nan" not in open(f).read() and "inf" not in open(f).read()   # Java spellings only
+    r = A.read_random_distribution_file(f)
+    for ct in (a, c):
+        assert np.array_equal(r[ct.n][0].view(np.uint32), ct.randomEnrichmentScores.view(np.uint32))
+        assert np.array_equal(r[ct.n][1].view(np.uint32), ct.randomKSTestStatistics.view(np.uint32))
+    assert np.isnan(r["a cell"][0]).all() and r["a cell"][0].size == 9
