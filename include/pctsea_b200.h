@@ -85,6 +85,11 @@ typedef struct pctsea_type_result {
     float   norm_ews;   /* a11 */
     double  p_emp;      /* a10 */
     double  fdr;        /* a12 */
+    /* observed-only extras of EnrichmentWeigthedScoreParallel.run (set for valid types, else 0 / 0 / NaN) */
+    float   sec_ews;    /* setSecondaryEnrichment (:244-312): secondary supremum, 0 when none */
+    int32_t sec_supX;   /* its 1-based position, 0 when none */
+    double  ks_d;       /* setKSTestPvalue (:211-212,228) = commons-math kolmogorovSmirnovStatistic of the type's
+                           scores vs the others; (float) of it is setEnrichmentUnweightedScore (PCTSEA.java:2606-2616) */
 } pctsea_type_result;
 
 /* Per-stage device times (CUDA events on the ctx stream) of the most recent call. */

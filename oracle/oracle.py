@@ -32,12 +32,14 @@ class ScoreParams(C.Structure):
 class TypeResult(C.Structure):
     _fields_ = [("ews", C.c_float), ("dstat", C.c_float), ("supX", C.c_int32), ("norm_supX", C.c_double),
                 ("sizeA", C.c_int32), ("sizeB", C.c_int32), ("raw_sup", C.c_float), ("norm_ews", C.c_float),
-                ("p_emp", C.c_double), ("fdr", C.c_double)]
+                ("p_emp", C.c_double), ("fdr", C.c_double), ("sec_ews", C.c_float), ("sec_supX", C.c_int32),
+                ("ks_d", C.c_double)]
 
 
 TYPE_RESULT_DTYPE = np.dtype([("ews", "<f4"), ("dstat", "<f4"), ("supX", "<i4"), ("_pad0", "<i4"),
                               ("norm_supX", "<f8"), ("sizeA", "<i4"), ("sizeB", "<i4"), ("raw_sup", "<f4"),
-                              ("norm_ews", "<f4"), ("p_emp", "<f8"), ("fdr", "<f8")])
+                              ("norm_ews", "<f4"), ("p_emp", "<f8"), ("fdr", "<f8"), ("sec_ews", "<f4"),
+                              ("sec_supX", "<i4"), ("ks_d", "<f8")])
 assert TYPE_RESULT_DTYPE.itemsize == C.sizeof(TypeResult)
 
 _lib = None
@@ -57,6 +59,7 @@ def lib():
         L.orc_jitter_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_pearson.restype = C.c_double
         L.orc_pearson_strided32.restype = C.c_double
+        L.orc_ks_statistic.restype = C.c_double
         L.orc_score2.restype = C.c_int
         L.orc_rank.restype = C.c_int64
         L.orc_score.restype = C.c_int
@@ -130,6 +133,12 @@ def pearson(x, y) -> float:
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
     return lib().orc_pearson(_p(x, C.c_double), _p(y, C.c_double), C.c_int32(x.size))
+
+
+def ks_statistic(x, y) -> float:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    return lib().orc_ks_statistic(_p(x, C.c_double), C.c_int64(x.size), _p(y, C.c_double), C.c_int64(y.size))
 
 
 def pearson_strided32(x, y) -> float:

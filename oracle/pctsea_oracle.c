@@ -433,12 +433,42 @@ static ks_walk ks_one_type(int64_t Nu, const double* s, const int32_t* lab, int3
     return w;
 }
 
+static int cmp_f64_java(const void* pa, const void* pb) {
+    return orc_java_double_compare(*(const double*)pa, *(const double*)pb);
+}
+
+double orc_ks_statistic(const double* x, int64_t n, const double* y, int64_t m) {
+    /* KolmogorovSmirnovTest.integralKolmogorovSmirnovStatistic (commons-math3 3.6.x), un-vendored */
+    double* sx = (double*)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+    double* sy = (double*)malloc((size_t)(m > 0 ? m : 1) * sizeof(double));
+    memcpy(sx, x, (size_t)n * sizeof(double));
+    memcpy(sy, y, (size_t)m * sizeof(double));
+    qsort(sx, (size_t)n, sizeof(double), cmp_f64_java);
+    qsort(sy, (size_t)m, sizeof(double), cmp_f64_java);
+    int64_t rankX = 0, rankY = 0, curD = 0, supD = 0;
+    do {
+        double z = orc_java_double_compare(sx[rankX], sy[rankY]) <= 0 ? sx[rankX] : sy[rankY];
+        while (rankX < n && orc_java_double_compare(sx[rankX], z) == 0) { rankX += 1; curD += m; }
+        while (rankY < m && orc_java_double_compare(sy[rankY], z) == 0) { rankY += 1; curD -= n; }
+        if (curD > supD) supD = curD;
+        else if (-curD > supD) supD = -curD;
+    } while (rankX < n && rankY < m);
+    free(sx); free(sy);
+    return (double)supD / ((double)(n * m));
+}
+
 void orc_ks_observed(int64_t Nu, const double* s, const int32_t* lab, int32_t T, orc_type_result* out) {
+    float* diffs = (float*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(float));
+    float* as = (float*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(float));
+    float* bs = (float*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(float));
+    double* xa = (double*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(double));
+    double* xb = (double*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(double));
     for (int32_t t = 0; t < T; t++) {
         ks_walk w = ks_one_type(Nu, s, lab, t, 1);
         orc_type_result* r = &out[t];
         r->sizeA = w.nk; r->sizeB = (int32_t)(Nu - w.nk);
         r->norm_ews = NAN; r->p_emp = NAN; r->fdr = NAN;
+        r->sec_ews = 0.0f; r->sec_supX = 0; r->ks_d = NAN;
         if (!w.valid) { /* :120-127, :317-323 */
             r->ews = NAN; r->dstat = NAN; r->supX = -1; r->norm_supX = -1.0; r->raw_sup = NAN;
             continue;
@@ -450,7 +480,49 @@ void orc_ks_observed(int64_t Nu, const double* s, const int32_t* lab, int32_t T,
         r->norm_supX = 1.0 * (double)w.supX / (double)Nu; /* :215 */
         if (w.has_neg_at_sup) sup = sup - fabsf(w.last_neg_at_sup); /* :216-227 */
         r->ews = sup;
+
+        /* ---- observed-only extras ---- */
+        /* KS D of the two score samples, :211-212 (NaN scores are not collected, :152,171) */
+        int64_t na = 0, nb = 0;
+        float denomA = 0.0f, denomB = 0.0f;
+        for (int64_t i = 0; i < Nu; i++) {
+            if (lab[i] == t) { denomA = (float)((double)denomA + s[i]); if (!isnan(s[i])) xa[na++] = s[i]; }
+            else { denomB = (float)((double)denomB + s[i]); if (!isnan(s[i])) xb[nb++] = s[i]; }
+        }
+        r->ks_d = (na > 0 && nb > 0) ? orc_ks_statistic(xa, na, xb, nb) : NAN;
+        /* differences again, then lookForSecondaryEnrichmentIndex :514-533 and the second walk :244-312 */
+        float prevA = 0.0f, prevB = 0.0f, numA = 0.0f, numB = 0.0f;
+        for (int64_t i = 0; i < Nu; i++) {
+            float a, b;
+            if (lab[i] == t) { numA = (float)((double)numA + s[i]); a = numA / denomA; b = prevB; }
+            else             { numB = (float)((double)numB + s[i]); a = prevA; b = numB / denomB; }
+            diffs[i] = a - b; as[i] = a; bs[i] = b;
+            prevA = a; prevB = b;
+        }
+        int64_t secIdx = 0;
+        double previousDifference = 0;
+        for (int64_t i = (int64_t)w.supX - 1; i >= 0; i--) {
+            double difference = diffs[i];
+            if (difference > 0 && previousDifference < 0.0) { secIdx = i; break; }
+            previousDifference = difference;
+        }
+        if (secIdx != 0) {
+            float secSup = 0.0f; int32_t secX = 0;
+            prevA = 0.0f; prevB = 0.0f; numA = 0.0f; numB = 0.0f;
+            for (int64_t i = 0; i <= secIdx; i++) {
+                float a, b;
+                if (lab[i] == t) { numA = (float)((double)numA + fabs(s[i])); a = numA / denomA; b = prevB; }
+                else             { numB = (float)((double)numB + fabs(s[i])); a = prevA; b = numB / denomB; }
+                if (a > b) {
+                    float difference = a - b;
+                    if (fabsf(difference) > fabsf(secSup)) { secSup = difference; secX = (int32_t)(i + 1); }
+                }
+                prevA = a; prevB = b;
+            }
+            if (secX != 0) { r->sec_ews = secSup; r->sec_supX = secX; }
+        }
     }
+    free(diffs); free(as); free(bs); free(xa); free(xb);
 }
 
 void orc_ks_null_one(int64_t Nu, const double* s, const int32_t* lab_perm, int32_t T,

@@ -99,7 +99,15 @@ typedef struct {
     float   norm_ews;   /* a11 */
     double  p_emp;      /* a10 */
     double  fdr;        /* a12 */
+    /* observed-only extras */
+    float   sec_ews;    /* secondary supremum, ...Parallel.java:244-312 (0 when none) */
+    int32_t sec_supX;   /* 1-based; 0 when none */
+    double  ks_d;       /* two-sample KS D of the type's scores vs the others (:211-212), NaN when invalid */
 } orc_type_result;
+
+/* commons-math3 3.x KolmogorovSmirnovTest.kolmogorovSmirnovStatistic(x, y) (restated: sort both, merge walk
+ * with ties processed together, integer running difference). */
+double orc_ks_statistic(const double* x, int64_t n, const double* y, int64_t m);
 
 /* s[Nu] ranked scores, lab[Nu] ranked labels in [-1, T). */
 void orc_ks_observed(int64_t Nu, const double* s, const int32_t* lab, int32_t T, orc_type_result* out);

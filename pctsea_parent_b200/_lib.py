@@ -48,7 +48,8 @@ class NullParams(C.Structure):
 class TypeResult(C.Structure):
     _fields_ = [("ews", C.c_float), ("dstat", C.c_float), ("supX", C.c_int32), ("norm_supX", C.c_double),
                 ("sizeA", C.c_int32), ("sizeB", C.c_int32), ("raw_sup", C.c_float), ("norm_ews", C.c_float),
-                ("p_emp", C.c_double), ("fdr", C.c_double)]
+                ("p_emp", C.c_double), ("fdr", C.c_double), ("sec_ews", C.c_float), ("sec_supX", C.c_int32),
+                ("ks_d", C.c_double)]
 
 
 class Timings(C.Structure):
@@ -63,8 +64,9 @@ class Timings(C.Structure):
 
 TYPE_RESULT_DTYPE = np.dtype([("ews", "<f4"), ("dstat", "<f4"), ("supX", "<i4"), ("_pad0", "<i4"),
                               ("norm_supX", "<f8"), ("sizeA", "<i4"), ("sizeB", "<i4"), ("raw_sup", "<f4"),
-                              ("norm_ews", "<f4"), ("p_emp", "<f8"), ("fdr", "<f8")])
-assert TYPE_RESULT_DTYPE.itemsize == C.sizeof(TypeResult) == 56
+                              ("norm_ews", "<f4"), ("p_emp", "<f8"), ("fdr", "<f8"), ("sec_ews", "<f4"),
+                              ("sec_supX", "<i4"), ("ks_d", "<f8")])
+assert TYPE_RESULT_DTYPE.itemsize == C.sizeof(TypeResult) == 72
 
 _lib = None
 

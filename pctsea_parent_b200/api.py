@@ -233,6 +233,12 @@ class CellTypeClassification:
         self.normalizedEnrichmentScore = float(r["norm_ews"])
         self.enrichmentSignificance = float(r["p_emp"])
         self.enrichmentFDR = float(r["fdr"])
+        # observed-only extras: setSecondaryEnrichment, setKSTestPvalue (EnrichmentWeigthedScoreParallel.java:228,310),
+        # setEnrichmentUnweightedScore (PCTSEA.java:2571-2621: 0 for an empty type, NaN for sizes <= 1)
+        self.secondaryEnrichmentScore = float(r["sec_ews"])
+        self.secondarySupremumX = int(r["sec_supX"])
+        self.ksTestPvalue = float(r["ks_d"])
+        self.enrichmentUnweightedScore = 0.0 if self.sizeA == 0 else float(np.float32(r["ks_d"]))
         self.randomEnrichmentScores: Optional[np.ndarray] = None
         self.randomKSTestStatistics: Optional[np.ndarray] = None
 
@@ -248,6 +254,10 @@ class CellTypeClassification:
     def getEnrichmentSignificance(self): return self.enrichmentSignificance
     def getEnrichmentFDR(self): return self.enrichmentFDR
     def getRandomEnrichmentScores(self): return self.randomEnrichmentScores
+    def getSecondaryEnrichmentScore(self): return self.secondaryEnrichmentScore
+    def getSecondarySupremumX(self): return self.secondarySupremumX
+    def getKSTestPvalue(self): return self.ksTestPvalue
+    def getEnrichmentUnweightedScore(self): return self.enrichmentUnweightedScore
 
 
 class PCTSEAResult:

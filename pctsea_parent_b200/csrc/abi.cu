@@ -288,7 +288,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->score, &c->nused, &c->nnzc, &c->kept,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
-                       &c->order, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
+                       &c->order, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
                        &c->replay, &c->segsum, &c->coef, &c->supkey, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
                        &c->red_keys, &c->red_keys2, &c->red_vals, &c->red_vals2, &c->red_misc };
     for (DevBuf* b : bufs) b->release();

@@ -103,7 +103,7 @@ struct pctsea_ctx {
     pctsea::DevBuf order;                                       // [N] int32
     pctsea::DevBuf label_tmp;                                   // [N] int32 (when labels passed per call)
     pctsea::DevBuf s_rank, lab_rank, fx, Sfx, class_cnt;        // ranked arrays [Nu]
-    pctsea::DevBuf obs_chain, obs_misc;                         // observed KS: accumulator history [Nu][Tpad]
+    pctsea::DevBuf obs_chain, obs_misc, obs_tiles;                       // observed KS: accumulator history [Nu][Tpad]
     pctsea::DevBuf labels;                                      // [Pc][Nu_pad] permuted labels
     pctsea::DevBuf replay;                                      // [Pc][Nu] int32
     pctsea::DevBuf segsum, coef, supkey, fxT;                   // FAST mode

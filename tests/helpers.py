@@ -26,9 +26,9 @@ def assert_bits_equal_f32(a, b, what=""):
     assert ok.all(), f"{what}: {np.count_nonzero(~ok)} of {ok.size} values differ in bits"
 
 
-RESULT_EXACT_F32 = ("ews", "dstat", "raw_sup", "norm_ews")
-RESULT_EXACT_F64 = ("norm_supX", "p_emp", "fdr")
-RESULT_EXACT_INT = ("supX", "sizeA", "sizeB")
+RESULT_EXACT_F32 = ("ews", "dstat", "raw_sup", "norm_ews", "sec_ews")
+RESULT_EXACT_F64 = ("norm_supX", "p_emp", "fdr", "ks_d")
+RESULT_EXACT_INT = ("supX", "sizeA", "sizeB", "sec_supX")
 
 
 def assert_results_equal(a, b, fields=None, what=""):
@@ -43,4 +43,4 @@ def assert_results_equal(a, b, fields=None, what=""):
             assert_bits_equal_f64(a[f], b[f], f"{what}.{f}")
 
 
-OBSERVED_FIELDS = ("ews", "dstat", "raw_sup", "supX", "norm_supX", "sizeA", "sizeB")
+OBSERVED_FIELDS = ("ews", "dstat", "raw_sup", "supX", "norm_supX", "sizeA", "sizeB", "sec_ews", "sec_supX", "ks_d")

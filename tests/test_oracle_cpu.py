@@ -338,7 +338,7 @@ def test_no_gpu_means_error_not_fallback():
 
 def test_struct_layouts_match_header():
     from pctsea_parent_b200 import _lib
-    assert ctypes.sizeof(_lib.TypeResult) == 56 and ctypes.sizeof(_lib.ScoreParams) == 32
+    assert ctypes.sizeof(_lib.TypeResult) == 72 and ctypes.sizeof(_lib.ScoreParams) == 32
     assert ctypes.sizeof(_lib.NullParams) == 40 and ctypes.sizeof(_lib.Timings) == 72
     assert _lib.TYPE_RESULT_DTYPE.fields["norm_supX"][1] == 16 and _lib.TYPE_RESULT_DTYPE.fields["fdr"][1] == 48
 
