@@ -30,6 +30,16 @@ if ROOT not in sys.path:
 ALGO_BYTES_PER_UNIT = 10.0  # 8 B fp64 score + 2 B label per (ranked cell x permutation)
 
 
+def profiled_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full
+    capture of this same command (profiles/r1_traffic.json); None if that kernel was not captured."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+        return float(d[kernel]["dram_bytes"]) if kernel in d else None
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -224,7 +234,11 @@ def run_ours(args):
             "gpu_launches": int(sum(t["launches"] for t in tms)),
             "stage_ms": {k: mean(k) for k in ("setup_ms", "score_ms", "rank_ms", "observed_ms", "labels_ms", "null_ms", "reduce_ms", "total_ms")},
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": profiled_traffic(dom_name) if cfg.name == "B" and P_per_gpu == 1000 else None,
+                         "traffic_note": "DRAM bytes of one launch from profiles/r1_top_kernels.txt (ncu --set full, config B); the "
+                                         "kernel's inputs (ranked scores, labels of the resident permutations) are L2-resident by "
+                                         "design, so DRAM traffic is far below the notional 10 B/unit stream",
+                         "algorithmic_bytes": ALGO_BYTES_PER_UNIT * units_gpu, "peak_source": peak_src,
                          "kernel_ms": dom_ms, "labels_kernel_ms": lab_ms, "ks_kernel_ms": null_ms,
                          "null_stage_ms": overl_ms,
                          "null_stage_achieved": stage_ach, "null_stage_frac": stage_ach / peak,
