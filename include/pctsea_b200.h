@@ -176,6 +176,13 @@ int pctsea_analyze(pctsea_ctx* ctx, const pctsea_matrix* m, int32_t L, const int
                    const int32_t* replay_perm, pctsea_type_result* out /*[n_types]*/,
                    float* null_out, float* nullD_out, double* score_out, int32_t* n_genes_used_out,
                    uint8_t* kept_out, int32_t* order_out, int64_t* n_pass_out);
+/* Inputs of PCTSEA.calculateHyperGeometricStatistics (PCTSEA.java:2169-2264) from the last pctsea_analyze on
+ * this ctx: per type, the cells surviving the min_genes_cells filter (numCellsOfType) and those of them passing
+ * the score threshold (numCellsOfTypeWithPositiveCorrelation); n_cells_kept = the population size N. A type
+ * with n_cells_of_type == 0 has no CellTypeClassification in the reference (PCTSEA.java:2172-2174). */
+int pctsea_last_type_counts(pctsea_ctx* ctx, int32_t n_types, int32_t* n_cells_of_type /*[n_types] or NULL*/,
+                            int32_t* n_cells_of_type_passing /*[n_types] or NULL*/, int64_t* n_cells_kept /*or NULL*/);
+
 /* Device pointers of the null slice left by the last pctsea_analyze / pctsea_enrich on this ctx:
  * [n_types][perm_count] fp32 each. Valid until the next call on the ctx. For NCCL all-gathers. */
 int pctsea_last_null_dev(pctsea_ctx* ctx, float** null_dev, float** nullD_dev, int32_t* n_types,

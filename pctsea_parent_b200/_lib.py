@@ -23,7 +23,7 @@ EXPORTS = [
     "pctsea_abi_version", "pctsea_create", "pctsea_destroy", "pctsea_last_error", "pctsea_get_timings",
     "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels",
     "pctsea_matrix_free", "pctsea_score", "pctsea_rank", "pctsea_enrich", "pctsea_reduce_null",
-    "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_last_null_dev",
+    "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_last_null_dev", "pctsea_last_type_counts",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
     L.pctsea_analyze.argtypes = [vp, vp, i32, vp, vp, C.POINTER(ScoreParams), f64, vp, i32, C.POINTER(NullParams),
                                  vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
     L.pctsea_last_null_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
+    L.pctsea_last_type_counts.argtypes = [vp, i32, vp, vp, C.POINTER(i64)]
     for name in EXPORTS:
         if name not in ("pctsea_last_error", "pctsea_stream"):
             getattr(L, name).restype = C.c_int
@@ -262,6 +263,13 @@ class Context:
         if want_order:
             out["order"] = order[:npass.value].copy()
         return out
+
+    def last_type_counts(self, n_types: int):
+        """(numCellsOfType[T], numCellsOfTypePassing[T], N kept) of the last analyze — hypergeometric inputs."""
+        a, b = np.zeros(n_types, np.int32), np.zeros(n_types, np.int32)
+        n = C.c_int64()
+        self._check(self.L.pctsea_last_type_counts(self.h, n_types, _ptr(a), _ptr(b), C.byref(n)))
+        return a, b, int(n.value)
 
     def last_null_dev(self):
         a, b = C.c_void_p(), C.c_void_p()

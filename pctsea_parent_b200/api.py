@@ -184,6 +184,14 @@ def read_random_distribution_file(path: str):
     return out
 
 
+def hypergeometric_upper_cumulative(N: int, K: int, n: int, k: int) -> float:
+    """commons-math3 HypergeometricDistribution(N, K, n).upperCumulativeProbability(k) = P(X >= k), clamped at 0 like
+    PCTSEA.java:2221-2225. O(T) host-side work on the counts the GPU returns (pctsea_last_type_counts)."""
+    from scipy.stats import hypergeom
+    p = float(hypergeom.sf(k - 1, N, K, n))
+    return max(p, 0.0)
+
+
 class SingleCellDataset:
     """The dataset the reference keeps in MongoDB (db/Expression.java, db/SingleCell.java), held as
     device-resident CSR: rows = cells in DB order, columns = upper-cased gene names."""
@@ -241,6 +249,11 @@ class CellTypeClassification:
         self.enrichmentUnweightedScore = 0.0 if self.sizeA == 0 else float(np.float32(r["ks_d"]))
         self.randomEnrichmentScores: Optional[np.ndarray] = None
         self.randomKSTestStatistics: Optional[np.ndarray] = None
+        # calculateHyperGeometricStatistics (PCTSEA.java:2169-2264), filled by PCTSEA.run from the GPU's counts
+        self.numCellsOfType = 0
+        self.numCellsOfTypePassingCorrelationThreshold = 0
+        self.hypergeometricPValue = float("nan")
+        self.casimirsEnrichmentScore = float("nan")
 
     def getName(self): return self.name
     def getCellTypeID(self): return self.cellTypeID
@@ -254,6 +267,10 @@ class CellTypeClassification:
     def getEnrichmentSignificance(self): return self.enrichmentSignificance
     def getEnrichmentFDR(self): return self.enrichmentFDR
     def getRandomEnrichmentScores(self): return self.randomEnrichmentScores
+    def getNumCellsOfType(self): return self.numCellsOfType
+    def getNumCellsOfTypePassingCorrelationThreshold(self): return self.numCellsOfTypePassingCorrelationThreshold
+    def getHypergeometricPValue(self): return self.hypergeometricPValue
+    def getCasimirsEnrichmentScore(self): return self.casimirsEnrichmentScore
     def getSecondaryEnrichmentScore(self): return self.secondaryEnrichmentScore
     def getSecondarySupremumX(self): return self.secondarySupremumX
     def getKSTestPvalue(self): return self.ksTestPvalue
@@ -372,8 +389,19 @@ class PCTSEA:
                 raise
             result.timings.append(self.ctx.timings())
             types = []
+            n_of_type, n_of_type_pass, n_kept = self.ctx.last_type_counts(self.dataset.matrix.n_types)
+            K = int(out["n_pass"])
             for t, name in enumerate(self.dataset.type_names):
+                if n_of_type[t] == 0:
+                    continue   # no CellTypeClassification for a type without cells after the filter (PCTSEA.java:2172-2174)
                 ct = CellTypeClassification(name, t, out["results"][t])
+                ct.numCellsOfType = int(n_of_type[t])
+                ct.numCellsOfTypePassingCorrelationThreshold = int(n_of_type_pass[t])
+                ct.hypergeometricPValue = hypergeometric_upper_cumulative(n_kept, K, ct.numCellsOfType,
+                                                                           ct.numCellsOfTypePassingCorrelationThreshold)
+                if ct.numCellsOfType > 0 and K > 0:
+                    x = (1.0 * ct.numCellsOfTypePassingCorrelationThreshold / K) / (1.0 * ct.numCellsOfType / n_kept)
+                    ct.casimirsEnrichmentScore = float(np.float32(math.log(x) / math.log(2))) if x > 0 else float("-inf")
                 if "null" in out:
                     ct.randomEnrichmentScores = out["null"][t]
                     ct.randomKSTestStatistics = out["nullD"][t]

@@ -288,7 +288,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->score, &c->nused, &c->nnzc, &c->kept,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
-                       &c->order, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
+                       &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
                        &c->replay, &c->segsum, &c->coef, &c->supkey, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
                        &c->red_keys, &c->red_keys2, &c->red_vals, &c->red_vals2, &c->red_misc };
     for (DevBuf* b : bufs) b->release();
@@ -527,6 +527,7 @@ int pctsea_analyze(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32
         ScoreArgs sa{ m, L, c->list_gene.as<int32_t>(), c->list_abund.as<float>(), *sprm };
         launch_score(c, sa);
         rec(c, EV_SCORE);
+        launch_type_counts(c, N, c->score.as<double>(), c->kept.as<uint8_t>(), label_dev, min_score, n_types);
         const int64_t Np = launch_rank(c, N, c->score.as<double>(), c->kept.as<uint8_t>(), min_score);
         if (n_pass_out) *n_pass_out = Np;
         c->tm.n_pass = Np;
@@ -555,6 +556,19 @@ int pctsea_analyze(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32
         finish_timings(c, ls, ns);
         c->tm.n_pass = Np;
         c->tm.n_used = Nu;
+    });
+}
+
+int pctsea_last_type_counts(pctsea_ctx* c, int32_t n_types, int32_t* n_cells_of_type, int32_t* n_cells_of_type_passing,
+                            int64_t* n_cells_kept) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(c->type_counts_T == n_types && n_types >= 0, "no type counts for this n_types: call pctsea_analyze first");
+        std::vector<int32_t> tmp((size_t)2 * n_types + 1);
+        PCT_CUDA(cudaMemcpyAsync(tmp.data(), c->type_counts.p, tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        PCT_CUDA(cudaStreamSynchronize(c->stream));
+        if (n_cells_of_type) memcpy(n_cells_of_type, tmp.data(), (size_t)n_types * 4);
+        if (n_cells_of_type_passing) memcpy(n_cells_of_type_passing, tmp.data() + n_types, (size_t)n_types * 4);
+        if (n_cells_kept) *n_cells_kept = tmp[2 * (size_t)n_types];
     });
 }
 

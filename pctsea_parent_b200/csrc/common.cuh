@@ -101,6 +101,8 @@ struct pctsea_ctx {
     pctsea::DevBuf score, nused, nnzc, kept;                    // stage 1 outputs [N]
     pctsea::DevBuf keysA, keysB, valsA, valsB, hist, tile_hist, scan_tmp, counters;  // radix sort
     pctsea::DevBuf order;                                       // [N] int32
+    pctsea::DevBuf type_counts;                                 // [2T+1] int32 (hypergeometric inputs)
+    int32_t type_counts_T = -1;
     pctsea::DevBuf label_tmp;                                   // [N] int32 (when labels passed per call)
     pctsea::DevBuf s_rank, lab_rank, fx, Sfx, class_cnt;        // ranked arrays [Nu]
     pctsea::DevBuf obs_chain, obs_misc, obs_tiles;                       // observed KS: accumulator history [Nu][Tpad]
@@ -160,6 +162,9 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& a);
 
 // Threshold + stable radix sort; writes c->order ([Np]); returns Np (syncs the stream once).
 int64_t launch_rank(pctsea_ctx* c, int64_t N, const double* score_dev, const uint8_t* kept_dev, double min_score);
+
+void launch_type_counts(pctsea_ctx* c, int64_t N, const double* score_dev, const uint8_t* kept_dev,
+                        const int32_t* label_dev, double min_score, int32_t T);
 
 // Generic stable LSD radix sort of (u64 key, u32 value) pairs; result lands in keys_out/vals_out
 // (which of the two supplied buffers that is, is returned through the pointers).

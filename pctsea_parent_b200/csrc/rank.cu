@@ -267,6 +267,44 @@ void radix_sort_pairs(pctsea_ctx* c, int64_t n, uint64_t** keys, uint64_t** keys
     radix_passes(c, n, c->pin_small.as<uint32_t>(), ndig, keys, keys_alt, vals, vals_alt);
 }
 
+// Per-type cell counts for the host-side hypergeometric statistics (PCTSEA.java:2169-2264): cells of the type
+// among the cells that survive the min_genes_cells filter, and among those the ones passing the score threshold.
+// counts[0..T) = kept, counts[T..2T) = kept and passing, counts[2T] = all kept cells (unknown types included).
+__global__ void __launch_bounds__(256) k_type_counts(const double* __restrict__ score, const uint8_t* __restrict__ kept,
+                                                     const int32_t* __restrict__ label, int64_t N, double thr, int32_t T,
+                                                     int32_t* __restrict__ counts, int32_t hist_n) {
+    extern __shared__ int32_t sh[];
+    for (int j = threadIdx.x; j < hist_n; j += 256) sh[j] = 0;
+    __syncthreads();
+    int32_t* dst = hist_n ? sh : counts;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < N; i += (int64_t)gridDim.x * 256) {
+        if (kept != nullptr && !kept[i]) continue;
+        atomicAdd(&dst[2 * T], 1);
+        const int32_t lab = label[i];
+        if (lab < 0 || lab >= T) continue;
+        atomicAdd(&dst[lab], 1);
+        if (passes(score[i], thr)) atomicAdd(&dst[T + lab], 1);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < hist_n; j += 256)
+        if (sh[j]) atomicAdd(&counts[j], sh[j]);
+}
+
+void launch_type_counts(pctsea_ctx* c, int64_t N, const double* score_dev, const uint8_t* kept_dev,
+                        const int32_t* label_dev, double min_score, int32_t T) {
+    const int32_t n = 2 * T + 1;
+    c->type_counts.reserve((size_t)n * 4 + 64);
+    PCT_CUDA(cudaMemsetAsync(c->type_counts.p, 0, (size_t)n * 4, c->stream));
+    c->type_counts_T = T;
+    if (N == 0) return;
+    const int32_t hist_n = (n <= 8192) ? n : 0;
+    int grid = (int)std::min<int64_t>(div_up(N, 256), (int64_t)kNumSMs * 4);
+    k_type_counts<<<grid, 256, (size_t)hist_n * 4, c->stream>>>(score_dev, kept_dev, label_dev, N, min_score, T,
+                                                                c->type_counts.as<int32_t>(), hist_n);
+    count_launch(c);
+    PCT_CUDA(cudaGetLastError());
+}
+
 int64_t launch_rank(pctsea_ctx* c, int64_t N, const double* score_dev, const uint8_t* kept_dev, double min_score) {
     c->order.reserve((size_t)std::max<int64_t>(N, 1) * 4 + 16);
     if (N == 0) return 0;

@@ -320,6 +320,7 @@ def test_host_api_mirror(ctx, small):
     r = p.run()
     types = r.cellTypesPerRound[0]
     assert len(types) == cfg.n_types
+    assert all(0.0 <= c.getHypergeometricPValue() <= 1.0 and c.getNumCellsOfType() >= c.getNumCellsOfTypePassingCorrelationThreshold() for c in types)
     es = [c.getEnrichmentScore() for c in types if not np.isnan(c.getEnrichmentScore())]
     assert es == sorted(es, reverse=True)
     assert all(c.getEnrichmentFDR() <= 0.05 for c in r.getSignificantTypes())
@@ -440,3 +441,22 @@ def test_load_random_checkpoint(ctx, small, tmp_path):
         if a.randomEnrichmentScores is not None and not np.isnan(a.getEnrichmentScore()):
             assert np.array_equal(np.asarray(a.randomEnrichmentScores).view(np.uint32),
                                   np.asarray(b.randomEnrichmentScores).view(np.uint32))
+
+
+def test_type_counts_for_hypergeometric_statistics(ctx, oracle, small):
+    """§8 f4: numCellsOfType / numCellsOfTypeWithPositiveCorrelation / N of PCTSEA.java:2169-2264 from the GPU."""
+    d, cfg = small, small["cfg"]
+    m = _load(ctx, d)
+    sprm = P.ScoreParams(0, 4, 0.2, 1, P.JITTER_PHILOX, 3)
+    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, 0.3, cfg.n_types, ctx.null_params(0, min_pass=10),
+                      want_scores=True)
+    a, b, n_kept = ctx.last_type_counts(cfg.n_types)
+    sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["gene_idx"], d["abundance"],
+                                      method=0, min_genes_cells=4, min_corr=0.2, jitter_mode=1, seed=3)
+    lab = d["label"]
+    keep = kept == 1
+    passing = keep & (sc >= 0.3)
+    assert n_kept == int(keep.sum()) and out["n_pass"] == int(passing.sum())
+    for t in range(cfg.n_types):
+        assert a[t] == int((keep & (lab == t)).sum()) and b[t] == int((passing & (lab == t)).sum())
+    m.free()
