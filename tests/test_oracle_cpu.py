@@ -397,3 +397,40 @@ def test_random_distribution_file_round_trip(tmp_path):
         assert np.array_equal(r[ct.n][0].view(np.uint32), ct.randomEnrichmentScores.view(np.uint32))
         assert np.array_equal(r[ct.n][1].view(np.uint32), ct.randomKSTestStatistics.view(np.uint32))
     assert np.isnan(r["a cell"][0]).all() and r["a cell"][0].size == 9
+
+
+def test_hcl_ingestion_to_csr(tmp_path):
+    """§8 f1: the HCL source format -> CSR with the reference's conventions
+    (HumanSingleCellsDatasetCreation.java:158-232, SingleCellsMetaInformationReader.java:151-175)."""
+    import gzip
+    from pctsea_parent_b200 import ingest
+    expr = tmp_path / "expr"
+    ann = tmp_path / "ann"
+    expr.mkdir()
+    ann.mkdir()
+    # R-style header: one column shorter than the data rows
+    with gzip.open(expr / "a.txt.gz", "wt") as fh:
+        fh.write('"c1","c2","c3"\n')
+        fh.write('"actb",0,3,0\n')       # first positive: c2 -> cell 0
+        fh.write('"Gapdh",2,0,5\n')      # c1 -> cell 1, c3 -> cell 2
+        fh.write('"empty",0,0,0\n')      # no positive count: the gene never enters the dictionary
+        fh.write('"ACTB",7,0,0\n')       # same gene upper-cased; (c1, ACTB) = 7
+    with gzip.open(expr / "b.txt.gz", "wt") as fh:
+        fh.write('"c2","c4"\n"gapdh",9,1\n')   # (c2, GAPDH) new; c4 -> cell 3
+    (ann / "x.csv").write_text('"Cell_id","Celltype","Biomaterial"\n"c1"," T Cell ","Blood"\n"c2","b cell","blood"\n"c4","Neuron","brain"\n')
+    ds = ingest.ingest_hcl(str(expr), str(ann))
+    assert ds.cell_names == ["c2", "c1", "c3", "c4"] and ds.gene_names == ["ACTB", "GAPDH"]
+    assert ds.cell_types == ["b cell", "t cell", "", "neuron"]
+    dense = np.zeros(ds.shape, np.float32)
+    for c in range(ds.shape[0]):
+        for k in range(ds.row_ptr[c], ds.row_ptr[c + 1]):
+            dense[c, ds.col[k]] = ds.val[k]
+        assert np.all(np.diff(ds.col[ds.row_ptr[c]:ds.row_ptr[c + 1]]) > 0)
+    assert dense.tolist() == [[3, 9], [7, 2], [0, 5], [0, 1]]
+    ds.save(str(tmp_path / "ds.npz"))
+    back = ingest.CSRDataset.load(str(tmp_path / "ds.npz"))
+    assert back.cell_names == ds.cell_names and np.array_equal(back.col, ds.col) and np.array_equal(back.val, ds.val)
+    with gzip.open(expr / "c.txt.gz", "wt") as fh:
+        fh.write('"c9"\n"bad",-1\n')
+    with pytest.raises(ValueError):
+        ingest.ingest_hcl(str(expr), str(ann))
