@@ -420,7 +420,9 @@ def test_hcl_ingestion_to_csr(tmp_path):
     (ann / "x.csv").write_text('"Cell_id","Celltype","Biomaterial"\n"c1"," T Cell ","Blood"\n"c2","b cell","blood"\n"c4","Neuron","brain"\n')
     ds = ingest.ingest_hcl(str(expr), str(ann))
     assert ds.cell_names == ["c2", "c1", "c3", "c4"] and ds.gene_names == ["ACTB", "GAPDH"]
-    assert ds.cell_types == ["b cell", "t cell", "", "neuron"]
+    # trim() runs before the quotes are removed (SingleCellsMetaInformationReader.java:160-163), so blanks
+    # inside the quotes survive
+    assert ds.cell_types == ["b cell", " t cell ", "", "neuron"]
     dense = np.zeros(ds.shape, np.float32)
     for c in range(ds.shape[0]):
         for k in range(ds.row_ptr[c], ds.row_ptr[c + 1]):
