@@ -84,11 +84,20 @@ struct RowChunk {
     float x[4];
 };
 
-// 4 consecutive non-zeros of the row per lane (one 128-bit load each for col and val when the quad lies
-// inside the row; element-wise at the row's head and tail). Elements outside [beg, end) come back as g = -1.
+// 4 consecutive non-zeros of the row per lane, starting at row offset j (a multiple of 4 relative to the
+// 16-byte-aligned position at or below the row start): one 128-bit load each for col and val when the warp's
+// whole 128-element step lies inside the row (`interior`, warp-uniform), element-wise at the row's head and
+// tail. Elements outside the row come back as g = -1.
 __device__ __forceinline__ RowChunk load_chunk(const int32_t* __restrict__ col, const float* __restrict__ val,
-                                               int64_t kk, int64_t beg, int64_t end) {
+                                               int64_t kk, int64_t beg, int64_t end, bool interior) {
     RowChunk c;
+    if (interior) {
+        const int4 gv = __ldcs(reinterpret_cast<const int4*>(col + kk));
+        const float4 xv = __ldcs(reinterpret_cast<const float4*>(val + kk));
+        c.g[0] = gv.x; c.g[1] = gv.y; c.g[2] = gv.z; c.g[3] = gv.w;
+        c.x[0] = xv.x; c.x[1] = xv.y; c.x[2] = xv.z; c.x[3] = xv.w;
+        return c;
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) { c.g[q] = -1; c.x[q] = 0.0f; }
     if (kk < end) {
@@ -129,48 +138,61 @@ __global__ void __launch_bounds__(WARPS * 32) k_score(const ScoreKernelArgs a) {
     int64_t cell = warp_global;
     if (cell >= a.N) return;
     int64_t beg = a.row_ptr[cell], end = a.row_ptr[cell + 1];
-    RowChunk cur = load_chunk(a.col, a.val, (beg & ~(int64_t)3) + 4 * lane, beg, end);
+    // chunk `idx` (128 non-zeros per warp) of the row [b, e); past the row's last chunk it comes back empty
+    auto fetch = [&](int64_t b, int64_t e, int64_t idx) {
+        const int64_t k0 = (b & ~(int64_t)3) + idx * 128;
+        return load_chunk(a.col, a.val, k0 + 4 * lane, b, e, k0 >= b && k0 + 128 <= e);
+    };
+    // software pipeline two steps deep: while step i is compacted, steps i+1 and i+2 (or the first steps of the
+    // warp's next cell) are in flight
+    RowChunk cur = fetch(beg, end, 0), n1 = fetch(beg, end, 1);
     while (cell < a.N) {
         // row bounds of the warp's next cell, fetched while this one is scanned
         const int64_t ncell = cell + warp_stride;
         int64_t nbeg = 0, nend = 0;
         if (ncell < a.N) { nbeg = a.row_ptr[ncell]; nend = a.row_ptr[ncell + 1]; }
+        const int64_t kstart = beg & ~(int64_t)3;
+        const int64_t m = (end > beg) ? (end - kstart + 127) / 128 : 0;   // steps of this row
         int cnt = 0, my_nz = 0;
-        for (int64_t k0 = beg & ~(int64_t)3; k0 < end; k0 += 128) {
-            // software pipeline: the next 128 non-zeros (or the first 128 of the next cell) are in flight
-            // while this step is compacted
-            RowChunk nxt;
-            if (k0 + 128 < end) nxt = load_chunk(a.col, a.val, k0 + 128 + 4 * lane, beg, end);
-            else nxt = load_chunk(a.col, a.val, (nbeg & ~(int64_t)3) + 4 * lane, nbeg, nend);
-            bool ispair[4];
-            int mine = 0;
+        for (int64_t i = 0; i < m; i++) {
+            const RowChunk n2 = (i + 2 < m) ? fetch(beg, end, i + 2) : fetch(nbeg, nend, i + 2 - m);
+            unsigned pmask = 0u, zmask = 0u;   // bit q: element q is a pair / a non-zero list gene
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const unsigned g = min((unsigned)cur.g[q], Gu);   // -1 (padding) and bad columns -> the zero entry
                 const unsigned bits = (bm[g >> 4] >> ((g & 15u) * 2u)) & 3u;
-                ispair[q] = (bits & 2u) && (cur.x[q] > 0.0f);
-                my_nz += ((bits & 1u) && (cur.x[q] != 0.0f)) ? 1 : 0;  // true for NaN
-                mine += ispair[q] ? 1 : 0;
+                pmask |= ((bits >> 1) & (cur.x[q] > 0.0f ? 1u : 0u)) << q;
+                zmask |= ((bits & 1u) & (cur.x[q] != 0.0f ? 1u : 0u)) << q;  // true for NaN
             }
+            my_nz += __popc(zmask);
+            const int mine = __popc(pmask);
             // exclusive prefix over lanes of `mine` (0..4) from the ballots of its three bit planes;
             // CSR order inside the step is (lane, q): lower lanes first, then my own earlier elements
             const unsigned p0 = __ballot_sync(0xffffffffu, mine & 1), p1 = __ballot_sync(0xffffffffu, mine & 2),
                            p2 = __ballot_sync(0xffffffffu, mine & 4);
             int pos = cnt + __popc(p0 & lt_mask) + 2 * __popc(p1 & lt_mask) + 4 * __popc(p2 & lt_mask);
             cnt += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
+            if (pmask) {
+                if (cnt <= a.cap) {   // warp-uniform: the whole step fits (always, unless a row repeats columns)
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (ispair[q]) {
-                    if (pos < a.cap) pairs[pos] = make_float2(__int_as_float(cur.g[q]), cur.x[q]);
-                    pos++;
+                    for (int q = 0; q < 4; q++)
+                        if (pmask & (1u << q)) pairs[pos++] = make_float2(__int_as_float(cur.g[q]), cur.x[q]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (pmask & (1u << q)) { if (pos < a.cap) pairs[pos] = make_float2(__int_as_float(cur.g[q]), cur.x[q]); pos++; }
                 }
             }
-            cur = nxt;
+            cur = n1;
+            n1 = n2;
         }
+        // invariant for the next cell: cur = its step 0, n1 = its step 1. Rows with fewer than two steps were
+        // primed with their own (empty) steps instead, so refill those slots here.
+        if (m == 0) { cur = fetch(nbeg, nend, 0); n1 = fetch(nbeg, nend, 1); }
+        else if (m == 1) cur = fetch(nbeg, nend, 0);
         int cnt_nz = my_nz;
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) cnt_nz += __shfl_xor_sync(0xffffffffu, cnt_nz, o);
-        if (beg == end) cur = load_chunk(a.col, a.val, (nbeg & ~(int64_t)3) + 4 * lane, nbeg, nend);  // empty row
         __syncwarp();
         const int np = min(cnt, a.cap);  // cnt > cap only with duplicate columns in a row (unsupported input)
         const bool keep = (cnt_nz > 0) && (cnt >= a.min_genes);
