@@ -169,12 +169,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler (NVML thread) starts before the warm-up so that its start-up cost is not inside the timed
+    # region; it keeps sampling through the timed steps
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 0)):
         flush.zero_()
         step()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     stage_ms = []
     tms = []
     t_begin = time.perf_counter()
