@@ -460,3 +460,72 @@ def test_type_counts_for_hypergeometric_statistics(ctx, oracle, small):
     for t in range(cfg.n_types):
         assert a[t] == int((keep & (lab == t)).sum()) and b[t] == int((passing & (lab == t)).sum())
     m.free()
+
+
+def test_negative_threshold_mode(ctx, oracle):
+    """min_score < 0: cells with score < threshold pass, all ranked scores are negative (scoring/ScoreThreshold.java:
+    66-74 + PCTSEA.java:2497). Accumulators, denominators and the observed extras run on negative sums."""
+    rng = np.random.default_rng(31)
+    n, T = 9000, 9
+    score = rng.uniform(-1.0, 0.4, n)
+    score[rng.random(n) < 0.05] = np.nan
+    label = rng.integers(-1, T, n).astype(np.int32)
+    thr = -0.2
+    go, gn = ctx.rank(score, None, thr)
+    oo, on = oracle.rank(score, None, thr)
+    assert gn == on and np.array_equal(go, oo)
+    nu = gn - 1
+    order = go[:nu]
+    s_r, lab_r = score[order], label[order]
+    assert np.all(s_r < 0)
+    Pn = 6
+    res, ne, nd = ctx.enrich(score, order, label, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=4))
+    ores = oracle.ks_observed(s_r, lab_r, T)
+    one, ond = oracle.null(s_r, lab_r, T, Pn, perm_mode=1, seed=4)
+    assert_bits_equal_f32(ne, one, "null (negative scores)")
+    assert_results_equal(res, oracle.reduce(ores, one), None, "negative-threshold analysis")
+    fast = ctx.enrich(score, order, label, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=4))[1]
+    F = oracle.fast_frac_bits(s_r)
+    for p in range(Pn):
+        exp = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(4, p, nu, 6)], T, F)
+        assert_bits_equal_f32(fast[:, p], exp, f"fast null (negative scores) perm {p}")
+
+
+def test_ties_zeros_and_many_types(ctx, oracle):
+    """Heavily tied scores with a block of exact zeros at the end (the accumulators stop moving, tie groups matter for
+    the KS D statistic), 200 types (lane kernel at its smallest thread count) and 1000 types (u16 labels)."""
+    for n_used, T in ((30_000, 200), (6000, 1000)):
+        rng = np.random.default_rng(n_used)
+        s = np.round(np.sort(rng.uniform(0.0, 1.0, n_used))[::-1], 2)
+        s[-n_used // 5:] = 0.0
+        lab = rng.integers(-1, T, n_used).astype(np.int32)
+        order = np.arange(n_used, dtype=np.int32)
+        Pn = 3
+        res, ne, _ = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_EXACT, seed=6))
+        ores = oracle.ks_observed(s, lab, T)
+        one, _ = oracle.null(s, lab, T, Pn, perm_mode=1, seed=6)
+        assert_bits_equal_f32(ne, one, f"null T={T}")
+        assert_results_equal(res, oracle.reduce(ores, one), None, f"ties/zeros T={T}")
+        fast = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=6))[1]
+        F = oracle.fast_frac_bits(s)
+        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(6, 1, n_used, 6)], T, F)
+        assert_bits_equal_f32(fast[:, 1], exp, f"fast null T={T}")
+
+
+def test_degenerate_shapes(ctx, oracle):
+    s, lab = synth.synthetic_ranked(500, 4, seed=2)
+    order = np.arange(500, dtype=np.int32)
+    # no permutations: observed only, a10-a12 on an empty null are NaN
+    res, ne, nd = ctx.enrich(s, order, lab, 4, ctx.null_params(0))
+    assert ne.shape == (4, 0) and np.isnan(res["p_emp"]).all() and np.isnan(res["norm_ews"]).all()
+    assert_results_equal(res, oracle.reduce(oracle.ks_observed(s, lab, 4), np.zeros((4, 0), np.float32)), None, "P=0")
+    # a single permutation, two ranked cells, all labels unknown
+    res, ne, _ = ctx.enrich(s[:2], order[:2], np.array([-1, -1], np.int32), 3, ctx.null_params(1, ks_mode=P.KS_FAST))
+    assert np.isnan(res["ews"]).all() and np.isnan(ne).all() and (res["supX"] == -1).all()
+    # bad arguments come back as errors, not crashes
+    with pytest.raises(P.PctseaError):
+        ctx.enrich(s, order, lab, 4, ctx.null_params(3, perm_mode=P.PERM_REPLAY, ks_mode=P.KS_EXACT))   # no replay array
+    with pytest.raises(P.PctseaError):
+        ctx.enrich(s, order, lab, 4, ctx.null_params(3, perm_begin=2, perm_count=5))                   # slice out of range
+    with pytest.raises(P.PctseaError):
+        ctx.enrich(s, np.array([0, 1, 10**6], np.int32), lab, 4, ctx.null_params(1))                   # order out of range
