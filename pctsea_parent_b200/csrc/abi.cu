@@ -286,7 +286,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     if (!c) return PCTSEA_EINVAL;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->score, &c->nused, &c->nnzc, &c->kept,
+    DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->list_rank, &c->score_sums, &c->score, &c->nused, &c->nnzc, &c->kept,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
                        &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
                        &c->replay, &c->segsum, &c->coef, &c->supkey, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
@@ -344,6 +344,12 @@ int pctsea_matrix_load_csr(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, cons
             throw;
         }
         m->row_ptr = (const int64_t*)rp; m->col = (const int32_t*)ci; m->val = (const float*)vv;
+        int bad = 0;
+        try { bad = validate_csr(c, m); } catch (...) { pctsea_matrix_free(c, m); throw; }
+        if (bad) {
+            pctsea_matrix_free(c, m);
+            throw Error(PCTSEA_EINVAL, "col_idx entries must lie in [0, n_genes)");
+        }
         *out = m;
     });
 }
@@ -360,6 +366,16 @@ int pctsea_matrix_wrap_device(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, c
         pctsea_matrix* m = new pctsea_matrix();
         m->n_cells = n_cells; m->n_genes = n_genes; m->nnz = nnz; m->owned = false;
         m->row_ptr = row_ptr_dev; m->col = col_idx_dev; m->val = val_dev;
+        int bad = 0;
+        try {
+            PCT_REQUIRE(nnz >= 0, "row_ptr_dev[n_cells] is negative");
+            PCT_REQUIRE(nnz == 0 || (col_idx_dev && val_dev), "col_idx_dev / val_dev are NULL");
+            PCT_REQUIRE(((uintptr_t)col_idx_dev & 15) == 0 && ((uintptr_t)val_dev & 15) == 0,
+                        "col_idx_dev / val_dev must be 16-byte aligned");
+            bad = validate_csr(c, m);
+            if (bad & 1) throw Error(PCTSEA_EINVAL, "row_ptr_dev must start at 0 and be non-decreasing");
+            if (bad & 2) throw Error(PCTSEA_EINVAL, "col_idx_dev entries must lie in [0, n_genes)");
+        } catch (...) { delete m; throw; }
         *out = m;
     });
 }

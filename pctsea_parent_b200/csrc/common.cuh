@@ -97,7 +97,7 @@ struct pctsea_ctx {
     int64_t launches = 0;
 
     // workspaces (grow-only)
-    pctsea::DevBuf list_gene, list_abund, ybg, bitmap;          // stage 1 lookup
+    pctsea::DevBuf list_gene, list_abund, ybg, bitmap, list_rank, score_sums;  // stage 1 lookup + per-cell centred sums
     pctsea::DevBuf score, nused, nnzc, kept;                    // stage 1 outputs [N]
     pctsea::DevBuf keysA, keysB, valsA, valsB, hist, tile_hist, scan_tmp, counters;  // radix sort
     pctsea::DevBuf order;                                       // [N] int32
@@ -159,6 +159,9 @@ struct ScoreArgs {
     pctsea_score_params prm;
 };
 void launch_score(pctsea_ctx* c, const ScoreArgs& a);
+// One pass over a device CSR: bit 0 = row_ptr not 0-based / non-decreasing / not ending at nnz, bit 1 = a column
+// outside [0, n_genes). Syncs the stream.
+int validate_csr(pctsea_ctx* c, const pctsea_matrix* m);
 
 // Threshold + stable radix sort; writes c->order ([Np]); returns Np (syncs the stream once).
 int64_t launch_rank(pctsea_ctx* c, int64_t N, const double* score_dev, const uint8_t* kept_dev, double min_score);
