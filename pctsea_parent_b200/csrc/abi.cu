@@ -171,6 +171,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
         const size_t per_perm = row_bytes + (prm->perm_mode == PCTSEA_PERM_REPLAY ? (size_t)g.Nu * 4 : 0);
         size_t budget = std::max<size_t>(free_b / 2 + c->labels.cap + c->replay.cap, (size_t)64 << 20);
         int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)Pc_all, budget / std::max<size_t>(per_perm, 1)));
+        if (const char* e = std::getenv("PCTSEA_PERM_CHUNK")) chunk = std::max(1, std::min(chunk, std::atoi(e)));   // tuning aid
         c->labels.reserve((size_t)chunk * row_bytes + 64);
         const FastPlan plan0 = plan_fast(g, Pc_all);
         if (fast) launch_fast_prepare(c, g, plan0);
