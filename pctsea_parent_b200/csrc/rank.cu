@@ -145,12 +145,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_count(const uint64_t* __res
         if (i < n) atomicAdd(&sh[(int)((keys[i] >> shift) & 0xff)], 1u);
     }
     __syncthreads();
-    tile_hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
+    tile_hist[(size_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];   // [tile][digit]
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_tile_scatter(const uint64_t* __restrict__ keys_in,
                                                             const uint32_t* __restrict__ vals_in, int64_t n, int shift,
-                                                            const uint32_t* __restrict__ tile_off, int n_tiles,
+                                                            const uint32_t* __restrict__ tile_hist, int n_tiles,
                                                             uint64_t* __restrict__ keys_out,
                                                             uint32_t* __restrict__ vals_out) {
     // Element order inside the tile: (warp, round, lane) <-> index warp*256 + round*32 + lane.
@@ -159,7 +159,34 @@ __global__ void __launch_bounds__(RS_THREADS) k_tile_scatter(const uint64_t* __r
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
-    toff[threadIdx.x] = tile_off[(size_t)threadIdx.x * n_tiles + blockIdx.x];
+    // Output offset of (digit d, this tile) = keys with a smaller digit anywhere + keys with digit d in earlier
+    // tiles, straight from the per-tile counts ([tile][digit], L2-resident): thread d sums its column, then the
+    // block scans the 256 digit totals. This replaces a separate single-CTA scan launch per pass.
+    {
+        __shared__ uint32_t wtot[RS_THREADS / 32];
+        const uint32_t* col = tile_hist + threadIdx.x;
+        uint32_t before = 0, total = 0;
+        int j = 0;
+        for (; j + 8 <= n_tiles; j += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = col[(size_t)(j + u) * 256];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { total += v[u]; before += (j + u < (int)blockIdx.x) ? v[u] : 0u; }
+        }
+        for (; j < n_tiles; j++) { const uint32_t v = col[(size_t)j * 256]; total += v; before += (j < (int)blockIdx.x) ? v : 0u; }
+        uint32_t incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += wtot[w];
+        toff[threadIdx.x] = wbase + incl - total + before;
+    }
     __syncthreads();
     int64_t base = (int64_t)blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
     uint64_t key[RS_ITEMS];
@@ -237,10 +264,9 @@ static void radix_passes(pctsea_ctx* c, int64_t n, const uint32_t* hist_host, in
         if (trivial) continue;
         const int shift = 8 * d;
         k_tile_count<<<n_tiles, RS_THREADS, 0, c->stream>>>(*keys, n, shift, c->tile_hist.as<uint32_t>(), n_tiles);
-        k_scan_u32<<<1, 1024, 0, c->stream>>>(c->tile_hist.as<uint32_t>(), (int64_t)256 * n_tiles, nullptr);
         k_tile_scatter<<<n_tiles, RS_THREADS, 0, c->stream>>>(*keys, *vals, n, shift, c->tile_hist.as<uint32_t>(),
                                                               n_tiles, *keys_alt, *vals_alt);
-        count_launch(c, 3);
+        count_launch(c, 2);
         std::swap(*keys, *keys_alt);
         std::swap(*vals, *vals_alt);
     }
