@@ -111,6 +111,90 @@ def test_score_long_list_small_buffer(ctx, oracle):
     m.free()
 
 
+def _random_csr(rng, N, G, mean_nnz, unsorted_rows=False):
+    nnz_c = np.clip(rng.poisson(mean_nnz, N), 0, G)
+    nnz_c[rng.integers(0, N, max(1, N // 50))] = 0            # a few empty rows
+    row_ptr = np.zeros(N + 1, np.int64)
+    row_ptr[1:] = np.cumsum(nnz_c)
+    col = np.empty(int(row_ptr[-1]), np.int32)
+    for i in range(N):
+        c = rng.choice(G, int(nnz_c[i]), replace=False)
+        col[row_ptr[i]:row_ptr[i + 1]] = c if unsorted_rows else np.sort(c)
+    val = rng.integers(1, 12, col.size).astype(np.float32)
+    return row_ptr, col, val
+
+
+@pytest.mark.parametrize("G,L,unsorted_rows", [
+    (120_000, 900, False),   # gene table too large for one byte per gene: two-bit membership table
+    (6_000, 5_000, True),    # list longer than the on-chip rank directory: abundances gathered from L2
+    (40_000, 64, False),     # short list, byte table, many warps per CTA
+])
+def test_score_kernel_table_variants(ctx, oracle, G, L, unsorted_rows):
+    rng = np.random.default_rng(G + L)
+    N = 1500
+    row_ptr, col, val = _random_csr(rng, N, G, 700 if L >= 900 else 4000, unsorted_rows)
+    # bias the list towards genes that occur, so that cells reach min_genes_cells
+    present = np.unique(col)
+    gene_idx = rng.permutation(present)[:L].astype(np.int32) if present.size >= L else rng.permutation(G)[:L].astype(np.int32)
+    gene_idx[rng.integers(0, L, 3)] = -1                       # proteins without a matrix gene
+    abundance = rng.integers(0, 40, L).astype(np.float32)      # includes zero abundances
+    m = ctx.load_csr(row_ptr, col, val, G)
+    for method, jitter in ((0, 1), (1, 0)):
+        kw = dict(method=method, min_genes_cells=3, min_corr=-1.0, has_min_corr=True, jitter_mode=jitter, seed=99)
+        g = ctx.score(m, gene_idx, abundance, **kw)
+        o = oracle.score(row_ptr, col, val, G, gene_idx, abundance, **kw)
+        assert np.array_equal(g[1], o[1]), "n_genes_used"
+        assert np.array_equal(g[2], o[2]), "n_nonzero"
+        assert np.array_equal(g[3], o[3]), "kept"
+        assert_bits_equal_f64(g[0], o[0], "score")
+        assert np.isfinite(g[0]).sum() > 20
+    m.free()
+
+
+def test_score_row_alignment_and_tails(ctx, oracle):
+    # rows of every length 0..300 back to back: every (row begin mod 4, row length mod 128) combination that the
+    # 128-bit head / tail handling of the scoring kernel sees, including the very last quad of the arrays
+    rng = np.random.default_rng(11)
+    G = 2000
+    lens = np.concatenate([np.arange(0, 301), rng.integers(0, 700, 400)])
+    N = lens.size
+    row_ptr = np.zeros(N + 1, np.int64)
+    row_ptr[1:] = np.cumsum(lens)
+    col = np.empty(int(row_ptr[-1]), np.int32)
+    for i in range(N):
+        col[row_ptr[i]:row_ptr[i + 1]] = np.sort(rng.choice(G, int(lens[i]), replace=False))
+    val = rng.integers(1, 6, col.size).astype(np.float32)
+    gene_idx = rng.permutation(G)[:600].astype(np.int32)
+    abundance = rng.integers(1, 30, 600).astype(np.float32)
+    for trim in (0, 1, 2, 3):   # move the end of the arrays through all four alignments
+        n_rows = N - trim
+        rp = row_ptr[:n_rows + 1]
+        nnz = int(rp[-1]) - trim if rp[-1] - rp[-2] >= trim else int(rp[-1])
+        rp = rp.copy(); rp[-1] = nnz
+        m = ctx.load_csr(rp, col[:nnz], val[:nnz], G)
+        g = ctx.score(m, gene_idx, abundance, min_genes_cells=2, min_corr=-1.0, seed=3)
+        o = oracle.score(rp, col[:nnz], val[:nnz], G, gene_idx, abundance, min_genes_cells=2, min_corr=-1.0, seed=3)
+        assert np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2]) and np.array_equal(g[3], o[3])
+        assert_bits_equal_f64(g[0], o[0], f"score trim{trim}")
+        m.free()
+
+
+def test_matrix_validation(ctx):
+    row_ptr = np.array([0, 2, 4], np.int64)
+    val = np.ones(4, np.float32)
+    with pytest.raises(P.PctseaError) as e:   # column outside [0, n_genes)
+        ctx.load_csr(row_ptr, np.array([0, 1, 2, 7], np.int32), val, 5)
+    assert e.value.code == -1
+    with pytest.raises(P.PctseaError) as e:   # negative column
+        ctx.load_csr(row_ptr, np.array([0, 1, -2, 3], np.int32), val, 5)
+    assert e.value.code == -1
+    with pytest.raises(P.PctseaError) as e:   # row_ptr not monotone
+        ctx.load_csr(np.array([0, 3, 2], np.int64), np.array([0, 1, 2], np.int32), val[:3], 5)
+    assert e.value.code == -1
+    m = ctx.load_csr(row_ptr, np.array([0, 1, 2, 4], np.int32), val, 5)   # the context still works afterwards
+    m.free()
+
+
 # ---------------------------------------------------------------------------------------------------
 # stage 2
 # ---------------------------------------------------------------------------------------------------
