@@ -53,10 +53,23 @@ __global__ void __launch_bounds__(32) k_red_type(const float* __restrict__ null_
         npos += __popc(__ballot_sync(0xffffffffu, in && v >= 0.0f));
         nneg += __popc(__ballot_sync(0xffffffffu, in && v < 0.0f));
         const int n = min(32, P - p0);
-        for (int j = 0; j < n; j++) {
-            const float vj = __shfl_sync(0xffffffffu, v, j);
-            if (vj >= 0.0f) { fsum_pos = __fadd_rn(fsum_pos, vj); dsum_pos = __dadd_rn(dsum_pos, (double)vj); }
-            else if (vj < 0.0f) { fsum_neg = __fadd_rn(fsum_neg, vj); dsum_neg = __dadd_rn(dsum_neg, (double)vj); }
+        // only the accumulator of the selected mean policy: the two sequential chains (positives, negatives) are
+        // what bounds this kernel
+        if (mean_policy) {
+            for (int j = 0; j < n; j++) {
+                const float vj = __shfl_sync(0xffffffffu, v, j);
+                if (vj >= 0.0f) dsum_pos = __dadd_rn(dsum_pos, (double)vj);
+                else if (vj < 0.0f) dsum_neg = __dadd_rn(dsum_neg, (double)vj);
+            }
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < n; j++) {
+                const float vj = __shfl_sync(0xffffffffu, v, j);
+                // adding -0.0f leaves any fp32 accumulator bit-unchanged (also a -0.0f one), so the two chains can
+                // be branch-free
+                fsum_pos = __fadd_rn(fsum_pos, (vj >= 0.0f) ? vj : -0.0f);
+                fsum_neg = __fadd_rn(fsum_neg, (vj < 0.0f) ? vj : -0.0f);
+            }
         }
     }
     if (lane != 0) return;
