@@ -154,6 +154,7 @@ def run_ours(args):
     nprm = ctx.null_params(P_total, perm_mode=P.PERM_PHILOX, ks_mode=ks_mode, seed=20261019,
                            perm_begin=rank * P_per_gpu, perm_count=P_per_gpu, min_pass=1000)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     def step():
         out = ctx.analyze(m, gene_idx, abundance, sprm, cfg.min_score, cfg.n_types, nprm)
@@ -162,10 +163,18 @@ def run_ours(args):
         if world > 1:
             nptr, _, T, Pc = ctx.last_null_dev()
             loc = torch.as_tensor(pdist.DevicePointer(nptr, (T, Pc)), device=dev)
-            full = pdist.all_gather_null(loc, P_total)
-            torch.cuda.synchronize()
+            # the exchange runs on the library's own stream (torch sees it as an external stream), so the reduction
+            # call that follows is ordered behind it without a host synchronisation
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(lib_stream):
+                g0.record()
+                full = pdist.all_gather_null(loc, P_total)
+                g1.record()
             res = ctx.reduce_null_dev(res, full.data_ptr(), T, P_total, 0)
             tm2 = ctx.timings()
+            # device time of the step = the analysis + the all-gather (torch's stream) + the reduction call
+            tm["gather_ms"] = g0.elapsed_time(g1)
+            tm["total_ms"] += tm["gather_ms"] + tm2["total_ms"]
             tm["reduce_ms"] += tm2["reduce_ms"]
             tm["launches"] += tm2["launches"]
             tm["h2d_bytes"] += tm2["h2d_bytes"]
@@ -246,7 +255,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(mean("h2d_bytes")), "d2h_bytes_per_step": int(mean("d2h_bytes")),
                     "analysis_seconds": e2e_ms * 1e-3},
             "gpu_launches": int(sum(t["launches"] for t in tms)),
-            "stage_ms": {k: mean(k) for k in ("setup_ms", "score_ms", "rank_ms", "observed_ms", "labels_ms", "null_ms", "reduce_ms", "total_ms")},
+            "stage_ms": {k: mean(k) for k in ("setup_ms", "score_ms", "rank_ms", "observed_ms", "labels_ms", "null_ms", "reduce_ms", "total_ms")
+                         + (("gather_ms",) if world > 1 else ())},
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": profiled_traffic(dom_name) if cfg.name == "B" and P_per_gpu == 1000 else None,
                          "traffic_note": "DRAM bytes of one launch from profiles/r1_top_kernels.txt (ncu --set full, config B); the "

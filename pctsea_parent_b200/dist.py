@@ -28,6 +28,10 @@ def all_gather_null(local: torch.Tensor, n_perm: int) -> torch.Tensor:
     T = local.shape[0]
     counts = [perm_slice(n_perm, r, world)[1] for r in range(world)]
     width = max(counts)
+    if min(counts) == width and local.is_cuda:   # equal slices on NCCL: one collective into [world][T][width], one transpose copy
+        out = torch.empty((world, T, width), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out.permute(1, 0, 2).reshape(T, world * width)
     padded = torch.zeros((T, width), dtype=local.dtype, device=local.device)
     padded[:, : local.shape[1]] = local
     parts: List[torch.Tensor] = [torch.empty_like(padded) for _ in range(world)]
