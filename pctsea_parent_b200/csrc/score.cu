@@ -541,8 +541,9 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
 
     // Shared memory: the membership table (one byte per gene when that leaves room for >= 16 warps, else two
     // bits per gene), the rank directory with the sorted abundances, and one pair buffer of >= L pairs per warp so that any cell fits.
-    const int cap = (int)round_up(std::max(sa.L, 32), 32);
-    const size_t smem_limit = 222 * 1024;  // the kernel also holds ~4 KB of static shared memory
+    const int cap = (int)round_up(std::max(sa.L, 32), 4);
+    // 227 KB per CTA minus the kernel's static shared memory (cell counter and per-warp queues, ~4 KB)
+    const size_t smem_limit = 227 * 1024 - (sizeof(int4) * 8 * kScoreMaxWarps + 64);
     const size_t pair_bytes = (size_t)cap * 8, rank_smem = rank_bytes;
     const size_t byte_tab = (size_t)round_up((int64_t)G + 1, 16), bit_tab = (size_t)round_up((int64_t)bm_words * 4, 16);
     const bool byte_mode = byte_tab + rank_smem + 16 * pair_bytes <= smem_limit;
