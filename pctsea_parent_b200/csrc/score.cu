@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) k_score(const ScoreKernelArgs a)
         const unsigned p0 = __ballot_sync(FULL, (S & 1u) != 0u), p1 = __ballot_sync(FULL, (S & 2u) != 0u),
                        p2 = __ballot_sync(FULL, (S & 4u) != 0u);
         int pos = cnt + __popc(p0 & lt_mask) + 2 * __popc(p1 & lt_mask) + 4 * __popc(p2 & lt_mask);
-        cnt += __popc(p0) + 2 * __popc(p1) + 4 * __popc(p2);
+        cnt += __reduce_add_sync(FULL, (int)(S & 15u));
         if (S & 15u) {
             if (cnt <= a.cap) {   // warp-uniform: the whole step fits (always, unless a row repeats columns)
 #pragma unroll
