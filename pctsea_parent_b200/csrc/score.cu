@@ -98,6 +98,38 @@ __device__ __forceinline__ double warp_sum_tree(double v) {
     return v;
 }
 
+// The same two (three) trees as warp_sum_tree, but packed: after the offset-16 exchange the lower half-warp
+// carries the first value and the upper half the second, so every level costs one shuffle + add for both (and
+// the means need one division per lane instead of two). Each partial sum pairs exactly the operands the plain
+// butterfly pairs (fp add commutes), so the results are bit-identical to warp_sum_tree on each value.
+__device__ __forceinline__ void warp_means_packed(double sx, double sy, double n, int lane, double& xbar, double& ybar) {
+    const bool hi = (lane & 16) != 0;
+    double v = __dadd_rn(hi ? sy : sx, __shfl_xor_sync(0xffffffffu, hi ? sx : sy, 16));
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const double m = __ddiv_rn(v, n);   // lanes 0-15: mean of x, lanes 16-31: mean of y
+    xbar = __shfl_sync(0xffffffffu, m, 0);
+    ybar = __shfl_sync(0xffffffffu, m, 16);
+}
+
+// Three sums; lane 0 ends with all three (the other lanes' outputs are unspecified).
+__device__ __forceinline__ void warp_sum3_packed(double& a, double& b, double& c, int lane) {
+    const bool hi = (lane & 16) != 0, q8 = (lane & 8) != 0;
+    // offset 16: lower half keeps (a, b), upper half keeps (c, -); c travels down, a and b travel up
+    const double r0 = __shfl_xor_sync(0xffffffffu, hi ? a : c, 16);
+    const double r1 = __shfl_xor_sync(0xffffffffu, b, 16);
+    double u = __dadd_rn(hi ? c : a, r0);   // lower: a_l + a_{l+16}; upper: c_l + c_{l-16}
+    double w = __dadd_rn(b, r1);            // b_l + b_{l^16} (used by the lower half only)
+    // offset 8: inside the lower half, lanes with bit 3 clear keep a, the others keep b; the upper half keeps c
+    const double r2 = __shfl_xor_sync(0xffffffffu, (hi || q8) ? u : w, 8);
+    double v = __dadd_rn((hi || !q8) ? u : w, r2);
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    a = v;                                      // lane 0
+    b = __shfl_sync(0xffffffffu, v, 8);
+    c = __shfl_sync(0xffffffffu, v, 16);
+}
+
 // SimpleRegression.getR(): sign(slope) * sqrt(RSquare)
 __device__ __forceinline__ double pearson_finish(double sumXX, double sumYY, double sumXY) {
     const double ten_min = __longlong_as_double(10LL);  // 10 * Double.MIN_VALUE
@@ -377,8 +409,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) k_score(const ScoreKernelArgs a)
             if (!(degenerate && a.jitter_mode == PCTSEA_JITTER_NAN)) {
                 double sxx = 0.0, syy = 0.0, sxy = 0.0;
                 if (!degenerate) {
-                    const double xbar = __ddiv_rn(warp_sum_tree(sx), (double)np);
-                    const double ybar = __ddiv_rn(warp_sum_tree(sy), (double)np);
+                    double xbar, ybar;
+                    warp_means_packed(sx, sy, (double)np, lane, xbar, ybar);
 #pragma unroll 2
                     for (int k = lane; k < np; k += 32) {
                         const double dx = __dsub_rn((double)pair_a[k], xbar), dy = __dsub_rn((double)pair_e[k], ybar);
@@ -386,9 +418,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) k_score(const ScoreKernelArgs a)
                         syy = __dadd_rn(syy, __dmul_rn(dy, dy));
                         sxy = __dadd_rn(sxy, __dmul_rn(dx, dy));
                     }
-                    sxx = warp_sum_tree(sxx);
-                    syy = warp_sum_tree(syy);
-                    sxy = warp_sum_tree(sxy);
+                    warp_sum3_packed(sxx, syy, sxy, lane);   // complete in lane 0, which writes them
                 } else {
                     const CentredSums cs = pearson_sums_jittered(pair_a, pair_e, np, lane, eq_list, eq_cell, a.seed, (uint64_t)cell);
                     sxx = cs.sxx; syy = cs.syy; sxy = cs.sxy;
