@@ -121,10 +121,13 @@ void*       pctsea_stream(pctsea_ctx* ctx);
  * Replaces GeneExpressionsRetriever.getSingleCellExpressionsFromDB (GeneExpressionsRetriever.java:120-274)
  * + the per-cell sparse vectors of model/SingleCell.java:49-104. Rows are cells in DB order (= tie-break
  * order), columns are dataset genes. Columns within a row must be unique; storage order of a row is the
- * canonical order of the Pearson update. */
+ * canonical order of the Pearson update. Both entry points check the CSR once on the device (row_ptr starts at
+ * 0, is non-decreasing and ends at nnz; every column lies in [0, n_genes)) and return PCTSEA_EINVAL otherwise:
+ * the scoring kernel indexes its on-chip gene tables with the stored columns unchecked. */
 int pctsea_matrix_load_csr(pctsea_ctx* ctx, int64_t n_cells, int32_t n_genes, const int64_t* row_ptr,
                            const int32_t* col_idx, const float* val, pctsea_matrix** out);
-/* Adopt device arrays without copying (they must outlive the matrix). */
+/* Adopt device arrays without copying (they must outlive the matrix and stay unmodified; col_idx_dev and
+ * val_dev must be 16-byte aligned, as any cudaMalloc / framework allocation is). */
 int pctsea_matrix_wrap_device(pctsea_ctx* ctx, int64_t n_cells, int32_t n_genes, const int64_t* row_ptr_dev,
                               const int32_t* col_idx_dev, const float* val_dev, pctsea_matrix** out);
 /* Cell-type ids per cell in [-1, n_types); -1 = unknown type (model/SingleCell.java:224-229). */
