@@ -38,7 +38,6 @@ float between(pctsea_ctx* c, int a, int b) {
 
 void begin_call(pctsea_ctx* c) {
     PCT_CUDA(cudaSetDevice(c->device));
-    cudaStreamSynchronize(c->stream_aux);  // idle unless a previous call failed half-way
     c->err.clear();
     memset(&c->tm, 0, sizeof c->tm);
     for (int i = 0; i < EV_COUNT; i++) c->ev_rec[i] = false;
@@ -177,12 +176,6 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
         if (fast) launch_fast_prepare(c, g, plan0);
         if (prm->perm_mode == PCTSEA_PERM_REPLAY && fast)
             throw Error(PCTSEA_EINVAL, "REPLAY permutations are a validation mode: use ks_mode EXACT");
-        // Experimental (PCTSEA_OVERLAP=1): label generation on the auxiliary stream one sub-chunk ahead of the KS
-        // kernel. Measured slower on B200 (config B: 3.9 ms vs 2.4 ms): the FAST lane kernel needs ~209 KB of
-        // shared memory per CTA, so it cannot become resident while label CTAs fill the SM, and the sub-chunks
-        // add partial waves. Off by default.
-        const bool overlap = prm->perm_mode == PCTSEA_PERM_PHILOX && std::getenv("PCTSEA_OVERLAP") != nullptr;
-        cudaEvent_t prev_chunk_done = nullptr;
         for (int32_t p0 = 0; p0 < Pc_all; p0 += chunk) {
             const int32_t pc = std::min(chunk, Pc_all - p0);
             cudaEvent_t e0 = et.mark(c->stream);
@@ -197,33 +190,16 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
                 null_spans.push_back({ e1, e2 });
                 continue;
             }
-            if (!overlap) {
-                launch_labels_philox(c, g, prm->seed, np.begin + p0, pc, np.rounds, fast, plan0, c->stream, 0);
-                cudaEvent_t e1 = et.mark(c->stream);
-                if (fast) launch_ks_fast_null(c, g, pc, plan0, Pc_all, p0, 0);
-                else launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);
-                cudaEvent_t e2 = et.mark(c->stream);
-                lab_spans.push_back({ e0, e1 });
-                null_spans.push_back({ e1, e2 });
-                continue;
-            }
-            // aux stream starts after everything queued so far on the main stream (ranked arrays, fxT, and the
-            // previous chunk's KS kernels, which read the label buffer this chunk overwrites)
-            PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, prev_chunk_done ? prev_chunk_done : e0, 0));
-            const int32_t n_sub = std::max(1, std::min(4, pc / 148));
-            const int32_t sub = (int32_t)div_up(pc, n_sub);
-            for (int32_t q0 = 0; q0 < pc; q0 += sub) {
-                const int32_t qc = std::min(sub, pc - q0);
-                const size_t off = (size_t)q0 * plan0.label_row_bytes;
-                launch_labels_philox(c, g, prm->seed, np.begin + p0 + q0, qc, np.rounds, fast, plan0, c->stream_aux, off);
-                cudaEvent_t lab_done = et.mark(c->stream_aux);
-                PCT_CUDA(cudaStreamWaitEvent(c->stream, lab_done, 0));
-                if (fast) launch_ks_fast_null(c, g, qc, plan0, Pc_all, p0 + q0, off);
-                else launch_ks_exact_null(c, g, qc, Pc_all, p0 + q0, off);
-            }
+            // Labels and KS kernel of a chunk run back to back on one stream. (Generating the labels of the next
+            // sub-chunk on a second stream was measured slower on B200: both kernels fill the SMs' shared memory,
+            // so they cannot co-reside, and the sub-chunks only add partial waves.)
+            launch_labels_philox(c, g, prm->seed, np.begin + p0, pc, np.rounds, fast, plan0, c->stream, 0);
+            cudaEvent_t e1 = et.mark(c->stream);
+            if (fast) launch_ks_fast_null(c, g, pc, plan0, Pc_all, p0, 0);
+            else launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);
             cudaEvent_t e2 = et.mark(c->stream);
-            prev_chunk_done = e2;
-            null_spans.push_back({ e0, e2 });   // labels overlap the KS kernels: one span for both
+            lab_spans.push_back({ e0, e1 });
+            null_spans.push_back({ e1, e2 });
         }
     }
     rec(c, EV_NULL);
@@ -268,8 +244,7 @@ int pctsea_create(int device_id, pctsea_ctx** out) {
     if (!c) return PCTSEA_ENOMEM;
     c->device = device_id;
     if (cudaSetDevice(device_id) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
         delete c;
         return PCTSEA_ECUDA;
@@ -290,13 +265,11 @@ int pctsea_destroy(pctsea_ctx* c) {
     DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->list_rank, &c->score_sums, &c->score, &c->nused, &c->nnzc, &c->kept,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
                        &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
-                       &c->replay, &c->segsum, &c->coef, &c->supkey, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
+                       &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
                        &c->red_keys, &c->red_keys2, &c->red_vals, &c->red_vals2, &c->red_misc };
     for (DevBuf* b : bufs) b->release();
     c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
-    cudaStreamSynchronize(c->stream_aux);
-    cudaStreamDestroy(c->stream_aux);
     cudaStreamDestroy(c->stream);
     delete c;
     return PCTSEA_OK;

@@ -89,7 +89,6 @@ struct pctsea_matrix {
 struct pctsea_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream_aux = nullptr;  // label generation runs here, one sub-chunk ahead of the KS kernels
     std::string err;
     cudaEvent_t ev[pctsea::EV_COUNT];
     bool ev_rec[pctsea::EV_COUNT];
@@ -108,7 +107,7 @@ struct pctsea_ctx {
     pctsea::DevBuf obs_chain, obs_misc, obs_tiles;                       // observed KS: accumulator history [Nu][Tpad]
     pctsea::DevBuf labels;                                      // [Pc][Nu_pad] permuted labels
     pctsea::DevBuf replay;                                      // [Pc][Nu] int32
-    pctsea::DevBuf segsum, coef, supkey, fxT;                   // FAST mode
+    pctsea::DevBuf fxT;                                         // FAST mode: lane layout of the fixed-point scores
     pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
     pctsea::DevBuf results;                                     // [T] pctsea_type_result
     pctsea::DevBuf red_tmp, red_keys, red_keys2, red_vals, red_vals2, red_misc;  // reduce
