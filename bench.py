@@ -78,7 +78,7 @@ class ClockSampler:
         self._names = names
         while not self._stop.is_set():
             self._sample()
-            self._stop.wait(0.05)
+            self._stop.wait(0.005)
 
     def _sample(self):
         nv = self.nv
@@ -364,11 +364,13 @@ def run_reference(args):
     t0 = time.perf_counter()
     O.ks_observed(s_r, lab_r, cfg.n_types)
     t_obs = time.perf_counter() - t0
-    # calibrate the per-step permutation count to ~10 s
+    # calibrate the per-step permutation count: ~10 s of CPU work per step, less when many steps are asked for, so
+    # that the whole run stays within a few minutes
     t0 = time.perf_counter()
     O.null(s_r, lab_r, cfg.n_types, 2, perm_mode=0, seed=1, nthreads=cores)
     per = (time.perf_counter() - t0) / 2
-    p_cpu = int(max(2, min(50, 10.0 / max(per, 1e-6))))
+    step_budget_s = max(1.0, min(10.0, 120.0 / max(args.steps, 1)))
+    p_cpu = int(max(2, min(50, step_budget_s / max(per, 1e-6))))
     for _ in range(min(args.warmup, 1)):
         O.null(s_r, lab_r, cfg.n_types, 2, perm_mode=0, seed=1, nthreads=cores)
     t0 = time.perf_counter()
@@ -399,8 +401,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="B", help="workload from pctsea_parent_b200.synth.CONFIGS (default B)")
     ap.add_argument("--perm", type=int, default=0, help="permutations per GPU (default: the config's)")
