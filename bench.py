@@ -228,10 +228,9 @@ def run_ours(args):
         peak, peak_src = measured_hbm_peak()
         mean = lambda k: float(np.mean([t[k] for t in tms]))
         lab_ms, null_ms = mean("labels_ms"), mean("null_ms")
-        lane = (cfg.n_types + 1) * 8 * 128 + (cfg.n_types + 1) * 24 + 256 <= 220 * 1024 and cfg.n_types < 255
+        lane = nu >= 4096   # the lane kernel (type-sliced above ~218 cell types) serves every ranking of that size
         ks_name = ("k_ks_fast_lane" if lane else "k_ks_fast") if ks_mode == P.KS_FAST else "k_ks_exact"
-        lab_name = ("k_labels_philox_smem" if nu + 6 * 2 * int(np.ceil(np.sqrt(max(nu, 1)))) + 64 <= 226 * 1024 else "k_labels_philox_t") \
-            if lane else "k_labels_philox"
+        lab_name = "k_labels_philox_lane" if lane else "k_labels_philox"
         dom_name, dom_ms = (lab_name, lab_ms) if lab_ms >= null_ms else (ks_name, null_ms)
         units_gpu = float(nu) * float(P_per_gpu)
         ach = ALGO_BYTES_PER_UNIT * units_gpu / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

@@ -191,7 +191,8 @@ struct FastPlan {
     int32_t K = 0;              // ... and tasks per permutation
     bool lane_path = false;     // FAST lane kernel: one thread per segment
     int32_t Kp = 0;             // threads (segments) per permutation
-    int32_t lane_seg = 0;       // positions per thread (multiple of 4)
+    int32_t lane_seg = 0;       // positions per thread (multiple of 32)
+    int32_t slice_T = 0;        // cell types per pass of the lane kernel (== T unless sliced)
     size_t label_row_bytes = 0; // bytes of permuted labels per permutation in the chosen layout
 };
 FastPlan plan_fast(const EnrichGeom& g, int32_t Pc);

@@ -301,7 +301,11 @@ def test_null_philox_exact_bit_exact(ctx, oracle, n_used, T, Pn):
 
 
 @pytest.mark.parametrize("n_used,T,Pn,simple", [(5000, 12, 16, False), (2500, 300, 5, False), (9000, 40, 8, True),
-                                                 (140_000, 20, 3, False)])
+                                                 (140_000, 20, 3, False),
+                                                 # more types than one pass of the lane kernel holds: type slices,
+                                                 # with 8-bit (T <= 254) and 16-bit labels
+                                                 (6000, 230, 3, False), (7000, 300, 3, False), (9000, 1000, 2, True),
+                                                 (5000, 218, 3, False)])
 def test_null_philox_fast_matches_oracle_fast(ctx, oracle, n_used, T, Pn, simple):
     s, lab, order = _ranked(n_used, T, seed=3, simple=simple)
     prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=5)
