@@ -266,7 +266,7 @@ int pctsea_destroy(pctsea_ctx* c) {
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
                        &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
                        &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
-                       &c->red_keys, &c->red_keys2, &c->red_vals, &c->red_vals2, &c->red_misc };
+                       &c->red_misc };
     for (DevBuf* b : bufs) b->release();
     c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);

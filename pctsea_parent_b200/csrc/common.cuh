@@ -110,7 +110,7 @@ struct pctsea_ctx {
     pctsea::DevBuf fxT;                                         // FAST mode: lane layout of the fixed-point scores
     pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
     pctsea::DevBuf results;                                     // [T] pctsea_type_result
-    pctsea::DevBuf red_tmp, red_keys, red_keys2, red_vals, red_vals2, red_misc;  // reduce
+    pctsea::DevBuf red_tmp, red_misc;  // reduce: staged null of pctsea_reduce_null; expected values, sorted scores, bins
     pctsea::PinnedBuf pin_in, pin_out, pin_small;
     int32_t last_T = 0, last_Pc = 0;
 };

@@ -273,11 +273,6 @@ static void radix_passes(pctsea_ctx* c, int64_t n, const uint32_t* hist_host, in
     PCT_CUDA(cudaGetLastError());
 }
 
-void radix_passes_public(pctsea_ctx* c, int64_t n, const uint32_t* hist_host, int ndig, uint64_t** keys,
-                         uint64_t** keys_alt, uint32_t** vals, uint32_t** vals_alt) {
-    radix_passes(c, n, hist_host, ndig, keys, keys_alt, vals, vals_alt);
-}
-
 void radix_sort_pairs(pctsea_ctx* c, int64_t n, uint64_t** keys, uint64_t** keys_alt, uint32_t** vals,
                       uint32_t** vals_alt, int key_bits) {
     if (n <= 1) return;

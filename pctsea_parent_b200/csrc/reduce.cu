@@ -4,18 +4,19 @@
 //   a10 PCTSEA.java:1449-1477 + calculateProportionPositive/Negative :1799-1832
 //   a11 model/CellTypeClassification.java:407-441 (getNormalizedEnrichmentScore; Maths.mean un-vendored:
 //       policy 0 = fp32 running sum in permutation order / count, policy 1 = fp64 sum)
-//   a12 PCTSEA.java:1479-1549 (pooled, sorted, Arrays.binarySearch — restated probe for probe so the
-//       duplicate-key corner lands on the same index as the JDK)
+//   a12 PCTSEA.java:1479-1549 (pooled, sorted, Arrays.binarySearch). The reference sorts the pooled normalised
+//       null only to binary-search the observed scores in it. The index that search returns depends on nothing
+//       but the array length and, for the searched key, how many pooled values are smaller and how many are equal
+//       (the probe at `mid` sees "< key" iff mid < #smaller and "> key" iff mid >= #smaller + #equal). So the pool
+//       is never materialised or sorted: one pass counts the pooled values between and at the observed scores,
+//       and the search is replayed probe for probe on those counts — the duplicate-key corner lands on the same
+//       index as the JDK.
 //
-// Inputs: null fp32 [T][P] (device), results[t].ews (device). All of it is O(T*P) <= a few MB; the
-// only heavy step is sorting the pooled normalised null (<= T*P floats) with the stage-2 radix sort.
+// Inputs: null fp32 [T][P] (device), results[t].ews (device). All of it is O(T*P) <= a few MB.
 #include "common.cuh"
 #include <cstring>
 
 namespace pctsea {
-
-void radix_passes_public(pctsea_ctx* c, int64_t n, const uint32_t* hist_host, int ndig, uint64_t** keys,
-                         uint64_t** keys_alt, uint32_t** vals, uint32_t** vals_alt);
 
 __device__ __forceinline__ uint32_t java_orderable_f32(float f) {
     // Float.compare / Arrays.sort(float[]) total order: -0.0 < 0.0, every NaN = canonical NaN, last
@@ -81,48 +82,23 @@ __global__ void __launch_bounds__(32) k_red_type(const float* __restrict__ null_
     expct_out[t] = expct;
 }
 
-// Pool the normalised nulls of every type whose normalised ES is not NaN, dropping entries < 0.
-__global__ void __launch_bounds__(256) k_red_pool(const float* __restrict__ null_ews, int32_t T, int32_t P,
-                                                  const pctsea_type_result* __restrict__ res,
-                                                  const float* __restrict__ expct, uint64_t* __restrict__ keys,
-                                                  unsigned long long* __restrict__ count, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t shist[4 * 256];
-    for (int i = threadIdx.x; i < 4 * 256; i += 256) shist[i] = 0;
-    __syncthreads();
-    const int64_t n = (int64_t)T * P;
-    const int lane = threadIdx.x & 31;
-    for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
-        int64_t id = base + threadIdx.x;
-        bool take = false;
-        uint32_t k = 0;
-        if (id < n) {
-            int t = (int)(id / P);
-            float ne = res[t].norm_ews;
-            if (ne == ne) {
-                float v = __fdiv_rn(null_ews[id], expct[t]);
-                if (!(v < 0.0f)) { take = true; k = java_orderable_f32(v); }
-            }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, take);
-        unsigned long long wbase = 0;
-        if (lane == 0 && m) wbase = atomicAdd(count, (unsigned long long)__popc(m));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (take) {
-            keys[wbase + __popc(m & ((1u << lane) - 1u))] = (uint64_t)k;
-#pragma unroll
-            for (int d = 0; d < 4; d++) atomicAdd(&shist[d * 256 + ((k >> (8 * d)) & 0xff)], 1u);
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * 256; i += 256)
-        if (shist[i]) atomicAdd(&hist[i], shist[i]);
-}
-
-__device__ __forceinline__ int32_t java_binary_search(const uint64_t* a, int32_t n, uint64_t key) {
+// Arrays.binarySearch on a sorted array of length n that holds `less` elements below the key and `eq` equal to it.
+__device__ __forceinline__ int32_t java_binary_search_counts(int32_t n, int32_t less, int32_t eq) {
     int32_t low = 0, high = n - 1;
     while (low <= high) {
-        int32_t mid = (int32_t)(((uint32_t)low + (uint32_t)high) >> 1);
-        uint64_t mv = a[mid];
+        const int32_t mid = (int32_t)(((uint32_t)low + (uint32_t)high) >> 1);
+        if (mid < less) low = mid + 1;
+        else if (mid >= less + eq) high = mid - 1;
+        else return mid;
+    }
+    return -(low + 1);
+}
+
+__device__ __forceinline__ int32_t java_binary_search(const uint32_t* a, int32_t n, uint32_t key) {
+    int32_t low = 0, high = n - 1;
+    while (low <= high) {
+        const int32_t mid = (int32_t)(((uint32_t)low + (uint32_t)high) >> 1);
+        const uint32_t mv = a[mid];
         if (mv < key) low = mid + 1;
         else if (mv > key) high = mid - 1;
         else return mid;
@@ -130,44 +106,105 @@ __device__ __forceinline__ int32_t java_binary_search(const uint64_t* a, int32_t
     return -(low + 1);
 }
 
-// One block: sorts the observed normalised scores (rank sort, T is small) and evaluates the FDR per type.
-__global__ void __launch_bounds__(1024) k_red_fdr(int32_t T, pctsea_type_result* __restrict__ res,
-                                                  const uint64_t* __restrict__ Z, const unsigned long long* __restrict__ nnull_p,
-                                                  uint64_t* __restrict__ Rsorted) {
-    __shared__ int32_t nobs_s;
-    if (threadIdx.x == 0) nobs_s = 0;
-    __syncthreads();
-    // R = non-NaN normalised scores that are not < 0
+__device__ __forceinline__ bool fdr_candidate(float ne) { return ne == ne && !(ne < 0.0f); }
+
+// One block: R = the observed normalised scores that are not NaN and not < 0, sorted (rank sort, T is small).
+// Also clears the pooled-null bins: bins[2j] counts pooled values strictly between R[j-1] and R[j] (bins[2 nobs]:
+// above R[nobs-1]), bins[2j+1] those equal to R[j] (accumulated at the first index of a run of equal scores).
+__global__ void __launch_bounds__(1024) k_red_rank(int32_t T, const pctsea_type_result* __restrict__ res,
+                                                   uint32_t* __restrict__ Rsorted, int32_t* __restrict__ nobs_out,
+                                                   unsigned int* __restrict__ bins) {
+    for (int i = threadIdx.x; i < 2 * T + 2; i += 1024) bins[i] = 0u;
+    int32_t mine = 0;
     for (int t = threadIdx.x; t < T; t += 1024) {
-        float ne = res[t].norm_ews;
-        if (ne == ne && !(ne < 0.0f)) atomicAdd(&nobs_s, 1);
-    }
-    __syncthreads();
-    const int32_t nobs = nobs_s;
-    for (int t = threadIdx.x; t < T; t += 1024) {
-        float ne = res[t].norm_ews;
-        if (!(ne == ne && !(ne < 0.0f))) continue;
-        uint32_t k = java_orderable_f32(ne);
+        const float ne = res[t].norm_ews;
+        if (!fdr_candidate(ne)) continue;
+        mine++;
+        const uint32_t k = java_orderable_f32(ne);
         int32_t rank = 0;
         for (int u = 0; u < T; u++) {
-            float nu = res[u].norm_ews;
-            if (!(nu == nu && !(nu < 0.0f))) continue;
-            uint32_t ku = java_orderable_f32(nu);
+            const float nu = res[u].norm_ews;
+            if (!fdr_candidate(nu)) continue;
+            const uint32_t ku = java_orderable_f32(nu);
             if (ku < k || (ku == k && u < t)) rank++;
         }
-        Rsorted[rank] = (uint64_t)k;
+        Rsorted[rank] = k;
+    }
+    if (threadIdx.x == 0) *nobs_out = 0;
+    __syncthreads();
+    if (mine) atomicAdd(nobs_out, mine);
+}
+
+// The pooled normalised null = null[t][p] / expected[t] of every type whose normalised ES is not NaN, entries < 0
+// dropped (PCTSEA.java:1479-1500). Each value is located among the observed scores and counted into its bin.
+__global__ void __launch_bounds__(256) k_red_count(const float* __restrict__ null_ews, int32_t T, int32_t P,
+                                                   const pctsea_type_result* __restrict__ res, const float* __restrict__ expct,
+                                                   const uint32_t* __restrict__ Rsorted, const int32_t* __restrict__ nobs_p,
+                                                   unsigned int* __restrict__ bins, int use_smem) {
+    extern __shared__ unsigned int sbins[];
+    const int32_t nobs = *nobs_p;
+    const int nb = 2 * nobs + 1;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < nb; i += 256) sbins[i] = 0u;
+        __syncthreads();
+    }
+    unsigned int* dst = use_smem ? sbins : bins;
+    const int64_t n = (int64_t)T * P;
+    for (int64_t id = (int64_t)blockIdx.x * 256 + threadIdx.x; id < n; id += (int64_t)gridDim.x * 256) {
+        const int t = (int)(id / P);
+        const float ne = res[t].norm_ews;
+        if (ne != ne) continue;
+        const float v = __fdiv_rn(null_ews[id], expct[t]);
+        if (v < 0.0f) continue;
+        const uint32_t k = java_orderable_f32(v);
+        int lo = 0, hi = nobs;   // lower bound: first j with R[j] >= k
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (Rsorted[mid] < k) lo = mid + 1; else hi = mid;
+        }
+        const bool eq = lo < nobs && Rsorted[lo] == k;
+        atomicAdd(&dst[2 * lo + (eq ? 1 : 0)], 1u);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += 256)
+            if (sbins[i]) atomicAdd(&bins[i], sbins[i]);
+    }
+}
+
+// One block: prefix over the bins, then per type the two binary searches of PCTSEA.java:1502-1549.
+__global__ void __launch_bounds__(1024) k_red_fdr(int32_t T, pctsea_type_result* __restrict__ res,
+                                                  const uint32_t* __restrict__ Rsorted, const int32_t* __restrict__ nobs_p,
+                                                  unsigned int* __restrict__ bins) {
+    __shared__ long long s_nnull;
+    const int32_t nobs = *nobs_p;
+    const int nb = 2 * nobs + 1;
+    // exclusive prefix of the bins in place (nb is a few hundred to a few thousand): one thread, sequential
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int i = 0; i < nb; i++) { const unsigned int v = bins[i]; bins[i] = (unsigned int)run; run += v; }
+        bins[nb] = (unsigned int)run;
+        s_nnull = run;
     }
     __syncthreads();
-    const long long nnull = (long long)(*nnull_p);
+    const long long nnull = s_nnull;
     const double dnan = __longlong_as_double(0x7ff8000000000000LL);
     for (int t = threadIdx.x; t < T; t += 1024) {
-        float ne = res[t].norm_ews;
+        const float ne = res[t].norm_ews;
         if (ne != ne || ne < 0.0f) { res[t].fdr = dnan; continue; }
-        uint64_t k = (uint64_t)java_orderable_f32(ne);
-        int32_t i1 = java_binary_search(Rsorted, nobs, k);
-        int32_t i2 = java_binary_search(Z, (int32_t)nnull, k);
-        int32_t sobs = nobs - (i1 >= 0 ? i1 + 1 : -i1 - 1);
-        int32_t snull = (int32_t)nnull - (i2 >= 0 ? i2 + 1 : -i2 - 1);
+        const uint32_t k = java_orderable_f32(ne);
+        const int32_t i1 = java_binary_search(Rsorted, nobs, k);
+        // first index of this score's run in R: its bins hold the pooled values below / equal to the score
+        int lo = 0, hi = nobs;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (Rsorted[mid] < k) lo = mid + 1; else hi = mid;
+        }
+        const int32_t less = (int32_t)bins[2 * lo + 1];                   // everything before the "equal" bin
+        const int32_t eq = (int32_t)(bins[2 * lo + 2] - bins[2 * lo + 1]);
+        const int32_t i2 = java_binary_search_counts((int32_t)nnull, less, eq);
+        const int32_t sobs = nobs - (i1 >= 0 ? i1 + 1 : -i1 - 1);
+        const int32_t snull = (int32_t)nnull - (i2 >= 0 ? i2 + 1 : -i2 - 1);
         double fdr;
         if (snull == 0) fdr = 0.0;
         else fdr = __dmul_rn(__ddiv_rn(__dmul_rn(1.0, (double)snull), (double)sobs),
@@ -180,39 +217,27 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
                    pctsea_type_result* results_dev) {
     if (T == 0) return;
     const int64_t n = (int64_t)T * P;
-    c->red_misc.reserve((size_t)T * 4 + (size_t)T * 8 + 256);
-    float* expct = c->red_misc.as<float>();
-    uint64_t* Rsorted = reinterpret_cast<uint64_t*>(c->red_misc.as<unsigned char>() + round_up((int64_t)T * 4, 16));
-    c->red_keys.reserve((size_t)std::max<int64_t>(n, 1) * 8 + 64);
-    c->red_keys2.reserve((size_t)std::max<int64_t>(n, 1) * 8 + 64);
-    c->red_vals.reserve((size_t)std::max<int64_t>(n, 1) * 4 + 64);
-    c->red_vals2.reserve((size_t)std::max<int64_t>(n, 1) * 4 + 64);
-    c->hist.reserve(8 * 256 * 4);
-    c->counters.reserve(64);
-    c->pin_small.reserve(8 * 256 * 4 + 64);
-    PCT_CUDA(cudaMemsetAsync(c->hist.p, 0, 8 * 256 * 4, c->stream));
-    PCT_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
-    unsigned long long* count = c->counters.as<unsigned long long>() + 4;
+    if (n > 0x7fffffffll) throw Error(PCTSEA_EINVAL, "pooled null larger than a Java int");
+    // [T] expected values | [T] sorted observed keys | nobs | [2T + 2] bins
+    const size_t off_r = (size_t)round_up((int64_t)T * 4, 16), off_n = off_r + (size_t)round_up((int64_t)T * 4, 16),
+                 off_b = off_n + 16, total = off_b + ((size_t)2 * T + 2) * 4;
+    c->red_misc.reserve(total + 64);
+    unsigned char* base = c->red_misc.as<unsigned char>();
+    float* expct = reinterpret_cast<float*>(base);
+    uint32_t* Rsorted = reinterpret_cast<uint32_t*>(base + off_r);
+    int32_t* nobs = reinterpret_cast<int32_t*>(base + off_n);
+    unsigned int* bins = reinterpret_cast<unsigned int*>(base + off_b);
 
     k_red_type<<<(unsigned)T, 32, 0, c->stream>>>(null_dev, T, P, mean_policy, results_dev, expct);
-    count_launch(c);
-    uint64_t *k = c->red_keys.as<uint64_t>(), *k2 = c->red_keys2.as<uint64_t>();
-    uint32_t *v = c->red_vals.as<uint32_t>(), *v2 = c->red_vals2.as<uint32_t>();
+    k_red_rank<<<1, 1024, 0, c->stream>>>(T, results_dev, Rsorted, nobs, bins);
     if (n > 0) {
-        int grid = (int)std::min<int64_t>(div_up(n, 256), (int64_t)kNumSMs * 8);
-        k_red_pool<<<grid, 256, 0, c->stream>>>(null_dev, T, P, results_dev, expct, k, count, c->hist.as<uint32_t>());
-        count_launch(c);
+        const int use_smem = T <= 4096;
+        const int grid = (int)std::min<int64_t>(div_up(n, 256), (int64_t)kNumSMs * 8);
+        k_red_count<<<grid, 256, use_smem ? ((size_t)2 * T + 2) * 4 : 0, c->stream>>>(null_dev, T, P, results_dev, expct, Rsorted,
+                                                                                     nobs, bins, use_smem);
     }
-    uint32_t* hh = c->pin_small.as<uint32_t>();
-    PCT_CUDA(cudaMemcpyAsync(hh, c->hist.p, 8 * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
-    PCT_CUDA(cudaMemcpyAsync(hh + 8 * 256, count, 8, cudaMemcpyDeviceToHost, c->stream));
-    PCT_CUDA(cudaStreamSynchronize(c->stream));
-    unsigned long long nn;
-    memcpy(&nn, hh + 8 * 256, 8);
-    if (nn > 0x7fffffffull) throw Error(PCTSEA_EINVAL, "pooled null larger than a Java int");
-    if (nn > 1) radix_passes_public(c, (int64_t)nn, hh, 4, &k, &k2, &v, &v2);
-    k_red_fdr<<<1, 1024, 0, c->stream>>>(T, results_dev, k, count, Rsorted);
-    count_launch(c);
+    k_red_fdr<<<1, 1024, 0, c->stream>>>(T, results_dev, Rsorted, nobs, bins);
+    count_launch(c, n > 0 ? 4 : 3);
     PCT_CUDA(cudaGetLastError());
 }
 
