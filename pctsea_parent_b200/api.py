@@ -184,6 +184,25 @@ def read_random_distribution_file(path: str):
     return out
 
 
+def p_adjust_bh(pvalues: Sequence[float]) -> np.ndarray:
+    """Benjamini-Hochberg adjusted values, the way R's p.adjust(p, "BH") computes them: NaNs stay NaN and do not count
+    towards n; sorted descending, cumulative minimum of n/i * p, capped at 1. PCTSEA.java:1551-1557 calls
+    edu.scripps.yates.utilities.maths.PValueCorrection.pAdjust(.., BH) — an un-vendored dependency of the reference
+    (utilities artifact, no source under /root/reference) — restated here from the published algorithm."""
+    p = np.asarray(pvalues, dtype=np.float64)
+    out = np.full(p.shape, np.nan)
+    ok = ~np.isnan(p)
+    n = int(ok.sum())
+    if n == 0:
+        return out
+    idx = np.nonzero(ok)[0]
+    order = idx[np.argsort(-p[idx], kind="stable")]           # descending
+    ranks = np.arange(n, 0, -1, dtype=np.float64)              # n, n-1, ..., 1
+    adj = np.minimum(1.0, np.minimum.accumulate(n / ranks * p[order]))
+    out[order] = adj
+    return out
+
+
 def hypergeometric_upper_cumulative(N: int, K: int, n: int, k: int) -> float:
     """commons-math3 HypergeometricDistribution(N, K, n).upperCumulativeProbability(k) = P(X >= k), clamped at 0 like
     PCTSEA.java:2221-2225. O(T) host-side work on the counts the GPU returns (pctsea_last_type_counts)."""
@@ -247,6 +266,9 @@ class CellTypeClassification:
         self.secondarySupremumX = int(r["sec_supX"])
         self.ksTestPvalue = float(r["ks_d"])
         self.enrichmentUnweightedScore = 0.0 if self.sizeA == 0 else float(np.float32(r["ks_d"]))
+        # BH-corrected KS value and its stars (PCTSEA.java:1551-1570), filled by PCTSEA.run over the round's types
+        self.ksTestCorrectedPvalue = float("nan")
+        self.ksTestSignificancyString = ""
         self.randomEnrichmentScores: Optional[np.ndarray] = None
         self.randomKSTestStatistics: Optional[np.ndarray] = None
         # calculateHyperGeometricStatistics (PCTSEA.java:2169-2264), filled by PCTSEA.run from the GPU's counts
@@ -274,6 +296,8 @@ class CellTypeClassification:
     def getSecondaryEnrichmentScore(self): return self.secondaryEnrichmentScore
     def getSecondarySupremumX(self): return self.secondarySupremumX
     def getKSTestPvalue(self): return self.ksTestPvalue
+    def getKSTestCorrectedPvalue(self): return self.ksTestCorrectedPvalue
+    def getKSTestSignificancyString(self): return self.ksTestSignificancyString
     def getEnrichmentUnweightedScore(self): return self.enrichmentUnweightedScore
 
 
@@ -408,6 +432,10 @@ class PCTSEA:
                 types.append(ct)
             if rnd_file is not None and loaded is None:
                 print_to_random_distribution_file(rnd_file, types)   # PCTSEA.java:1431
+            # BH correction of the KS values over the round's cell types (PCTSEA.java:1551-1570)
+            for ct, padj in zip(types, p_adjust_bh([c.ksTestPvalue for c in types])):
+                ct.ksTestCorrectedPvalue = float(padj)
+                ct.ksTestSignificancyString = "***" if padj < 0.001 else "**" if padj < 0.01 else "*" if padj < 0.05 else ""
             # PCTSEA.java:2476-2482: sorted by enrichment score, descending (Double.compare: NaN first)
             types.sort(key=lambda c: (0 if math.isnan(c.enrichmentScore) else 1, -c.enrichmentScore if not math.isnan(c.enrichmentScore) else 0.0))
             result.cellTypesPerRound.append(types)

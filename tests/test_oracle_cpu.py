@@ -436,3 +436,15 @@ def test_hcl_ingestion_to_csr(tmp_path):
         fh.write('"c9"\n"bad",-1\n')
     with pytest.raises(ValueError):
         ingest.ingest_hcl(str(expr), str(ann))
+
+
+def test_bh_adjustment_matches_r_p_adjust():
+    # known answers of R's p.adjust(p, "BH"), the algorithm PCTSEA.java:1551-1557 applies to the KS values through
+    # the un-vendored PValueCorrection class
+    from pctsea_parent_b200.api import p_adjust_bh
+    got = p_adjust_bh([0.01, 0.04, 0.03, float("nan"), 0.5, 0.002])
+    exp = [0.025, 0.05, 0.05, float("nan"), 0.5, 0.01]
+    assert np.allclose(got, exp, equal_nan=True, rtol=0, atol=1e-15)
+    assert np.allclose(p_adjust_bh([0.9, 0.8, 0.7]), [0.9, 0.9, 0.9])
+    assert np.allclose(p_adjust_bh([0.5, 0.6]), [0.6, 0.6])    # n/i * p capped by the running minimum, and at 1
+    assert p_adjust_bh([]).size == 0
