@@ -186,6 +186,14 @@ int pctsea_analyze(pctsea_ctx* ctx, const pctsea_matrix* m, int32_t L, const int
 int pctsea_last_type_counts(pctsea_ctx* ctx, int32_t n_types, int32_t* n_cells_of_type /*[n_types] or NULL*/,
                             int32_t* n_cells_of_type_passing /*[n_types] or NULL*/, int64_t* n_cells_kept /*or NULL*/);
 
+/* The observed running-sum curves of one cell type from the last pctsea_analyze / pctsea_enrich on this ctx
+ * (the accumulator history is still resident): a_out[i] = weighted fraction of the type's cells at ranked
+ * positions <= i, b_out[i] = the same for all other cells, i in [0, n_used) — the two series
+ * EnrichmentWeigthedScoreParallel.java:138-186 builds and :355-410 writes to "<type>_ews" (position i is the
+ * reference's x = i + 1). Bit-identical to the reference's a / b, including the 0.0f a series keeps until the
+ * type's first cell. n_used must be the n_used of that call. */
+int pctsea_last_observed_curve(pctsea_ctx* ctx, int32_t type_id, int64_t n_used, float* a_out, float* b_out);
+
 /* Device pointers of the null slice left by the last pctsea_analyze / pctsea_enrich on this ctx:
  * [n_types][perm_count] fp32 each. Valid until the next call on the ctx. For NCCL all-gathers. */
 int pctsea_last_null_dev(pctsea_ctx* ctx, float** null_dev, float** nullD_dev, int32_t* n_types,

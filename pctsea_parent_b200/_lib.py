@@ -24,6 +24,7 @@ EXPORTS = [
     "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels",
     "pctsea_matrix_free", "pctsea_score", "pctsea_rank", "pctsea_enrich", "pctsea_reduce_null",
     "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_last_null_dev", "pctsea_last_type_counts",
+    "pctsea_last_observed_curve",
 ]
 
 
@@ -102,6 +103,7 @@ def load_library() -> C.CDLL:
                                  vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
     L.pctsea_last_null_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.pctsea_last_type_counts.argtypes = [vp, i32, vp, vp, C.POINTER(i64)]
+    L.pctsea_last_observed_curve.argtypes = [vp, i32, i64, vp, vp]
     for name in EXPORTS:
         if name not in ("pctsea_last_error", "pctsea_stream"):
             getattr(L, name).restype = C.c_int
@@ -270,6 +272,12 @@ class Context:
         n = C.c_int64()
         self._check(self.L.pctsea_last_type_counts(self.h, n_types, _ptr(a), _ptr(b), C.byref(n)))
         return a, b, int(n.value)
+
+    def last_observed_curve(self, type_id: int, n_used: int):
+        """a / b running-sum series of one cell type from the last analyze / enrich call (fp32 [n_used] each)."""
+        a, b = np.empty(n_used, np.float32), np.empty(n_used, np.float32)
+        self._check(self.L.pctsea_last_observed_curve(self.h, int(type_id), int(n_used), _ptr(a), _ptr(b)))
+        return a, b
 
     def last_null_dev(self):
         a, b = C.c_void_p(), C.c_void_p()

@@ -141,6 +141,88 @@ def _java_float_str(v) -> str:
     return repr(v)
 
 
+def _java_number_str(x) -> str:
+    """Float.toString / Double.toString of a numpy float32 / float64: shortest digits that round-trip, plain decimal
+    for 1e-3 <= |x| < 1e7 and d.dddE±n otherwise, always at least one fractional digit."""
+    if np.isnan(x):
+        return "NaN"
+    if np.isinf(x):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0:
+        return "-0.0" if np.signbit(x) else "0.0"
+    ax = abs(float(x))
+    if 1e-3 <= ax < 1e7:
+        r = np.format_float_positional(x, unique=True, trim="0")     # trim="0": keep one digit after the point
+        return r
+    r = np.format_float_scientific(x, unique=True, trim="0")          # e.g. 1.e-05 / 1.5e+300 with trim rules
+    mant, ex = r.split("e")
+    if mant.endswith("."):
+        mant += "0"
+    return f"{mant}E{int(ex)}"
+
+
+def _java_double_str(v) -> str:
+    return _java_number_str(np.float64(v))
+
+
+def _java_float32_str(v) -> str:
+    return _java_number_str(np.float32(v))
+
+
+def get_output_txt_file_name(file_name: str, prefix: str, scoring_method: "ScoringMethod") -> str:
+    """PCTSEAUtils.getOutputTXTFile (PCTSEAUtils.java:109-114)."""
+    return f"{prefix}_{scoring_method.getScoreName()}_{file_name}.txt"
+
+
+def write_score_calculation_file(path: str, cell_type_name: str, a: np.ndarray, b: np.ndarray, supremum_x: int,
+                                 secondary_supremum_x: int = 0):
+    """EnrichmentWeigthedScoreParallel.writeScoreCalculationFile (:355-410): the two cumulative series with runs of
+    equal y collapsed to their end points, then the supremum line(s). x = ranked position, 1-based."""
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("-\tcell #\tCumulative Probability [Fn(X)]\n")
+        for label, series in ((cell_type_name, a), ("others", b)):
+            series = np.asarray(series, np.float32)
+            bits = series.view(np.uint32)
+            prev = -1
+            for i in range(series.size):
+                # Float.compare(y, previous.y) == 0: same bits (NaNs are canonical in the reference; -0.0 != 0.0)
+                if prev >= 0 and bits[i] == bits[prev]:
+                    prev = i
+                    continue
+                if prev >= 0:
+                    f.write(f"{label}\t{prev + 1}\t{_java_float32_str(series[prev])}\n")
+                f.write(f"{label}\t{i + 1}\t{_java_float32_str(series[i])}\n")
+                prev = i
+        if supremum_x >= 1:
+            f.write(f"supremum\t{supremum_x}\t{_java_float32_str(a[supremum_x - 1])}\n")
+            f.write(f"supremum\t{supremum_x}\t{_java_float32_str(b[supremum_x - 1])}\n")
+        if secondary_supremum_x >= 1:
+            f.write(f"secondary supremum\t{secondary_supremum_x}\t{_java_float32_str(a[secondary_supremum_x - 1])}\n")
+            f.write(f"secondary supremum\t{secondary_supremum_x}\t{_java_float32_str(b[secondary_supremum_x - 1])}\n")
+
+
+def write_score_distribution_file(path: str, score_name: str, scores_from_cell_type: Sequence[float]):
+    """writeScoreDistributionFile (:437-447): the type's non-NaN ranking scores, in ranked order."""
+    with open(path, "w") as f:
+        f.write(score_name + "\n")
+        for sc in scores_from_cell_type:
+            f.write(_java_double_str(sc) + "\n")
+
+
+def write_num_genes_histogram_file(path: str, score_name: str, num_genes: Sequence[int]):
+    """writeNumGenesHistogramFile (:412-435): histogram of the number of genes used for the score over the type's
+    cells, plain and cumulative from the top. (The reference iterates a trove hash map, so its row order is the map's;
+    here rows are in ascending key order.)"""
+    keys, counts = np.unique(np.asarray(num_genes, np.int64), return_counts=True)
+    with open(path, "w") as f:
+        f.write("-\t# of genes with " + score_name + " > threshold\t# cells\n")
+        for k, c in zip(keys, counts):
+            f.write(f"# genes\t{int(k)}\t{int(c)}\n")
+        acc = np.cumsum(counts[::-1])[::-1]
+        for k, c in zip(keys, acc):
+            f.write(f"# genes or more\t{int(k)}\t{int(c)}\n")
+
+
 def get_random_scores_file_name(prefix: str, scoring_method: "ScoringMethod", max_iterations: int) -> str:
     """PCTSEA.getRandomScoresFile (PCTSEA.java:1911-1914), without the time-stamp folder."""
     return f"{prefix}_{scoring_method.getScoreName()}_{max_iterations}_random_scores.txt"
@@ -330,6 +412,10 @@ class PCTSEA:
         self.loadRandomDistributionsIfExist = False
         self.prefix: Optional[str] = None
         self.outputFolder = "."
+        # per-type curve / distribution files of EnrichmentWeigthedScoreParallel.java:325-349 (off by default: they are
+        # reporting output; needs a prefix). plotNegativeEnrichedCellTypes as in the reference's constructor flag.
+        self.writeCellTypeFiles = False
+        self.plotNegativeEnrichedCellTypes = False
         if inputParameters is not None:
             self.sequentialScoringSchemas = list(inputParameters.scoringSchemas)
             self.experimentExpressionFile = inputParameters.inputDataFile
@@ -354,6 +440,30 @@ class PCTSEA:
     def logStatus(self, msg: str):
         if self.statusListener:
             self.statusListener(msg)
+
+    def _write_cell_type_files(self, types, out, method):
+        """The three per-type text files of EnrichmentWeigthedScoreParallel.java:325-349 for every type with an
+        enrichment score (nk > 1) — skipping negatively enriched types unless plotNegativeEnrichedCellTypes — from
+        the curves still resident on the GPU (pctsea_last_observed_curve) and the ranked scores."""
+        import os
+        n_used = int(out["n_pass"]) - 1            # the ranked list drops its last cell (PCTSEA.java:421-424)
+        order = out["order"][:n_used]
+        lab_r = self.dataset.label[order]
+        sc_r = out["score"][order]
+        used_r = out["n_genes_used"][order]
+        name = method.getScoreName()
+        for ct in types:
+            if math.isnan(ct.enrichmentScore):
+                continue
+            if not self.plotNegativeEnrichedCellTypes and ct.enrichmentScore < 0:
+                continue
+            a, b = self.ctx.last_observed_curve(ct.cellTypeID, n_used)
+            base = lambda suffix: os.path.join(self.outputFolder, get_output_txt_file_name(ct.name + suffix, self.prefix, method))
+            write_score_calculation_file(base("_ews"), ct.name, a, b, ct.supremumX, ct.secondarySupremumX)
+            mine = lab_r == ct.cellTypeID
+            s_mine = sc_r[mine]
+            write_score_distribution_file(base("_corr"), name, s_mine[~np.isnan(s_mine)])
+            write_num_genes_histogram_file(base("_genes_per_cell_hist"), name, used_r[mine])
 
     def run(self) -> PCTSEAResult:
         """PCTSEA.run (PCTSEA.java:257-534), the per-schema loop :348-475 with the bodies of a2-a12 on the GPU."""
@@ -388,10 +498,12 @@ class PCTSEA:
                 loaded = read_random_distribution_file(rnd_file)     # PCTSEA.java:1385-1387
             try:
                 if loaded is None:
+                    want_files = self.writeCellTypeFiles and self.prefix is not None
                     out = self.ctx.analyze(self.dataset.matrix, gene_idx, self.inputAbundance, sprm,
                                            schema.getScoringThreshold().getThresholdValue(),
                                            self.dataset.matrix.n_types, nprm,
-                                           want_null=self.keepNull or rnd_file is not None)
+                                           want_null=self.keepNull or rnd_file is not None,
+                                           want_scores=want_files, want_order=want_files)
                 else:
                     # observed scores on the GPU, null from the file, a10-a12 on the GPU (pctsea_reduce_null)
                     nprm0 = Context.null_params(0, min_pass=self.MIN_CELLS_PASSING_SCORE_TRESHOLD)
@@ -432,6 +544,8 @@ class PCTSEA:
                 types.append(ct)
             if rnd_file is not None and loaded is None:
                 print_to_random_distribution_file(rnd_file, types)   # PCTSEA.java:1431
+            if self.writeCellTypeFiles and self.prefix is not None and "order" in out:
+                self._write_cell_type_files(types, out, method)
             # BH correction of the KS values over the round's cell types (PCTSEA.java:1551-1570)
             for ct, padj in zip(types, p_adjust_bh([c.ksTestPvalue for c in types])):
                 ct.ksTestCorrectedPvalue = float(padj)

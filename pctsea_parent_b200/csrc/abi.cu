@@ -154,6 +154,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     launch_prepare_ranked(c, N, score_dev, label_dev, order_dev, g, fast);
     rec(c, EV_RANK);
     launch_ks_observed(c, g);
+    c->last_obs_Nu = T > 0 ? Nu : -1;
     rec(c, EV_OBS);
 
     const int32_t Pc_all = np.count;
@@ -559,6 +560,25 @@ int pctsea_last_type_counts(pctsea_ctx* c, int32_t n_types, int32_t* n_cells_of_
         if (n_cells_of_type) memcpy(n_cells_of_type, tmp.data(), (size_t)n_types * 4);
         if (n_cells_of_type_passing) memcpy(n_cells_of_type_passing, tmp.data() + n_types, (size_t)n_types * 4);
         if (n_cells_kept) *n_cells_kept = tmp[2 * (size_t)n_types];
+    });
+}
+
+int pctsea_last_observed_curve(pctsea_ctx* c, int32_t type_id, int64_t n_used, float* a_out, float* b_out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(c->last_obs_Nu >= 0, "no observed enrichment on this ctx yet: call pctsea_analyze / pctsea_enrich first");
+        PCT_REQUIRE(n_used == c->last_obs_Nu, "n_used differs from the last enrichment call");
+        PCT_REQUIRE(type_id >= 0 && type_id < c->last_T, "type_id out of range");
+        PCT_REQUIRE(a_out != nullptr && b_out != nullptr, "outputs are NULL");
+        if (n_used == 0) return;
+        // the fixed-point score buffers are free between calls: reuse them as the two staging arrays
+        c->fx.reserve((size_t)n_used * 4 + 64);
+        c->Sfx.reserve((size_t)n_used * 8 + 64);
+        float* a_dev = c->fx.as<float>();
+        float* b_dev = c->Sfx.as<float>();
+        launch_obs_curve(c, type_id, n_used, c->last_T, a_dev, b_dev);
+        d2h(c, a_out, a_dev, (size_t)n_used * 4);
+        d2h(c, b_out, b_dev, (size_t)n_used * 4);
+        PCT_CUDA(cudaStreamSynchronize(c->stream));
     });
 }
 

@@ -113,6 +113,7 @@ struct pctsea_ctx {
     pctsea::DevBuf red_tmp, red_misc;  // reduce: staged null of pctsea_reduce_null; expected values, sorted scores, bins
     pctsea::PinnedBuf pin_in, pin_out, pin_small;
     int32_t last_T = 0, last_Pc = 0;
+    int64_t last_obs_Nu = -1;   // n_used of the resident observed accumulator history (obs_chain), -1 = none
 };
 
 namespace pctsea {
@@ -185,6 +186,8 @@ struct EnrichGeom {
 void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, const int32_t* label_dev,
                            const int32_t* order_dev, EnrichGeom& g, bool want_fixed);
 void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g);
+// a / b series of one type from the resident accumulator history into two device arrays of Nu floats
+void launch_obs_curve(pctsea_ctx* c, int32_t type_id, int64_t Nu, int32_t T, float* a_dev, float* b_dev);
 void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* replay_dev, int32_t Pc);
 struct FastPlan {
     int64_t seg = 0;            // cooperative / label kernels: positions per warp task

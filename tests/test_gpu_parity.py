@@ -394,7 +394,7 @@ def test_analyze_end_to_end_vs_oracle(ctx, oracle, small):
     m.free()
 
 
-def test_host_api_mirror(ctx, small):
+def test_host_api_mirror(ctx, small, tmp_path):
     d = small
     cfg = d["cfg"]
     ds = P.SingleCellDataset.from_arrays(ctx, d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["label"], cfg.n_types)
@@ -412,6 +412,23 @@ def test_host_api_mirror(ctx, small):
     es = [c.getEnrichmentScore() for c in types if not np.isnan(c.getEnrichmentScore())]
     assert es == sorted(es, reverse=True)
     assert all(c.getEnrichmentFDR() <= 0.05 for c in r.getSignificantTypes())
+    # BH-corrected KS values (PCTSEA.java:1551-1570) and the per-type report files (:325-349)
+    adj = np.array([c.getKSTestCorrectedPvalue() for c in types])
+    raw = np.array([c.getKSTestPvalue() for c in types])
+    ok = ~np.isnan(raw)
+    assert np.all(adj[ok] >= raw[ok] - 1e-15) and np.all(adj[ok] <= 1.0)
+    p.setPrefix("run1")
+    p.outputFolder = str(tmp_path)
+    p.writeCellTypeFiles = True
+    r2 = p.run()
+    import os
+    written = sorted(os.listdir(tmp_path))
+    pos = [c for c in r2.cellTypesPerRound[0] if not np.isnan(c.getEnrichmentScore()) and c.getEnrichmentScore() >= 0]
+    assert pos and all(f"run1_{P.ScoringMethod.PEARSONS_CORRELATION.getScoreName()}_{c.getName()}_ews.txt" in written for c in pos)
+    assert sum(f.endswith("_corr.txt") for f in written) == len(pos) == sum(f.endswith("_genes_per_cell_hist.txt") for f in written)
+    c0 = pos[0]
+    corr = open(os.path.join(tmp_path, f"run1_{P.ScoringMethod.PEARSONS_CORRELATION.getScoreName()}_{c0.getName()}_corr.txt")).read().splitlines()
+    assert len(corr) - 1 == c0.getSizeA()   # one score per cell of the type in the ranked list
 
 
 def test_against_committed_golden_fixture(ctx, tiny):
@@ -617,3 +634,45 @@ def test_degenerate_shapes(ctx, oracle):
         ctx.enrich(s, order, lab, 4, ctx.null_params(3, perm_begin=2, perm_count=5))                   # slice out of range
     with pytest.raises(P.PctseaError):
         ctx.enrich(s, np.array([0, 1, 10**6], np.int32), lab, 4, ctx.null_params(1))                   # order out of range
+
+
+def test_observed_curves_and_cell_type_files(ctx, tmp_path):
+    # pctsea_last_observed_curve: the a / b series of EnrichmentWeigthedScoreParallel.java:138-186, bit for bit against a
+    # sequential float32 emulation of the reference loop; then the "<type>_ews" writer on top of it
+    from pctsea_parent_b200 import api
+    n_used, T = 3000, 5
+    s, lab, order = _ranked(n_used, T, seed=12)
+    res, _, _ = ctx.enrich(s, order, lab, T, ctx.null_params(0), want_null=False)
+    sr, lr = s[order[:n_used]], lab[order[:n_used]]
+    for t in range(T):
+        a, b = ctx.last_observed_curve(t, n_used)
+        numA = np.float32(0.0); numB = np.float32(0.0)
+        ra = np.zeros(n_used, np.float32); rb = np.zeros(n_used, np.float32)
+        anyA = anyB = False
+        for i in range(n_used):
+            if lr[i] == t:
+                numA = np.float32(np.float64(numA) + sr[i]); anyA = True
+            else:
+                numB = np.float32(np.float64(numB) + sr[i]); anyB = True
+            ra[i] = numA if anyA else np.float32(0.0)
+            rb[i] = numB if anyB else np.float32(0.0)
+        ea = np.where(np.arange(n_used) >= np.argmax(lr == t) if (lr == t).any() else False, ra / numA, np.float32(0.0)).astype(np.float32)
+        eb = np.where(np.arange(n_used) >= np.argmax(lr != t), rb / numB, np.float32(0.0)).astype(np.float32)
+        assert_bits_equal_f32(a, ea, f"a series type {t}")
+        assert_bits_equal_f32(b, eb, f"b series type {t}")
+        # the supremum the kernel reported is the first position of max |a - b|
+        d = np.abs(a - b)
+        assert int(res["supX"][t]) == int(np.argmax(d)) + 1
+    with pytest.raises(P.PctseaError):
+        ctx.last_observed_curve(T, n_used)
+    with pytest.raises(P.PctseaError):
+        ctx.last_observed_curve(0, n_used - 1)
+    a, b = ctx.last_observed_curve(0, n_used)
+    path = tmp_path / "t0_ews.txt"
+    api.write_score_calculation_file(str(path), "type0", a, b, int(res["supX"][0]), int(res["sec_supX"][0]))
+    lines = path.read_text().splitlines()
+    assert lines[0] == "-\tcell #\tCumulative Probability [Fn(X)]"
+    assert lines[1].startswith("type0\t1\t")
+    sup = [l for l in lines if l.startswith("supremum\t")]
+    assert len(sup) == 2 and sup[0].split("\t")[1] == str(int(res["supX"][0]))
+    assert float(np.float32(sup[0].split("\t")[2])) == float(a[int(res["supX"][0]) - 1])

@@ -448,3 +448,28 @@ def test_bh_adjustment_matches_r_p_adjust():
     assert np.allclose(p_adjust_bh([0.9, 0.8, 0.7]), [0.9, 0.9, 0.9])
     assert np.allclose(p_adjust_bh([0.5, 0.6]), [0.6, 0.6])    # n/i * p capped by the running minimum, and at 1
     assert p_adjust_bh([]).size == 0
+
+
+def test_cell_type_file_writers(tmp_path):
+    # EnrichmentWeigthedScoreParallel.java:355-447: runs of equal y collapse to their end points; Java number formats
+    from pctsea_parent_b200 import api
+    a = np.array([0.0, 0.0, 0.5, 0.5, 0.5, 1.0], np.float32)
+    b = np.array([0.25, 0.5, 0.5, 0.75, 1.0, 1.0], np.float32)
+    p = tmp_path / "x_ews.txt"
+    api.write_score_calculation_file(str(p), "T cell", a, b, 3, 0)
+    assert p.read_text().splitlines() == [
+        "-\tcell #\tCumulative Probability [Fn(X)]",
+        "T cell\t1\t0.0", "T cell\t2\t0.0", "T cell\t3\t0.5", "T cell\t5\t0.5", "T cell\t6\t1.0",
+        "others\t1\t0.25", "others\t1\t0.25", "others\t2\t0.5", "others\t3\t0.5", "others\t4\t0.75",
+        "others\t4\t0.75", "others\t5\t1.0",
+        "supremum\t3\t0.5", "supremum\t3\t0.5"]
+    assert api._java_double_str(1e-5) == "1.0E-5" and api._java_double_str(123456789.0) == "1.23456789E8"
+    assert api._java_double_str(0.001) == "0.001" and api._java_float32_str(0.1) == "0.1" and api._java_double_str(-0.0) == "-0.0"
+    q = tmp_path / "x_corr.txt"
+    api.write_score_distribution_file(str(q), "correlation", [0.5, 0.25])
+    assert q.read_text() == "correlation\n0.5\n0.25\n"
+    h = tmp_path / "x_hist.txt"
+    api.write_num_genes_histogram_file(str(h), "correlation", [4, 4, 7, 9, 9, 9])
+    assert h.read_text().splitlines()[1:] == ["# genes\t4\t2", "# genes\t7\t1", "# genes\t9\t3",
+                                              "# genes or more\t4\t6", "# genes or more\t7\t4", "# genes or more\t9\t3"]
+    assert api.get_output_txt_file_name("T_ews", "run1", api.ScoringMethod.PEARSONS_CORRELATION).startswith("run1_")
