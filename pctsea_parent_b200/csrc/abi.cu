@@ -321,7 +321,8 @@ int pctsea_matrix_load_csr(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, cons
         m->row_ptr = (const int64_t*)rp; m->col = (const int32_t*)ci; m->val = (const float*)vv;
         int bad = 0;
         try { bad = validate_csr(c, m); } catch (...) { pctsea_matrix_free(c, m); throw; }
-        if (bad) {
+        m->all_positive = !(bad & 4);
+        if (bad & 3) {
             pctsea_matrix_free(c, m);
             throw Error(PCTSEA_EINVAL, "col_idx entries must lie in [0, n_genes)");
         }
@@ -348,6 +349,7 @@ int pctsea_matrix_wrap_device(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, c
             PCT_REQUIRE(((uintptr_t)col_idx_dev & 15) == 0 && ((uintptr_t)val_dev & 15) == 0,
                         "col_idx_dev / val_dev must be 16-byte aligned");
             bad = validate_csr(c, m);
+            m->all_positive = !(bad & 4);
             if (bad & 1) throw Error(PCTSEA_EINVAL, "row_ptr_dev must start at 0 and be non-decreasing");
             if (bad & 2) throw Error(PCTSEA_EINVAL, "col_idx_dev entries must lie in [0, n_genes)");
         } catch (...) { delete m; throw; }

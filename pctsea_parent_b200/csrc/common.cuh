@@ -82,6 +82,7 @@ struct pctsea_matrix {
     const int32_t* col = nullptr;      // device
     const float* val = nullptr;        // device
     bool owned = false;
+    bool all_positive = false;  // every stored value > 0 (found by the load-time validation)
     int32_t* label = nullptr;  // device, [n_cells], owned
     int32_t n_types = 0;
 };

@@ -229,7 +229,7 @@ __device__ __forceinline__ uint32_t tab_lookup(const unsigned char* tab, uint32_
 //     the two-pass Pearson regression over the buffer.
 // The in-flight steps live in DEPTH named register sets that the unrolled loop visits in turn, so no register
 // moves are needed to rotate the pipeline.
-template <bool BYTE_TAB, int MAXW, int DEPTH>
+template <bool BYTE_TAB, int MAXW, int DEPTH, bool ALL_POSITIVE>
 __global__ void __launch_bounds__(MAXW * 32, 1) k_score(const ScoreKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_next;
@@ -348,8 +348,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) k_score(const ScoreKernelArgs a)
         uint32_t t[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) t[q] = tab_lookup<BYTE_TAB>(tab, (uint32_t)c.g[q]);
-        const bool pos4 = (c.x[0] > 0.0f) && (c.x[1] > 0.0f) && (c.x[2] > 0.0f) && (c.x[3] > 0.0f);
-        if (!__all_sync(FULL, pos4)) {   // zeros, negatives or NaN stored in the matrix: rare
+        // ALL_POSITIVE: the load-time check found every stored value > 0 (the usual CSR of counts), nothing to test
+        const bool pos4 = ALL_POSITIVE || ((c.x[0] > 0.0f) && (c.x[1] > 0.0f) && (c.x[2] > 0.0f) && (c.x[3] > 0.0f));
+        if (!ALL_POSITIVE && !__all_sync(FULL, pos4)) {   // zeros, negatives or NaN stored in the matrix: rare
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 if (!(c.x[q] > 0.0f)) t[q] &= 0xF0u;    // cannot form a pair
@@ -501,26 +502,29 @@ __global__ void k_score_final(const double* __restrict__ sums, const int32_t* __
     score[i] = r;
 }
 
-__global__ void k_validate_csr(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int64_t N,
-                               int32_t G, int64_t nnz, int* __restrict__ bad) {
+__global__ void k_validate_csr(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                               const float* __restrict__ val, int64_t N, int32_t G, int64_t nnz, int* __restrict__ bad) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int b = 0;
     for (int64_t i = t0; i < N; i += stride)
         if (row_ptr[i + 1] < row_ptr[i]) b |= 1;
     if (t0 == 0 && (row_ptr[0] != 0 || row_ptr[N] != nnz)) b |= 1;
-    for (int64_t k = t0; k < nnz; k += stride)
+    for (int64_t k = t0; k < nnz; k += stride) {
         if ((unsigned)col[k] >= (unsigned)G) b |= 2;
+        if (!(val[k] > 0.0f)) b |= 4;   // a stored zero, negative or NaN: not an error, but the scorer must test for it
+    }
     if (b) atomicOr(bad, b);
 }
 
 // Checks the device CSR once when a matrix is loaded or wrapped: the scoring kernel indexes its shared-memory
-// membership table with the stored columns and trusts the row bounds.
+// membership table with the stored columns and trusts the row bounds. Bit 2 of the result is informational: some
+// stored value is not > 0 (the scoring kernel then keeps its per-step test for such values).
 int validate_csr(pctsea_ctx* c, const pctsea_matrix* m) {
     c->counters.reserve(64);
     int* bad = c->counters.as<int>();
     PCT_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
-    k_validate_csr<<<kNumSMs * 8, 256, 0, c->stream>>>(m->row_ptr, m->col, m->n_cells, m->n_genes, m->nnz, bad);
+    k_validate_csr<<<kNumSMs * 8, 256, 0, c->stream>>>(m->row_ptr, m->col, m->val, m->n_cells, m->n_genes, m->nnz, bad);
     PCT_CUDA(cudaGetLastError());
     int h = 0;
     PCT_CUDA(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -587,11 +591,16 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     ka.cap = cap;
     ka.tab_bytes = (int32_t)tab_bytes;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, div_up(N, kScoreCellBatch)));
+#define PCT_LAUNCH_SCORE2(B, W, AP)                                                                           \
+    do {                                                                                                      \
+        PCT_CUDA(cudaFuncSetAttribute(k_score<B, W, 3, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_score<B, W, 3, AP><<<grid, warps * 32, smem, c->stream>>>(ka);                                      \
+    } while (0)
 #define PCT_LAUNCH_SCORE(B, W)                                                                                \
     do {                                                                                                      \
-        PCT_CUDA(cudaFuncSetAttribute(k_score<B, W, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_score<B, W, 3><<<grid, warps * 32, smem, c->stream>>>(ka);                                          \
+        if (m->all_positive) PCT_LAUNCH_SCORE2(B, W, true); else PCT_LAUNCH_SCORE2(B, W, false);              \
     } while (0)
+    // the launch bound (registers per thread) follows the warp count that shared memory allows
     if (byte_mode) {
         if (warps > 20) PCT_LAUNCH_SCORE(true, 24);
         else if (warps > 16) PCT_LAUNCH_SCORE(true, 20);
@@ -601,6 +610,7 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
         else if (warps > 16) PCT_LAUNCH_SCORE(false, 20);
         else PCT_LAUNCH_SCORE(false, 16);
     }
+#undef PCT_LAUNCH_SCORE2
 #undef PCT_LAUNCH_SCORE
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
