@@ -676,3 +676,27 @@ def test_observed_curves_and_cell_type_files(ctx, tmp_path):
     sup = [l for l in lines if l.startswith("supremum\t")]
     assert len(sup) == 2 and sup[0].split("\t")[1] == str(int(res["supX"][0]))
     assert float(np.float32(sup[0].split("\t")[2])) == float(a[int(res["supX"][0]) - 1])
+
+
+def test_stage3_random_shapes_sweep(ctx, oracle):
+    # Random ranking sizes and type counts around the switch points of the stage-3 kernels (4096 cells: cooperative
+    # vs lane kernel; ~218 / 254 types: plain vs sliced lane kernel, 8- vs 16-bit labels; segment and macro-step
+    # remainders), each checked bit for bit: observed statistics, FAST null vs the oracle's definition, reduction.
+    rng = np.random.default_rng(2026)
+    shapes = [(4095, 7), (4096, 7), (4097, 219), (4100, 255), (4128, 256), (12_345, 110), (8191, 33), (33_000, 3),
+              (5003, 500), (6001, 1), (4099, 254)]
+    shapes += [(int(rng.integers(4096, 30_000)), int(rng.integers(1, 400))) for _ in range(6)]
+    for n_used, T in shapes:
+        s, lab, order = _ranked(n_used, T, seed=n_used + T, simple=bool(n_used & 1))
+        Pn = 3
+        prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=n_used)
+        res, ne, nd = ctx.enrich(s, order, lab, T, prm)
+        ores = oracle.ks_observed(s, lab, T)
+        assert_results_equal(res, ores, OBSERVED_FIELDS, f"observed n={n_used} T={T}")
+        F = oracle.fast_frac_bits(s)
+        for p in range(Pn):
+            perm = oracle.feistel_perm(n_used, p, n_used, 6)
+            exp = oracle.ks_null_fast_one(s, lab[perm], T, F)
+            assert_bits_equal_f32(ne[:, p], exp, f"fast null n={n_used} T={T} perm {p}")
+        ored = oracle.reduce(ores, ne)
+        assert_results_equal(res, ored, ("norm_ews", "p_emp", "fdr"), f"reduce n={n_used} T={T}")
