@@ -97,7 +97,8 @@ typedef struct pctsea_timings {
     float   setup_ms;     /* list upload + lookup tables */
     float   score_ms;     /* stage 1 kernel */
     float   rank_ms;      /* stage 2: compaction + radix sort + gather */
-    float   observed_ms;  /* stage 3 observed (exact) */
+    float   observed_ms;  /* stage 3 observed (exact): span of its kernels, which run on a second stream beside
+                             labels_ms + null_ms (so the stage times do not add up to total_ms) */
     float   labels_ms;    /* permuted label generation (+ per-type denominators in FAST mode) */
     float   null_ms;      /* KS over the permuted labels */
     float   reduce_ms;    /* a10-a12 */

@@ -38,6 +38,7 @@ float between(pctsea_ctx* c, int a, int b) {
 
 void begin_call(pctsea_ctx* c) {
     PCT_CUDA(cudaSetDevice(c->device));
+    cudaStreamSynchronize(c->stream_aux);  // idle unless a previous call failed half-way
     c->err.clear();
     memset(&c->tm, 0, sizeof c->tm);
     for (int i = 0; i < EV_COUNT; i++) c->ev_rec[i] = false;
@@ -153,7 +154,26 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     const bool fast = prm->ks_mode == PCTSEA_KS_FAST;
     launch_prepare_ranked(c, N, score_dev, label_dev, order_dev, g, fast);
     rec(c, EV_RANK);
-    launch_ks_observed(c, g);
+    // The observed statistics and the permutation null both depend only on the ranked arrays. The observed
+    // kernels are small, latency-bound launches of 512-thread CTAs with ~40 registers: they fit on an SM next to a
+    // label CTA or a lane-KS CTA, so by default they go to the auxiliary stream and run in the shadow of the null
+    // stage; the reduction waits for both. PCTSEA_OBS_OVERLAP=0 keeps them on the main stream. With the overlap
+    // observed_ms is the span of the observed kernels on their own stream, not a share of total_ms.
+    const char* ov_env = std::getenv("PCTSEA_OBS_OVERLAP");
+    const bool obs_overlap = !(ov_env && ov_env[0] == '0') && np.count > 0 && T > 0 &&
+                             prm->perm_mode == PCTSEA_PERM_PHILOX;
+    c->obs_span_valid = false;
+    if (obs_overlap) PCT_CUDA(cudaEventRecord(c->ev_obs[0], c->stream));   // ranked arrays are ready
+    else launch_ks_observed(c, g, c->stream);
+    bool obs_queued = false;
+    auto queue_observed_aux = [&]() {
+        PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, c->ev_obs[0], 0));
+        PCT_CUDA(cudaEventRecord(c->ev_obs[1], c->stream_aux));
+        launch_ks_observed(c, g, c->stream_aux);
+        PCT_CUDA(cudaEventRecord(c->ev_obs[2], c->stream_aux));
+        c->obs_span_valid = true;
+        obs_queued = true;
+    };
     c->last_obs_Nu = T > 0 ? Nu : -1;
     rec(c, EV_OBS);
 
@@ -196,6 +216,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
             // so they cannot co-reside, and the sub-chunks only add partial waves.)
             launch_labels_philox(c, g, prm->seed, np.begin + p0, pc, np.rounds, fast, plan0, c->stream, 0);
             cudaEvent_t e1 = et.mark(c->stream);
+            if (obs_overlap && !obs_queued) queue_observed_aux();   // after the first label launch: the big kernel gets its SMs first
             if (fast) launch_ks_fast_null(c, g, pc, plan0, Pc_all, p0, 0);
             else launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);
             cudaEvent_t e2 = et.mark(c->stream);
@@ -203,6 +224,8 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
             null_spans.push_back({ e1, e2 });
         }
     }
+    if (obs_overlap && !obs_queued) queue_observed_aux();
+    if (obs_queued) PCT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_obs[2], 0));
     rec(c, EV_NULL);
     if (np.full && T > 0) launch_reduce(c, T, np.P, c->null_ews.as<float>(), prm->mean_policy,
                                         c->results.as<pctsea_type_result>());
@@ -216,6 +239,10 @@ void finish_timings(pctsea_ctx* c, const std::vector<std::pair<cudaEvent_t, cuda
     c->tm.score_ms = between(c, EV_SETUP, EV_SCORE);
     c->tm.rank_ms = between(c, EV_SCORE, EV_RANK);
     c->tm.observed_ms = between(c, EV_RANK, EV_OBS);
+    if (c->obs_span_valid) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_obs[1], c->ev_obs[2]) == cudaSuccess) c->tm.observed_ms = ms;
+    }
     c->tm.reduce_ms = between(c, EV_NULL, EV_REDUCE);
     c->tm.total_ms = between(c, EV_BEGIN, EV_END);
     float lm = 0, nm = 0;
@@ -244,8 +271,13 @@ int pctsea_create(int device_id, pctsea_ctx** out) {
     pctsea_ctx* c = new (std::nothrow) pctsea_ctx();
     if (!c) return PCTSEA_ENOMEM;
     c->device = device_id;
+    // the auxiliary stream carries the observed-statistics kernels: a chain of small launches that shares the SMs with
+    // the big null kernels; its CTAs go first whenever resources free up, or the chain becomes the critical path
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaSetDevice(device_id) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         cudaGetLastError();
         delete c;
         return PCTSEA_ECUDA;
@@ -254,6 +286,8 @@ int pctsea_create(int device_id, pctsea_ctx** out) {
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { cudaGetLastError(); delete c; return PCTSEA_ECUDA; }
         c->ev_rec[i] = false;
     }
+    for (int i = 0; i < 3; i++)
+        if (cudaEventCreate(&c->ev_obs[i]) != cudaSuccess) { cudaGetLastError(); delete c; return PCTSEA_ECUDA; }
     memset(&c->tm, 0, sizeof c->tm);
     *out = c;
     return PCTSEA_OK;
@@ -271,6 +305,9 @@ int pctsea_destroy(pctsea_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 3; i++) if (c->ev_obs[i]) cudaEventDestroy(c->ev_obs[i]);
+    cudaStreamSynchronize(c->stream_aux);
+    cudaStreamDestroy(c->stream_aux);
     cudaStreamDestroy(c->stream);
     delete c;
     return PCTSEA_OK;

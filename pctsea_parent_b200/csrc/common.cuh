@@ -91,7 +91,10 @@ struct pctsea_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
+    cudaStream_t stream_aux = nullptr;  // the observed-statistics kernels run here, beside the null on `stream`
     cudaEvent_t ev[pctsea::EV_COUNT];
+    cudaEvent_t ev_obs[3] = { nullptr, nullptr, nullptr };  // ranked arrays ready; begin / end of the observed kernels
+    bool obs_span_valid = false;
     bool ev_rec[pctsea::EV_COUNT];
     pctsea_timings tm;
     int64_t launches = 0;
@@ -186,7 +189,7 @@ struct EnrichGeom {
 // Gather ranked arrays (s_rank, lab_rank), class counts, fixed-point prefix (fx, Sfx).
 void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, const int32_t* label_dev,
                            const int32_t* order_dev, EnrichGeom& g, bool want_fixed);
-void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g);
+void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st);
 // a / b series of one type from the resident accumulator history into two device arrays of Nu floats
 void launch_obs_curve(pctsea_ctx* c, int32_t type_id, int64_t Nu, int32_t T, float* a_dev, float* b_dev);
 void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* replay_dev, int32_t Pc);
