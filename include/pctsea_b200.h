@@ -180,6 +180,23 @@ int pctsea_analyze(pctsea_ctx* ctx, const pctsea_matrix* m, int32_t L, const int
                    const int32_t* replay_perm, pctsea_type_result* out /*[n_types]*/,
                    float* null_out, float* nullD_out, double* score_out, int32_t* n_genes_used_out,
                    uint8_t* kept_out, int32_t* order_out, int64_t* n_pass_out);
+/* ---- many input lists against one resident matrix (BASELINE config E; SURVEY.md §8 b "batched"). The reference
+ * has no batch call: the web front-end submits one PCTSEA.run() per list to a 40-thread pool
+ * (pctseaweb/src/main/java/edu/scripps/yates/pctsea/views/analyze/AnalyzeView.java:163,747-766) and each run repeats the per-schema loop PCTSEA.java:348-434. Here
+ * the lists of one GPU's share go through one call: list i is gene_idx / abundance[list_ptr[i] .. list_ptr[i+1]),
+ * labels are uploaded (or taken from the matrix) once, and every list gets the same parameters and the same
+ * permutation stream, so out[i] is bit-identical to what pctsea_analyze returns for list i alone.
+ * out: [n_lists][n_types]; n_pass_out: [n_lists] or NULL; null_out / nullD_out: [n_lists][n_types][perm_count] or
+ * NULL. status_out[i] = PCTSEA_OK, or PCTSEA_ETOOFEW / PCTSEA_EMINGENES when list i fails the reference's own input
+ * checks (its results are then NaN; the other lists are unaffected). Any other error aborts the call. Lists are
+ * independent, so multi-GPU = each rank passes its share of the lists (no collective). pctsea_get_timings reports
+ * the sums over the lists. */
+int pctsea_analyze_batch(pctsea_ctx* ctx, const pctsea_matrix* m, int32_t n_lists, const int64_t* list_ptr /*[n_lists+1]*/,
+                         const int32_t* gene_idx, const float* abundance, const pctsea_score_params* sprm,
+                         double min_score, const int32_t* label /*[N] or NULL*/, int32_t n_types,
+                         const pctsea_null_params* nprm, pctsea_type_result* out, int64_t* n_pass_out,
+                         int32_t* status_out /*[n_lists]*/, float* null_out, float* nullD_out);
+
 /* Inputs of PCTSEA.calculateHyperGeometricStatistics (PCTSEA.java:2169-2264) from the last pctsea_analyze on
  * this ctx: per type, the cells surviving the min_genes_cells filter (numCellsOfType) and those of them passing
  * the score threshold (numCellsOfTypeWithPositiveCorrelation); n_cells_kept = the population size N. A type

@@ -23,7 +23,7 @@ EXPORTS = [
     "pctsea_abi_version", "pctsea_create", "pctsea_destroy", "pctsea_last_error", "pctsea_get_timings",
     "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels",
     "pctsea_matrix_free", "pctsea_score", "pctsea_rank", "pctsea_enrich", "pctsea_reduce_null",
-    "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_last_null_dev", "pctsea_last_type_counts",
+    "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_analyze_batch", "pctsea_last_null_dev", "pctsea_last_type_counts",
     "pctsea_last_observed_curve",
 ]
 
@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
     L.pctsea_reduce_null_dev.argtypes = [vp, i32, i32, vp, i32, vp]
     L.pctsea_analyze.argtypes = [vp, vp, i32, vp, vp, C.POINTER(ScoreParams), f64, vp, i32, C.POINTER(NullParams),
                                  vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    L.pctsea_analyze_batch.argtypes = [vp, vp, i32, vp, vp, vp, C.POINTER(ScoreParams), f64, vp, i32,
+                                       C.POINTER(NullParams), vp, vp, vp, vp, vp]
     L.pctsea_last_null_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.pctsea_last_type_counts.argtypes = [vp, i32, vp, vp, C.POINTER(i64)]
     L.pctsea_last_observed_curve.argtypes = [vp, i32, i64, vp, vp]
@@ -264,6 +266,32 @@ class Context:
             out["score"], out["n_genes_used"], out["kept"] = sc, used, kept
         if want_order:
             out["order"] = order[:npass.value].copy()
+        return out
+
+    def analyze_batch(self, m: Matrix, lists, sprm: ScoreParams, min_score, n_types, nprm: NullParams, label=None,
+                      want_null=False):
+        """Many input lists against one resident matrix (BASELINE config E). `lists` = sequence of
+        (gene_idx, abundance). Returns results [n_lists][n_types], n_pass [n_lists], status [n_lists] (0, or the
+        PCTSEA_ETOOFEW / PCTSEA_EMINGENES code of a list that failed the reference's input checks)."""
+        lens = [len(g) for g, _ in lists]
+        ptr = np.zeros(len(lists) + 1, np.int64)
+        ptr[1:] = np.cumsum(lens)
+        gi = _c(np.concatenate([np.asarray(g, np.int32) for g, _ in lists]) if lists else [], np.int32)
+        ab = _c(np.concatenate([np.asarray(a, np.float32) for _, a in lists]) if lists else [], np.float32)
+        label = None if label is None else _c(label, np.int32)
+        cnt = nprm.perm_count or (nprm.n_perm - nprm.perm_begin)
+        res = np.zeros((len(lists), n_types), TYPE_RESULT_DTYPE)
+        npass = np.zeros(len(lists), np.int64)
+        status = np.zeros(len(lists), np.int32)
+        ne = np.empty((len(lists), n_types, cnt), np.float32) if want_null else None
+        nd = np.empty((len(lists), n_types, cnt), np.float32) if want_null else None
+        self._check(self.L.pctsea_analyze_batch(self.h, m.handle, len(lists), _ptr(ptr), _ptr(gi), _ptr(ab),
+                                                C.byref(sprm), float(min_score), _ptr(label), n_types,
+                                                C.byref(nprm), _ptr(res), _ptr(npass), _ptr(status), _ptr(ne),
+                                                _ptr(nd)))
+        out = {"results": res, "n_pass": npass, "status": status}
+        if want_null:
+            out["null"], out["nullD"] = ne, nd
         return out
 
     def last_type_counts(self, n_types: int):

@@ -253,6 +253,82 @@ void finish_timings(pctsea_ctx* c, const std::vector<std::pair<cudaEvent_t, cuda
     c->tm.launches = c->launches;
 }
 
+NullPlan validate_analysis(const pctsea_matrix* m, double min_score, const int32_t* label, int32_t n_types,
+                           const pctsea_null_params* nprm) {
+    PCT_REQUIRE(min_score == min_score, "min_score is NaN");
+    PCT_REQUIRE(m->n_cells >= 1, "empty matrix");
+    if (!label) {
+        PCT_REQUIRE(m->label != nullptr, "no labels: pass label[] or call pctsea_matrix_set_labels");
+        PCT_REQUIRE(n_types == m->n_types, "n_types differs from the matrix's resident labels");
+    }
+    return validate_null_params(nprm);
+}
+
+// The matrix's resident labels, or the caller's uploaded to the ctx.
+const int32_t* resident_labels(pctsea_ctx* c, const pctsea_matrix* m, const int32_t* label) {
+    if (!label) return m->label;
+    c->label_tmp.reserve((size_t)m->n_cells * 4);
+    h2d(c, c->label_tmp.p, label, (size_t)m->n_cells * 4);
+    return c->label_tmp.as<int32_t>();
+}
+
+void fill_nan_results(pctsea_type_result* out, int32_t T) {
+    const float fn = std::numeric_limits<float>::quiet_NaN();
+    const double dn = std::numeric_limits<double>::quiet_NaN();
+    for (int32_t t = 0; t < T; t++) {
+        pctsea_type_result r;
+        memset(&r, 0, sizeof r);
+        r.ews = fn; r.dstat = fn; r.supX = -1; r.norm_supX = -1.0; r.raw_sup = fn; r.norm_ews = fn;
+        r.p_emp = dn; r.fdr = dn; r.ks_d = dn;
+        out[t] = r;
+    }
+}
+
+// One list through the whole path (the per-schema loop body, PCTSEA.java:348-434) on resident labels; EV_BEGIN is
+// already recorded. Ends with the stream synchronised and the ctx timings filled.
+void analyze_core(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_t* gene_idx, const float* abundance,
+                  const pctsea_score_params* sprm, double min_score, const int32_t* label_dev, int32_t n_types,
+                  const pctsea_null_params* nprm, const NullPlan& np, const int32_t* replay_perm,
+                  pctsea_type_result* out, float* null_out, float* nullD_out, double* score_out,
+                  int32_t* n_genes_used_out, uint8_t* kept_out, int32_t* order_out, int64_t* n_pass_out) {
+    const int64_t N = m->n_cells;
+    upload_list(c, m, L, gene_idx, abundance);
+    validate_score_params(sprm, L);
+    rec(c, EV_SETUP);
+    ScoreArgs sa{ m, L, c->list_gene.as<int32_t>(), c->list_abund.as<float>(), *sprm };
+    launch_score(c, sa);
+    rec(c, EV_SCORE);
+    launch_type_counts(c, N, c->score.as<double>(), c->kept.as<uint8_t>(), label_dev, min_score, n_types);
+    const int64_t Np = launch_rank(c, N, c->score.as<double>(), c->kept.as<uint8_t>(), min_score);
+    if (n_pass_out) *n_pass_out = Np;
+    c->tm.n_pass = Np;
+    c->tm.n_used = Np > 0 ? Np - 1 : 0;
+    if (score_out) d2h(c, score_out, c->score.p, (size_t)N * 8);
+    if (n_genes_used_out) d2h(c, n_genes_used_out, c->nused.p, (size_t)N * 4);
+    if (kept_out) d2h(c, kept_out, c->kept.p, (size_t)N);
+    if (order_out) d2h(c, order_out, c->order.p, (size_t)Np * 4);
+    if (Np < (int64_t)nprm->min_pass || Np < 2) {
+        PCT_CUDA(cudaStreamSynchronize(c->stream));
+        // PCTSEA.java:389-395
+        throw Error(PCTSEA_ETOOFEW, "There is not enough cells passing the threshold (only " + std::to_string(Np) +
+                                        " pass the threshold and the minimum is " +
+                                        std::to_string(std::max(nprm->min_pass, 2)) + ")");
+    }
+    const int64_t Nu = Np - 1;
+    EvTimer et;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ls, ns;
+    float lm = 0, nm = 0;
+    enrich_device(c, N, c->score.as<double>(), label_dev, c->order.as<int32_t>(), Nu, n_types, nprm, np, replay_perm,
+                  et, &lm, &nm, ls, ns);
+    d2h(c, out, c->results.p, (size_t)n_types * sizeof(pctsea_type_result));
+    if (null_out) d2h(c, null_out, c->null_ews.p, (size_t)n_types * np.count * 4);
+    if (nullD_out) d2h(c, nullD_out, c->null_d.p, (size_t)n_types * np.count * 4);
+    rec(c, EV_END);
+    finish_timings(c, ls, ns);
+    c->tm.n_pass = Np;
+    c->tm.n_used = Nu;
+}
+
 }  // namespace
 
 extern "C" {
@@ -536,56 +612,70 @@ int pctsea_analyze(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32
                    int32_t* order_out, int64_t* n_pass_out) {
     return guarded(c, [&] {
         PCT_REQUIRE(m != nullptr && out != nullptr, "matrix / out are NULL");
-        PCT_REQUIRE(min_score == min_score, "min_score is NaN");
-        const int64_t N = m->n_cells;
-        PCT_REQUIRE(N >= 1, "empty matrix");
-        if (!label) {
-            PCT_REQUIRE(m->label != nullptr, "no labels: pass label[] or call pctsea_matrix_set_labels");
-            PCT_REQUIRE(n_types == m->n_types, "n_types differs from the matrix's resident labels");
-        }
-        NullPlan np = validate_null_params(nprm);
+        const NullPlan np = validate_analysis(m, min_score, label, n_types, nprm);
         rec(c, EV_BEGIN);
-        upload_list(c, m, L, gene_idx, abundance);
-        validate_score_params(sprm, L);
-        const int32_t* label_dev = m->label;
-        if (label) {
-            c->label_tmp.reserve((size_t)N * 4);
-            h2d(c, c->label_tmp.p, label, (size_t)N * 4);
-            label_dev = c->label_tmp.as<int32_t>();
+        const int32_t* label_dev = resident_labels(c, m, label);
+        analyze_core(c, m, L, gene_idx, abundance, sprm, min_score, label_dev, n_types, nprm, np, replay_perm, out,
+                     null_out, nullD_out, score_out, n_genes_used_out, kept_out, order_out, n_pass_out);
+    });
+}
+
+int pctsea_analyze_batch(pctsea_ctx* c, const pctsea_matrix* m, int32_t n_lists, const int64_t* list_ptr,
+                         const int32_t* gene_idx, const float* abundance, const pctsea_score_params* sprm,
+                         double min_score, const int32_t* label, int32_t n_types, const pctsea_null_params* nprm,
+                         pctsea_type_result* out, int64_t* n_pass_out, int32_t* status_out, float* null_out,
+                         float* nullD_out) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(m != nullptr && out != nullptr && status_out != nullptr, "matrix / out / status_out are NULL");
+        PCT_REQUIRE(n_lists >= 0, "negative n_lists");
+        PCT_REQUIRE(n_lists == 0 || list_ptr != nullptr, "list_ptr is NULL");
+        PCT_REQUIRE(n_lists == 0 || list_ptr[0] == 0, "list_ptr must start at 0");
+        for (int32_t i = 0; i < n_lists; i++) {
+            PCT_REQUIRE(list_ptr[i + 1] >= list_ptr[i], "list_ptr is decreasing");
+            PCT_REQUIRE(list_ptr[i + 1] - list_ptr[i] <= 32767, "list longer than the reference's short gene ids allow (32767)");
         }
-        rec(c, EV_SETUP);
-        ScoreArgs sa{ m, L, c->list_gene.as<int32_t>(), c->list_abund.as<float>(), *sprm };
-        launch_score(c, sa);
-        rec(c, EV_SCORE);
-        launch_type_counts(c, N, c->score.as<double>(), c->kept.as<uint8_t>(), label_dev, min_score, n_types);
-        const int64_t Np = launch_rank(c, N, c->score.as<double>(), c->kept.as<uint8_t>(), min_score);
-        if (n_pass_out) *n_pass_out = Np;
-        c->tm.n_pass = Np;
-        c->tm.n_used = Np > 0 ? Np - 1 : 0;
-        if (score_out) d2h(c, score_out, c->score.p, (size_t)N * 8);
-        if (n_genes_used_out) d2h(c, n_genes_used_out, c->nused.p, (size_t)N * 4);
-        if (kept_out) d2h(c, kept_out, c->kept.p, (size_t)N);
-        if (order_out) d2h(c, order_out, c->order.p, (size_t)Np * 4);
-        if (Np < (int64_t)nprm->min_pass || Np < 2) {
-            PCT_CUDA(cudaStreamSynchronize(c->stream));
-            // PCTSEA.java:389-395
-            throw Error(PCTSEA_ETOOFEW, "There is not enough cells passing the threshold (only " + std::to_string(Np) +
-                                            " pass the threshold and the minimum is " +
-                                            std::to_string(std::max(nprm->min_pass, 2)) + ")");
+        const NullPlan np = validate_analysis(m, min_score, label, n_types, nprm);
+        PCT_REQUIRE(nprm->perm_mode == PCTSEA_PERM_PHILOX, "the batch entry point generates its permutations (perm_mode PHILOX)");
+        rec(c, EV_BEGIN);
+        const int32_t* label_dev = resident_labels(c, m, label);   // uploaded once for the whole batch
+        pctsea_timings acc;
+        memset(&acc, 0, sizeof acc);
+        const size_t null_stride = (size_t)n_types * np.count;
+        for (int32_t i = 0; i < n_lists; i++) {
+            const int64_t b = list_ptr[i];
+            const int32_t L = (int32_t)(list_ptr[i + 1] - b);
+            pctsea_type_result* out_i = out + (size_t)i * n_types;
+            int64_t npass = 0;
+            status_out[i] = PCTSEA_OK;
+            if (i > 0) rec(c, EV_BEGIN);
+            try {
+                analyze_core(c, m, L, gene_idx + b, abundance + b, sprm, min_score, label_dev, n_types, nprm, np, nullptr,
+                             out_i, null_out ? null_out + i * null_stride : nullptr,
+                             nullD_out ? nullD_out + i * null_stride : nullptr, nullptr, nullptr, nullptr, nullptr, &npass);
+            } catch (const Error& e) {
+                // A list that fails one of the reference's own input checks (PCTSEA.java:389-395,
+                // model/SingleCell.java:347-352) fails alone, as one analysis of the web app's pool does.
+                if (e.code != PCTSEA_ETOOFEW && e.code != PCTSEA_EMINGENES) throw;
+                PCT_CUDA(cudaStreamSynchronize(c->stream));
+                status_out[i] = e.code;
+                c->err = "list " + std::to_string(i) + ": " + e.what();
+                fill_nan_results(out_i, n_types);
+                if (null_out) std::fill_n(null_out + i * null_stride, null_stride, std::numeric_limits<float>::quiet_NaN());
+                if (nullD_out) std::fill_n(nullD_out + i * null_stride, null_stride, std::numeric_limits<float>::quiet_NaN());
+            }
+            if (n_pass_out) n_pass_out[i] = npass;
+            // per-stage device times, copies and launches add up over the lists; n_pass / n_used are the last list's
+            acc.setup_ms += c->tm.setup_ms; acc.score_ms += c->tm.score_ms; acc.rank_ms += c->tm.rank_ms;
+            acc.observed_ms += c->tm.observed_ms; acc.labels_ms += c->tm.labels_ms; acc.null_ms += c->tm.null_ms;
+            acc.reduce_ms += c->tm.reduce_ms; acc.total_ms += c->tm.total_ms;
+            acc.launches += c->launches; acc.h2d_bytes += c->tm.h2d_bytes; acc.d2h_bytes += c->tm.d2h_bytes;
+            acc.n_pass = c->tm.n_pass; acc.n_used = c->tm.n_used;
+            memset(&c->tm, 0, sizeof c->tm);
+            for (int k = 0; k < EV_COUNT; k++) c->ev_rec[k] = false;
+            c->launches = 0;
         }
-        const int64_t Nu = Np - 1;
-        EvTimer et;
-        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ls, ns;
-        float lm = 0, nm = 0;
-        enrich_device(c, N, c->score.as<double>(), label_dev, c->order.as<int32_t>(), Nu, n_types, nprm, np, replay_perm,
-                      et, &lm, &nm, ls, ns);
-        d2h(c, out, c->results.p, (size_t)n_types * sizeof(pctsea_type_result));
-        if (null_out) d2h(c, null_out, c->null_ews.p, (size_t)n_types * np.count * 4);
-        if (nullD_out) d2h(c, nullD_out, c->null_d.p, (size_t)n_types * np.count * 4);
-        rec(c, EV_END);
-        finish_timings(c, ls, ns);
-        c->tm.n_pass = Np;
-        c->tm.n_used = Nu;
+        c->tm = acc;
+        c->launches = acc.launches;
     });
 }
 

@@ -19,6 +19,29 @@ def perm_slice(n_perm: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, base + (1 if rank < rem else 0)
 
 
+def list_slice(n_lists: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first list, number of lists) of `rank` when independent input lists are sharded (BASELINE config E): the
+    same contiguous split as perm_slice. Lists need no data-path collective; the per-list results are gathered by
+    the host (gather_list_results)."""
+    return perm_slice(n_lists, rank, world)
+
+
+def gather_list_results(local: torch.Tensor, n_lists: int) -> torch.Tensor:
+    """local: [lists of this rank][...] -> [n_lists][...] on every rank, in list order (uint8 views of the result
+    structs travel as bytes)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        assert local.shape[0] == n_lists
+        return local.contiguous()
+    world = dist.get_world_size()
+    counts = [list_slice(n_lists, r, world)[1] for r in range(world)]
+    width = max(counts)
+    padded = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    parts: List[torch.Tensor] = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0).contiguous()
+
+
 def all_gather_null(local: torch.Tensor, n_perm: int) -> torch.Tensor:
     """local: [T][P_rank] fp32 slice of this rank -> [T][n_perm] on every rank, permutations in global order."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -62,3 +62,48 @@ def test_two_rank_null_gather_matches_single_process(tmp_path, n_perm):
         assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
         fdr = np.load(os.path.join(tmp_path, f"fdr_{r}.npy"))
         assert np.array_equal(np.isnan(fdr), np.isnan(ref_fdr)) and np.array_equal(fdr[~np.isnan(fdr)], ref_fdr[~np.isnan(ref_fdr)])
+
+
+def _list_worker(rank, world, port, n_lists, out_dir):
+    """Config E plumbing: independent lists sharded over ranks, per-list result structs gathered as bytes."""
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T = 5
+    first, count = pdist.list_slice(n_lists, rank, world)
+    rows = []
+    for i in range(first, first + count):
+        s, lab = synth.synthetic_ranked(1200, T, seed=100 + i)
+        ne, _ = O.null(s, lab, T, 8, perm_mode=1, seed=5)
+        rows.append(O.reduce(O.ks_observed(s, lab, T), ne))
+    local = np.stack(rows) if rows else np.zeros((0, T), O.TYPE_RESULT_DTYPE)
+    as_bytes = torch.from_numpy(local.view(np.uint8).reshape(local.shape[0], -1).copy())
+    full = pdist.gather_list_results(as_bytes, n_lists)
+    np.save(os.path.join(out_dir, f"lists_{rank}.npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_lists", [4, 5])
+def test_two_rank_list_sharding_matches_single_process(tmp_path, n_lists):
+    from oracle import oracle as O
+    world, T = 2, 5
+    mp.spawn(_list_worker, args=(world, _free_port(), n_lists, str(tmp_path)), nprocs=world, join=True)
+    rows = []
+    for i in range(n_lists):
+        s, lab = synth.synthetic_ranked(1200, T, seed=100 + i)
+        ne, _ = O.null(s, lab, T, 8, perm_mode=1, seed=5)
+        rows.append(O.reduce(O.ks_observed(s, lab, T), ne))
+    ref = np.stack(rows)
+    ref_bytes = ref.view(np.uint8).reshape(n_lists, -1)
+    for r in range(world):
+        got = np.load(os.path.join(tmp_path, f"lists_{r}.npy"))
+        assert got.shape == ref_bytes.shape and np.array_equal(got, ref_bytes)
+
+
+def test_list_slice_covers_everything():
+    for n in (0, 1, 31, 256):
+        for w in (1, 2, 8):
+            sl = [pdist.list_slice(n, r, w) for r in range(w)]
+            assert sl[0][0] == 0 and sum(c for _, c in sl) == n

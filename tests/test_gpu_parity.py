@@ -700,3 +700,62 @@ def test_stage3_random_shapes_sweep(ctx, oracle):
             assert_bits_equal_f32(ne[:, p], exp, f"fast null n={n_used} T={T} perm {p}")
         ored = oracle.reduce(ores, ne)
         assert_results_equal(res, ored, ("norm_ews", "p_emp", "fdr"), f"reduce n={n_used} T={T}")
+
+
+def test_analyze_batch_equals_single_analyses(ctx, oracle, small):
+    """BASELINE config E in miniature: many lists against one resident matrix. Every list's results are
+    bit-identical to pctsea_analyze on that list alone; a list that fails the reference's own input checks fails
+    alone; one list is checked end to end against the oracle."""
+    d = small
+    cfg = d["cfg"]
+    m = _load(ctx, d)
+    m.set_labels(d["label"], cfg.n_types)
+    sprm = P.ScoreParams(0, 4, 0.2, 1, P.JITTER_PHILOX, 77)
+    Pn = 24
+    nprm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=9, min_pass=100)
+    lists = []
+    for seed in range(5):
+        g, a = synth.make_list(cfg, "cpu", seed)
+        lists.append((g.numpy(), a.numpy()))
+    lists.insert(2, (lists[0][0][:3], lists[0][1][:3]))                          # 3 genes < min_genes_cells 4
+    lists.insert(4, (np.array([-1, -1, -1, -1, -1], np.int32), np.ones(5, np.float32)))  # no gene in the dataset
+    out = ctx.analyze_batch(m, lists, sprm, 0.0, cfg.n_types, nprm, want_null=True)
+    tm = ctx.timings()
+    assert list(out["status"]) == [0, 0, -5, 0, -4, 0, 0]
+    n_ok = 0
+    for i, (g, a) in enumerate(lists):
+        if out["status"][i] != 0:
+            assert np.isnan(out["results"][i]["ews"]).all() and np.isnan(out["results"][i]["fdr"]).all()
+            assert (out["results"][i]["supX"] == -1).all() and np.isnan(out["null"][i]).all()
+            with pytest.raises(P.PctseaError) as e:
+                ctx.analyze(m, g, a, sprm, 0.0, cfg.n_types, nprm)
+            assert e.value.code == out["status"][i]
+            continue
+        one = ctx.analyze(m, g, a, sprm, 0.0, cfg.n_types, nprm, want_null=True)
+        assert one["n_pass"] == out["n_pass"][i]
+        assert_results_equal(out["results"][i], one["results"], None, f"list {i}")
+        assert_bits_equal_f32(out["null"][i], one["null"], f"list {i} null")
+        assert_bits_equal_f32(out["nullD"][i], one["nullD"], f"list {i} nullD")
+        n_ok += 1
+    assert n_ok == 5 and tm["launches"] > 5 * 20 and tm["score_ms"] > 0
+    # resident labels and labels passed with the call give the same batch
+    out2 = ctx.analyze_batch(m, lists[:2], sprm, 0.0, cfg.n_types, nprm, label=d["label"])
+    assert_results_equal(out2["results"][1], out["results"][1], None, "labels per call")
+    # list 3 against the oracle, end to end (FAST arithmetic on the Philox permutations)
+    g, a = lists[3]
+    sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, g, a, method=0, min_genes_cells=4,
+                                      min_corr=0.2, jitter_mode=1, seed=77)
+    order, npass = oracle.rank(sc, kept, 0.0)
+    assert npass == out["n_pass"][3]
+    nu = npass - 1
+    s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
+    F = oracle.fast_frac_bits(s_r)
+    one = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(9, p, nu, 6)], cfg.n_types, F)
+                    for p in range(Pn)], axis=1)
+    ores = oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), one)
+    assert_bits_equal_f32(out["null"][3], one, "batch list 3 null vs oracle")
+    assert_results_equal(out["results"][3], ores, None, "batch list 3 vs oracle")
+    # empty batch
+    empty = ctx.analyze_batch(m, [], sprm, 0.0, cfg.n_types, nprm)
+    assert empty["results"].shape == (0, cfg.n_types)
+    m.free()
