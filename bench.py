@@ -57,6 +57,7 @@ class ClockSampler:
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop = threading.Event()
         self._t = None
+        self.interval_s = float(os.environ.get("PCTSEA_BENCH_SAMPLE_MS", "25")) * 1e-3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -78,7 +79,7 @@ class ClockSampler:
         self._names = names
         while not self._stop.is_set():
             self._sample()
-            self._stop.wait(0.005)
+            self._stop.wait(self.interval_s)
 
     def _sample(self):
         nv = self.nv
