@@ -131,6 +131,15 @@ int pctsea_matrix_load_csr(pctsea_ctx* ctx, int64_t n_cells, int32_t n_genes, co
  * val_dev must be 16-byte aligned, as any cudaMalloc / framework allocation is). */
 int pctsea_matrix_wrap_device(pctsea_ctx* ctx, int64_t n_cells, int32_t n_genes, const int64_t* row_ptr_dev,
                               const int32_t* col_idx_dev, const float* val_dev, pctsea_matrix** out);
+/* Optional, once per matrix: build the gene-major copy that lets the scoring stage read only the list's genes
+ * instead of scanning the whole CSR (the role of the per-list SingleCell.expressionIndexes the reference fills from
+ * MongoDB, model/SingleCell.java:49-104, without a per-list rebuild). Costs 8 B * n_genes * n_cells/32 + 4 B * nnz
+ * of device memory (config B: 7 GB next to the 6.5 GB CSR). With it pctsea_score / pctsea_analyze[_batch] run the
+ * lane-per-cell kernel, whose pair order is ascending gene (matrix column) order and whose Pearson sums are the
+ * shifted-data form (oracle: orc_pearson_shifted); without it they run the CSR scan (pair order = row storage
+ * order, two-pass centred sums; oracle: orc_pearson_strided32). Both are within 1e-9 relative of the reference's
+ * sequential SimpleRegression update; they differ from each other in the last bits. n_genes <= 51200. */
+int pctsea_matrix_build_gene_index(pctsea_ctx* ctx, pctsea_matrix* m);
 /* Cell-type ids per cell in [-1, n_types); -1 = unknown type (model/SingleCell.java:224-229). */
 int pctsea_matrix_set_labels(pctsea_ctx* ctx, pctsea_matrix* m, const int32_t* label, int32_t n_types);
 int pctsea_matrix_free(pctsea_ctx* ctx, pctsea_matrix* m);

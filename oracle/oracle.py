@@ -59,6 +59,7 @@ def lib():
         L.orc_jitter_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_pearson.restype = C.c_double
         L.orc_pearson_strided32.restype = C.c_double
+        L.orc_pearson_shifted.restype = C.c_double
         L.orc_ks_statistic.restype = C.c_double
         L.orc_score2.restype = C.c_int
         L.orc_rank.restype = C.c_int64
@@ -141,6 +142,12 @@ def ks_statistic(x, y) -> float:
     return lib().orc_ks_statistic(_p(x, C.c_double), C.c_int64(x.size), _p(y, C.c_double), C.c_int64(y.size))
 
 
+def pearson_shifted(x, y) -> float:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    return lib().orc_pearson_shifted(_p(x, C.c_double), _p(y, C.c_double), C.c_int32(x.size))
+
+
 def pearson_strided32(x, y) -> float:
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
@@ -149,7 +156,8 @@ def pearson_strided32(x, y) -> float:
 
 def score(row_ptr, col, val, n_genes, gene_idx, abundance, method=0, min_genes_cells=4, min_corr=0.2,
           has_min_corr=True, jitter_mode=1, seed=0, canonical=True):
-    """canonical=True: the accelerated path's reduction order (what the GPU is bit-identical to);
+    """canonical=True (or 1): the CSR-scan kernel's reduction order; canonical=2: the gene-major kernel's (pairs
+    in ascending gene order, shifted sequential sums) — the GPU is bit-identical to the one of the path it runs;
     canonical=False: the reference-faithful sequential SimpleRegression update."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
     col = np.ascontiguousarray(col, dtype=np.int32)
@@ -164,7 +172,7 @@ def score(row_ptr, col, val, n_genes, gene_idx, abundance, method=0, min_genes_c
     kept = np.empty(n, dtype=np.uint8)
     rc = lib().orc_score2(C.c_int64(n), C.c_int32(n_genes), _p(row_ptr, C.c_int64), _p(col, C.c_int32),
                           _p(val, C.c_float), C.c_int32(gene_idx.size), _p(gene_idx, C.c_int32),
-                          _p(abundance, C.c_float), C.byref(prm), C.c_int(1 if canonical else 0),
+                          _p(abundance, C.c_float), C.byref(prm), C.c_int(int(canonical)),
                           _p(sc, C.c_double), _p(used, C.c_int32), _p(nz, C.c_int32), _p(kept, C.c_uint8))
     if rc != 0:
         raise ValueError(f"orc_score rc={rc}")

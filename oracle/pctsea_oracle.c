@@ -272,6 +272,31 @@ double orc_pearson_strided32(const double* x, const double* y, int32_t n) {
     return pearson_finish(SXX, SYY, SXY);
 }
 
+/* The gene-major scoring path's canonical Pearson (this repo's choice, see orc_pearson_strided32 for why a
+ * choice is needed): pairs in ASCENDING GENE (matrix column) order, one sequential pass of sums shifted by the
+ * first pair (dx = x - x[0], dy = y - y[0]: the textbook shifted-data algorithm, well conditioned because the
+ * pivot is a sample), then Sxx = sum(dx^2) - sum(dx)^2/n (same for yy, xy) through the same getR() formula.
+ * What the GPU's lane-per-cell gene-major kernel computes, bit for bit. */
+double orc_pearson_shifted(const double* x, const double* y, int32_t n) {
+    if (n < 2) return NAN;
+    const double x0 = x[0], y0 = y[0];
+    double sdx = 0.0, sdy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
+    for (int32_t i = 0; i < n; i++) {
+        double dx = x[i] - x0, dy = y[i] - y0;
+        sdx += dx; sdy += dy;
+        sxx += dx * dx; syy += dy * dy; sxy += dx * dy;
+    }
+    const double nn = (double)n;
+    double SXX = sxx - sdx * sdx / nn, SYY = syy - sdy * sdy / nn, SXY = sxy - sdx * sdy / nn;
+    return pearson_finish(SXX, SYY, SXY);
+}
+
+typedef struct { int32_t g; double x, y; } gene_pair;
+static int cmp_gene_pair(const void* a, const void* b) {
+    int32_t ga = ((const gene_pair*)a)->g, gb = ((const gene_pair*)b)->g;
+    return (ga > gb) - (ga < gb);
+}
+
 static int all_equal(const double* v, int32_t n) {
     /* edu.scripps.yates Maths.var(double[]) is un-vendored; only "== 0" is used
      * (CORE/model/SingleCell.java:430-441): policy = zero iff every element is equal (n>=1). */
@@ -290,6 +315,7 @@ int orc_score2(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const i
     for (int32_t l = 0; l < L; l++) if (gene_idx[l] >= 0 && gene_idx[l] < n_genes) slot[gene_idx[l]] = l;
     double* xs = (double*)malloc((size_t)(L > 0 ? L : 1) * sizeof(double)); /* interactors (abundance) */
     double* ys = (double*)malloc((size_t)(L > 0 ? L : 1) * sizeof(double)); /* gene expression in cell */
+    gene_pair* gp = (gene_pair*)malloc((size_t)(L > 0 ? L : 1) * sizeof(gene_pair)); /* canonical == 2: by gene */
     for (int64_t c = 0; c < n_cells; c++) {
         int32_t np = 0, nz = 0;
         for (int64_t k = row_ptr[c]; k < row_ptr[c + 1]; k++) {
@@ -300,7 +326,7 @@ int orc_score2(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const i
             float x = val[k];
             float y = abundance[l];
             if (x > 0.0f && y > 0.0f) { /* SingleCell.java:403 */
-                if (np < L) { xs[np] = (double)y; ys[np] = (double)x; }
+                if (np < L) { xs[np] = (double)y; ys[np] = (double)x; gp[np].g = g; gp[np].x = (double)y; gp[np].y = (double)x; }
                 np++;
             }
             if (x != 0.0f) nz++; /* true for NaN, SingleCell.java:409 */
@@ -313,18 +339,23 @@ int orc_score2(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const i
         kept[c] = (uint8_t)k;
         if (!k) { score[c] = NAN; continue; }
         if (np < 2) { score[c] = NAN; continue; } /* reference would throw inside commons-math */
+        if (canonical == 2) { /* pair order of the gene-major path: ascending matrix column, whatever the row's storage order */
+            qsort(gp, (size_t)np, sizeof(gene_pair), cmp_gene_pair);
+            for (int32_t i = 0; i < np; i++) { xs[i] = gp[i].x; ys[i] = gp[i].y; }
+        }
         int zx = all_equal(ys, np); /* geneExpressionVariance == 0, checked first (:433) */
         int zy = all_equal(xs, np); /* interactorsExpressionVariance == 0 (:441) */
         if ((zx || zy) && prm->jitter_mode == 0) { score[c] = NAN; continue; }
         if (zx) for (int32_t i = 0; i < np; i++) ys[i] = ys[i] + orc_jitter_uniform(prm->seed, (uint64_t)c, 0u, (uint32_t)i) / 1000000.0;
         if (zy) for (int32_t i = 0; i < np; i++) xs[i] = xs[i] + orc_jitter_uniform(prm->seed, (uint64_t)c, 1u, (uint32_t)i) / 1000000.0;
         /* correlation(interactors, genes) :449-450 */
-        double r = canonical ? orc_pearson_strided32(xs, ys, np) : orc_pearson(xs, ys, np);
+        double r = canonical == 2 ? orc_pearson_shifted(xs, ys, np)
+                 : canonical ? orc_pearson_strided32(xs, ys, np) : orc_pearson(xs, ys, np);
         if (prm->has_min_corr && r < prm->min_corr) r = NAN;     /* :455-456 */
         else if (prm->method == 1) r += (double)nz;              /* :457-458 */
         score[c] = r;
     }
-    free(slot); free(xs); free(ys);
+    free(slot); free(xs); free(ys); free(gp);
     return 0;
 }
 

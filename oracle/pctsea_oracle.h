@@ -68,7 +68,8 @@ int orc_score(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const in
               const orc_score_params* prm, double* score, int32_t* n_genes_used,
               int32_t* n_nonzero, uint8_t* kept);
 
-/* Same with canonical != 0: the accelerated path's canonical reduction order (orc_pearson_strided32). */
+/* Same with canonical == 1: the CSR-scan kernel's canonical reduction order (orc_pearson_strided32);
+ * canonical == 2: the gene-major kernel's (orc_pearson_shifted over the pairs in ascending gene order). */
 int orc_score2(int64_t n_cells, int32_t n_genes, const int64_t* row_ptr, const int32_t* col,
                const float* val, int32_t L, const int32_t* gene_idx, const float* abundance,
                const orc_score_params* prm, int canonical, double* score, int32_t* n_genes_used,
@@ -80,6 +81,8 @@ double orc_pearson(const double* x, const double* y, int32_t n);
 /* Canonical Pearson of the accelerated path: two-pass centred sums over 32 strided sub-streams
  * (pair k -> k % 32) added pairwise in a fixed tree, then SimpleRegression's getR() formula. */
 double orc_pearson_strided32(const double* x, const double* y, int32_t n);
+/* canonical == 2 in orc_score2: pairs in ascending gene order, sequential sums shifted by the first pair. */
+double orc_pearson_shifted(const double* x, const double* y, int32_t n);
 
 /* ---- stage 2: threshold + rank (a4, a5, a7) ------------------------------------------------ */
 /* order_out[n_pass]: the first n_pass-1 entries are the KS list in its final order (score desc by

@@ -21,7 +21,7 @@ KS_EXACT, KS_FAST = 0, 1
 
 EXPORTS = [
     "pctsea_abi_version", "pctsea_create", "pctsea_destroy", "pctsea_last_error", "pctsea_get_timings",
-    "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels",
+    "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels", "pctsea_matrix_build_gene_index",
     "pctsea_matrix_free", "pctsea_score", "pctsea_rank", "pctsea_enrich", "pctsea_reduce_null",
     "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_analyze_batch", "pctsea_last_null_dev", "pctsea_last_type_counts",
     "pctsea_last_observed_curve",
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     L.pctsea_matrix_load_csr.argtypes = [vp, i64, i32, vp, vp, vp, C.POINTER(vp)]
     L.pctsea_matrix_wrap_device.argtypes = [vp, i64, i32, vp, vp, vp, C.POINTER(vp)]
     L.pctsea_matrix_set_labels.argtypes = [vp, vp, vp, i32]
+    L.pctsea_matrix_build_gene_index.argtypes = [vp, vp]
     L.pctsea_matrix_free.argtypes = [vp, vp]
     L.pctsea_score.argtypes = [vp, vp, i32, vp, vp, C.POINTER(ScoreParams), vp, vp, vp, vp]
     L.pctsea_rank.argtypes = [vp, i64, vp, vp, f64, vp, C.POINTER(i64)]
@@ -125,6 +126,7 @@ class Matrix:
     def __init__(self, ctx: "Context", handle, n_cells: int, n_genes: int, keepalive=None):
         self.ctx, self.handle, self.n_cells, self.n_genes = ctx, handle, n_cells, n_genes
         self.n_types = 0
+        self.gene_index = False
         self._keepalive = keepalive
 
     def set_labels(self, label, n_types: int):
@@ -132,6 +134,12 @@ class Matrix:
         assert label.size == self.n_cells
         self.ctx._check(self.ctx.L.pctsea_matrix_set_labels(self.ctx.h, self.handle, _ptr(label), n_types))
         self.n_types = n_types
+
+    def build_gene_index(self):
+        """Gene-major copy of the matrix (once per dataset): scoring then reads only the list's genes."""
+        self.ctx._check(self.ctx.L.pctsea_matrix_build_gene_index(self.ctx.h, self.handle))
+        self.gene_index = True
+        return self
 
     def free(self):
         if self.handle is not None:

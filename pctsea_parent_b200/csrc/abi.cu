@@ -12,13 +12,17 @@ using namespace pctsea;
 namespace {
 
 struct EvTimer {
-    // per-chunk events for the null loop
-    std::vector<cudaEvent_t> ev;
-    ~EvTimer() { for (auto e : ev) cudaEventDestroy(e); }
+    // per-chunk events for the null loop, taken from a pool the ctx keeps (no event creation inside a call once
+    // the pool is warm: every runtime call that reaches the driver is a chance for the launching thread to stall)
+    pctsea_ctx* c;
+    explicit EvTimer(pctsea_ctx* ctx) : c(ctx) { c->ev_used = 0; }
     cudaEvent_t mark(cudaStream_t s) {
-        cudaEvent_t e;
-        PCT_CUDA(cudaEventCreate(&e));
-        ev.push_back(e);
+        if (c->ev_used == c->ev_pool.size()) {
+            cudaEvent_t e;
+            PCT_CUDA(cudaEventCreate(&e));
+            c->ev_pool.push_back(e);
+        }
+        cudaEvent_t e = c->ev_pool[c->ev_used++];
         PCT_CUDA(cudaEventRecord(e, s));
         return e;
     }
@@ -104,6 +108,7 @@ void upload_list(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_t
         PCT_REQUIRE(gene_idx[l] >= -1 && gene_idx[l] < m->n_genes, "gene_idx out of range");
         if (gene_idx[l] >= 0) tmp.push_back(gene_idx[l]);
     }
+    c->list_mapped = (int32_t)tmp.size();
     std::sort(tmp.begin(), tmp.end());
     PCT_REQUIRE(std::adjacent_find(tmp.begin(), tmp.end()) == tmp.end(), "duplicate matrix column in gene_idx");
     c->list_gene.reserve((size_t)std::max(L, 1) * 4);
@@ -185,12 +190,19 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     if (Pc_all > 0 && T > 0) {
         if (prm->perm_mode == PCTSEA_PERM_REPLAY) PCT_REQUIRE(replay_host != nullptr, "REPLAY mode needs replay_perm");
         // chunk the permutations so the label matrix stays within half of the free device memory
-        size_t free_b = 0, total_b = 0;
-        PCT_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t row_bytes = plan_fast(g, Pc_all).label_row_bytes;  // layout-dependent (row-major or lane layout)
         const size_t per_perm = row_bytes + (prm->perm_mode == PCTSEA_PERM_REPLAY ? (size_t)g.Nu * 4 : 0);
-        size_t budget = std::max<size_t>(free_b / 2 + c->labels.cap + c->replay.cap, (size_t)64 << 20);
-        int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)Pc_all, budget / std::max<size_t>(per_perm, 1)));
+        int32_t chunk = Pc_all;
+        // The free-memory query goes to the kernel-mode driver and was measured to stall the launching thread for
+        // 1-70 ms now and then, with the stream idle behind it: ask only when the label buffers have to grow.
+        const bool fits = (size_t)Pc_all * row_bytes + 64 <= c->labels.cap &&
+                          (prm->perm_mode != PCTSEA_PERM_REPLAY || (size_t)Pc_all * g.Nu * 4 + 64 <= c->replay.cap);
+        if (!fits) {
+            size_t free_b = 0, total_b = 0;
+            PCT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t budget = std::max<size_t>(free_b / 2 + c->labels.cap + c->replay.cap, (size_t)64 << 20);
+            chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)Pc_all, budget / std::max<size_t>(per_perm, 1)));
+        }
         if (const char* e = std::getenv("PCTSEA_PERM_CHUNK")) chunk = std::max(1, std::min(chunk, std::atoi(e)));   // tuning aid
         c->labels.reserve((size_t)chunk * row_bytes + 64);
         const FastPlan plan0 = plan_fast(g, Pc_all);
@@ -251,6 +263,14 @@ void finish_timings(pctsea_ctx* c, const std::vector<std::pair<cudaEvent_t, cuda
     c->tm.labels_ms = lm;
     c->tm.null_ms = nm;
     c->tm.launches = c->launches;
+    if (std::getenv("PCTSEA_DEBUG_GAPS") && !lab_spans.empty()) {   // diagnosis: where the stream sat idle
+        auto el = [](cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; };
+        const float pre = el(c->ev[EV_RANK], lab_spans.front().first), post = el(null_spans.back().second, c->ev[EV_NULL]);
+        const float tail = el(c->ev[EV_REDUCE], c->ev[EV_END]);
+        if (c->tm.total_ms > 1.3f * (c->tm.setup_ms + c->tm.score_ms + c->tm.rank_ms + lm + nm + c->tm.reduce_ms))
+            fprintf(stderr, "[pctsea gaps] total %.3f setup %.3f score %.3f rank %.3f | rank->labels %.3f | labels %.3f null %.3f | null->join %.3f (observed span %.3f) | reduce %.3f | results d2h %.3f\n",
+                    c->tm.total_ms, c->tm.setup_ms, c->tm.score_ms, c->tm.rank_ms, pre, lm, nm, post, c->tm.observed_ms, c->tm.reduce_ms, tail);
+    }
 }
 
 NullPlan validate_analysis(const pctsea_matrix* m, double min_score, const int32_t* label, int32_t n_types,
@@ -315,7 +335,7 @@ void analyze_core(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_
                                         std::to_string(std::max(nprm->min_pass, 2)) + ")");
     }
     const int64_t Nu = Np - 1;
-    EvTimer et;
+    EvTimer et(c);
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ls, ns;
     float lm = 0, nm = 0;
     enrich_device(c, N, c->score.as<double>(), label_dev, c->order.as<int32_t>(), Nu, n_types, nprm, np, replay_perm,
@@ -373,7 +393,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     if (!c) return PCTSEA_EINVAL;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->list_rank, &c->score_sums, &c->score, &c->nused, &c->nnzc, &c->kept,
+    DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->list_rank, &c->score_sums, &c->score, &c->nused, &c->nnzc, &c->kept, &c->gm_fix,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
                        &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels,
                        &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
@@ -381,6 +401,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++) if (c->ev_obs[i]) cudaEventDestroy(c->ev_obs[i]);
     cudaStreamSynchronize(c->stream_aux);
     cudaStreamDestroy(c->stream_aux);
@@ -470,6 +491,13 @@ int pctsea_matrix_wrap_device(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, c
     });
 }
 
+int pctsea_matrix_build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
+    return guarded(c, [&] {
+        PCT_REQUIRE(m != nullptr, "matrix is NULL");
+        build_gene_index(c, m);
+    });
+}
+
 int pctsea_matrix_set_labels(pctsea_ctx* c, pctsea_matrix* m, const int32_t* label, int32_t n_types) {
     return guarded(c, [&] {
         PCT_REQUIRE(m != nullptr && label != nullptr, "matrix / label are NULL");
@@ -485,6 +513,8 @@ int pctsea_matrix_free(pctsea_ctx* c, pctsea_matrix* m) {
     if (c) cudaSetDevice(c->device);
     if (m->owned) { cudaFree((void*)m->row_ptr); cudaFree((void*)m->col); cudaFree((void*)m->val); }
     if (m->label) cudaFree(m->label);
+    if (m->gm_mo) cudaFree(m->gm_mo);
+    if (m->gm_val) cudaFree(m->gm_val);
     delete m;
     return PCTSEA_OK;
 }
@@ -555,7 +585,7 @@ int pctsea_enrich(pctsea_ctx* c, int64_t n_cells, const double* score, int64_t n
         h2d(c, c->order.p, order, (size_t)n_used * 4);
         rec(c, EV_SETUP);
         rec(c, EV_SCORE);
-        EvTimer et;
+        EvTimer et(c);
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ls, ns;
         float lm = 0, nm = 0;
         enrich_device(c, n_cells, c->score.as<double>(), c->label_tmp.as<int32_t>(), c->order.as<int32_t>(), n_used,

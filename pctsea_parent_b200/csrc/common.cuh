@@ -84,6 +84,10 @@ struct pctsea_matrix {
     bool owned = false;
     bool all_positive = false;  // every stored value > 0 (found by the load-time validation)
     int32_t* label = nullptr;  // device, [n_cells], owned
+    // gene-major copy for the lane-per-cell scoring kernel (score_gm.cu), built on request, owned
+    uint2* gm_mo = nullptr;    // [n_groups][n_genes] {cell mask of the gene in the group, offset of its values}
+    float* gm_val = nullptr;   // [nnz] values in (group, gene, cell) order
+    int64_t n_groups = 0;      // groups of 32 cells
     int32_t n_types = 0;
 };
 
@@ -95,6 +99,8 @@ struct pctsea_ctx {
     cudaEvent_t ev[pctsea::EV_COUNT];
     cudaEvent_t ev_obs[3] = { nullptr, nullptr, nullptr };  // ranked arrays ready; begin / end of the observed kernels
     bool obs_span_valid = false;
+    std::vector<cudaEvent_t> ev_pool;   // reusable events of the per-chunk label / null spans
+    size_t ev_used = 0;
     bool ev_rec[pctsea::EV_COUNT];
     pctsea_timings tm;
     int64_t launches = 0;
@@ -102,6 +108,8 @@ struct pctsea_ctx {
     // workspaces (grow-only)
     pctsea::DevBuf list_gene, list_abund, ybg, bitmap, list_rank, score_sums;  // stage 1 lookup + per-cell centred sums
     pctsea::DevBuf score, nused, nnzc, kept;                    // stage 1 outputs [N]
+    pctsea::DevBuf gm_fix;                                      // gene-major scoring: zero-variance cells to jitter
+    int32_t list_mapped = 0;                                    // list entries with a matrix column (set by the upload)
     pctsea::DevBuf keysA, keysB, valsA, valsB, hist, tile_hist, scan_tmp, counters;  // radix sort
     pctsea::DevBuf order;                                       // [N] int32
     pctsea::DevBuf type_counts;                                 // [2T+1] int32 (hypergeometric inputs)
@@ -162,7 +170,11 @@ struct ScoreArgs {
     const float* abund_dev;
     pctsea_score_params prm;
 };
-void launch_score(pctsea_ctx* c, const ScoreArgs& a);
+void launch_score(pctsea_ctx* c, const ScoreArgs& a);   // picks the gene-major kernel when the matrix has its index
+void launch_list_lookup(pctsea_ctx* c, const ScoreArgs& a);   // by-gene abundance table + 2-bit membership bitmap
+void launch_score_final(pctsea_ctx* c, const ScoreArgs& a);   // centred sums -> getR() + thresholds
+void launch_score_gm(pctsea_ctx* c, const ScoreArgs& a);      // score_gm.cu
+void build_gene_index(pctsea_ctx* c, pctsea_matrix* m);       // score_gm.cu; syncs the stream
 // One pass over a device CSR: bit 0 = row_ptr not 0-based / non-decreasing / not ending at nnz, bit 1 = a column
 // outside [0, n_genes). Syncs the stream.
 int validate_csr(pctsea_ctx* c, const pctsea_matrix* m);

@@ -532,8 +532,27 @@ int validate_csr(pctsea_ctx* c, const pctsea_matrix* m) {
     return h;
 }
 
+void launch_list_lookup(pctsea_ctx* c, const ScoreArgs& sa) {
+    k_list_lookup<<<(sa.L + 255) / 256, 256, 0, c->stream>>>(sa.gene_idx_dev, sa.abund_dev, sa.L, sa.m->n_genes,
+                                                              c->ybg.as<float>(), c->bitmap.as<uint32_t>());
+    count_launch(c);
+}
+
+void launch_score_final(pctsea_ctx* c, const ScoreArgs& sa) {
+    const int64_t N = sa.m->n_cells;
+    k_score_final<<<(unsigned)div_up(N, 256), 256, 0, c->stream>>>(c->score_sums.as<double>(), c->nnzc.as<int32_t>(), N,
+                                                                    sa.prm.method, sa.prm.has_min_corr, sa.prm.min_corr,
+                                                                    c->score.as<double>());
+    count_launch(c);
+    PCT_CUDA(cudaGetLastError());
+}
+
 void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     const pctsea_matrix* m = sa.m;
+    if (m->gm_mo && m->n_cells > 0) {   // the matrix carries its gene-major copy: lane-per-cell kernel (score_gm.cu)
+        const char* e = std::getenv("PCTSEA_SCORE_PATH");   // testing aid: "csr" forces the CSR scan
+        if (!(e && e[0] == 'c')) { launch_score_gm(c, sa); return; }
+    }
     const int64_t N = m->n_cells;
     const int32_t G = m->n_genes;
     const int32_t bm_words = (G + 1 + 15) / 16;  // 2 bits per gene, plus the always-zero entry G
@@ -552,9 +571,7 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     PCT_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (size_t)bm_words * 4, c->stream));
     if (rank_bytes) PCT_CUDA(cudaMemsetAsync(c->list_rank.p, 0, rank_bytes, c->stream));
     if (sa.L > 0) {
-        k_list_lookup<<<(sa.L + 255) / 256, 256, 0, c->stream>>>(sa.gene_idx_dev, sa.abund_dev, sa.L, G,
-                                                                  c->ybg.as<float>(), c->bitmap.as<uint32_t>());
-        count_launch(c);
+        launch_list_lookup(c, sa);
         if (rank_words) {
             k_list_rank<<<1, 1024, 0, c->stream>>>(c->bitmap.as<uint32_t>(), c->ybg.as<float>(), G, rank_words,
                                                    c->list_rank.as<int2>(), c->list_rank.as<float>() + 2 * (size_t)rank_words);
@@ -614,11 +631,7 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
 #undef PCT_LAUNCH_SCORE
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
-    k_score_final<<<(unsigned)div_up(N, 256), 256, 0, c->stream>>>(c->score_sums.as<double>(), c->nnzc.as<int32_t>(), N,
-                                                                    sa.prm.method, sa.prm.has_min_corr, sa.prm.min_corr,
-                                                                    c->score.as<double>());
-    count_launch(c);
-    PCT_CUDA(cudaGetLastError());
+    launch_score_final(c, sa);
 }
 
 }  // namespace pctsea

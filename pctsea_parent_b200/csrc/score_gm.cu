@@ -1,0 +1,396 @@
+// score_gm.cu — stage 1 over a gene-major copy of the matrix (built once per dataset, opt-in).
+//
+// Replaces the same reference code as score.cu (a2: model/SingleCell.java:344-369, a3: :380-463, drivers
+// PCTSEA.java:544-572, 2305-2343; paths under pctsea-core/src/main/java/edu/scripps/yates/pctsea/).
+//
+// Why a second layout: the CSR scan of score.cu reads all 8 B * nnz of the matrix although only the list's genes
+// (~4 % of the columns, ~13 % of the non-zeros of config B) can form pairs, and it is bound by the instructions of
+// the membership test per non-zero, not by HBM. The reference holds, per cell, exactly the list-gene values
+// (SingleCell.expressionIndexes, model/SingleCell.java:49-104, filled per input list from MongoDB); the layout
+// here lets the GPU fetch just those without a per-list rebuild:
+//
+//   cells are grouped by 32 (group = warp, lane = cell). For every (group, gene):
+//     mo[group][gene] = { mask: bit l set iff cell 32*group + l has a non-zero of this gene,
+//                         off : number of non-zeros of the group in lower-numbered genes }
+//   gval[row_ptr[32*group] + off + popc(mask & lanes below l)] = that cell's value: the group's non-zeros in
+//   (gene, cell) order. Size: 8 B * G * N/32 (config B 3.75 GB, D 15 GB) + 4 B * nnz.
+//
+// Scoring a list: one warp per group walks the list's genes in ascending gene order; per gene one 8-byte broadcast
+// entry tells every lane whether its cell expresses the gene and where the value is; each lane keeps its own cell's
+// running sums in registers. No shared memory, no atomics, no cross-lane reduction; the pair order of a cell is the
+// gene order whatever the storage order of its CSR row. The Pearson sums are the shifted-data form (deviations from
+// the cell's first pair), bit-identical to the oracle's orc_pearson_shifted and within 1e-9 relative of the
+// reference's sequential SimpleRegression update (measured <= 1e-11).
+//
+// Roofline: the bytes this path must read are 8 B per (list gene, group) entry + the matched values
+// (config B: 0.15 GB + ~0.45 GB in 32-byte sectors), not the CSR: it is latency/issue bound, not HBM bound.
+#include "common.cuh"
+
+namespace pctsea {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- build: one CTA per group of 32 cells ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                  const float* __restrict__ val, int64_t N, int32_t G,
+                                                  uint2* __restrict__ mo, float* __restrict__ gval) {
+    extern __shared__ unsigned s_mask[];   // [G]
+    __shared__ int s_part[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t grp = blockIdx.x, c0 = grp * 32;
+    for (int g = tid; g < G; g += blockDim.x) s_mask[g] = 0u;
+    __syncthreads();
+    for (int ci = warp; ci < 32 && c0 + ci < N; ci += nwarps) {
+        const int64_t b = row_ptr[c0 + ci], e = row_ptr[c0 + ci + 1];
+        for (int64_t k = b + lane; k < e; k += 32) atomicOr(&s_mask[col[k]], 1u << ci);
+    }
+    __syncthreads();
+    // exclusive prefix of popc(mask) over the genes: contiguous chunk per thread + block scan of the chunk sums
+    const int chunk = (G + blockDim.x - 1) / blockDim.x;
+    const int g0 = min(tid * chunk, G), g1 = min(g0 + chunk, G);
+    int sum = 0;
+    for (int g = g0; g < g1; g++) sum += __popc(s_mask[g]);
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    unsigned run = (unsigned)(s_part[tid] - sum);
+    uint2* row = mo + grp * (int64_t)G;
+    for (int g = g0; g < g1; g++) {
+        const unsigned m = s_mask[g];
+        row[g] = make_uint2(m, run);
+        run += __popc(m);
+    }
+    __syncthreads();   // the CTA's own global writes are visible to all of its threads from here
+    const int64_t base = row_ptr[c0];
+    for (int ci = warp; ci < 32 && c0 + ci < N; ci += nwarps) {
+        const int64_t b = row_ptr[c0 + ci], e = row_ptr[c0 + ci + 1];
+        const unsigned below = (1u << ci) - 1u;
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const uint2 x = row[col[k]];
+            gval[base + x.y + __popc(x.x & below)] = val[k];
+        }
+    }
+}
+
+// ---- list in ascending gene order (from the 2-bit membership bitmap and the by-gene abundance table) -----------
+// One CTA; same tile scan as k_list_rank of score.cu, but it emits (gene, abundance) of every list gene.
+__global__ void k_gm_sorted_list(const uint32_t* __restrict__ bitmap, const float* __restrict__ ybg, int G,
+                                 int32_t* __restrict__ gs_gene, float* __restrict__ gs_ab, int* __restrict__ n_out) {
+    __shared__ int s_scan[1024];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int bm_words = (G + 1 + 15) / 16;   // 16 genes per word, bit 0 of each 2-bit entry = in the list
+    for (int w0 = 0; w0 < bm_words; w0 += blockDim.x) {
+        const int w = w0 + threadIdx.x;
+        uint32_t bits = 0u;
+        if (w < bm_words) {
+            const uint32_t v = bitmap[w];
+#pragma unroll
+            for (int j = 0; j < 16; j++) bits |= ((v >> (2 * j)) & 1u) << j;
+        }
+        const int cnt = __popc(bits);
+        s_scan[threadIdx.x] = cnt;
+        __syncthreads();
+        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+            const int v = threadIdx.x >= (unsigned)o ? s_scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        int r = s_carry + s_scan[threadIdx.x] - cnt;
+        while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int g = 16 * w + j;
+            if (g < G) { gs_gene[r] = g; gs_ab[r] = ybg[g]; r++; }
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry += s_scan[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = s_carry;
+}
+
+struct GmArgs {
+    const uint2* mo;
+    const float* gval;
+    const int64_t* row_ptr;
+    int64_t N, n_groups;
+    int32_t G;
+    const int32_t* gs_gene;
+    const float* gs_ab;
+    int32_t Ls;
+    int32_t min_genes, jitter_mode;
+    uint64_t seed;
+    double* sums;
+    int32_t* nused;
+    int32_t* nnzc;
+    uint8_t* kept;
+    int2* fix_list;   // cells whose pairs have zero variance (jitter mode PHILOX): {cell, bit 0 = list vector constant, bit 1 = cell vector constant}
+    int* fix_count;
+};
+
+// Running sums of one cell (one lane): deviations from the first pair.
+struct CellSums {
+    double x0 = 0.0, y0 = 0.0, sdx = 0.0, sdy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
+    int n = 0;
+    bool varx = false, vary = false;
+    __device__ __forceinline__ void add(double x, double y) {
+        if (n == 0) { x0 = x; y0 = y; }
+        const double dx = __dsub_rn(x, x0), dy = __dsub_rn(y, y0);
+        sdx = __dadd_rn(sdx, dx);
+        sdy = __dadd_rn(sdy, dy);
+        sxx = __dadd_rn(sxx, __dmul_rn(dx, dx));
+        syy = __dadd_rn(syy, __dmul_rn(dy, dy));
+        sxy = __dadd_rn(sxy, __dmul_rn(dx, dy));
+        varx = varx || (dx != 0.0);
+        vary = vary || (dy != 0.0);
+        n++;
+    }
+    // centred sums: Sxx = sum(dx^2) - sum(dx)^2 / n, ...
+    __device__ __forceinline__ void centred(double& SXX, double& SYY, double& SXY) const {
+        const double nn = (double)n;
+        SXX = __dsub_rn(sxx, __ddiv_rn(__dmul_rn(sdx, sdx), nn));
+        SYY = __dsub_rn(syy, __ddiv_rn(__dmul_rn(sdy, sdy), nn));
+        SXY = __dsub_rn(sxy, __ddiv_rn(__dmul_rn(sdx, sdy), nn));
+    }
+};
+
+__device__ __forceinline__ double gm_jitter(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t i) {
+    uint32_t o[4];
+    philox4x32_10(i, vec | 0x4A000000u, (uint32_t)cell, (uint32_t)(cell >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    const uint64_t u = ((uint64_t)(o[0] >> 6) << 27) | (uint64_t)(o[1] >> 5);
+    return __ddiv_rn(__dmul_rn((double)u, 1.0 / 9007199254740992.0), 1000000.0);
+}
+
+// 32 x 32 bit-matrix transpose across a warp: lane j gives row j (bit l = column l), lane l gets column l
+// (bit j = row j's bit l). Five butterfly stages.
+__device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
+    unsigned m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const unsigned y = __shfl_xor_sync(FULL, x, j);
+        if ((lane & j) == 0) { const unsigned t = ((x >> j) ^ y) & m; x ^= (t << j); }
+        else { const unsigned t = ((y >> j) ^ x) & m; x ^= t; }
+        m ^= (m << (j >> 1));
+    }
+    return x;
+}
+
+// One warp per group of 32 cells, lane = cell. The list is walked in chunks of 32 genes: lane j fetches gene j's
+// {mask, offset} entry, the 32 masks are bit-transposed so that every lane holds the set of the chunk's genes ITS
+// cell expresses, and each lane then pops its own genes in ascending order (the entry of the popped gene comes
+// from the lane that fetched it, by a variable-source shuffle). A chunk costs as many steps as its busiest cell
+// has genes (not 32), and the lanes of a step all do useful work as long as they have genes left. U steps are
+// fetched together so that several value loads of a lane are in flight.
+template <bool ALL_POSITIVE>
+__global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (grp >= a.n_groups) return;
+    const int64_t cell = grp * 32 + lane;
+    const float* gv = a.gval + a.row_ptr[grp * 32];
+    const uint2* mo_row = a.mo + grp * (int64_t)a.G;
+    const unsigned below = (1u << lane) - 1u;
+    CellSums cs;
+    int nz = 0;
+
+    auto fetch = [&](int j0, uint2& mo, float& ab) {
+        const int j = j0 + lane;
+        mo = make_uint2(0u, 0u);
+        ab = 0.0f;
+        if (j < a.Ls) {
+            ab = __ldg(a.gs_ab + j);
+            mo = __ldg(mo_row + __ldg(a.gs_gene + j));
+        }
+    };
+    uint2 mo_n; float ab_n;
+    fetch(0, mo_n, ab_n);
+    for (int j0 = 0; j0 < a.Ls; j0 += 32) {
+        const uint2 mo = mo_n;
+        const float ab = ab_n;
+        fetch(j0 + 32, mo_n, ab_n);   // the next chunk's entries travel while this chunk is processed
+        unsigned mine = warp_bit_transpose(mo.x, lane);   // bit k: my cell expresses the chunk's gene k
+        constexpr int U = 2;
+        int iters = __reduce_max_sync(FULL, (unsigned)__popc(mine));
+        for (; iters > 0; iters -= U) {   // warp-uniform trip count
+            unsigned m[U]; float abk[U], e[U]; bool has[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                has[u] = mine != 0u;
+                const int k = has[u] ? (__ffs(mine) - 1) : 0;
+                mine &= mine - 1u;   // 0 stays 0
+                m[u] = __shfl_sync(FULL, mo.x, k);
+                const unsigned off = __shfl_sync(FULL, mo.y, k);
+                abk[u] = __shfl_sync(FULL, ab, k);
+                e[u] = 0.0f;
+                if (has[u]) e[u] = __ldg(gv + off + __popc(m[u] & below));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (has[u]) {
+                    if (ALL_POSITIVE || e[u] != 0.0f) nz++;                     // NaN counts (model/SingleCell.java:409)
+                    if (abk[u] > 0.0f && (ALL_POSITIVE || e[u] > 0.0f))         // :403
+                        cs.add((double)abk[u], (double)e[u]);
+                }
+            }
+        }
+    }
+    if (cell >= a.N) return;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool keep = (nz > 0) && (cs.n >= a.min_genes);
+    double o_xx = qnan, o_yy = qnan, o_xy = qnan;
+    if (keep && cs.n >= 2) {
+        const bool degenerate = !cs.varx || !cs.vary;   // Maths.var == 0 <=> all elements equal (:430-441)
+        if (!degenerate) cs.centred(o_xx, o_yy, o_xy);
+        else if (a.jitter_mode == PCTSEA_JITTER_PHILOX) {
+            const int slot = atomicAdd(a.fix_count, 1);
+            a.fix_list[slot] = make_int2((int)cell, (cs.varx ? 0 : 1) | (cs.vary ? 0 : 2));
+        }
+    }
+    double* o = a.sums + 3 * (size_t)cell;
+    o[0] = o_xx; o[1] = o_yy; o[2] = o_xy;
+    a.nused[cell] = cs.n;
+    a.nnzc[cell] = nz;
+    a.kept[cell] = keep ? 1 : 0;
+}
+
+// Zero-variance cells (rare): one warp per listed cell re-walks the list's genes, the lane holding a pair adds
+// the Philox jitter of its pair index to the constant vector(s), and the pairs are folded in gene order.
+__global__ void __launch_bounds__(256) k_score_gm_jitter(const GmArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_fix = *a.fix_count;
+    const unsigned below = (1u << lane) - 1u;
+    for (int i = w; i < n_fix; i += gridDim.x * (blockDim.x >> 5)) {
+        const int2 f = a.fix_list[i];
+        const int64_t cell = f.x, grp = cell >> 5;
+        const int cl = (int)(cell & 31);
+        const bool eq_list = (f.y & 1) != 0, eq_cell = (f.y & 2) != 0;
+        const float* gv = a.gval + a.row_ptr[grp * 32];
+        const uint2* mo_row = a.mo + grp * (int64_t)a.G;
+        CellSums cs;
+        int kbase = 0;
+        for (int j0 = 0; j0 < a.Ls; j0 += 32) {
+            const int j = j0 + lane;
+            bool has = false;
+            double x = 0.0, y = 0.0;
+            if (j < a.Ls) {
+                const float ab = a.gs_ab[j];
+                const uint2 mo = mo_row[a.gs_gene[j]];
+                if ((mo.x >> cl) & 1u) {
+                    const float e = gv[mo.y + __popc(mo.x & ((1u << cl) - 1u))];
+                    if (ab > 0.0f && e > 0.0f) { has = true; x = (double)ab; y = (double)e; }
+                }
+            }
+            unsigned bal = __ballot_sync(FULL, has);
+            if (has) {
+                const uint32_t k = (uint32_t)(kbase + __popc(bal & below));
+                if (eq_cell) y = __dadd_rn(y, gm_jitter(a.seed, (uint64_t)cell, 0u, k));
+                if (eq_list) x = __dadd_rn(x, gm_jitter(a.seed, (uint64_t)cell, 1u, k));
+            }
+            kbase += __popc(bal);
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1u;
+                cs.add(__shfl_sync(FULL, x, l), __shfl_sync(FULL, y, l));
+            }
+        }
+        if (lane == 0) {
+            double* o = a.sums + 3 * (size_t)cell;
+            cs.centred(o[0], o[1], o[2]);
+        }
+    }
+}
+
+}  // namespace
+
+void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
+    if (m->gm_mo) return;
+    const int64_t N = m->n_cells;
+    const int32_t G = m->n_genes;
+    PCT_REQUIRE(N >= 1 && G >= 1, "empty matrix");
+    const size_t smem = (size_t)G * 4;
+    if (smem > 200 * 1024) throw Error(PCTSEA_EINVAL, "gene index: more than 51200 genes are not supported by the build kernel");
+    const int64_t n_groups = div_up(N, 32);
+    PCT_REQUIRE(n_groups < ((int64_t)1 << 31), "too many cells");
+    uint2* mo = nullptr;
+    float* gval = nullptr;
+    const size_t mo_bytes = (size_t)n_groups * (size_t)G * sizeof(uint2);
+    cudaError_t e = cudaMalloc((void**)&mo, mo_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&gval, std::max<size_t>((size_t)m->nnz * 4, 16));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (mo) cudaFree(mo);
+        throw Error(PCTSEA_ENOMEM, "gene index: cudaMalloc of " + std::to_string(mo_bytes + (size_t)m->nnz * 4) + " bytes failed");
+    }
+    PCT_CUDA(cudaFuncSetAttribute(k_gm_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gm_build<<<(unsigned)n_groups, 256, smem, c->stream>>>(m->row_ptr, m->col, m->val, N, G, mo, gval);
+    count_launch(c);
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) le = cudaStreamSynchronize(c->stream);
+    if (le != cudaSuccess) {
+        cudaFree(mo); cudaFree(gval);
+        throw Error(PCTSEA_ECUDA, std::string("gene index build failed: ") + cudaGetErrorString(le));
+    }
+    m->gm_mo = mo;
+    m->gm_val = gval;
+    m->n_groups = n_groups;
+}
+
+// Stage 1 over the gene-major copy. List tables (ybg, bitmap) as in launch_score; then the sorted list, the
+// scoring kernel, the jitter fix-up and the shared k_score_final.
+void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
+    const pctsea_matrix* m = sa.m;
+    const int64_t N = m->n_cells;
+    const int32_t G = m->n_genes;
+    const int32_t bm_words = (G + 1 + 15) / 16;
+    c->ybg.reserve((size_t)G * 4 + 16);
+    c->bitmap.reserve((size_t)bm_words * 4 + 16);
+    c->list_rank.reserve((size_t)std::max(sa.L, 1) * 8 + 64);
+    c->score.reserve((size_t)N * 8 + 16);
+    c->score_sums.reserve((size_t)N * 24 + 16);
+    c->nused.reserve((size_t)N * 4 + 16);
+    c->nnzc.reserve((size_t)N * 4 + 16);
+    c->kept.reserve((size_t)N + 16);
+    c->gm_fix.reserve((size_t)N * 8 + 128);   // [0] sorted list length, [1] cells to fix up; the cell list from byte 64
+    PCT_CUDA(cudaMemsetAsync(c->ybg.p, 0, (size_t)G * 4, c->stream));
+    PCT_CUDA(cudaMemsetAsync(c->bitmap.p, 0, (size_t)bm_words * 4, c->stream));
+    PCT_CUDA(cudaMemsetAsync(c->gm_fix.p, 0, 64, c->stream));
+    int32_t* gs_gene = c->list_rank.as<int32_t>();
+    float* gs_ab = c->list_rank.as<float>() + std::max(sa.L, 1);
+    int* counters = c->gm_fix.as<int>();
+    if (sa.L > 0) {
+        launch_list_lookup(c, sa);
+        k_gm_sorted_list<<<1, 1024, 0, c->stream>>>(c->bitmap.as<uint32_t>(), c->ybg.as<float>(), G, gs_gene, gs_ab, counters);
+        count_launch(c);
+    }
+    GmArgs a;
+    a.mo = m->gm_mo; a.gval = m->gm_val; a.row_ptr = m->row_ptr; a.N = N; a.n_groups = m->n_groups; a.G = G;
+    a.gs_gene = gs_gene; a.gs_ab = gs_ab; a.Ls = c->list_mapped;
+    a.min_genes = sa.prm.min_genes_cells; a.jitter_mode = sa.prm.jitter_mode; a.seed = sa.prm.seed;
+    a.sums = c->score_sums.as<double>(); a.nused = c->nused.as<int32_t>(); a.nnzc = c->nnzc.as<int32_t>();
+    a.kept = c->kept.as<uint8_t>();
+    a.fix_list = c->gm_fix.as<int2>() + 8; a.fix_count = counters + 1;
+    const unsigned grid = (unsigned)div_up(m->n_groups, 8);
+    if (m->all_positive) k_score_gm<true><<<grid, 256, 0, c->stream>>>(a);
+    else k_score_gm<false><<<grid, 256, 0, c->stream>>>(a);
+    count_launch(c);
+    PCT_CUDA(cudaGetLastError());
+    if (sa.prm.jitter_mode == PCTSEA_JITTER_PHILOX) {
+        k_score_gm_jitter<<<kNumSMs * 2, 256, 0, c->stream>>>(a);
+        count_launch(c);
+        PCT_CUDA(cudaGetLastError());
+    }
+    launch_score_final(c, sa);
+}
+
+}  // namespace pctsea

@@ -759,3 +759,118 @@ def test_analyze_batch_equals_single_analyses(ctx, oracle, small):
     empty = ctx.analyze_batch(m, [], sprm, 0.0, cfg.n_types, nprm)
     assert empty["results"].shape == (0, cfg.n_types)
     m.free()
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 1 over the gene-major copy (pctsea_matrix_build_gene_index): lane-per-cell kernel, pair order = ascending
+# gene, shifted-data sums; bit-exact against the oracle's canonical form 2
+# ---------------------------------------------------------------------------------------------------
+def _check_gm(ctx, oracle, row_ptr, col, val, G, gene_idx, abundance, what, **kw):
+    m = ctx.load_csr(row_ptr, col, val, G).build_gene_index()
+    g = ctx.score(m, gene_idx, abundance, **kw)
+    o = oracle.score(row_ptr, col, val, G, gene_idx, abundance, canonical=2, **kw)
+    assert np.array_equal(g[1], o[1]), f"{what}: n_genes_used"
+    assert np.array_equal(g[2], o[2]), f"{what}: n_nonzero"
+    assert np.array_equal(g[3], o[3]), f"{what}: kept"
+    assert_bits_equal_f64(g[0], o[0], f"{what}: score")
+    m.free()
+    return g
+
+
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("jitter", [0, 1])
+def test_score_gene_major_bit_exact(ctx, oracle, tiny, method, jitter):
+    d = tiny
+    kw = dict(method=method, min_genes_cells=4, min_corr=0.2 if method == 0 else -1.0, has_min_corr=True,
+              jitter_mode=jitter, seed=1234)
+    g = _check_gm(ctx, oracle, d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes, d["gene_idx"], d["abundance"],
+                  "tiny", **kw)
+    # <= 1e-9 relative against the reference-faithful sequential SimpleRegression update on every cell whose
+    # vectors are not constant (those get jitter: noise of relative condition ~1e7, see test_score_bit_exact)
+    f = oracle.score(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes, d["gene_idx"], d["abundance"],
+                     canonical=False, **kw)
+    assert np.array_equal(np.isnan(f[0]), np.isnan(g[0])), "NaN pattern vs sequential oracle"
+    nj = oracle.score(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes, d["gene_idx"], d["abundance"],
+                      canonical=False, method=0, min_genes_cells=4, min_corr=-1.0, jitter_mode=0, seed=1234)
+    zero_var = (nj[3] == 1) & (nj[1] >= 2) & np.isnan(nj[0])
+    ok = ~np.isnan(f[0])
+    regular = ok & ~zero_var
+    assert regular.sum() > 100
+    assert np.all(np.abs(g[0][regular] - f[0][regular]) <= 1e-9 * np.maximum(1.0, np.abs(f[0][regular])))
+    assert np.all(np.abs(g[0][ok] - f[0][ok]) <= 1e-7)
+    # and the CSR-scan kernel on the same matrix agrees to the same bar (PCTSEA_SCORE_PATH=csr is read per call)
+    m = ctx.load_csr(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes)
+    c = ctx.score(m, d["gene_idx"], d["abundance"], **kw)
+    assert np.array_equal(c[1], g[1]) and np.array_equal(c[2], g[2]) and np.array_equal(c[3], g[3])
+    assert np.all(np.abs(g[0][regular] - c[0][regular]) <= 1e-9 * np.maximum(1.0, np.abs(c[0][regular])))
+    m.free()
+
+
+def test_score_gene_major_edge_cases(ctx, oracle):
+    G = 50
+    rows = [
+        [],                                                        # empty cell
+        [(1, 1.0), (2, 1.0), (3, 1.0), (4, 1.0)],                 # zero variance in the cell
+        [(9, 3.0), (1, 2.0), (4, 7.0), (2, 5.0), (3, 1.0)],       # regular, row stored out of gene order
+        [(1, float("nan")), (2, 5.0), (3, 0.0), (4, -2.0), (5, 1.0), (6, 2.0), (7, 9.0)],
+        [(1, 3.0), (2, 1.0)],                                      # fewer than min_genes pairs
+        [(10, 4.0), (11, 4.0), (12, 2.0), (13, 8.0)],             # list genes 10..13 share one abundance
+        [(40, 1.0), (41, 2.0)],                                    # no list gene at all
+        [(10, 5.0), (11, 5.0), (12, 5.0)],                        # both vectors constant
+    ] + [[(1, 2.0), (2, float(i % 5 + 1)), (3, 1.0), (9, float(i % 3 + 1))] for i in range(70)]   # > 2 groups of 32
+    row_ptr = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64)
+    col = np.array([c for r in rows for c, _ in r], np.int32)
+    val = np.array([v for r in rows for _, v in r], np.float32)
+    gene_idx = np.array([1, 2, 3, 4, 5, 6, 7, 9, -1, 10, 11, 12, 13, 20], np.int32)
+    abundance = np.array([3, 1, 4, 1.5, 9, 2, 6, 5, 7, 2, 2, 2, 2, 0.0], np.float32)
+    for method in (0, 1):
+        for jitter in (0, 1):
+            kw = dict(method=method, min_genes_cells=3, min_corr=-1.0, has_min_corr=True, jitter_mode=jitter, seed=7)
+            _check_gm(ctx, oracle, row_ptr, col, val, G, gene_idx, abundance, f"edge m{method} j{jitter}", **kw)
+    # a matrix with more genes than the build kernel's shared-memory mask row holds is refused, not mis-scored
+    big = ctx.load_csr(np.array([0, 1], np.int64), np.array([5], np.int32), np.ones(1, np.float32), 60_000)
+    with pytest.raises(P.PctseaError) as e:
+        big.build_gene_index()
+    assert e.value.code == -1
+    big.free()
+
+
+@pytest.mark.parametrize("G,L,unsorted_rows,N", [(6_000, 5_000, True, 1500), (40_000, 64, False, 1501),
+                                                 (3_000, 33, True, 31), (2_000, 600, False, 701)])
+def test_score_gene_major_shapes(ctx, oracle, G, L, unsorted_rows, N):
+    rng = np.random.default_rng(G + L)
+    row_ptr, col, val = _random_csr(rng, N, G, 700 if G >= 6000 else 300, unsorted_rows)
+    val[rng.integers(0, val.size, 20)] = 0.0          # explicit zeros: not expressed
+    val[rng.integers(0, val.size, 5)] = np.nan        # NaN: expressed, never a pair
+    present = np.unique(col)
+    gene_idx = rng.permutation(present)[:L].astype(np.int32) if present.size >= L else rng.permutation(G)[:L].astype(np.int32)
+    gene_idx[rng.integers(0, L, 3)] = -1
+    abundance = rng.integers(0, 40, L).astype(np.float32)
+    for method, jitter in ((0, 1), (1, 0)):
+        kw = dict(method=method, min_genes_cells=3, min_corr=-1.0, has_min_corr=True, jitter_mode=jitter, seed=99)
+        g = _check_gm(ctx, oracle, row_ptr, col, val, G, gene_idx, abundance, f"G{G} L{L}", **kw)
+        assert np.isfinite(g[0]).sum() > 5
+
+
+def test_analyze_with_gene_index_vs_oracle(ctx, oracle, small):
+    d = small
+    cfg = d["cfg"]
+    m = _load(ctx, d).build_gene_index()
+    sprm = P.ScoreParams(0, 4, 0.2, 1, P.JITTER_PHILOX, 77)
+    Pn = 12
+    nprm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=123, min_pass=100)
+    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, 0.0, cfg.n_types, nprm, want_null=True,
+                      want_scores=True, want_order=True)
+    sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["gene_idx"], d["abundance"],
+                                      method=0, min_genes_cells=4, min_corr=0.2, jitter_mode=1, seed=77, canonical=2)
+    assert_bits_equal_f64(out["score"], sc, "score")
+    assert np.array_equal(out["n_genes_used"], used) and np.array_equal(out["kept"], kept)
+    order, npass = oracle.rank(sc, kept, 0.0)
+    assert out["n_pass"] == npass and np.array_equal(out["order"], order)
+    nu = npass - 1
+    s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
+    one, _ = oracle.null(s_r, lab_r, cfg.n_types, Pn, perm_mode=1, seed=123)
+    ores = oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), one)
+    assert_bits_equal_f32(out["null"], one, "null")
+    assert_results_equal(out["results"], ores, None, "analyze (gene index)")
+    m.free()
