@@ -515,6 +515,8 @@ int pctsea_matrix_free(pctsea_ctx* c, pctsea_matrix* m) {
     if (m->label) cudaFree(m->label);
     if (m->gm_mo) cudaFree(m->gm_mo);
     if (m->gm_val) cudaFree(m->gm_val);
+    if (m->gm_slot_cell) cudaFree(m->gm_slot_cell);
+    if (m->gm_base) cudaFree(m->gm_base);
     delete m;
     return PCTSEA_OK;
 }

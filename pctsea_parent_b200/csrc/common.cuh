@@ -87,6 +87,8 @@ struct pctsea_matrix {
     // gene-major copy for the lane-per-cell scoring kernel (score_gm.cu), built on request, owned
     uint2* gm_mo = nullptr;    // [n_groups][n_genes] {cell mask of the gene in the group, offset of its values}
     float* gm_val = nullptr;   // [nnz] values in (group, gene, cell) order
+    int32_t* gm_slot_cell = nullptr;   // [n_groups * 32] cell of every (group, lane) slot, -1 = empty
+    int64_t* gm_base = nullptr;        // [n_groups + 1] first value of each group in gm_val
     int64_t n_groups = 0;      // groups of 32 cells
     int32_t n_types = 0;
 };

@@ -26,6 +26,8 @@
 // (config B: 0.15 GB + ~0.45 GB in 32-byte sectors), not the CSR: it is latency/issue bound, not HBM bound.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace pctsea {
 
 namespace {
@@ -34,16 +36,20 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // ---- build: one CTA per group of 32 cells ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                                                  const float* __restrict__ val, int64_t N, int32_t G,
+                                                  const float* __restrict__ val, const int32_t* __restrict__ slot_cell,
+                                                  const int64_t* __restrict__ grp_base, int32_t G,
                                                   uint2* __restrict__ mo, float* __restrict__ gval) {
     extern __shared__ unsigned s_mask[];   // [G]
     __shared__ int s_part[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int64_t grp = blockIdx.x, c0 = grp * 32;
+    const int64_t grp = blockIdx.x;
+    const int32_t* cells = slot_cell + grp * 32;   // the group's cells (-1 = empty slot)
     for (int g = tid; g < G; g += blockDim.x) s_mask[g] = 0u;
     __syncthreads();
-    for (int ci = warp; ci < 32 && c0 + ci < N; ci += nwarps) {
-        const int64_t b = row_ptr[c0 + ci], e = row_ptr[c0 + ci + 1];
+    for (int ci = warp; ci < 32; ci += nwarps) {
+        const int32_t cl = cells[ci];
+        if (cl < 0) continue;
+        const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
         for (int64_t k = b + lane; k < e; k += 32) atomicOr(&s_mask[col[k]], 1u << ci);
     }
     __syncthreads();
@@ -68,9 +74,11 @@ __global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ ro
         run += __popc(m);
     }
     __syncthreads();   // the CTA's own global writes are visible to all of its threads from here
-    const int64_t base = row_ptr[c0];
-    for (int ci = warp; ci < 32 && c0 + ci < N; ci += nwarps) {
-        const int64_t b = row_ptr[c0 + ci], e = row_ptr[c0 + ci + 1];
+    const int64_t base = grp_base[grp];
+    for (int ci = warp; ci < 32; ci += nwarps) {
+        const int32_t cl = cells[ci];
+        if (cl < 0) continue;
+        const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
         const unsigned below = (1u << ci) - 1u;
         for (int64_t k = b + lane; k < e; k += 32) {
             const uint2 x = row[col[k]];
@@ -122,7 +130,8 @@ __global__ void k_gm_sorted_list(const uint32_t* __restrict__ bitmap, const floa
 struct GmArgs {
     const uint2* mo;
     const float* gval;
-    const int64_t* row_ptr;
+    const int32_t* slot_cell;   // [n_groups * 32] cell of every (group, lane) slot, -1 = empty
+    const int64_t* grp_base;    // [n_groups] first value of the group in gval
     int64_t N, n_groups;
     int32_t G;
     const int32_t* gs_gene;
@@ -134,7 +143,7 @@ struct GmArgs {
     int32_t* nused;
     int32_t* nnzc;
     uint8_t* kept;
-    int2* fix_list;   // cells whose pairs have zero variance (jitter mode PHILOX): {cell, bit 0 = list vector constant, bit 1 = cell vector constant}
+    int2* fix_list;   // slots whose pairs have zero variance (jitter mode PHILOX): {slot, bit 0 = list vector constant, bit 1 = cell vector constant}
     int* fix_count;
 };
 
@@ -196,8 +205,8 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (grp >= a.n_groups) return;
-    const int64_t cell = grp * 32 + lane;
-    const float* gv = a.gval + a.row_ptr[grp * 32];
+    const int64_t cell = a.slot_cell[grp * 32 + lane];
+    const float* gv = a.gval + a.grp_base[grp];
     const uint2* mo_row = a.mo + grp * (int64_t)a.G;
     const unsigned below = (1u << lane) - 1u;
     CellSums cs;
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
             }
         }
     }
-    if (cell >= a.N) return;
+    if (cell < 0) return;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const bool keep = (nz > 0) && (cs.n >= a.min_genes);
     double o_xx = qnan, o_yy = qnan, o_xy = qnan;
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
         if (!degenerate) cs.centred(o_xx, o_yy, o_xy);
         else if (a.jitter_mode == PCTSEA_JITTER_PHILOX) {
             const int slot = atomicAdd(a.fix_count, 1);
-            a.fix_list[slot] = make_int2((int)cell, (cs.varx ? 0 : 1) | (cs.vary ? 0 : 2));
+            a.fix_list[slot] = make_int2((int)(grp * 32 + lane), (cs.varx ? 0 : 1) | (cs.vary ? 0 : 2));
         }
     }
     double* o = a.sums + 3 * (size_t)cell;
@@ -272,10 +281,10 @@ __global__ void __launch_bounds__(256) k_score_gm_jitter(const GmArgs a) {
     const unsigned below = (1u << lane) - 1u;
     for (int i = w; i < n_fix; i += gridDim.x * (blockDim.x >> 5)) {
         const int2 f = a.fix_list[i];
-        const int64_t cell = f.x, grp = cell >> 5;
-        const int cl = (int)(cell & 31);
+        const int64_t grp = f.x >> 5, cell = a.slot_cell[f.x];
+        const int cl = f.x & 31;
         const bool eq_list = (f.y & 1) != 0, eq_cell = (f.y & 2) != 0;
-        const float* gv = a.gval + a.row_ptr[grp * 32];
+        const float* gv = a.gval + a.grp_base[grp];
         const uint2* mo_row = a.mo + grp * (int64_t)a.G;
         CellSums cs;
         int kbase = 0;
@@ -313,6 +322,10 @@ __global__ void __launch_bounds__(256) k_score_gm_jitter(const GmArgs a) {
 
 }  // namespace
 
+// Which cells share a group is free (cells are independent), and it matters: a chunk of the list costs a group as
+// many steps as its busiest cell has genes in it. Cells are therefore grouped by cell type (cells of a type have
+// similar expression profiles; unknown types first) and, inside a type, by their number of non-zeros. The order is a
+// layout decision only: every result is written to the cell's own index.
 void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
     if (m->gm_mo) return;
     const int64_t N = m->n_cells;
@@ -321,28 +334,62 @@ void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
     const size_t smem = (size_t)G * 4;
     if (smem > 200 * 1024) throw Error(PCTSEA_EINVAL, "gene index: more than 51200 genes are not supported by the build kernel");
     const int64_t n_groups = div_up(N, 32);
-    PCT_REQUIRE(n_groups < ((int64_t)1 << 31), "too many cells");
+    PCT_REQUIRE(N < ((int64_t)1 << 31), "too many cells");
+    std::vector<int64_t> rp((size_t)N + 1);
+    std::vector<int32_t> lab;
+    PCT_CUDA(cudaMemcpyAsync(rp.data(), m->row_ptr, ((size_t)N + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (m->label) {
+        lab.resize((size_t)N);
+        PCT_CUDA(cudaMemcpyAsync(lab.data(), m->label, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    PCT_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<int32_t> slot((size_t)n_groups * 32, -1);
+    for (int64_t i = 0; i < N; i++) slot[(size_t)i] = (int32_t)i;
+    std::stable_sort(slot.begin(), slot.begin() + N, [&](int32_t x, int32_t y) {
+        if (!lab.empty() && lab[x] != lab[y]) return lab[x] < lab[y];
+        return rp[(size_t)x + 1] - rp[x] < rp[(size_t)y + 1] - rp[y];
+    });
+    std::vector<int64_t> base((size_t)n_groups + 1, 0);
+    for (int64_t g = 0; g < n_groups; g++) {
+        int64_t cnt = 0;
+        for (int l = 0; l < 32; l++) {
+            const int32_t cl = slot[(size_t)g * 32 + l];
+            if (cl >= 0) cnt += rp[(size_t)cl + 1] - rp[cl];
+        }
+        base[(size_t)g + 1] = base[(size_t)g] + cnt;
+    }
     uint2* mo = nullptr;
     float* gval = nullptr;
+    int32_t* slot_dev = nullptr;
+    int64_t* base_dev = nullptr;
     const size_t mo_bytes = (size_t)n_groups * (size_t)G * sizeof(uint2);
+    auto release = [&]() { if (mo) cudaFree(mo); if (gval) cudaFree(gval); if (slot_dev) cudaFree(slot_dev); if (base_dev) cudaFree(base_dev); };
     cudaError_t e = cudaMalloc((void**)&mo, mo_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&gval, std::max<size_t>((size_t)m->nnz * 4, 16));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&slot_dev, slot.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&base_dev, base.size() * 8);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        if (mo) cudaFree(mo);
+        release();
         throw Error(PCTSEA_ENOMEM, "gene index: cudaMalloc of " + std::to_string(mo_bytes + (size_t)m->nnz * 4) + " bytes failed");
     }
-    PCT_CUDA(cudaFuncSetAttribute(k_gm_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gm_build<<<(unsigned)n_groups, 256, smem, c->stream>>>(m->row_ptr, m->col, m->val, N, G, mo, gval);
-    count_launch(c);
-    cudaError_t le = cudaGetLastError();
-    if (le == cudaSuccess) le = cudaStreamSynchronize(c->stream);
+    cudaError_t le = cudaMemcpyAsync(slot_dev, slot.data(), slot.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (le == cudaSuccess) le = cudaMemcpyAsync(base_dev, base.data(), base.size() * 8, cudaMemcpyHostToDevice, c->stream);
+    if (le == cudaSuccess) le = cudaFuncSetAttribute(k_gm_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (le == cudaSuccess) {
+        k_gm_build<<<(unsigned)n_groups, 256, smem, c->stream>>>(m->row_ptr, m->col, m->val, slot_dev, base_dev, G, mo, gval);
+        count_launch(c);
+        le = cudaGetLastError();
+    }
+    if (le == cudaSuccess) le = cudaStreamSynchronize(c->stream);   // the host vectors above are the copy sources
     if (le != cudaSuccess) {
-        cudaFree(mo); cudaFree(gval);
+        release();
         throw Error(PCTSEA_ECUDA, std::string("gene index build failed: ") + cudaGetErrorString(le));
     }
     m->gm_mo = mo;
     m->gm_val = gval;
+    m->gm_slot_cell = slot_dev;
+    m->gm_base = base_dev;
     m->n_groups = n_groups;
 }
 
@@ -374,7 +421,8 @@ void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
         count_launch(c);
     }
     GmArgs a;
-    a.mo = m->gm_mo; a.gval = m->gm_val; a.row_ptr = m->row_ptr; a.N = N; a.n_groups = m->n_groups; a.G = G;
+    a.mo = m->gm_mo; a.gval = m->gm_val; a.slot_cell = m->gm_slot_cell; a.grp_base = m->gm_base; a.N = N;
+    a.n_groups = m->n_groups; a.G = G;
     a.gs_gene = gs_gene; a.gs_ab = gs_ab; a.Ls = c->list_mapped;
     a.min_genes = sa.prm.min_genes_cells; a.jitter_mode = sa.prm.jitter_mode; a.seed = sa.prm.seed;
     a.sums = c->score_sums.as<double>(); a.nused = c->nused.as<int32_t>(); a.nnzc = c->nnzc.as<int32_t>();
