@@ -298,7 +298,7 @@ class SingleCellDataset:
     device-resident CSR: rows = cells in DB order, columns = upper-cased gene names."""
 
     def __init__(self, ctx: Context, row_ptr, col, val, gene_names: Sequence[str], cell_types: Sequence[str],
-                 cell_names: Optional[Sequence[str]] = None):
+                 cell_names: Optional[Sequence[str]] = None, gene_major: bool = False):
         self.ctx = ctx
         self.gene_names = [g.upper() for g in gene_names]
         self.gene_index: Dict[str, int] = {g: i for i, g in enumerate(self.gene_names)}
@@ -309,9 +309,12 @@ class SingleCellDataset:
         self.label = np.asarray([tid.get(t, -1) if t else -1 for t in cell_types], dtype=np.int32)
         self.matrix = ctx.load_csr(row_ptr, col, val, len(self.gene_names))
         self.matrix.set_labels(self.label, len(self.type_names))
+        if gene_major:   # once per dataset: the scoring stage then reads only the list's genes (score_gm.cu)
+            self.matrix.build_gene_index()
 
     @classmethod
-    def from_arrays(cls, ctx: Context, row_ptr, col, val, n_genes: int, label: np.ndarray, n_types: int):
+    def from_arrays(cls, ctx: Context, row_ptr, col, val, n_genes: int, label: np.ndarray, n_types: int,
+                    gene_major: bool = False):
         self = cls.__new__(cls)
         self.ctx = ctx
         self.gene_names = [f"G{i}" for i in range(n_genes)]
@@ -321,6 +324,8 @@ class SingleCellDataset:
         self.label = np.asarray(label, dtype=np.int32)
         self.matrix = ctx.load_csr(row_ptr, col, val, n_genes)
         self.matrix.set_labels(self.label, n_types)
+        if gene_major:
+            self.matrix.build_gene_index()
         return self
 
     def map_list(self, genes: Sequence[str]) -> np.ndarray:

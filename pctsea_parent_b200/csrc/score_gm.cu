@@ -27,6 +27,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace pctsea {
 
@@ -200,13 +201,16 @@ __device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
 // from the lane that fetched it, by a variable-source shuffle). A chunk costs as many steps as its busiest cell
 // has genes (not 32), and the lanes of a step all do useful work as long as they have genes left. U steps are
 // fetched together so that several value loads of a lane are in flight.
-template <bool ALL_POSITIVE>
+template <bool ALL_POSITIVE, int U>
 __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (grp >= a.n_groups) return;
     const int64_t cell = a.slot_cell[grp * 32 + lane];
     const float* gv = a.gval + a.grp_base[grp];
+    // A group's entries are one contiguous row ([group][gene]): the 32 scattered loads of a chunk stay inside one
+    // 8 B * G region (one or two pages). The transposed layout ([gene][group], sectors shared by the groups of a
+    // CTA) was measured 10-35 % slower: every load of a chunk then lands on a different page.
     const uint2* mo_row = a.mo + grp * (int64_t)a.G;
     const unsigned below = (1u << lane) - 1u;
     CellSums cs;
@@ -228,7 +232,6 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
         const float ab = ab_n;
         fetch(j0 + 32, mo_n, ab_n);   // the next chunk's entries travel while this chunk is processed
         unsigned mine = warp_bit_transpose(mo.x, lane);   // bit k: my cell expresses the chunk's gene k
-        constexpr int U = 2;
         int iters = __reduce_max_sync(FULL, (unsigned)__popc(mine));
         for (; iters > 0; iters -= U) {   // warp-uniform trip count
             unsigned m[U]; float abk[U], e[U]; bool has[U];
@@ -349,6 +352,8 @@ void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
         if (!lab.empty() && lab[x] != lab[y]) return lab[x] < lab[y];
         return rp[(size_t)x + 1] - rp[x] < rp[(size_t)y + 1] - rp[y];
     });
+    // (Ordering the groups by decreasing size, so that the short ones fill the tail of the last wave, was measured
+    // 12 % slower: the long groups then all run at the same time.)
     std::vector<int64_t> base((size_t)n_groups + 1, 0);
     for (int64_t g = 0; g < n_groups; g++) {
         int64_t cnt = 0;
@@ -429,8 +434,13 @@ void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
     a.kept = c->kept.as<uint8_t>();
     a.fix_list = c->gm_fix.as<int2>() + 8; a.fix_count = counters + 1;
     const unsigned grid = (unsigned)div_up(m->n_groups, 8);
-    if (m->all_positive) k_score_gm<true><<<grid, 256, 0, c->stream>>>(a);
-    else k_score_gm<false><<<grid, 256, 0, c->stream>>>(a);
+    int unroll = 4;
+    if (const char* e = std::getenv("PCTSEA_GM_UNROLL")) unroll = std::atoi(e);   // tuning aid
+    if (m->all_positive) {
+        if (unroll >= 4) k_score_gm<true, 4><<<grid, 256, 0, c->stream>>>(a);
+        else if (unroll <= 1) k_score_gm<true, 1><<<grid, 256, 0, c->stream>>>(a);
+        else k_score_gm<true, 2><<<grid, 256, 0, c->stream>>>(a);
+    } else k_score_gm<false, 4><<<grid, 256, 0, c->stream>>>(a);
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
     if (sa.prm.jitter_mode == PCTSEA_JITTER_PHILOX) {

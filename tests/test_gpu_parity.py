@@ -394,10 +394,12 @@ def test_analyze_end_to_end_vs_oracle(ctx, oracle, small):
     m.free()
 
 
-def test_host_api_mirror(ctx, small, tmp_path):
+@pytest.mark.parametrize("gene_major", [False, True])
+def test_host_api_mirror(ctx, small, tmp_path, gene_major):
     d = small
     cfg = d["cfg"]
-    ds = P.SingleCellDataset.from_arrays(ctx, d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["label"], cfg.n_types)
+    ds = P.SingleCellDataset.from_arrays(ctx, d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["label"], cfg.n_types,
+                                         gene_major=gene_major)
     ip = P.InputParameters()
     ip.addScoringSchema(P.ScoringMethod.PEARSONS_CORRELATION, 0.0, 4)
     ip.setNumPermutations(20)
@@ -798,7 +800,7 @@ def test_score_gene_major_bit_exact(ctx, oracle, tiny, method, jitter):
     assert regular.sum() > 100
     assert np.all(np.abs(g[0][regular] - f[0][regular]) <= 1e-9 * np.maximum(1.0, np.abs(f[0][regular])))
     assert np.all(np.abs(g[0][ok] - f[0][ok]) <= 1e-7)
-    # and the CSR-scan kernel on the same matrix agrees to the same bar (PCTSEA_SCORE_PATH=csr is read per call)
+    # and the CSR-scan kernel (a matrix without the index) agrees to the same bar
     m = ctx.load_csr(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes)
     c = ctx.score(m, d["gene_idx"], d["abundance"], **kw)
     assert np.array_equal(c[1], g[1]) and np.array_equal(c[2], g[2]) and np.array_equal(c[3], g[3])
