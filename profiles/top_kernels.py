@@ -27,7 +27,7 @@ for r in rows[2:]:
             except ValueError: pass
     tot = sum(v for v, _ in stalls) or 1.0
     lines.append("  stall samples: " + "  ".join(f"{n}={100 * v / tot:.1f}%" for v, n in sorted(stalls, reverse=True)[:7]))
-    name = d["Kernel Name"].replace("void ", "").split("<")[0].split("(")[0].strip()
+    name = d["Kernel Name"].replace("void ", "").replace("<unnamed>::", "").replace("unnamed>::", "").split("<")[0].split("(")[0].strip().split("::")[-1]
     rd = float(d["dram__bytes_read.sum"].replace(",", "")) * SCALE[u["dram__bytes_read.sum"]]
     wr = float(d["dram__bytes_write.sum"].replace(",", "")) * SCALE[u["dram__bytes_write.sum"]]
     traffic[name] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr}
