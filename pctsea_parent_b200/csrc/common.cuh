@@ -120,6 +120,7 @@ struct pctsea_ctx {
     pctsea::DevBuf s_rank, lab_rank, fx, Sfx, class_cnt;        // ranked arrays [Nu]
     pctsea::DevBuf obs_chain, obs_misc, obs_tiles;                       // observed KS: accumulator history [Nu][Tpad]
     pctsea::DevBuf labels;                                      // [Pc][Nu_pad] permuted labels
+    pctsea::DevBuf lab_ticket;                                  // permutation ticket counter of the label kernel
     pctsea::DevBuf replay;                                      // [Pc][Nu] int32
     pctsea::DevBuf fxT;                                         // FAST mode: lane layout of the fixed-point scores
     pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
