@@ -171,8 +171,11 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     if (obs_overlap) PCT_CUDA(cudaEventRecord(c->ev_obs[0], c->stream));   // ranked arrays are ready
     else launch_ks_observed(c, g, c->stream);
     bool obs_queued = false;
+    const char* oa_env = std::getenv("PCTSEA_OBS_AFTER_LABELS");
+    const bool obs_after_labels = oa_env && oa_env[0] == '1';
+    cudaEvent_t labels_done = nullptr;
     auto queue_observed_aux = [&]() {
-        PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, c->ev_obs[0], 0));
+        PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, (obs_after_labels && labels_done) ? labels_done : c->ev_obs[0], 0));
         PCT_CUDA(cudaEventRecord(c->ev_obs[1], c->stream_aux));
         launch_ks_observed(c, g, c->stream_aux);
         PCT_CUDA(cudaEventRecord(c->ev_obs[2], c->stream_aux));
@@ -228,6 +231,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
             // so they cannot co-reside, and the sub-chunks only add partial waves.)
             launch_labels_philox(c, g, prm->seed, np.begin + p0, pc, np.rounds, fast, plan0, c->stream, 0);
             cudaEvent_t e1 = et.mark(c->stream);
+            labels_done = e1;
             if (obs_overlap && !obs_queued) queue_observed_aux();   // after the first label launch: the big kernel gets its SMs first
             if (fast) launch_ks_fast_null(c, g, pc, plan0, Pc_all, p0, 0);
             else launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);

@@ -132,6 +132,37 @@ def test_pearson_against_numpy_and_canonical(oracle):
     assert oracle.pearson([1.0, 2.0, 3.0], [6.0, 4.0, 2.0]) == -1.0
 
 
+def test_pearson_shifted_form_and_gene_order(oracle, tiny):
+    """The gene-major kernel's canonical form (orc_pearson_shifted, pairs in ascending gene order): close to the
+    reference-faithful sequential update also on badly centred data, and independent of the row storage order."""
+    rng = np.random.default_rng(3)
+    for n in (2, 3, 17, 500):
+        for _ in range(20):
+            x, y = rng.lognormal(2.0, 1.0, n).round() + 1, rng.geometric(0.45, n).astype(float)
+            if np.all(x == x[0]) or np.all(y == y[0]):
+                continue
+            r = oracle.pearson(x, y)
+            assert abs(r - oracle.pearson_shifted(x, y)) <= 1e-12 * max(1.0, abs(r))
+        x, y = 1e4 + rng.standard_normal(n), 50 + 0.1 * rng.standard_normal(n)   # mean >> spread
+        assert abs(oracle.pearson(x, y) - oracle.pearson_shifted(x, y)) <= 1e-9
+    assert oracle.pearson_shifted([1.0, 2.0, 3.0], [2.0, 4.0, 6.0]) == 1.0
+    assert math.isnan(oracle.pearson_shifted([1.0], [2.0]))
+    d = tiny
+    kw = dict(method=0, min_genes_cells=4, min_corr=-1.0, jitter_mode=1, seed=5)
+    base = oracle.score(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes, d["gene_idx"], d["abundance"], canonical=2, **kw)
+    # the same matrix with every row stored in reverse column order: form 2 does not care, form 1 (storage order) may
+    col, val = d["col"].copy(), d["val"].copy()
+    for i in range(d["row_ptr"].size - 1):
+        b, e = d["row_ptr"][i], d["row_ptr"][i + 1]
+        col[b:e], val[b:e] = col[b:e][::-1].copy(), val[b:e][::-1].copy()
+    rev = oracle.score(d["row_ptr"], col, val, d["cfg"].n_genes, d["gene_idx"], d["abundance"], canonical=2, **kw)
+    assert np.array_equal(base[0].view(np.uint64), rev[0].view(np.uint64))
+    seq = oracle.score(d["row_ptr"], d["col"], d["val"], d["cfg"].n_genes, d["gene_idx"], d["abundance"], canonical=False,
+                       method=0, min_genes_cells=4, min_corr=-1.0, jitter_mode=0, seed=5)
+    ok = ~np.isnan(seq[0])
+    assert ok.sum() > 100 and np.all(np.abs(base[0][ok] - seq[0][ok]) <= 1e-9 * np.maximum(1.0, np.abs(seq[0][ok])))
+
+
 def test_score_semantics(oracle):
     # cell 0: regular; cell 1: zero variance; cell 2: below min_genes; cell 3: no list gene; cell 4: NaN value
     rows = [[(1, 2.0), (2, 5.0), (3, 1.0), (4, 7.0)], [(1, 1.0), (2, 1.0), (3, 1.0), (4, 1.0)],
