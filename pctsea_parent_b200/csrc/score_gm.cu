@@ -152,7 +152,6 @@ struct GmArgs {
 struct CellSums {
     double x0 = 0.0, y0 = 0.0, sdx = 0.0, sdy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
     int n = 0;
-    bool varx = false, vary = false;
     __device__ __forceinline__ void add(double x, double y) {
         if (n == 0) { x0 = x; y0 = y; }
         const double dx = __dsub_rn(x, x0), dy = __dsub_rn(y, y0);
@@ -161,10 +160,13 @@ struct CellSums {
         sxx = __dadd_rn(sxx, __dmul_rn(dx, dx));
         syy = __dadd_rn(syy, __dmul_rn(dy, dy));
         sxy = __dadd_rn(sxy, __dmul_rn(dx, dy));
-        varx = varx || (dx != 0.0);
-        vary = vary || (dy != 0.0);
         n++;
     }
+    // "All elements equal" (Maths.var == 0, model/SingleCell.java:430-441) without a flag per pair: a sum of squares
+    // of deviations from the first element is zero iff every deviation is (x and y are floats widened to double,
+    // so a non-zero deviation is at least 2^-149 and its square cannot underflow).
+    __device__ __forceinline__ bool varx() const { return sxx != 0.0; }
+    __device__ __forceinline__ bool vary() const { return syy != 0.0; }
     // centred sums: Sxx = sum(dx^2) - sum(dx)^2 / n, ...
     __device__ __forceinline__ void centred(double& SXX, double& SYY, double& SXY) const {
         const double nn = (double)n;
@@ -244,14 +246,16 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
                 const unsigned off = __shfl_sync(FULL, mo.y, k);
                 abk[u] = __shfl_sync(FULL, ab, k);
                 e[u] = 0.0f;
-                if (has[u]) e[u] = __ldg(gv + off + __popc(m[u] & below));
+                if (has[u]) e[u] = __ldg(gv + (uint32_t)(off + __popc(m[u] & below)));   // a group holds < 2^32 values
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                if (has[u]) {
-                    if (ALL_POSITIVE || e[u] != 0.0f) nz++;                     // NaN counts (model/SingleCell.java:409)
-                    if (abk[u] > 0.0f && (ALL_POSITIVE || e[u] > 0.0f))         // :403
-                        cs.add((double)abk[u], (double)e[u]);
+                if (ALL_POSITIVE) {
+                    nz += has[u] ? 1 : 0;
+                    if (has[u] && abk[u] > 0.0f) cs.add((double)abk[u], (double)e[u]);   // model/SingleCell.java:403
+                } else if (has[u]) {
+                    if (e[u] != 0.0f) nz++;                                      // NaN counts (:409)
+                    if (abk[u] > 0.0f && e[u] > 0.0f) cs.add((double)abk[u], (double)e[u]);
                 }
             }
         }
@@ -261,11 +265,11 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
     const bool keep = (nz > 0) && (cs.n >= a.min_genes);
     double o_xx = qnan, o_yy = qnan, o_xy = qnan;
     if (keep && cs.n >= 2) {
-        const bool degenerate = !cs.varx || !cs.vary;   // Maths.var == 0 <=> all elements equal (:430-441)
+        const bool degenerate = !cs.varx() || !cs.vary();   // Maths.var == 0 <=> all elements equal (:430-441)
         if (!degenerate) cs.centred(o_xx, o_yy, o_xy);
         else if (a.jitter_mode == PCTSEA_JITTER_PHILOX) {
             const int slot = atomicAdd(a.fix_count, 1);
-            a.fix_list[slot] = make_int2((int)(grp * 32 + lane), (cs.varx ? 0 : 1) | (cs.vary ? 0 : 2));
+            a.fix_list[slot] = make_int2((int)(grp * 32 + lane), (cs.varx() ? 0 : 1) | (cs.vary() ? 0 : 2));
         }
     }
     double* o = a.sums + 3 * (size_t)cell;
