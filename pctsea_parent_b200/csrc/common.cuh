@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <utility>
+#include <mutex>
 #include <stdexcept>
 #include <cstdio>
 #include <cmath>
@@ -230,5 +232,31 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
                    pctsea_type_result* results_dev);
 
 inline void count_launch(pctsea_ctx* c, int n = 1) { c->launches += n; }
+
+// Opt a kernel in to `bytes` of dynamic shared memory, once per (device, kernel) and size: the attribute call
+// reaches the driver, and a warm analysis call should make no driver round-trips beyond its launches (DESIGN.md
+// "Host-side stalls"). The attribute belongs to the device function, not to a ctx, so the record is process-wide
+// (several ctxs may share a device) and the limit is only ever raised.
+struct SmemOptIn {
+    std::mutex mu;
+    std::vector<std::pair<std::pair<int, const void*>, size_t>> seen;
+};
+inline SmemOptIn& smem_opt_in() { static SmemOptIn s; return s; }
+
+template <typename K>
+inline void ensure_dyn_smem(pctsea_ctx* c, K kernel, size_t bytes) {
+    const std::pair<int, const void*> key{ c->device, reinterpret_cast<const void*>(kernel) };
+    SmemOptIn& r = smem_opt_in();
+    std::lock_guard<std::mutex> lock(r.mu);
+    for (auto& e : r.seen)
+        if (e.first == key) {
+            if (e.second >= bytes) return;
+            PCT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.second = bytes;
+            return;
+        }
+    PCT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    r.seen.push_back({ key, bytes });
+}
 
 }  // namespace pctsea

@@ -610,7 +610,7 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, div_up(N, kScoreCellBatch)));
 #define PCT_LAUNCH_SCORE2(B, W, AP)                                                                           \
     do {                                                                                                      \
-        PCT_CUDA(cudaFuncSetAttribute(k_score<B, W, 3, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ensure_dyn_smem(c, k_score<B, W, 3, AP>, (size_t)(smem)); \
         k_score<B, W, 3, AP><<<grid, warps * 32, smem, c->stream>>>(ka);                                      \
     } while (0)
 #define PCT_LAUNCH_SCORE(B, W)                                                                                \
