@@ -10,9 +10,10 @@
 // here lets the GPU fetch just those without a per-list rebuild:
 //
 //   cells are grouped by 32 (group = warp, lane = cell). For every (group, gene):
-//     mo[group][gene] = { mask: bit l set iff cell 32*group + l has a non-zero of this gene,
+//     mo(group, gene) = { mask: bit l set iff the group's cell l has a non-zero of this gene,
 //                         off : number of non-zeros of the group in lower-numbered genes }
-//   gval[row_ptr[32*group] + off + popc(mask & lanes below l)] = that cell's value: the group's non-zeros in
+//   stored in tiles of 8 groups, gene-major inside a tile (see gm_row_offset),
+//   gval[grp_base[group] + off + popc(mask & lanes below l)] = that cell's value: the group's non-zeros in
 //   (gene, cell) order. Size: 8 B * G * N/32 (config B 3.75 GB, D 15 GB) + 4 B * nnz.
 //
 // Scoring a list: one warp per group walks the list's genes in ascending gene order; per gene one 8-byte broadcast
@@ -34,6 +35,15 @@ namespace pctsea {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// Layout of the {mask, offset} entries: tiles of GM_TILE consecutive groups (= the warps of one scoring CTA), and
+// inside a tile gene-major: entry(group, gene) = mo[((group / GM_TILE) * G + gene) * GM_TILE + group % GM_TILE].
+// The eight entries of a gene for the eight groups of a CTA share one 64-byte line, and a CTA's whole tile is one
+// contiguous 64 B * G region.
+constexpr int GM_TILE = 8;
+__host__ __device__ __forceinline__ size_t gm_row_offset(int64_t grp, int32_t G) {
+    return (size_t)(grp / GM_TILE) * (size_t)G * GM_TILE + (size_t)(grp % GM_TILE);
+}
 
 // ---- build: one CTA per group of 32 cells ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
@@ -68,10 +78,10 @@ __global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ ro
         __syncthreads();
     }
     unsigned run = (unsigned)(s_part[tid] - sum);
-    uint2* row = mo + grp * (int64_t)G;
+    uint2* row = mo + gm_row_offset(grp, G);   // entry of gene g: row[g * GM_TILE]
     for (int g = g0; g < g1; g++) {
         const unsigned m = s_mask[g];
-        row[g] = make_uint2(m, run);
+        row[(size_t)g * GM_TILE] = make_uint2(m, run);
         run += __popc(m);
     }
     __syncthreads();   // the CTA's own global writes are visible to all of its threads from here
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ ro
         const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
         const unsigned below = (1u << ci) - 1u;
         for (int64_t k = b + lane; k < e; k += 32) {
-            const uint2 x = row[col[k]];
+            const uint2 x = row[(size_t)col[k] * GM_TILE];
             gval[base + x.y + __popc(x.x & below)] = val[k];
         }
     }
@@ -210,10 +220,9 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
     if (grp >= a.n_groups) return;
     const int64_t cell = a.slot_cell[grp * 32 + lane];
     const float* gv = a.gval + a.grp_base[grp];
-    // A group's entries are one contiguous row ([group][gene]): the 32 scattered loads of a chunk stay inside one
-    // 8 B * G region (one or two pages). The transposed layout ([gene][group], sectors shared by the groups of a
-    // CTA) was measured 10-35 % slower: every load of a chunk then lands on a different page.
-    const uint2* mo_row = a.mo + grp * (int64_t)a.G;
+    // (Fully gene-major entries, [gene][group], were measured 10-35 % slower: every load of a chunk then lands on a
+    // different page. The tiled layout keeps a CTA inside one contiguous region.)
+    const uint2* mo_row = a.mo + gm_row_offset(grp, a.G);
     const unsigned below = (1u << lane) - 1u;
     CellSums cs;
     int nz = 0;
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
         ab = 0.0f;
         if (j < a.Ls) {
             ab = __ldg(a.gs_ab + j);
-            mo = __ldg(mo_row + __ldg(a.gs_gene + j));
+            mo = __ldg(mo_row + (size_t)__ldg(a.gs_gene + j) * GM_TILE);
         }
     };
     uint2 mo_n; float ab_n;
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(256) k_score_gm_jitter(const GmArgs a) {
         const int cl = f.x & 31;
         const bool eq_list = (f.y & 1) != 0, eq_cell = (f.y & 2) != 0;
         const float* gv = a.gval + a.grp_base[grp];
-        const uint2* mo_row = a.mo + grp * (int64_t)a.G;
+        const uint2* mo_row = a.mo + gm_row_offset(grp, a.G);
         CellSums cs;
         int kbase = 0;
         for (int j0 = 0; j0 < a.Ls; j0 += 32) {
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(256) k_score_gm_jitter(const GmArgs a) {
             double x = 0.0, y = 0.0;
             if (j < a.Ls) {
                 const float ab = a.gs_ab[j];
-                const uint2 mo = mo_row[a.gs_gene[j]];
+                const uint2 mo = mo_row[(size_t)a.gs_gene[j] * GM_TILE];
                 if ((mo.x >> cl) & 1u) {
                     const float e = gv[mo.y + __popc(mo.x & ((1u << cl) - 1u))];
                     if (ab > 0.0f && e > 0.0f) { has = true; x = (double)ab; y = (double)e; }
@@ -371,7 +380,7 @@ void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
     float* gval = nullptr;
     int32_t* slot_dev = nullptr;
     int64_t* base_dev = nullptr;
-    const size_t mo_bytes = (size_t)n_groups * (size_t)G * sizeof(uint2);
+    const size_t mo_bytes = (size_t)round_up(n_groups, GM_TILE) * (size_t)G * sizeof(uint2);
     auto release = [&]() { if (mo) cudaFree(mo); if (gval) cudaFree(gval); if (slot_dev) cudaFree(slot_dev); if (base_dev) cudaFree(base_dev); };
     cudaError_t e = cudaMalloc((void**)&mo, mo_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&gval, std::max<size_t>((size_t)m->nnz * 4, 16));
