@@ -876,3 +876,49 @@ def test_analyze_with_gene_index_vs_oracle(ctx, oracle, small):
     assert_bits_equal_f32(out["null"], one, "null")
     assert_results_equal(out["results"], ores, None, "analyze (gene index)")
     m.free()
+
+
+@pytest.mark.parametrize("gene_major", [False, True])
+def test_baseline_config_A_end_to_end(ctx, oracle, gene_major):
+    """BASELINE configs[0] at full size — 20k cells x 20k genes, 40 cell types, 500-protein list, PEARSONS_CORRELATION,
+    -perm 50, min_genes_cells 4, min_corr 0.2 (the README example the reference runs on CPU) — through pctsea_analyze
+    with the reference's own guard of 1000 passing cells, against the oracle: scores, ranking, observed statistics,
+    the null in validation mode (REPLAY of the oracle's JDK Collections.shuffle indices, EXACT arithmetic), p-values,
+    normalised scores and FDR, all bit-exact; then the production mode (PHILOX permutations, FAST arithmetic) against
+    the oracle's restatement of the same definition. Both scoring kernels."""
+    cfg = synth.CONFIGS["A"]
+    d = synth.make_dataset(cfg, "cpu").numpy()
+    m = ctx.load_csr(d["row_ptr"], d["col"], d["val"], cfg.n_genes)
+    m.set_labels(d["label"], cfg.n_types)
+    if gene_major:
+        m.build_gene_index()
+    kw = dict(method=cfg.method, min_genes_cells=cfg.min_genes_cells, min_corr=cfg.min_corr, jitter_mode=1, seed=11)
+    sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, d["gene_idx"], d["abundance"],
+                                      canonical=2 if gene_major else 1, **kw)
+    order, npass = oracle.rank(sc, kept, cfg.min_score)
+    assert npass >= 1000
+    nu = npass - 1
+    s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
+    one, ond, replay = oracle.null(s_r, lab_r, cfg.n_types, cfg.n_perm, perm_mode=0, seed=2026, want_replay=True)
+    ores = oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), one)
+    sprm = P.ScoreParams(cfg.method, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 11)
+    nprm = ctx.null_params(cfg.n_perm, perm_mode=P.PERM_REPLAY, ks_mode=P.KS_EXACT, min_pass=1000)
+    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm, replay=replay,
+                      want_null=True, want_scores=True, want_order=True)
+    assert_bits_equal_f64(out["score"], sc, "score")
+    assert np.array_equal(out["n_genes_used"], used) and np.array_equal(out["kept"], kept)
+    assert out["n_pass"] == npass and np.array_equal(out["order"], order)
+    assert_bits_equal_f32(out["null"], one, "REPLAY null")
+    assert_bits_equal_f32(out["nullD"], ond, "REPLAY null dStat")
+    assert_results_equal(out["results"], ores, None, "config A")
+    assert np.isfinite(out["results"]["fdr"]).sum() >= 3 and (out["results"]["fdr"] <= 0.05).sum() >= 1   # planted types are found
+    # production mode
+    nprm = ctx.null_params(cfg.n_perm, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=7, min_pass=1000)
+    fast = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm, want_null=True)
+    F = oracle.fast_frac_bits(s_r)
+    exp = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(7, p, nu, 6)], cfg.n_types, F)
+                    for p in range(cfg.n_perm)], axis=1)
+    assert_bits_equal_f32(fast["null"], exp, "PHILOX FAST null")
+    assert_results_equal(fast["results"], oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), exp), None,
+                         "config A, production mode")
+    m.free()
