@@ -704,7 +704,24 @@ def test_stage3_random_shapes_sweep(ctx, oracle):
         assert_results_equal(res, ored, ("norm_ews", "p_emp", "fdr"), f"reduce n={n_used} T={T}")
 
 
-def test_analyze_batch_equals_single_analyses(ctx, oracle, small):
+def test_two_contexts_on_one_device(ctx, oracle):
+    """Several ctxs may share a device (one per PCTSEA instance of the web front-end's pool): interleaved calls with
+    different shapes — hence different dynamic shared-memory sizes of the same kernels — stay correct."""
+    other = P.Context(0)
+    try:
+        for (c, n_used, T) in ((ctx, 9000, 40), (other, 5000, 150), (ctx, 140_000, 20), (other, 9000, 40), (ctx, 5000, 150)):
+            s, lab, order = _ranked(n_used, T, seed=4)
+            prm = c.null_params(3, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=5)
+            res, ne, nd = c.enrich(s, order, lab, T, prm)
+            F = oracle.fast_frac_bits(s)
+            exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(5, 1, n_used, 6)], T, F)
+            assert_bits_equal_f32(ne[:, 1], exp, f"ctx {'A' if c is ctx else 'B'} Nu={n_used} T={T}")
+    finally:
+        other.close()
+
+
+@pytest.mark.parametrize("gene_major", [False, True])
+def test_analyze_batch_equals_single_analyses(ctx, oracle, small, gene_major):
     """BASELINE config E in miniature: many lists against one resident matrix. Every list's results are
     bit-identical to pctsea_analyze on that list alone; a list that fails the reference's own input checks fails
     alone; one list is checked end to end against the oracle."""
@@ -712,6 +729,8 @@ def test_analyze_batch_equals_single_analyses(ctx, oracle, small):
     cfg = d["cfg"]
     m = _load(ctx, d)
     m.set_labels(d["label"], cfg.n_types)
+    if gene_major:
+        m.build_gene_index()
     sprm = P.ScoreParams(0, 4, 0.2, 1, P.JITTER_PHILOX, 77)
     Pn = 24
     nprm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=9, min_pass=100)
@@ -746,7 +765,7 @@ def test_analyze_batch_equals_single_analyses(ctx, oracle, small):
     # list 3 against the oracle, end to end (FAST arithmetic on the Philox permutations)
     g, a = lists[3]
     sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, g, a, method=0, min_genes_cells=4,
-                                      min_corr=0.2, jitter_mode=1, seed=77)
+                                      min_corr=0.2, jitter_mode=1, seed=77, canonical=2 if gene_major else 1)
     order, npass = oracle.rank(sc, kept, 0.0)
     assert npass == out["n_pass"][3]
     nu = npass - 1
