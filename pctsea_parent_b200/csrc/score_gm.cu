@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace pctsea {
 
@@ -162,8 +163,10 @@ struct GmArgs {
 struct CellSums {
     double x0 = 0.0, y0 = 0.0, sdx = 0.0, sdy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
     int n = 0;
+    // FIRST_POSSIBLE = false: the caller knows that this cell already has its first pair (no pivot select)
+    template <bool FIRST_POSSIBLE = true>
     __device__ __forceinline__ void add(double x, double y) {
-        if (n == 0) { x0 = x; y0 = y; }
+        if (FIRST_POSSIBLE && n == 0) { x0 = x; y0 = y; }
         const double dx = __dsub_rn(x, x0), dy = __dsub_rn(y, y0);
         sdx = __dadd_rn(sdx, dx);
         sdy = __dadd_rn(sdy, dy);
@@ -238,10 +241,10 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
     };
     uint2 mo_n; float ab_n;
     fetch(0, mo_n, ab_n);
-    for (int j0 = 0; j0 < a.Ls; j0 += 32) {
-        const uint2 mo = mo_n;
-        const float ab = ab_n;
-        fetch(j0 + 32, mo_n, ab_n);   // the next chunk's entries travel while this chunk is processed
+    // One chunk of 32 list genes. `first_tag`: some cell of the group may still be waiting for its first pair (the
+    // pivot of its shifted sums); once every cell has one, the chunks run without the pivot select.
+    auto chunk = [&](auto first_tag, const uint2 mo, const float ab) {
+        constexpr bool FIRST = decltype(first_tag)::value;
         unsigned mine = warp_bit_transpose(mo.x, lane);   // bit k: my cell expresses the chunk's gene k
         int iters = __reduce_max_sync(FULL, (unsigned)__popc(mine));
         for (; iters > 0; iters -= U) {   // warp-uniform trip count
@@ -261,12 +264,23 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
             for (int u = 0; u < U; u++) {
                 if (ALL_POSITIVE) {
                     nz += has[u] ? 1 : 0;
-                    if (has[u] && abk[u] > 0.0f) cs.add((double)abk[u], (double)e[u]);   // model/SingleCell.java:403
+                    if (has[u] && abk[u] > 0.0f) cs.template add<FIRST>((double)abk[u], (double)e[u]);   // model/SingleCell.java:403
                 } else if (has[u]) {
                     if (e[u] != 0.0f) nz++;                                      // NaN counts (:409)
-                    if (abk[u] > 0.0f && e[u] > 0.0f) cs.add((double)abk[u], (double)e[u]);
+                    if (abk[u] > 0.0f && e[u] > 0.0f) cs.template add<FIRST>((double)abk[u], (double)e[u]);
                 }
             }
+        }
+    };
+    bool all_started = false;   // warp-uniform
+    for (int j0 = 0; j0 < a.Ls; j0 += 32) {
+        const uint2 mo = mo_n;
+        const float ab = ab_n;
+        fetch(j0 + 32, mo_n, ab_n);   // the next chunk's entries travel while this chunk is processed
+        if (all_started) chunk(std::false_type{}, mo, ab);
+        else {
+            chunk(std::true_type{}, mo, ab);
+            all_started = __all_sync(FULL, cs.n > 0 || cell < 0);
         }
     }
     if (cell < 0) return;
