@@ -164,7 +164,8 @@ struct CellSums {
     double x0 = 0.0, y0 = 0.0, sdx = 0.0, sdy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
     int n = 0;
     // FIRST_POSSIBLE = false: the caller knows that this cell already has its first pair (no pivot select)
-    template <bool FIRST_POSSIBLE = true>
+    // COUNT = false: the caller has already added this pair to n
+    template <bool FIRST_POSSIBLE = true, bool COUNT = true>
     __device__ __forceinline__ void add(double x, double y) {
         if (FIRST_POSSIBLE && n == 0) { x0 = x; y0 = y; }
         const double dx = __dsub_rn(x, x0), dy = __dsub_rn(y, y0);
@@ -173,7 +174,7 @@ struct CellSums {
         sxx = __dadd_rn(sxx, __dmul_rn(dx, dx));
         syy = __dadd_rn(syy, __dmul_rn(dy, dy));
         sxy = __dadd_rn(sxy, __dmul_rn(dx, dy));
-        n++;
+        if (COUNT) n++;
     }
     // "All elements equal" (Maths.var == 0, model/SingleCell.java:430-441) without a flag per pair: a sum of squares
     // of deviations from the first element is zero iff every deviation is (x and y are floats widened to double,
@@ -217,12 +218,13 @@ __device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
 // has genes (not 32), and the lanes of a step all do useful work as long as they have genes left. U steps are
 // fetched together so that several value loads of a lane are in flight.
 template <bool ALL_POSITIVE, int U>
-__global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
+__global__ void __launch_bounds__(256, 4) k_score_gm(const GmArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (grp >= a.n_groups) return;
     const int64_t cell = a.slot_cell[grp * 32 + lane];
     const float* gv = a.gval + a.grp_base[grp];
+    asm volatile("" : "+l"(gv));   // one pointer for the group's values: a value address is then base + 32-bit index
     // (Fully gene-major entries, [gene][group], were measured 10-35 % slower: every load of a chunk then lands on a
     // different page. The tiled layout keeps a CTA inside one contiguous region.)
     const uint2* mo_row = a.mo + gm_row_offset(grp, a.G);
@@ -246,6 +248,13 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
     auto chunk = [&](auto first_tag, const uint2 mo, const float ab) {
         constexpr bool FIRST = decltype(first_tag)::value;
         unsigned mine = warp_bit_transpose(mo.x, lane);   // bit k: my cell expresses the chunk's gene k
+        if (ALL_POSITIVE) {
+            // every stored value is > 0: an expressed list gene always counts, and it pairs iff its abundance is
+            // > 0 — both are known for the whole chunk from the bit sets, nothing to test per gene
+            nz += __popc(mine);
+            mine &= __ballot_sync(FULL, ab > 0.0f);
+            if (!FIRST) cs.n += __popc(mine);
+        }
         int iters = __reduce_max_sync(FULL, (unsigned)__popc(mine));
         for (; iters > 0; iters -= U) {   // warp-uniform trip count
             unsigned m[U]; float abk[U], e[U]; bool has[U];
@@ -263,8 +272,7 @@ __global__ void __launch_bounds__(256) k_score_gm(const GmArgs a) {
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 if (ALL_POSITIVE) {
-                    nz += has[u] ? 1 : 0;
-                    if (has[u] && abk[u] > 0.0f) cs.template add<FIRST>((double)abk[u], (double)e[u]);   // model/SingleCell.java:403
+                    if (has[u]) cs.template add<FIRST, FIRST>((double)abk[u], (double)e[u]);   // model/SingleCell.java:403
                 } else if (has[u]) {
                     if (e[u] != 0.0f) nz++;                                      // NaN counts (:409)
                     if (abk[u] > 0.0f && e[u] > 0.0f) cs.template add<FIRST>((double)abk[u], (double)e[u]);

@@ -856,13 +856,18 @@ def test_score_gene_major_edge_cases(ctx, oracle):
     big.free()
 
 
-@pytest.mark.parametrize("G,L,unsorted_rows,N", [(6_000, 5_000, True, 1500), (40_000, 64, False, 1501),
-                                                 (3_000, 33, True, 31), (2_000, 600, False, 701)])
-def test_score_gene_major_shapes(ctx, oracle, G, L, unsorted_rows, N):
+@pytest.mark.parametrize("G,L,unsorted_rows,N,all_positive", [
+    (6_000, 5_000, True, 1500, False), (40_000, 64, False, 1501, False), (3_000, 33, True, 31, False),
+    (2_000, 600, False, 701, False),
+    # every stored value > 0: the kernel variant that counts expressed genes and pairs per chunk from the bit sets
+    # (the list below still has zero abundances and proteins without a matrix gene)
+    (2_000, 600, False, 701, True), (6_000, 1_000, True, 333, True)])
+def test_score_gene_major_shapes(ctx, oracle, G, L, unsorted_rows, N, all_positive):
     rng = np.random.default_rng(G + L)
     row_ptr, col, val = _random_csr(rng, N, G, 700 if G >= 6000 else 300, unsorted_rows)
-    val[rng.integers(0, val.size, 20)] = 0.0          # explicit zeros: not expressed
-    val[rng.integers(0, val.size, 5)] = np.nan        # NaN: expressed, never a pair
+    if not all_positive:
+        val[rng.integers(0, val.size, 20)] = 0.0          # explicit zeros: not expressed
+        val[rng.integers(0, val.size, 5)] = np.nan        # NaN: expressed, never a pair
     present = np.unique(col)
     gene_idx = rng.permutation(present)[:L].astype(np.int32) if present.size >= L else rng.permutation(G)[:L].astype(np.int32)
     gene_idx[rng.integers(0, L, 3)] = -1
