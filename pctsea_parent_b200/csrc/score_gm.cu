@@ -469,13 +469,14 @@ void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
     a.kept = c->kept.as<uint8_t>();
     a.fix_list = c->gm_fix.as<int2>() + 8; a.fix_count = counters + 1;
     const unsigned grid = (unsigned)div_up(m->n_groups, 8);
-    int unroll = 4;
+    int unroll = 8;
     if (const char* e = std::getenv("PCTSEA_GM_UNROLL")) unroll = std::atoi(e);   // tuning aid
     if (m->all_positive) {
-        if (unroll >= 4) k_score_gm<true, 4><<<grid, 256, 0, c->stream>>>(a);
+        if (unroll >= 8) k_score_gm<true, 8><<<grid, 256, 0, c->stream>>>(a);
+        else if (unroll >= 4) k_score_gm<true, 4><<<grid, 256, 0, c->stream>>>(a);
         else if (unroll <= 1) k_score_gm<true, 1><<<grid, 256, 0, c->stream>>>(a);
         else k_score_gm<true, 2><<<grid, 256, 0, c->stream>>>(a);
-    } else k_score_gm<false, 4><<<grid, 256, 0, c->stream>>>(a);
+    } else k_score_gm<false, 8><<<grid, 256, 0, c->stream>>>(a);
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
     if (sa.prm.jitter_mode == PCTSEA_JITTER_PHILOX) {
