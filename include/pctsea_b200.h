@@ -138,7 +138,7 @@ int pctsea_matrix_wrap_device(pctsea_ctx* ctx, int64_t n_cells, int32_t n_genes,
  * lane-per-cell kernel, whose pair order is ascending gene (matrix column) order and whose Pearson sums are the
  * shifted-data form (oracle: orc_pearson_shifted); without it they run the CSR scan (pair order = row storage
  * order, two-pass centred sums; oracle: orc_pearson_strided32). Both are within 1e-9 relative of the reference's
- * sequential SimpleRegression update; they differ from each other in the last bits. n_genes <= 51200. */
+ * sequential SimpleRegression update; they differ from each other in the last bits. */
 int pctsea_matrix_build_gene_index(pctsea_ctx* ctx, pctsea_matrix* m);
 /* Cell-type ids per cell in [-1, n_types); -1 = unknown type (model/SingleCell.java:224-229). */
 int pctsea_matrix_set_labels(pctsea_ctx* ctx, pctsea_matrix* m, const int32_t* label, int32_t n_types);

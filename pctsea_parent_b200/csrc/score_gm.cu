@@ -46,56 +46,70 @@ __host__ __device__ __forceinline__ size_t gm_row_offset(int64_t grp, int32_t G)
     return (size_t)(grp / GM_TILE) * (size_t)G * GM_TILE + (size_t)(grp % GM_TILE);
 }
 
-// ---- build: one CTA per group of 32 cells ---------------------------------------------------------------------
+// ---- build: one CTA per group of 32 cells; the genes go through shared memory in ranges of Gs (one pass for
+// matrices of up to ~51 k genes, more passes over the group's rows for larger gene sets) ------------------------
 __global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                                   const float* __restrict__ val, const int32_t* __restrict__ slot_cell,
-                                                  const int64_t* __restrict__ grp_base, int32_t G,
+                                                  const int64_t* __restrict__ grp_base, int32_t G, int32_t Gs,
                                                   uint2* __restrict__ mo, float* __restrict__ gval) {
-    extern __shared__ unsigned s_mask[];   // [G]
+    extern __shared__ unsigned s_mask[];   // [Gs]
     __shared__ int s_part[256];
+    __shared__ unsigned s_run;             // values of the group in the gene ranges already done
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t grp = blockIdx.x;
     const int32_t* cells = slot_cell + grp * 32;   // the group's cells (-1 = empty slot)
-    for (int g = tid; g < G; g += blockDim.x) s_mask[g] = 0u;
-    __syncthreads();
-    for (int ci = warp; ci < 32; ci += nwarps) {
-        const int32_t cl = cells[ci];
-        if (cl < 0) continue;
-        const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
-        for (int64_t k = b + lane; k < e; k += 32) atomicOr(&s_mask[col[k]], 1u << ci);
-    }
-    __syncthreads();
-    // exclusive prefix of popc(mask) over the genes: contiguous chunk per thread + block scan of the chunk sums
-    const int chunk = (G + blockDim.x - 1) / blockDim.x;
-    const int g0 = min(tid * chunk, G), g1 = min(g0 + chunk, G);
-    int sum = 0;
-    for (int g = g0; g < g1; g++) sum += __popc(s_mask[g]);
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < (int)blockDim.x; o <<= 1) {
-        const int v = tid >= o ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
-    }
-    unsigned run = (unsigned)(s_part[tid] - sum);
-    uint2* row = mo + gm_row_offset(grp, G);   // entry of gene g: row[g * GM_TILE]
-    for (int g = g0; g < g1; g++) {
-        const unsigned m = s_mask[g];
-        row[(size_t)g * GM_TILE] = make_uint2(m, run);
-        run += __popc(m);
-    }
-    __syncthreads();   // the CTA's own global writes are visible to all of its threads from here
+    uint2* row = mo + gm_row_offset(grp, G);       // entry of gene g: row[g * GM_TILE]
     const int64_t base = grp_base[grp];
-    for (int ci = warp; ci < 32; ci += nwarps) {
-        const int32_t cl = cells[ci];
-        if (cl < 0) continue;
-        const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
-        const unsigned below = (1u << ci) - 1u;
-        for (int64_t k = b + lane; k < e; k += 32) {
-            const uint2 x = row[(size_t)col[k] * GM_TILE];
-            gval[base + x.y + __popc(x.x & below)] = val[k];
+    if (tid == 0) s_run = 0u;
+    for (int32_t r0 = 0; r0 < G; r0 += Gs) {
+        const int32_t r1 = min(r0 + Gs, G), ng = r1 - r0;
+        for (int g = tid; g < ng; g += blockDim.x) s_mask[g] = 0u;
+        __syncthreads();
+        for (int ci = warp; ci < 32; ci += nwarps) {
+            const int32_t cl = cells[ci];
+            if (cl < 0) continue;
+            const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
+            for (int64_t k = b + lane; k < e; k += 32) {
+                const int32_t g = col[k];
+                if (g >= r0 && g < r1) atomicOr(&s_mask[g - r0], 1u << ci);
+            }
         }
+        __syncthreads();
+        // exclusive prefix of popc(mask) over the range: contiguous chunk per thread + block scan of the chunk sums
+        const int chunk = (ng + blockDim.x - 1) / blockDim.x;
+        const int g0 = min(tid * chunk, ng), g1 = min(g0 + chunk, ng);
+        int sum = 0;
+        for (int g = g0; g < g1; g++) sum += __popc(s_mask[g]);
+        s_part[tid] = sum;
+        __syncthreads();
+        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+            const int v = tid >= o ? s_part[tid - o] : 0;
+            __syncthreads();
+            s_part[tid] += v;
+            __syncthreads();
+        }
+        unsigned run = s_run + (unsigned)(s_part[tid] - sum);
+        for (int g = g0; g < g1; g++) {
+            const unsigned m = s_mask[g];
+            row[(size_t)(r0 + g) * GM_TILE] = make_uint2(m, run);
+            run += __popc(m);
+        }
+        __syncthreads();   // the CTA's own global writes are visible to all of its threads from here
+        for (int ci = warp; ci < 32; ci += nwarps) {
+            const int32_t cl = cells[ci];
+            if (cl < 0) continue;
+            const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
+            const unsigned below = (1u << ci) - 1u;
+            for (int64_t k = b + lane; k < e; k += 32) {
+                const int32_t g = col[k];
+                if (g < r0 || g >= r1) continue;
+                const uint2 x = row[(size_t)g * GM_TILE];
+                gval[base + x.y + __popc(x.x & below)] = val[k];
+            }
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) s_run += (unsigned)s_part[tid];
+        __syncthreads();
     }
 }
 
@@ -369,8 +383,8 @@ void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
     const int64_t N = m->n_cells;
     const int32_t G = m->n_genes;
     PCT_REQUIRE(N >= 1 && G >= 1, "empty matrix");
-    const size_t smem = (size_t)G * 4;
-    if (smem > 200 * 1024) throw Error(PCTSEA_EINVAL, "gene index: more than 51200 genes are not supported by the build kernel");
+    const int32_t Gs = std::min<int32_t>(G, 50 * 1024);   // genes per pass of the build kernel (one mask word each)
+    const size_t smem = (size_t)Gs * 4;
     const int64_t n_groups = div_up(N, 32);
     PCT_REQUIRE(N < ((int64_t)1 << 31), "too many cells");
     std::vector<int64_t> rp((size_t)N + 1);
@@ -417,7 +431,7 @@ void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
     if (le == cudaSuccess) le = cudaMemcpyAsync(base_dev, base.data(), base.size() * 8, cudaMemcpyHostToDevice, c->stream);
     if (le == cudaSuccess) le = cudaFuncSetAttribute(k_gm_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (le == cudaSuccess) {
-        k_gm_build<<<(unsigned)n_groups, 256, smem, c->stream>>>(m->row_ptr, m->col, m->val, slot_dev, base_dev, G, mo, gval);
+        k_gm_build<<<(unsigned)n_groups, 256, smem, c->stream>>>(m->row_ptr, m->col, m->val, slot_dev, base_dev, G, Gs, mo, gval);
         count_launch(c);
         le = cudaGetLastError();
     }

@@ -848,12 +848,6 @@ def test_score_gene_major_edge_cases(ctx, oracle):
         for jitter in (0, 1):
             kw = dict(method=method, min_genes_cells=3, min_corr=-1.0, has_min_corr=True, jitter_mode=jitter, seed=7)
             _check_gm(ctx, oracle, row_ptr, col, val, G, gene_idx, abundance, f"edge m{method} j{jitter}", **kw)
-    # a matrix with more genes than the build kernel's shared-memory mask row holds is refused, not mis-scored
-    big = ctx.load_csr(np.array([0, 1], np.int64), np.array([5], np.int32), np.ones(1, np.float32), 60_000)
-    with pytest.raises(P.PctseaError) as e:
-        big.build_gene_index()
-    assert e.value.code == -1
-    big.free()
 
 
 @pytest.mark.parametrize("G,L,unsorted_rows,N,all_positive", [
@@ -861,7 +855,9 @@ def test_score_gene_major_edge_cases(ctx, oracle):
     (2_000, 600, False, 701, False),
     # every stored value > 0: the kernel variant that counts expressed genes and pairs per chunk from the bit sets
     # (the list below still has zero abundances and proteins without a matrix gene)
-    (2_000, 600, False, 701, True), (6_000, 1_000, True, 333, True)])
+    (2_000, 600, False, 701, True), (6_000, 1_000, True, 333, True),
+    # more genes than one pass of the index build holds in shared memory (50 k): two and three gene ranges
+    (70_000, 900, False, 300, False), (120_000, 2_000, True, 200, True)])
 def test_score_gene_major_shapes(ctx, oracle, G, L, unsorted_rows, N, all_positive):
     rng = np.random.default_rng(G + L)
     row_ptr, col, val = _random_csr(rng, N, G, 700 if G >= 6000 else 300, unsorted_rows)
