@@ -158,7 +158,8 @@ def run_ours(args):
     abundance = ds.abundance.cpu().numpy()
     sprm = P.ScoreParams(cfg.method, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 1)
     nprm = ctx.null_params(P_total, perm_mode=P.PERM_PHILOX, ks_mode=ks_mode, seed=20261019,
-                           perm_begin=rank * P_per_gpu, perm_count=P_per_gpu, min_pass=1000)
+                           perm_begin=rank * P_per_gpu, perm_count=P_per_gpu, min_pass=1000,
+                           feistel_rounds=args.feistel_rounds)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
@@ -424,6 +425,7 @@ def main():
     ap.add_argument("--perm", type=int, default=0, help="permutations per GPU (default: the config's)")
     ap.add_argument("--ks", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--feistel-rounds", type=int, default=0, help="rounds of the keyed label permutation (0 = library default)")
     ap.add_argument("--gene-index", type=int, default=1,
                     help="1 (default): build the matrix gene-major copy at load, scoring reads only the list genes; 0: CSR scan")
     args = ap.parse_args()

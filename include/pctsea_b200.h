@@ -45,6 +45,12 @@ extern "C" {
 #define PCTSEA_PERM_REPLAY 0    /* consume uploaded permutation index arrays (validation) */
 #define PCTSEA_PERM_PHILOX 1    /* keyed Feistel bijection with Philox-generated round tables */
 
+/* Rounds of the keyed Feistel bijection behind PCTSEA_PERM_PHILOX. Every round function is an independent random
+ * table (Philox-generated per permutation); four such rounds are the Luby-Rackoff strong pseudo-random permutation.
+ * Measured on the null of the enrichment score against the JDK shuffle (two-sample KS per cell type, 20 000
+ * permutations each): 2 rounds are detectably different, 3, 4 and 6 are not. */
+#define PCTSEA_DEFAULT_FEISTEL_ROUNDS 4
+
 #define PCTSEA_KS_EXACT 0       /* sequential fp32/fp64 emulation of EnrichmentWeigthedScoreParallel.run */
 #define PCTSEA_KS_FAST  1       /* fixed-point prefix sums evaluated at hit / pre-hit positions only */
 
@@ -66,7 +72,7 @@ typedef struct pctsea_null_params {
     int32_t  perm_count;       /* permutations computed by this call; 0 = all n_perm */
     int32_t  perm_mode;        /* PCTSEA_PERM_* */
     int32_t  ks_mode;          /* PCTSEA_KS_* */
-    int32_t  feistel_rounds;   /* 0 = default (6) */
+    int32_t  feistel_rounds;   /* 0 = default (PCTSEA_DEFAULT_FEISTEL_ROUNDS); 2..32 */
     uint64_t seed;
     int32_t  mean_policy;      /* Maths.mean(TFloatList): 0 = fp32 running sum (default), 1 = fp64 sum */
     int32_t  min_pass;         /* PCTSEA_ETOOFEW guard; the reference uses 1000 (PCTSEA.java:138) */

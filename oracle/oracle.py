@@ -109,7 +109,10 @@ def jitter_uniform(seed, cell, vec, i):
     return lib().orc_jitter_uniform(seed, cell, vec, i)
 
 
-def feistel_perm(seed: int, p: int, n: int, rounds: int = 6) -> np.ndarray:
+DEFAULT_FEISTEL_ROUNDS = 4   # PCTSEA_DEFAULT_FEISTEL_ROUNDS of include/pctsea_b200.h
+
+
+def feistel_perm(seed: int, p: int, n: int, rounds: int = DEFAULT_FEISTEL_ROUNDS) -> np.ndarray:
     out = np.empty(max(n, 0), dtype=np.int32)
     lib().orc_feistel_perm(C.c_uint64(seed), C.c_uint32(p), C.c_int64(n), C.c_int(rounds), _p(out, C.c_int32))
     return out
@@ -201,7 +204,7 @@ def ks_observed(s, lab, T):
     return out
 
 
-def null(s, lab, T, P, perm_mode=0, seed=0, perm_begin=0, rounds=6, nthreads=1, want_replay=False):
+def null(s, lab, T, P, perm_mode=0, seed=0, perm_begin=0, rounds=DEFAULT_FEISTEL_ROUNDS, nthreads=1, want_replay=False):
     s = np.ascontiguousarray(s, dtype=np.float64)
     lab = np.ascontiguousarray(lab, dtype=np.int32)
     nu = s.size

@@ -19,6 +19,8 @@ JITTER_NAN, JITTER_PHILOX = 0, 1
 PERM_REPLAY, PERM_PHILOX = 0, 1
 KS_EXACT, KS_FAST = 0, 1
 
+DEFAULT_FEISTEL_ROUNDS = 4   # PCTSEA_DEFAULT_FEISTEL_ROUNDS of include/pctsea_b200.h
+
 EXPORTS = [
     "pctsea_abi_version", "pctsea_create", "pctsea_destroy", "pctsea_last_error", "pctsea_get_timings",
     "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels", "pctsea_matrix_build_gene_index",

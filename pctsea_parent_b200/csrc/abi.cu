@@ -123,7 +123,7 @@ void upload_list(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_t
 struct NullPlan {
     int32_t P = 0, begin = 0, count = 0;
     bool full = false;
-    int rounds = 6;
+    int rounds = PCTSEA_DEFAULT_FEISTEL_ROUNDS;
 };
 
 NullPlan validate_null_params(const pctsea_null_params* p) {
@@ -137,7 +137,7 @@ NullPlan validate_null_params(const pctsea_null_params* p) {
     np.count = p->perm_count == 0 ? (p->n_perm - p->perm_begin) : p->perm_count;
     PCT_REQUIRE(np.begin >= 0 && np.count >= 0 && np.begin + np.count <= np.P, "permutation slice out of range");
     np.full = (np.begin == 0 && np.count == np.P);
-    np.rounds = p->feistel_rounds == 0 ? 6 : p->feistel_rounds;
+    np.rounds = p->feistel_rounds == 0 ? PCTSEA_DEFAULT_FEISTEL_ROUNDS : p->feistel_rounds;
     PCT_REQUIRE(np.rounds >= 2 && np.rounds <= 32, "feistel_rounds out of range [2,32]");
     return np;
 }

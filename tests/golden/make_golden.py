@@ -62,7 +62,7 @@ def main():
     ne_f, nd_f = O.null(s_r, lab_r, cfg.n_types, 8, perm_mode=1, seed=42)
     red = O.reduce(res, ne_f)
     F = O.fast_frac_bits(s_r)
-    fast0 = O.ks_null_fast_one(s_r, lab_r[O.feistel_perm(42, 0, nu, 6)], cfg.n_types, F)
+    fast0 = O.ks_null_fast_one(s_r, lab_r[O.feistel_perm(42, 0, nu)], cfg.n_types, F)
     out["regression"] = {
         "config": "tiny", "n_pass": int(npass), "kept_sum": int(kept.sum()), "n_used_sum": int(used.sum()),
         "score_bits_first32_nonnan": bits64(sc[~np.isnan(sc)][:32]),
@@ -70,7 +70,7 @@ def main():
         "ews_bits": bits32(res["ews"]), "dstat_bits": bits32(res["dstat"]), "supX": [int(x) for x in res["supX"]],
         "null_jdk_seed42_bits": bits32(ne_j), "null_feistel_seed42_bits": bits32(ne_f),
         "norm_ews_bits": bits32(red["norm_ews"]), "p_emp_bits": bits64(red["p_emp"]), "fdr_bits": bits64(red["fdr"]),
-        "feistel_perm_seed42_p0_first16": [int(x) for x in O.feistel_perm(42, 0, nu, 6)[:16]],
+        "feistel_perm_seed42_p0_first16": [int(x) for x in O.feistel_perm(42, 0, nu)[:16]],
         "fast_frac_bits": int(F), "fast_null_p0_bits": bits32(fast0),
     }
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json"), "w") as fh:

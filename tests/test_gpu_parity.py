@@ -293,7 +293,7 @@ def test_null_replay_bit_exact(ctx, oracle, n_used, T, Pn):
 @pytest.mark.parametrize("n_used,T,Pn", [(5000, 12, 16), (2500, 300, 5), (777, 5, 9)])
 def test_null_philox_exact_bit_exact(ctx, oracle, n_used, T, Pn):
     s, lab, order = _ranked(n_used, T, seed=2)
-    one, ond = oracle.null(s, lab, T, Pn, perm_mode=1, seed=99, rounds=6)
+    one, ond = oracle.null(s, lab, T, Pn, perm_mode=1, seed=99)
     prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=99)
     res, ne, nd = ctx.enrich(s, order, lab, T, prm)
     assert_bits_equal_f32(ne, one, "null ews")
@@ -312,9 +312,26 @@ def test_null_philox_fast_matches_oracle_fast(ctx, oracle, n_used, T, Pn, simple
     res, ne, nd = ctx.enrich(s, order, lab, T, prm)
     F = oracle.fast_frac_bits(s)
     for p in range(Pn):
-        perm = oracle.feistel_perm(5, p, n_used, 6)
+        perm = oracle.feistel_perm(5, p, n_used)
         exp = oracle.ks_null_fast_one(s, lab[perm], T, F)
         assert_bits_equal_f32(ne[:, p], exp, f"fast null perm {p}")
+
+
+@pytest.mark.parametrize("rounds", [2, 5, 6, 7])
+@pytest.mark.parametrize("n_used,T", [(5000, 12), (9000, 300), (500, 4)])
+def test_null_philox_explicit_round_counts(ctx, oracle, rounds, n_used, T):
+    """feistel_rounds other than the default (4): the unrolled 6-round kernels and the generic-loop ones, in the lane
+    layout (rankings >= 4096 cells, 8- and 16-bit labels) and the row-major layout."""
+    s, lab, order = _ranked(n_used, T, seed=8)
+    prm = ctx.null_params(3, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=31, feistel_rounds=rounds)
+    res, ne, nd = ctx.enrich(s, order, lab, T, prm)
+    F = oracle.fast_frac_bits(s)
+    for p in range(3):
+        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(31, p, n_used, rounds)], T, F)
+        assert_bits_equal_f32(ne[:, p], exp, f"rounds {rounds} perm {p}")
+    one, _ = oracle.null(s, lab, T, 2, perm_mode=1, seed=31, rounds=rounds)
+    ex = ctx.enrich(s, order, lab, T, ctx.null_params(2, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=31, feistel_rounds=rounds))[1]
+    assert_bits_equal_f32(ex, one, f"rounds {rounds} exact")
 
 
 def test_fast_vs_exact_tolerance(ctx):
@@ -475,7 +492,9 @@ def test_full_size_properties(ctx):
     ok = ~np.isnan(ne)
     # the supremum is the larger of a positive and a negative excursion: when the two are within the tolerance
     # of each other the winner (hence the sign) can differ, so the bound is on the magnitude
-    assert np.all(np.abs(ne[ok]) <= 1.0) and np.max(np.abs(np.abs(ne[ok]) - np.abs(nf[ok]))) <= 2e-4
+    # (stated tolerance: 2e-4 up to 250k ranked cells, growing linearly with the ranking above that — what EXACT
+    # replays is the reference's fp32 accumulators, whose rounding drift grows with the number of additions)
+    assert np.all(np.abs(ne[ok]) <= 1.0) and np.max(np.abs(np.abs(ne[ok]) - np.abs(nf[ok]))) <= 2e-4 * n_used / 250_000
     assert np.mean(np.sign(ne[ok]) == np.sign(nf[ok])) > 0.97
     a = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=1, perm_begin=0, perm_count=2))[1]
     b = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=1, perm_begin=2, perm_count=4))[1]
@@ -511,7 +530,7 @@ def test_fast_lane_and_cooperative_kernels_agree(ctx, oracle):
     assert_bits_equal_f32(lane, coop, "lane vs cooperative FAST kernel")
     F = oracle.fast_frac_bits(s)
     for p in (0, Pn - 1):
-        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(21, p, n_used, 6)], T, F)
+        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(21, p, n_used)], T, F)
         assert_bits_equal_f32(lane[:, p], exp, f"lane kernel vs oracle, perm {p}")
 
 
@@ -594,7 +613,7 @@ def test_negative_threshold_mode(ctx, oracle):
     fast = ctx.enrich(score, order, label, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=4))[1]
     F = oracle.fast_frac_bits(s_r)
     for p in range(Pn):
-        exp = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(4, p, nu, 6)], T, F)
+        exp = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(4, p, nu)], T, F)
         assert_bits_equal_f32(fast[:, p], exp, f"fast null (negative scores) perm {p}")
 
 
@@ -615,7 +634,7 @@ def test_ties_zeros_and_many_types(ctx, oracle):
         assert_results_equal(res, oracle.reduce(ores, one), None, f"ties/zeros T={T}")
         fast = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=6))[1]
         F = oracle.fast_frac_bits(s)
-        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(6, 1, n_used, 6)], T, F)
+        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(6, 1, n_used)], T, F)
         assert_bits_equal_f32(fast[:, 1], exp, f"fast null T={T}")
 
 
@@ -697,7 +716,7 @@ def test_stage3_random_shapes_sweep(ctx, oracle):
         assert_results_equal(res, ores, OBSERVED_FIELDS, f"observed n={n_used} T={T}")
         F = oracle.fast_frac_bits(s)
         for p in range(Pn):
-            perm = oracle.feistel_perm(n_used, p, n_used, 6)
+            perm = oracle.feistel_perm(n_used, p, n_used)
             exp = oracle.ks_null_fast_one(s, lab[perm], T, F)
             assert_bits_equal_f32(ne[:, p], exp, f"fast null n={n_used} T={T} perm {p}")
         ored = oracle.reduce(ores, ne)
@@ -714,7 +733,7 @@ def test_two_contexts_on_one_device(ctx, oracle):
             prm = c.null_params(3, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=5)
             res, ne, nd = c.enrich(s, order, lab, T, prm)
             F = oracle.fast_frac_bits(s)
-            exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(5, 1, n_used, 6)], T, F)
+            exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(5, 1, n_used)], T, F)
             assert_bits_equal_f32(ne[:, 1], exp, f"ctx {'A' if c is ctx else 'B'} Nu={n_used} T={T}")
     finally:
         other.close()
@@ -771,7 +790,7 @@ def test_analyze_batch_equals_single_analyses(ctx, oracle, small, gene_major):
     nu = npass - 1
     s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
     F = oracle.fast_frac_bits(s_r)
-    one = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(9, p, nu, 6)], cfg.n_types, F)
+    one = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(9, p, nu)], cfg.n_types, F)
                     for p in range(Pn)], axis=1)
     ores = oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), one)
     assert_bits_equal_f32(out["null"][3], one, "batch list 3 null vs oracle")
@@ -936,7 +955,7 @@ def test_baseline_config_A_end_to_end(ctx, oracle, gene_major):
     nprm = ctx.null_params(cfg.n_perm, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=7, min_pass=1000)
     fast = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm, want_null=True)
     F = oracle.fast_frac_bits(s_r)
-    exp = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(7, p, nu, 6)], cfg.n_types, F)
+    exp = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(7, p, nu)], cfg.n_types, F)
                     for p in range(cfg.n_perm)], axis=1)
     assert_bits_equal_f32(fast["null"], exp, "PHILOX FAST null")
     assert_results_equal(fast["results"], oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), exp), None,

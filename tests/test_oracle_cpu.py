@@ -107,9 +107,9 @@ def test_regression_fixture(oracle, tiny):
     assert red["norm_ews"].view(np.uint32).tolist() == g["norm_ews_bits"]
     assert red["p_emp"].view(np.uint64).tolist() == g["p_emp_bits"]
     assert red["fdr"].view(np.uint64).tolist() == g["fdr_bits"]
-    assert oracle.feistel_perm(42, 0, nu, 6)[:16].tolist() == g["feistel_perm_seed42_p0_first16"]
+    assert oracle.feistel_perm(42, 0, nu)[:16].tolist() == g["feistel_perm_seed42_p0_first16"]
     assert oracle.fast_frac_bits(s_r) == g["fast_frac_bits"]
-    fast0 = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(42, 0, nu, 6)], cfg.n_types, g["fast_frac_bits"])
+    fast0 = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(42, 0, nu)], cfg.n_types, g["fast_frac_bits"])
     assert fast0.view(np.uint32).tolist() == g["fast_null_p0_bits"]
 
 
@@ -247,9 +247,9 @@ def test_ks_properties(oracle):
 
 def test_feistel_permutation_is_a_bijection_and_global_indexed(oracle):
     for n in (1, 2, 3, 17, 1000, 4097, 50_000):
-        p = oracle.feistel_perm(9, 3, n, 6)
+        p = oracle.feistel_perm(9, 3, n)
         assert np.array_equal(np.sort(p), np.arange(n))
-    a, b = oracle.feistel_perm(9, 3, 5000, 6), oracle.feistel_perm(9, 4, 5000, 6)
+    a, b = oracle.feistel_perm(9, 3, 5000), oracle.feistel_perm(9, 4, 5000)
     assert not np.array_equal(a, b)
     s, lab = synth.synthetic_ranked(2000, 6, seed=2)
     full, _ = oracle.null(s, lab, 6, 10, perm_mode=1, seed=11)
@@ -283,7 +283,7 @@ def test_fast_definition_close_to_exact(oracle):
     F = oracle.fast_frac_bits(s)
     assert F == 25  # max score in [0.5, 1)
     for p in range(3):
-        lp = lab[oracle.feistel_perm(1, p, s.size, 6)]
+        lp = lab[oracle.feistel_perm(1, p, s.size)]
         e, _ = oracle.ks_null_one(s, lp, 12)
         f = oracle.ks_null_fast_one(s, lp, 12, F)
         ok = ~np.isnan(e)
