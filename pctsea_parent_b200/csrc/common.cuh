@@ -138,7 +138,9 @@ namespace pctsea {
 // ---- Philox4x32-10 (device + host) ------------------------------------------------------------
 __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int r = 0; r < 10; r++) {
 #ifdef __CUDA_ARCH__
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
