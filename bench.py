@@ -320,7 +320,7 @@ def cpu_baseline(ctx, m, ds, cfg, sprm, gene_idx, abundance, label_host, args, p
     t0 = time.perf_counter()
     O.null(s_r, lab_r, cfg.n_types, 2, perm_mode=0, seed=1, nthreads=cores)
     per = (time.perf_counter() - t0) / 2
-    p_cpu = p_cpu or int(max(4, min(50, 15.0 / max(per, 1e-6))))
+    p_cpu = p_cpu or int(max(4, min(cfg.n_perm, 15.0 / max(per, 1e-6))))
     t0 = time.perf_counter()
     O.null(s_r, lab_r, cfg.n_types, p_cpu, perm_mode=0, seed=1, nthreads=cores)
     dt = time.perf_counter() - t0
