@@ -16,15 +16,18 @@
 //   gval[grp_base[group] + off + popc(mask & lanes below l)] = that cell's value: the group's non-zeros in
 //   (gene, cell) order. Size: 8 B * G * N/32 (config B 3.75 GB, D 15 GB) + 4 B * nnz.
 //
-// Scoring a list: one warp per group walks the list's genes in ascending gene order; per gene one 8-byte broadcast
-// entry tells every lane whether its cell expresses the gene and where the value is; each lane keeps its own cell's
-// running sums in registers. No shared memory, no atomics, no cross-lane reduction; the pair order of a cell is the
-// gene order whatever the storage order of its CSR row. The Pearson sums are the shifted-data form (deviations from
+// Scoring a list: one warp per group walks the list's genes, sorted by gene, in chunks of 32; the chunk's 32 masks
+// are bit-transposed so that each lane holds the set of the chunk's genes its own cell expresses and pops them in
+// ascending order (the popped gene's 8-byte entry comes from the lane that fetched it, by shuffle); each lane keeps
+// its cell's running sums in registers. No shared memory, no atomics, no cross-lane reduction; the pair order of a
+// cell is the gene order whatever the storage order of its CSR row. Cells are assigned to groups by cell type and row
+// length (a chunk costs a group as many steps as its busiest cell has genes in it). The Pearson sums are the shifted-data form (deviations from
 // the cell's first pair), bit-identical to the oracle's orc_pearson_shifted and within 1e-9 relative of the
 // reference's sequential SimpleRegression update (measured <= 1e-11).
 //
-// Roofline: the bytes this path must read are 8 B per (list gene, group) entry + the matched values
-// (config B: 0.15 GB + ~0.45 GB in 32-byte sectors), not the CSR: it is latency/issue bound, not HBM bound.
+// Roofline: the bytes this path must read are 8 B per (list gene, group) entry + the matched values (config B:
+// 0.15 GB + 0.7 GB useful, 2.06 GB of DRAM sectors measured), not the 6.5 GB CSR: it sits between instruction issue
+// (66 %) and the latency of the dependent entry -> value loads, not at the HBM roofline (profiles/README.md).
 #include "common.cuh"
 
 #include <algorithm>
