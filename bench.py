@@ -235,9 +235,7 @@ def run_ours(args):
         peak, peak_src = measured_hbm_peak()
         mean = lambda k: float(np.mean([t[k] for t in tms]))
         lab_ms, null_ms = mean("labels_ms"), mean("null_ms")
-        lane = nu >= 4096   # the lane kernel (type-sliced above ~218 cell types) serves every ranking of that size
-        ks_name = ("k_ks_fast_lane" if lane else "k_ks_fast") if ks_mode == P.KS_FAST else "k_ks_exact"
-        lab_name = "k_labels_philox_lane" if lane else "k_labels_philox"
+        ks_name = "k_null_fused" if ks_mode == P.KS_FAST else "k_ks_exact"
         # the kernel with the largest share of a step in the committed launch list (profiles/r1_launches.txt) is the
         # null KS kernel; the label kernel's span inside a step also contains the observed-statistics kernels that
         # run beside it on the second stream, so its span is reported (labels_kernel_ms) but is not a kernel time

@@ -43,16 +43,30 @@ extern "C" {
 #define PCTSEA_JITTER_PHILOX 1  /* U[0,1)/1e6 from Philox4x32-10 keyed by (seed, cell, vector, element) */
 
 #define PCTSEA_PERM_REPLAY 0    /* consume uploaded permutation index arrays (validation) */
-#define PCTSEA_PERM_PHILOX 1    /* keyed Feistel bijection with Philox-generated round tables */
+#define PCTSEA_PERM_PHILOX 1    /* generated: position x of permutation p carries the class at index pi_p(x) of the
+                                   TYPE-SORTED arrangement of the ranked labels (types ascending, unknown-type cells
+                                   last); pi_p = keyed Feistel bijection of [0, n_used) with arithmetic round
+                                   functions, one Philox4x32-10 key per round and permutation. A pure function of
+                                   (seed, global permutation index, x): identical for any GPU count or slicing.
+                                   Needs n_used <= 2^25. */
 
-/* Rounds of the keyed Feistel bijection behind PCTSEA_PERM_PHILOX. Every round function is an independent random
- * table (Philox-generated per permutation); four such rounds are the Luby-Rackoff strong pseudo-random permutation.
- * Measured on the null of the enrichment score against the JDK shuffle (two-sample KS per cell type, 20 000
- * permutations each): 2 rounds are detectably different, 3, 4 and 6 are not. */
-#define PCTSEA_DEFAULT_FEISTEL_ROUNDS 4
+/* Rounds of the keyed Feistel bijection behind PCTSEA_PERM_PHILOX. The class of a position is a range test on the
+ * high digit of pi_p(x), which exposes the unevenness of a random round function: measured on the null of the
+ * enrichment score against the JDK shuffle (standard deviation, 99th percentile and two-sample KS per cell type,
+ * DESIGN.md), 3 and 4 rounds inflate the null's spread by 2 %, 5 and more are indistinguishable. */
+#define PCTSEA_DEFAULT_FEISTEL_ROUNDS 5
 
 #define PCTSEA_KS_EXACT 0       /* sequential fp32/fp64 emulation of EnrichmentWeigthedScoreParallel.run */
-#define PCTSEA_KS_FAST  1       /* fixed-point prefix sums evaluated at hit / pre-hit positions only */
+#define PCTSEA_KS_FAST  1       /* needs PERM_PHILOX. Scores quantised to int32 fixed point (scale 2^F, F the largest
+                                   with the sum of |fx| over the ranking below 2^31), exact integer running sums,
+                                   supremum evaluated at hit / pre-hit positions only, each candidate one fp32 FMA.
+                                   Not the reference's arithmetic: within 2e-5 of the real-number value for rankings
+                                   of up to 2 M cells (the reference's own fp32 accumulators drift by 1e-5 at 220 k
+                                   cells and 2e-3 at 2 M). Semantic differences beyond rounding: a zero denominator
+                                   gives ES 0 (reference: NaN / Inf); equal |diff| resolves to the positive one
+                                   (reference: first position); assumes all ranked scores share a sign (true on the
+                                   reference's path: ScoreThreshold passes one side of the threshold). The observed
+                                   ES always uses the reference's float chain. */
 
 typedef struct pctsea_ctx    pctsea_ctx;
 typedef struct pctsea_matrix pctsea_matrix;
@@ -105,8 +119,8 @@ typedef struct pctsea_timings {
     float   rank_ms;      /* stage 2: compaction + radix sort + gather */
     float   observed_ms;  /* stage 3 observed (exact): span of its kernels, which run on a second stream beside
                              labels_ms + null_ms (so the stage times do not add up to total_ms) */
-    float   labels_ms;    /* permuted label generation (+ per-type denominators in FAST mode) */
-    float   null_ms;      /* KS over the permuted labels */
+    float   labels_ms;    /* EXACT null only: permuted label generation (the FAST null generates them in-kernel) */
+    float   null_ms;      /* the null: labels + KS of every (type, permutation) */
     float   reduce_ms;    /* a10-a12 */
     float   total_ms;     /* first to last event, includes the copies issued by the call */
     int64_t n_pass;       /* Np */
@@ -121,6 +135,20 @@ int         pctsea_create(int device_id, pctsea_ctx** out);
 int         pctsea_destroy(pctsea_ctx* ctx);
 const char* pctsea_last_error(pctsea_ctx* ctx);
 int         pctsea_get_timings(pctsea_ctx* ctx, pctsea_timings* out);
+
+/* Testing and tuning switches of a ctx (none is needed in production; results never depend on them except where
+ * noted). Returns PCTSEA_EINVAL for an unknown option or a value out of range. */
+#define PCTSEA_OPT_OBS_OVERLAP       1  /* 1 (default): observed-statistics kernels run on a second stream beside the null */
+#define PCTSEA_OPT_SCORE_PATH        2  /* 0 (default): gene-major kernel when the matrix has its index; 1: always the CSR
+                                           scan (the two differ in the last bits of a score, see build_gene_index) */
+#define PCTSEA_OPT_GM_UNROLL         3  /* value loads in flight per lane of the gene-major kernel: 1, 2, 4, 8 (0 = default) */
+#define PCTSEA_OPT_SCORE_WARPS       4  /* warps per CTA of the CSR-scan kernel (0 = as many as fit) */
+#define PCTSEA_OPT_PERM_CHUNK        5  /* permutations per label chunk of the EXACT null (0 = from the free memory) */
+#define PCTSEA_OPT_NULL_THREADS      6  /* threads (ranking segments) per permutation of the null kernel (0 = as many as fit) */
+#define PCTSEA_OPT_NULL_CTAS_PER_SM  7  /* resident CTAs per SM of the null kernel (0 = as many as fit) */
+#define PCTSEA_OPT_NULL_MIN_THREADS  8  /* cell types are processed in slices when fewer threads would fit (0 = 192) */
+#define PCTSEA_OPT_DEBUG_GAPS        9  /* 1: report idle gaps between the stages on stderr */
+int         pctsea_ctx_set_option(pctsea_ctx* ctx, int32_t option, int64_t value);
 /* cudaStream_t the ctx launches on (so a caller can time or order against it). */
 void*       pctsea_stream(pctsea_ctx* ctx);
 

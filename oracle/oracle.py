@@ -109,12 +109,22 @@ def jitter_uniform(seed, cell, vec, i):
     return lib().orc_jitter_uniform(seed, cell, vec, i)
 
 
-DEFAULT_FEISTEL_ROUNDS = 4   # PCTSEA_DEFAULT_FEISTEL_ROUNDS of include/pctsea_b200.h
+DEFAULT_FEISTEL_ROUNDS = 5   # PCTSEA_DEFAULT_FEISTEL_ROUNDS of include/pctsea_b200.h
 
 
 def feistel_perm(seed: int, p: int, n: int, rounds: int = DEFAULT_FEISTEL_ROUNDS) -> np.ndarray:
     out = np.empty(max(n, 0), dtype=np.int32)
     lib().orc_feistel_perm(C.c_uint64(seed), C.c_uint32(p), C.c_int64(n), C.c_int(rounds), _p(out, C.c_int32))
+    return out
+
+
+def perm_labels(seed: int, p: int, lab, T: int, rounds: int = DEFAULT_FEISTEL_ROUNDS) -> np.ndarray:
+    """Permuted labels of PHILOX mode: the type-sorted arrangement of `lab` read through the Feistel bijection of
+    permutation p (global index)."""
+    lab = np.ascontiguousarray(lab, dtype=np.int32)
+    out = np.empty(lab.size, dtype=np.int32)
+    lib().orc_perm_labels(C.c_uint64(seed), C.c_uint32(p), C.c_int64(lab.size), _p(lab, C.c_int32), C.c_int32(T),
+                          C.c_int(rounds), _p(out, C.c_int32))
     return out
 
 

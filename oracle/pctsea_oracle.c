@@ -155,36 +155,71 @@ static void feistel_dims(int64_t n, int64_t* a_out, int64_t* b_out) {
     *b_out = (n + a - 1) / a;
 }
 
+/* PHILOX-mode permutation, round 2 definition: a keyed Feistel bijection of [0,n) on Z_a x Z_b (a = ceil(sqrt n),
+ * b = ceil(n / a); cycle-walking for the < a out-of-range points) whose round functions are ARITHMETIC:
+ *   F(v, key, mod) = floor(mix(v, key) * mod / 2^32),  mix = multiply - xorshift - multiply hash of v and the round key,
+ * with one 32-bit key per round from Philox4x32-10(ctr = {j / 4, 0, p, "FEIS"}, key = seed)[j % 4]. No tables:
+ * the GPU evaluates it in registers inside the null kernel. Round j modifies the high digit L iff (rounds-1-j) is
+ * even, i.e. the LAST round always does: the class of a position is a range test on pi(x) (orc_perm_labels), decided
+ * by its high digit, and a trailing low-digit round would be wasted. Measured against Collections.shuffle on the null
+ * of the enrichment score (profiles/feistel_rounds_check.txt): 3 and 4 rounds inflate its standard deviation by 2 %
+ * (the value histogram of a random round FUNCTION is uneven, and with the sorted arrangement that unevenness reaches
+ * the class counts of long prefixes of the ranking); 5 and more rounds are indistinguishable. Default 5. */
+static inline uint32_t feistel_mix(uint32_t v, uint32_t key) {
+    uint32_t t = v * 0x9E3779B1u + key;
+    t ^= t >> 15;
+    t *= 0x2C1B3C6Du;
+    return t;
+}
+
+void orc_feistel_keys(uint64_t seed, uint32_t p, int rounds, uint32_t* keys_out) {
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int j0 = 0; j0 < rounds; j0 += 4) {
+        uint32_t ctr[4] = { (uint32_t)(j0 >> 2), 0u, p, 0x46454953u };
+        uint32_t o[4];
+        orc_philox4x32_10(ctr, key, o);
+        for (int q = 0; q < 4 && j0 + q < rounds; q++) keys_out[j0 + q] = o[q];
+    }
+}
+
 void orc_feistel_perm(uint64_t seed, uint32_t p, int64_t n, int rounds, int32_t* perm_out) {
     if (n <= 0) return;
-    int64_t a, b;
-    feistel_dims(n, &a, &b);
-    uint16_t* tab = (uint16_t*)malloc((size_t)rounds * (size_t)a * sizeof(uint16_t));
-    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-    for (int j = 0; j < rounds; j++) {
-        int64_t dom = (j & 1) ? a : b;          /* input half size */
-        uint32_t mod = (uint32_t)((j & 1) ? b : a); /* output half size */
-        for (int64_t v4 = 0; v4 < dom; v4 += 4) {
-            uint32_t ctr[4] = { (uint32_t)(v4 >> 2), (uint32_t)j, p, 0x46454953u };
-            uint32_t o[4];
-            orc_philox4x32_10(ctr, key, o);
-            for (int q = 0; q < 4 && v4 + q < dom; q++)
-                tab[(size_t)j * a + v4 + q] = (uint16_t)(((uint64_t)o[q] * mod) >> 32);
-        }
-    }
+    int64_t a64, b64;
+    feistel_dims(n, &a64, &b64);
+    const uint32_t a = (uint32_t)a64, b = (uint32_t)b64;
+    uint32_t keys[64];
+    orc_feistel_keys(seed, p, rounds, keys);
     for (int64_t x = 0; x < n; x++) {
         uint32_t L = (uint32_t)(x / b), R = (uint32_t)(x % b);
         int64_t y;
         do {
             for (int j = 0; j < rounds; j++) {
-                if (!(j & 1)) { L += tab[(size_t)j * a + R]; if (L >= (uint32_t)a) L -= (uint32_t)a; }
-                else          { R += tab[(size_t)j * a + L]; if (R >= (uint32_t)b) R -= (uint32_t)b; }
+                if (!((rounds - 1 - j) & 1)) { L += (uint32_t)(((uint64_t)feistel_mix(R, keys[j]) * a) >> 32); if (L >= a) L -= a; }
+                else          { R += (uint32_t)(((uint64_t)feistel_mix(L, keys[j]) * b) >> 32); if (R >= b) R -= b; }
             }
             y = (int64_t)L * b + R;
         } while (y >= n);
         perm_out[x] = (int32_t)y;
     }
-    free(tab);
+}
+
+/* Permuted labels of PHILOX mode: position x carries the class at index pi_p(x) of the TYPE-SORTED arrangement of
+ * the ranked labels (types 0..T-1 ascending, unknown-type cells last). A uniform permutation applied to any fixed
+ * arrangement of the same multiset is a uniform arrangement, so which arrangement is permuted does not matter for
+ * the null; the sorted one turns "class of index j" into a search in the T+1 cumulative class counts. */
+void orc_perm_labels(uint64_t seed, uint32_t p, int64_t Nu, const int32_t* lab, int32_t T, int rounds,
+                     int32_t* lab_perm_out) {
+    if (Nu <= 0) return;
+    int64_t* cum = (int64_t*)calloc((size_t)T + 2, sizeof(int64_t));
+    for (int64_t i = 0; i < Nu; i++) { int32_t c = (lab[i] < 0 || lab[i] >= T) ? T : lab[i]; cum[c + 1]++; }
+    for (int32_t c = 0; c <= T; c++) cum[c + 1] += cum[c];
+    int32_t* sorted = (int32_t*)malloc((size_t)Nu * sizeof(int32_t));
+    for (int32_t c = 0; c <= T; c++)
+        for (int64_t j = cum[c]; j < cum[c + 1]; j++) sorted[j] = (c == T) ? -1 : c;
+    int32_t* idx = (int32_t*)malloc((size_t)Nu * sizeof(int32_t));
+    orc_feistel_perm(seed, p, Nu, rounds, idx);
+    for (int64_t x = 0; x < Nu; x++) lab_perm_out[x] = sorted[idx[x]];
+    free(cum); free(sorted); free(idx);
 }
 
 /* ============================================================================================
@@ -607,11 +642,12 @@ void orc_null(int64_t Nu, const double* s, const int32_t* lab, int32_t T, int32_
             /* CORE/PCTSEA.java:1403-1413: copy, Collections.shuffle, label at rank i = shuffled[i] */
             for (int64_t i = 0; i < Nu; i++) idx[i] = (int32_t)i;
             orc_java_shuffle_i32(idx, Nu, &jr);
+            for (int64_t i = 0; i < Nu; i++) labp[i] = lab[idx[i]];
+            if (replay_out) memcpy(replay_out + (size_t)p * (size_t)Nu, idx, (size_t)Nu * sizeof(int32_t));
         } else {
-            orc_feistel_perm(seed, (uint32_t)(perm_begin + p), Nu, rounds, idx);
+            /* PHILOX mode permutes the type-sorted arrangement (orc_perm_labels); there is no index array to replay */
+            orc_perm_labels(seed, (uint32_t)(perm_begin + p), Nu, lab, T, rounds, labp);
         }
-        if (replay_out) memcpy(replay_out + (size_t)p * (size_t)Nu, idx, (size_t)Nu * sizeof(int32_t));
-        for (int64_t i = 0; i < Nu; i++) labp[i] = lab[idx[i]];
         null_one_perm(Nu, s, labp, T, P, p, nthreads, null_ews, null_d);
     }
     free(idx); free(labp);
@@ -699,19 +735,34 @@ void orc_reduce(int32_t T, int32_t P, const float* null_ews, int mean_policy, or
 }
 
 /* ============================================================================================
- * FAST-mode definition (this repo's own arithmetic, not the reference's): exact fixed-point
- * prefix sums, supremum evaluated only at hit and pre-hit positions.
+ * FAST-mode definition (this repo's own arithmetic, not the reference's; round 2 form): scores quantised to
+ * int32 fixed point fx = llrint(s * 2^F), F chosen so that the sum of |fx| over the ranking fits an int32;
+ * every running sum is then an exact int32, the supremum is evaluated only at hit and pre-hit positions, and
+ * each candidate difference is ONE fp32 fused multiply-add of the converted sums:
+ *     diff = numA/dA - (S - numA)/dB = fmaf((float)numA, c12, -((float)S * c2)),
+ *     c2 = (float)(1/dB), c12 = (float)(1/dA + 1/dB)   (reciprocals and their sum in fp64).
+ * Exact integer sums make the result independent of how the GPU splits the ranking into segments.
+ * Differences from the reference beyond rounding (documented in include/pctsea_b200.h, ks_mode): a zero
+ * denominator gives ES 0 (reference: NaN/Inf from the float division); equal |diff| resolves to the positive
+ * one (reference: first position, strict '>'); hit / pre-hit evaluation assumes all ranked scores share a sign
+ * (true on the reference's path: ScoreThreshold passes one side of the threshold).
  * ========================================================================================== */
 
 int orc_fast_frac_bits(int64_t Nu, const double* s) {
-    /* |fx| = |rint(s * 2^F)| <= 2^25 for every score: F = 25 - e with maxabs < 2^e */
+    /* F0 = 25 - e with maxabs < 2^e  =>  |llrint(s * 2^F0)| <= 2^25; then the smallest right shift sh with
+     * ceil(sum|fx0| / 2^sh) + Nu <= INT32_MAX  (=> sum |llrint(s * 2^(F0-sh))| <= INT32_MAX) */
     double maxabs = 0.0;
     for (int64_t i = 0; i < Nu; i++) { double v = fabs(s[i]); if (v > maxabs) maxabs = v; }
     int e = 0;
     if (maxabs > 0.0) e = ilogb(maxabs) + 1;
-    int F = 25 - e;
-    if (F > 1000) F = 1000;
-    return F;
+    int F0 = 25 - e;
+    if (F0 > 1000) F0 = 1000;
+    const double scale0 = ldexp(1.0, F0);
+    int64_t A = 0;
+    for (int64_t i = 0; i < Nu; i++) { int64_t v = llrint(s[i] * scale0); A += v < 0 ? -v : v; }
+    int sh = 0;
+    while (((A + (((int64_t)1 << sh) - 1)) >> sh) + Nu > (int64_t)INT32_MAX) sh++;
+    return F0 - sh;
 }
 
 static inline int fast_better(float f, float sup) {
@@ -724,32 +775,30 @@ static inline int fast_better(float f, float sup) {
 
 void orc_ks_null_fast_one(int64_t Nu, const double* s, const int32_t* lab, int32_t T,
                           int frac_bits, float* null_ews) {
-    int64_t* fx = (int64_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int64_t));
-    int64_t* S = (int64_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int64_t));
+    int32_t* fx = (int32_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int32_t));
+    int32_t* S = (int32_t*)malloc((size_t)(Nu > 0 ? Nu : 1) * sizeof(int32_t));
     int64_t acc = 0;
     double scale = ldexp(1.0, frac_bits);
-    for (int64_t i = 0; i < Nu; i++) { fx[i] = llrint(s[i] * scale); acc += fx[i]; S[i] = acc; }
-    int64_t Stot = acc;
+    for (int64_t i = 0; i < Nu; i++) { fx[i] = (int32_t)llrint(s[i] * scale); acc += fx[i]; S[i] = (int32_t)acc; }
+    int32_t Stot = (int32_t)acc;
     for (int32_t t = 0; t < T; t++) {
-        int64_t dA = 0; int32_t nk = 0;
+        int32_t dA = 0; int32_t nk = 0;
         for (int64_t i = 0; i < Nu; i++) if (lab[i] == t) { dA += fx[i]; nk++; }
-        int64_t dB = Stot - dA;
+        int32_t dB = Stot - dA;
         if (!(nk > 1 && Nu - nk > 1)) { null_ews[t] = NAN; continue; }
         if (dA == 0 || dB == 0) { null_ews[t] = 0.0f; continue; }
-        /* diff = numA/dA - (S - numA)/dB = numA * (1/dA + 1/dB) - S * (1/dB), one fused multiply-add */
-        double c2 = 1.0 / (double)dB;
-        double c12 = 1.0 / (double)dA + c2;
-        float sup = 0.0f; int64_t numA = 0;
+        const double r2 = 1.0 / (double)dB;
+        const float c2 = (float)r2;
+        const float c12 = (float)(1.0 / (double)dA + r2);
+        float sup = 0.0f; int32_t numA = 0;
         for (int64_t i = 0; i < Nu; i++) {
             if (lab[i] != t) continue;
             if (i > 0) {
-                double d0 = fma((double)numA, c12, -((double)S[i - 1] * c2));
-                float f0 = (float)d0;
+                float f0 = fmaf((float)numA, c12, -((float)S[i - 1] * c2));
                 if (fast_better(f0, sup)) sup = f0;
             }
             numA += fx[i];
-            double d1 = fma((double)numA, c12, -((double)S[i] * c2));
-            float f1 = (float)d1;
+            float f1 = fmaf((float)numA, c12, -((float)S[i] * c2));
             if (fast_better(f1, sup)) sup = f1;
         }
         null_ews[t] = sup;

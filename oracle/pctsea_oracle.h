@@ -44,9 +44,14 @@ void     orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
 /* U[0,1) with 53 bits, as a pure function of (seed, cell, vec, i) — the deterministic stand-in for
  * Math.random() in CORE/model/SingleCell.java:436-447. */
 double   orc_jitter_uniform(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t i);
-/* perm_out[i] = pi_p(i), a bijection of [0,n) built from `rounds` Feistel rounds whose round
- * functions are Philox-generated tables, keyed by (seed, p). */
+/* perm_out[i] = pi_p(i), a bijection of [0,n) built from `rounds` Feistel rounds with arithmetic round
+ * functions, one Philox-generated 32-bit key per round, keyed by (seed, p). */
 void     orc_feistel_perm(uint64_t seed, uint32_t p, int64_t n, int rounds, int32_t* perm_out);
+void     orc_feistel_keys(uint64_t seed, uint32_t p, int rounds, uint32_t* keys_out);
+/* Permuted labels of PHILOX mode: lab_perm_out[x] = class at index pi_p(x) of the type-sorted arrangement of
+ * lab[0..Nu) (types 0..T-1 ascending, unknown-type cells (-1) last). */
+void     orc_perm_labels(uint64_t seed, uint32_t p, int64_t Nu, const int32_t* lab, int32_t T, int rounds,
+                         int32_t* lab_perm_out);
 
 /* ---- stage 1: per-cell scoring (a1-a3) ----------------------------------------------------- */
 typedef struct {
@@ -131,8 +136,9 @@ void orc_null_replay(int64_t Nu, const double* s, const int32_t* lab, int32_t T,
 void orc_reduce(int32_t T, int32_t P, const float* null_ews, int mean_policy, orc_type_result* inout,
                 float* norm_null_out /* [T][P] or NULL */);
 
-/* Real-arithmetic evaluation of the null supremum at hit / pre-hit positions (the FAST mode's
- * definition, fixed-point scale 2^frac_bits): used to bound FAST-vs-EXACT differences on the CPU. */
+/* The FAST mode's definition: int32 fixed-point scores (scale 2^frac_bits, orc_fast_frac_bits: the largest
+ * scale that keeps the sum of |fx| over the ranking below 2^31), exact integer running sums, supremum at hit /
+ * pre-hit positions, one fp32 fused multiply-add per candidate. */
 void orc_ks_null_fast_one(int64_t Nu, const double* s, const int32_t* lab_perm, int32_t T,
                           int frac_bits, float* null_ews);
 int  orc_fast_frac_bits(int64_t Nu, const double* s);

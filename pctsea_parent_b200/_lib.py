@@ -19,10 +19,15 @@ JITTER_NAN, JITTER_PHILOX = 0, 1
 PERM_REPLAY, PERM_PHILOX = 0, 1
 KS_EXACT, KS_FAST = 0, 1
 
-DEFAULT_FEISTEL_ROUNDS = 4   # PCTSEA_DEFAULT_FEISTEL_ROUNDS of include/pctsea_b200.h
+DEFAULT_FEISTEL_ROUNDS = 5   # PCTSEA_DEFAULT_FEISTEL_ROUNDS of include/pctsea_b200.h
+
+# pctsea_ctx_set_option: testing / tuning switches (include/pctsea_b200.h)
+(OPT_OBS_OVERLAP, OPT_SCORE_PATH, OPT_GM_UNROLL, OPT_SCORE_WARPS, OPT_PERM_CHUNK, OPT_NULL_THREADS, OPT_NULL_CTAS_PER_SM,
+ OPT_NULL_MIN_THREADS, OPT_DEBUG_GAPS) = range(1, 10)
 
 EXPORTS = [
     "pctsea_abi_version", "pctsea_create", "pctsea_destroy", "pctsea_last_error", "pctsea_get_timings",
+    "pctsea_ctx_set_option",
     "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels", "pctsea_matrix_build_gene_index",
     "pctsea_matrix_free", "pctsea_score", "pctsea_rank", "pctsea_enrich", "pctsea_reduce_null",
     "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_analyze_batch", "pctsea_last_null_dev", "pctsea_last_type_counts",
@@ -90,6 +95,7 @@ def load_library() -> C.CDLL:
     L.pctsea_last_error.argtypes = [vp]
     L.pctsea_last_error.restype = C.c_char_p
     L.pctsea_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.pctsea_ctx_set_option.argtypes = [vp, i32, i64]
     L.pctsea_stream.argtypes = [vp]
     L.pctsea_stream.restype = vp
     L.pctsea_matrix_load_csr.argtypes = [vp, i64, i32, vp, vp, vp, C.POINTER(vp)]
@@ -180,6 +186,10 @@ class Context:
         t = Timings()
         self._check(self.L.pctsea_get_timings(self.h, C.byref(t)))
         return t.as_dict()
+
+    def set_option(self, option: int, value: int):
+        """Testing / tuning switch of this ctx (OPT_* constants; none is needed in production)."""
+        self._check(self.L.pctsea_ctx_set_option(self.h, int(option), int(value)))
 
     def stream(self) -> int:
         return int(self.L.pctsea_stream(self.h) or 0)

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpctsea_b200.so")
-SOURCES = ["abi.cu", "score.cu", "score_gm.cu", "rank.cu", "enrich.cu", "reduce.cu"]
+SOURCES = ["abi.cu", "score.cu", "score_gm.cu", "rank.cu", "enrich.cu", "null_fused.cu", "reduce.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "pctsea_b200.h")]
 
 NVCC_FLAGS = [

@@ -3,7 +3,6 @@
 #include "common.cuh"
 
 #include <algorithm>
-#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -157,25 +156,36 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     g.Nu = Nu;
     g.T = T;
     const bool fast = prm->ks_mode == PCTSEA_KS_FAST;
-    launch_prepare_ranked(c, N, score_dev, label_dev, order_dev, g, fast);
+    const bool philox = prm->perm_mode == PCTSEA_PERM_PHILOX;
+    if (fast && !philox) throw Error(PCTSEA_EINVAL, "REPLAY permutations are a validation mode: use ks_mode EXACT");
+    launch_prepare_ranked(c, N, score_dev, label_dev, order_dev, g);
+    const int32_t Pc_all = np.count;
+    const bool want_null = Pc_all > 0 && T > 0;
+    // Everything the call will allocate is reserved here, before any memory budget is taken (the grow-only buffers
+    // over-allocate by 1/8): the observed accumulator history first, then the null.
+    c->results.reserve((size_t)std::max(T, 1) * sizeof(pctsea_type_result) + 64);
+    reserve_ks_observed(c, g);
+    c->null_ews.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
+    c->null_d.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
+    NullPlanFast plan;
+    if (want_null && philox) {
+        plan = plan_null_fast(c, g);
+        launch_class_tables(c, g, plan.shift, plan.nb);
+        if (fast) launch_null_fast_prepare(c, g, plan);
+    }
     rec(c, EV_RANK);
     // The observed statistics and the permutation null both depend only on the ranked arrays. The observed
-    // kernels are small, latency-bound launches of 512-thread CTAs with ~40 registers: they fit on an SM next to a
-    // label CTA or a lane-KS CTA, so by default they go to the auxiliary stream and run in the shadow of the null
-    // stage; the reduction waits for both. PCTSEA_OBS_OVERLAP=0 keeps them on the main stream. With the overlap
-    // observed_ms is the span of the observed kernels on their own stream, not a share of total_ms.
-    const char* ov_env = std::getenv("PCTSEA_OBS_OVERLAP");
-    const bool obs_overlap = !(ov_env && ov_env[0] == '0') && np.count > 0 && T > 0 &&
-                             prm->perm_mode == PCTSEA_PERM_PHILOX;
+    // kernels are small, latency-bound launches of 512-thread CTAs with ~40 registers, so by default they go to the
+    // auxiliary stream and run in the shadow of the null stage; the reduction waits for both.
+    // PCTSEA_OPT_OBS_OVERLAP = 0 keeps them on the main stream. With the overlap observed_ms is the span of the
+    // observed kernels on their own stream, not a share of total_ms.
+    const bool obs_overlap = c->opt_obs_overlap && want_null && philox;
     c->obs_span_valid = false;
     if (obs_overlap) PCT_CUDA(cudaEventRecord(c->ev_obs[0], c->stream));   // ranked arrays are ready
     else launch_ks_observed(c, g, c->stream);
     bool obs_queued = false;
-    const char* oa_env = std::getenv("PCTSEA_OBS_AFTER_LABELS");
-    const bool obs_after_labels = oa_env && oa_env[0] == '1';
-    cudaEvent_t labels_done = nullptr;
     auto queue_observed_aux = [&]() {
-        PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, (obs_after_labels && labels_done) ? labels_done : c->ev_obs[0], 0));
+        PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, c->ev_obs[0], 0));
         PCT_CUDA(cudaEventRecord(c->ev_obs[1], c->stream_aux));
         launch_ks_observed(c, g, c->stream_aux);
         PCT_CUDA(cudaEventRecord(c->ev_obs[2], c->stream_aux));
@@ -185,56 +195,47 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     c->last_obs_Nu = T > 0 ? Nu : -1;
     rec(c, EV_OBS);
 
-    const int32_t Pc_all = np.count;
-    c->null_ews.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
-    c->null_d.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
     c->last_T = T;
     c->last_Pc = Pc_all;
-    if (Pc_all > 0 && T > 0) {
-        if (prm->perm_mode == PCTSEA_PERM_REPLAY) PCT_REQUIRE(replay_host != nullptr, "REPLAY mode needs replay_perm");
-        // chunk the permutations so the label matrix stays within half of the free device memory
-        const size_t row_bytes = plan_fast(g, Pc_all).label_row_bytes;  // layout-dependent (row-major or lane layout)
-        const size_t per_perm = row_bytes + (prm->perm_mode == PCTSEA_PERM_REPLAY ? (size_t)g.Nu * 4 : 0);
+    if (want_null && fast) {
+        // FAST arithmetic: one fused kernel generates the labels and evaluates them; nothing of size P x Nu exists
+        cudaEvent_t e0 = et.mark(c->stream);
+        launch_null_fused(c, g, plan, prm->seed, np.begin, Pc_all, np.rounds, Pc_all, 0);
+        cudaEvent_t e1 = et.mark(c->stream);
+        if (obs_overlap) queue_observed_aux();   // after the null launch: the big kernel gets its SMs first
+        null_spans.push_back({ e0, e1 });
+    } else if (want_null) {
+        if (!philox) PCT_REQUIRE(replay_host != nullptr, "REPLAY mode needs replay_perm");
+        // EXACT (validation) null: chunk the permutations so the label matrix stays within half of the free memory
+        const size_t row_bytes = (size_t)g.Nu_pad * g.lab_bytes;
+        const size_t per_perm = row_bytes + (philox ? 0 : (size_t)g.Nu * 4);
         int32_t chunk = Pc_all;
         // The free-memory query goes to the kernel-mode driver and was measured to stall the launching thread for
         // 1-70 ms now and then, with the stream idle behind it: ask only when the label buffers have to grow.
         const bool fits = (size_t)Pc_all * row_bytes + 64 <= c->labels.cap &&
-                          (prm->perm_mode != PCTSEA_PERM_REPLAY || (size_t)Pc_all * g.Nu * 4 + 64 <= c->replay.cap);
+                          (philox || (size_t)Pc_all * g.Nu * 4 + 64 <= c->replay.cap);
         if (!fits) {
             size_t free_b = 0, total_b = 0;
             PCT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            const size_t budget = std::max<size_t>(free_b / 2 + c->labels.cap + c->replay.cap, (size_t)64 << 20);
+            // the grow-only buffers over-allocate by 1/8 (DevBuf::reserve): budget for what will really be requested
+            const size_t budget = std::max<size_t>((free_b / 2 + c->labels.cap + c->replay.cap) / 9 * 8, (size_t)64 << 20);
             chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)Pc_all, budget / std::max<size_t>(per_perm, 1)));
         }
-        if (const char* e = std::getenv("PCTSEA_PERM_CHUNK")) chunk = std::max(1, std::min(chunk, std::atoi(e)));   // tuning aid
+        if (c->opt_perm_chunk > 0) chunk = std::max(1, std::min(chunk, c->opt_perm_chunk));   // PCTSEA_OPT_PERM_CHUNK
         c->labels.reserve((size_t)chunk * row_bytes + 64);
-        const FastPlan plan0 = plan_fast(g, Pc_all);
-        if (fast) launch_fast_prepare(c, g, plan0);
-        if (prm->perm_mode == PCTSEA_PERM_REPLAY && fast)
-            throw Error(PCTSEA_EINVAL, "REPLAY permutations are a validation mode: use ks_mode EXACT");
         for (int32_t p0 = 0; p0 < Pc_all; p0 += chunk) {
             const int32_t pc = std::min(chunk, Pc_all - p0);
             cudaEvent_t e0 = et.mark(c->stream);
-            if (prm->perm_mode == PCTSEA_PERM_REPLAY) {
+            if (!philox) {
                 c->replay.reserve((size_t)pc * g.Nu * 4 + 64);
                 h2d(c, c->replay.p, replay_host + (size_t)p0 * g.Nu, (size_t)pc * g.Nu * 4);
                 launch_labels_replay(c, g, c->replay.as<int32_t>(), pc);
-                cudaEvent_t e1 = et.mark(c->stream);
-                launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);
-                cudaEvent_t e2 = et.mark(c->stream);
-                lab_spans.push_back({ e0, e1 });
-                null_spans.push_back({ e1, e2 });
-                continue;
+            } else {
+                launch_labels_philox_rm(c, g, prm->seed, np.begin + p0, pc, np.rounds);
             }
-            // Labels and KS kernel of a chunk run back to back on one stream. (Generating the labels of the next
-            // sub-chunk on a second stream was measured slower on B200: both kernels fill the SMs' shared memory,
-            // so they cannot co-reside, and the sub-chunks only add partial waves.)
-            launch_labels_philox(c, g, prm->seed, np.begin + p0, pc, np.rounds, fast, plan0, c->stream, 0);
             cudaEvent_t e1 = et.mark(c->stream);
-            labels_done = e1;
-            if (obs_overlap && !obs_queued) queue_observed_aux();   // after the first label launch: the big kernel gets its SMs first
-            if (fast) launch_ks_fast_null(c, g, pc, plan0, Pc_all, p0, 0);
-            else launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);
+            if (obs_overlap && !obs_queued) queue_observed_aux();
+            launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);
             cudaEvent_t e2 = et.mark(c->stream);
             lab_spans.push_back({ e0, e1 });
             null_spans.push_back({ e1, e2 });
@@ -267,9 +268,10 @@ void finish_timings(pctsea_ctx* c, const std::vector<std::pair<cudaEvent_t, cuda
     c->tm.labels_ms = lm;
     c->tm.null_ms = nm;
     c->tm.launches = c->launches;
-    if (std::getenv("PCTSEA_DEBUG_GAPS") && !lab_spans.empty()) {   // diagnosis: where the stream sat idle
+    if (c->opt_debug_gaps && !null_spans.empty()) {   // PCTSEA_OPT_DEBUG_GAPS: where the stream sat idle
         auto el = [](cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; };
-        const float pre = el(c->ev[EV_RANK], lab_spans.front().first), post = el(null_spans.back().second, c->ev[EV_NULL]);
+        const float pre = el(c->ev[EV_RANK], lab_spans.empty() ? null_spans.front().first : lab_spans.front().first);
+        const float post = el(null_spans.back().second, c->ev[EV_NULL]);
         const float tail = el(c->ev[EV_REDUCE], c->ev[EV_END]);
         if (c->tm.total_ms > 1.3f * (c->tm.setup_ms + c->tm.score_ms + c->tm.rank_ms + lm + nm + c->tm.reduce_ms))
             fprintf(stderr, "[pctsea gaps] total %.3f setup %.3f score %.3f rank %.3f | rank->labels %.3f | labels %.3f null %.3f | null->join %.3f (observed span %.3f) | reduce %.3f | results d2h %.3f\n",
@@ -371,6 +373,13 @@ int pctsea_create(int device_id, pctsea_ctx** out) {
     pctsea_ctx* c = new (std::nothrow) pctsea_ctx();
     if (!c) return PCTSEA_ENOMEM;
     c->device = device_id;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { cudaGetLastError(); delete c; return PCTSEA_ECUDA; }
+        c->num_sms = prop.multiProcessorCount;
+        c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+        c->smem_per_block_optin = (int)prop.sharedMemPerBlockOptin;
+    }
     // the auxiliary stream carries the observed-statistics kernels: a chain of small launches that shares the SMs with
     // the big null kernels; its CTAs go first whenever resources free up, or the chain becomes the critical path
     int prio_lo = 0, prio_hi = 0;
@@ -399,7 +408,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->list_rank, &c->score_sums, &c->score, &c->nused, &c->nnzc, &c->kept, &c->gm_fix,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
-                       &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels, &c->lab_ticket,
+                       &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels, &c->lab_ticket, &c->cls_tab,
                        &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
                        &c->red_misc };
     for (DevBuf* b : bufs) b->release();
@@ -415,6 +424,26 @@ int pctsea_destroy(pctsea_ctx* c) {
 }
 
 const char* pctsea_last_error(pctsea_ctx* c) { return c ? c->err.c_str() : "NULL ctx"; }
+
+int pctsea_ctx_set_option(pctsea_ctx* c, int32_t option, int64_t value) {
+    if (!c) return PCTSEA_EINVAL;
+    auto bad = [&](const char* what) { c->err = std::string("pctsea_ctx_set_option: ") + what; return PCTSEA_EINVAL; };
+    if (value < 0 || value > (1 << 20)) return bad("value out of range");
+    const int v = (int)value;
+    switch (option) {
+        case PCTSEA_OPT_OBS_OVERLAP: if (v > 1) return bad("0 or 1"); c->opt_obs_overlap = v; break;
+        case PCTSEA_OPT_SCORE_PATH: if (v > 1) return bad("0 or 1"); c->opt_score_path = v; break;
+        case PCTSEA_OPT_GM_UNROLL: if (v > 8) return bad("at most 8"); c->opt_gm_unroll = v; break;
+        case PCTSEA_OPT_SCORE_WARPS: if (v > 32) return bad("at most 32"); c->opt_score_warps = v; break;
+        case PCTSEA_OPT_PERM_CHUNK: c->opt_perm_chunk = v; break;
+        case PCTSEA_OPT_NULL_THREADS: if (v > 512) return bad("at most 512"); c->opt_null_threads = v; break;
+        case PCTSEA_OPT_NULL_CTAS_PER_SM: if (v > 4) return bad("at most 4"); c->opt_null_ctas_per_sm = v; break;
+        case PCTSEA_OPT_NULL_MIN_THREADS: if (v > 512) return bad("at most 512"); c->opt_null_min_threads = v; break;
+        case PCTSEA_OPT_DEBUG_GAPS: if (v > 1) return bad("0 or 1"); c->opt_debug_gaps = v; break;
+        default: return bad("unknown option");
+    }
+    return PCTSEA_OK;
+}
 
 int pctsea_get_timings(pctsea_ctx* c, pctsea_timings* out) {
     if (!c || !out) return PCTSEA_EINVAL;

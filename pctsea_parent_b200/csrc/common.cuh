@@ -14,7 +14,6 @@
 
 namespace pctsea {
 
-constexpr int kNumSMs = 148;  // B200
 
 struct Error : public std::runtime_error {
     int code;
@@ -97,6 +96,20 @@ struct pctsea_matrix {
 
 struct pctsea_ctx {
     int device = 0;
+    // device properties, queried once in pctsea_create
+    int num_sms = 0;
+    int smem_per_sm = 0;             // bytes of shared memory per SM
+    int smem_per_block_optin = 0;    // largest dynamic shared memory a CTA may opt in to
+    // pctsea_ctx_set_option (testing and tuning; none is needed in production)
+    int opt_obs_overlap = 1;         // observed-statistics kernels on the auxiliary stream beside the null
+    int opt_score_path = 0;          // 1 = CSR scan even when the matrix has its gene-major index
+    int opt_gm_unroll = 0;           // value loads in flight per lane of the gene-major kernel (0 = default)
+    int opt_score_warps = 0;         // warps per CTA of the CSR-scan kernel (0 = as many as fit)
+    int opt_perm_chunk = 0;          // permutations per label chunk of the EXACT null (0 = memory budget)
+    int opt_null_threads = 0;        // threads (segments) per permutation of the fused null kernel (0 = as many as fit)
+    int opt_null_ctas_per_sm = 0;    // resident CTAs per SM of the fused null kernel (0 = as many as fit)
+    int opt_null_min_threads = 0;    // below this many threads per permutation the cell types are sliced (0 = 192)
+    int opt_debug_gaps = 0;          // print a line to stderr when the stream sat idle between stages
     cudaStream_t stream = nullptr;
     std::string err;
     cudaStream_t stream_aux = nullptr;  // the observed-statistics kernels run here, beside the null on `stream`
@@ -121,8 +134,9 @@ struct pctsea_ctx {
     pctsea::DevBuf label_tmp;                                   // [N] int32 (when labels passed per call)
     pctsea::DevBuf s_rank, lab_rank, fx, Sfx, class_cnt;        // ranked arrays [Nu]
     pctsea::DevBuf obs_chain, obs_misc, obs_tiles;                       // observed KS: accumulator history [Nu][Tpad]
-    pctsea::DevBuf labels;                                      // [Pc][Nu_pad] permuted labels
-    pctsea::DevBuf lab_ticket;                                  // permutation ticket counter of the label kernel
+    pctsea::DevBuf labels;                                      // EXACT null: [Pc][Nu_pad] permuted labels; fused null: per-CTA label scratch
+    pctsea::DevBuf lab_ticket;                                  // permutation ticket counter of the fused null kernel
+    pctsea::DevBuf cls_tab;                                     // cumulative class counts [Tc+1] + bucket table of the sorted arrangement
     pctsea::DevBuf replay;                                      // [Pc][Nu] int32
     pctsea::DevBuf fxT;                                         // FAST mode: lane layout of the fixed-point scores
     pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
@@ -205,31 +219,34 @@ struct EnrichGeom {
     int lab_bytes = 1;   // 1 (u8) or 2 (u16)
     int frac_bits = 0;
 };
-// Gather ranked arrays (s_rank, lab_rank), class counts, fixed-point prefix (fx, Sfx).
+// Gather ranked arrays (s_rank, lab_rank), class counts, max |score|.
 void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, const int32_t* label_dev,
-                           const int32_t* order_dev, EnrichGeom& g, bool want_fixed);
+                           const int32_t* order_dev, EnrichGeom& g);
+void reserve_ks_observed(pctsea_ctx* c, const EnrichGeom& g);
 void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st);
 // a / b series of one type from the resident accumulator history into two device arrays of Nu floats
 void launch_obs_curve(pctsea_ctx* c, int32_t type_id, int64_t Nu, int32_t T, float* a_dev, float* b_dev);
 void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* replay_dev, int32_t Pc);
-struct FastPlan {
-    int64_t seg = 0;            // cooperative / label kernels: positions per warp task
-    int32_t K = 0;              // ... and tasks per permutation
-    bool lane_path = false;     // FAST lane kernel: one thread per segment
-    int32_t Kp = 0;             // threads (segments) per permutation
-    int32_t lane_seg = 0;       // positions per thread (multiple of 32)
-    int32_t slice_T = 0;        // cell types per pass of the lane kernel (== T unless sliced)
-    size_t label_row_bytes = 0; // bytes of permuted labels per permutation in the chosen layout
+// Geometry of the fused null kernel (null_fused.cu) for one ranking.
+struct NullPlanFast {
+    int32_t Kp = 0;           // threads (segments) per permutation
+    int32_t seg = 0;          // positions per thread (multiple of 4)
+    int32_t Ts = 0;           // cell types per pass (== T unless sliced)
+    int32_t ctas_per_sm = 1;
+    int32_t nb = 0;           // buckets of the class table
+    int shift = 0;            // log2 of the bucket width
+    int cum_smem = 0;         // cumulative class counts held in shared memory
+    int word_bytes = 4;       // bytes of one label word (4 positions)
+    size_t smem = 0;          // dynamic shared memory per CTA
 };
-FastPlan plan_fast(const EnrichGeom& g, int32_t Pc);
-// `st`: stream to launch on; `label_off`: byte offset of this sub-chunk inside c->labels
-void launch_labels_philox(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc,
-                          int rounds, bool want_sums, const FastPlan& fp, cudaStream_t st, size_t label_off);
+NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g);
+void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl);
+void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb);
+void launch_labels_philox_rm(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc, int rounds);
+void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl, uint64_t seed, int32_t perm_begin,
+                       int32_t Pc, int rounds, int32_t P_stride, int32_t p_off);
 void launch_ks_exact_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, int32_t P_stride, int32_t p_off,
                           size_t label_off);
-void launch_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const FastPlan& fp);
-void launch_ks_fast_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, const FastPlan& fp, int32_t P_stride,
-                         int32_t p_off, size_t label_off);
 void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, int mean_policy,
                    pctsea_type_result* results_dev);
 

@@ -1,91 +1,21 @@
-// enrich.cu — stage 3: weighted Kolmogorov-Smirnov enrichment score per cell type and its
-// label-permutation null.
+// enrich.cu — stage 3: the ranked arrays, the observed weighted Kolmogorov-Smirnov enrichment score per cell type
+// (reference arithmetic, bit-exact) and the validation-mode (EXACT) null. The production null (FAST arithmetic,
+// generated permutations) is null_fused.cu.
 //
 // Replaces (reference paths under pctsea-core/src/main/java/edu/scripps/yates/pctsea/):
 //   a8  utils/parallel/EnrichmentWeigthedScoreParallel.java:72-353 (run), :492-512 (lookForPriorNegativeSupremum)
-//   a9  PCTSEA.java:1390-1443 (permutation driver: Collections.shuffle of the ranked labels, P times)
+//   a9  PCTSEA.java:1390-1443 (permutation driver) in validation mode: replayed index arrays, sequential arithmetic
 //
 // Data layout in HBM (all in rank order, Nu = Np - 1 cells):
 //   s_rank  fp64 [Nu]            ranked scores
 //   lab_rank LabT [Nu_pad]       observed class per rank (class T = "unknown type", label -1)
-//   labels  LabT [Pc][Nu_pad]    permuted classes, one row per permutation (LabT = u8 if T < 256 else u16)
-//   fx int32 [Nu], Sfx int64 [Nu] fixed-point scores (|fx| <= 2^30) and their inclusive prefix (FAST mode)
+//   labels  LabT [Pc][Nu_pad]    permuted classes of the EXACT null, one row per permutation (u8 if T < 256 else u16)
 //
-// Two KS arithmetics:
-//   EXACT  one thread per (type, permutation) replays the reference's sequential float/double recurrence
-//          bit for bit (lanes = types; scores and labels are warp-broadcast loads). Used for the observed
-//          scores always, and for the null in validation mode.
-//   FAST   lanes = ranked positions. Each position is a hit for exactly one type, so the supremum of
-//          |a-b| can only sit at a hit or just before one; with exact int64 prefix sums the running sums at
-//          those positions are closed-form, which makes the work O(1) per (cell x permutation) instead of
-//          O(T). Per-type denominators need the whole permutation, hence two passes over the label stream:
-//          pass 1 generates the labels and accumulates per-segment type sums, pass 2 evaluates the suprema.
-//
-// Permutations (PHILOX mode): position x of permutation p carries the label of rank pi_p(x), where pi_p is
-// a keyed Feistel bijection of [0,Nu) on Z_a x Z_b (a = ceil(sqrt Nu), b = ceil(Nu/a), cycle-walking for
-// the < a out-of-range points) whose round functions are Philox4x32-10 generated tables held in shared
-// memory. Stateless in x, so any (permutation, segment) can be generated by any CTA on any GPU.
+// EXACT null: one thread per (type, permutation) replays the reference's sequential float/double recurrence bit for
+// bit (lanes = types; scores and labels are warp-broadcast loads) — O(T * Nu * P), validation only.
 #include "common.cuh"
-#include <cstdlib>
 
 namespace pctsea {
-
-constexpr int WPC = 8;  // warp tasks per CTA in the label / FAST kernels
-
-// ================================================================================================
-// small device-wide int64 inclusive scan (tile sums -> scan of sums -> tile scan)
-// ================================================================================================
-constexpr int SC_THREADS = 256;
-constexpr int SC_ITEMS = 8;
-constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
-
-__device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        long long u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-    }
-    return v;
-}
-
-// Exact prefix sums of the fixed-point scores: every tile first adds up the sums of the tiles before it (a few
-// hundred values written by k_fixed_point), then scans its own items.
-__global__ void __launch_bounds__(SC_THREADS) k_tile_scan_i64(const int* __restrict__ in, int64_t n,
-                                                             const long long* __restrict__ tile_sum,
-                                                             double* __restrict__ out) {
-    // thread t owns items [t*8, t*8+8) of the tile => contiguous, so the scan is in index order
-    __shared__ long long ws[SC_THREADS / 32];
-    __shared__ long long s_before;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        long long b = 0;
-        for (int j = threadIdx.x; j < (int)blockIdx.x; j += SC_THREADS) b += tile_sum[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) b += __shfl_down_sync(0xffffffffu, b, o);
-        if (lane == 0) ws[warp] = b;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long t = 0;
-            for (int w = 0; w < SC_THREADS / 32; w++) t += ws[w];
-            s_before = t;
-        }
-        __syncthreads();
-    }
-    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
-    long long v[SC_ITEMS];
-    long long s = 0;
-#pragma unroll
-    for (int r = 0; r < SC_ITEMS; r++) { int64_t i = base + r; v[r] = (i < n) ? in[i] : 0; s += v[r]; v[r] = s; }
-    long long incl = warp_incl_scan(s, lane);
-    if (lane == 31) ws[warp] = incl;
-    __syncthreads();
-    long long woff = 0;
-    for (int w = 0; w < warp; w++) woff += ws[w];
-    long long off = s_before + woff + (incl - s);
-#pragma unroll
-    // the prefix is an integer below 2^53, so the double holds it exactly
-    for (int r = 0; r < SC_ITEMS; r++) { int64_t i = base + r; if (i < n) out[i] = (double)(v[r] + off); }
-}
 
 // ================================================================================================
 // ranked arrays
@@ -126,63 +56,8 @@ __global__ void k_gather_ranked(const double* __restrict__ score, const int32_t*
         if (shist[j]) atomicAdd(&class_cnt[j], shist[j]);
 }
 
-// frac_bits F = 25 - e with maxabs < 2^e, so |fx| = |rint(s * 2^F)| <= 2^25 (same rule as the oracle):
-// 32 of them still fit an int32, and the prefix over <= 2^27 cells stays below 2^53 (exact in a double)
-__device__ __forceinline__ int fast_frac_bits(unsigned long long maxabs_bits) {
-    double maxabs = __longlong_as_double((long long)maxabs_bits);
-    int e = 0;
-    if (maxabs > 0.0) e = ilogb(maxabs) + 1;
-    int F = 25 - e;
-    return F > 1000 ? 1000 : F;
-}
-
-// fx = llrint(s * 2^F) per ranked cell, plus the sum of every SC_TILE-sized tile for the prefix scan.
-__global__ void __launch_bounds__(SC_THREADS) k_fixed_point(const double* __restrict__ s_rank, int64_t Nu,
-                                                           const unsigned long long* __restrict__ maxabs_bits,
-                                                           int* __restrict__ fx, int32_t* __restrict__ frac_out,
-                                                           long long* __restrict__ tile_sum) {
-    __shared__ long long ws[SC_THREADS / 32];
-    const int F = fast_frac_bits(*maxabs_bits);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *frac_out = F;
-    const double scale = __longlong_as_double((long long)(1023 + F) << 52);
-    const int64_t base = (int64_t)blockIdx.x * SC_TILE;
-    long long sum = 0;
-#pragma unroll
-    for (int r = 0; r < SC_ITEMS; r++) {
-        const int64_t i = base + r * SC_THREADS + threadIdx.x;
-        if (i < Nu) {
-            const int v = (int)__double2ll_rn(__dmul_rn(s_rank[i], scale));
-            fx[i] = v;
-            sum += v;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long t = 0;
-        for (int w = 0; w < SC_THREADS / 32; w++) t += ws[w];
-        tile_sum[blockIdx.x] = t;
-    }
-}
-
-// The two most frequent classes among the ranked cells get dedicated full-warp scans in the FAST kernel
-// (a class that owns a large share of the 32 lanes would otherwise make the by-type prefix loop long).
-__global__ void k_pick_peel(const int32_t* __restrict__ class_cnt, int32_t T, int32_t* __restrict__ peel) {
-    if (threadIdx.x != 0) return;
-    int b0 = -1, b1 = -1;
-    int c0 = 0, c1 = 0;
-    for (int t = 0; t < T; t++) {
-        int c = class_cnt[t];
-        if (c > c0) { b1 = b0; c1 = c0; b0 = t; c0 = c; }
-        else if (c > c1) { b1 = t; c1 = c; }
-    }
-    peel[0] = b0; peel[1] = b1;
-}
-
 void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, const int32_t* label_dev,
-                           const int32_t* order_dev, EnrichGeom& g, bool want_fixed) {
+                           const int32_t* order_dev, EnrichGeom& g) {
     (void)N;
     g.Tc = g.T + 1;
     g.lab_bytes = (g.Tc <= 256) ? 1 : 2;
@@ -209,22 +84,6 @@ void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, co
                                                                        c->lab_rank.as<uint16_t>(),
                                                                        c->class_cnt.as<int32_t>(), maxabs, hist_n);
     count_launch(c);
-    if (want_fixed && g.Nu > 0) {
-        c->fx.reserve((size_t)g.Nu * 4 + 64);
-        c->Sfx.reserve((size_t)g.Nu * 8 + 64);
-        const int n_tiles = (int)div_up(g.Nu, SC_TILE);
-        c->scan_tmp.reserve((size_t)n_tiles * 8 + 64);
-        k_fixed_point<<<n_tiles, SC_THREADS, 0, c->stream>>>(c->s_rank.as<double>(), g.Nu, maxabs, c->fx.as<int>(), frac_dev,
-                                                             c->scan_tmp.as<long long>());
-        k_tile_scan_i64<<<n_tiles, SC_THREADS, 0, c->stream>>>(c->fx.as<int>(), g.Nu, c->scan_tmp.as<long long>(),
-                                                               c->Sfx.as<double>());
-        // the cooperative kernel (rankings below 4096 cells) gives its two most frequent classes full-warp scans
-        if (g.Nu < 4096 || std::getenv("PCTSEA_FAST_PATH") != nullptr) {
-            k_pick_peel<<<1, 32, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.T, reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 5));
-            count_launch(c);
-        }
-        count_launch(c, 2);
-    }
     PCT_CUDA(cudaGetLastError());
 }
 
@@ -745,11 +604,20 @@ __global__ void k_obs_finish(const float2* __restrict__ chainT, const float* __r
     results[t] = r;
 }
 
-void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st) {
+// Workspaces of the observed stage, reserved up front (before the null takes its memory budget).
+void reserve_ks_observed(pctsea_ctx* c, const EnrichGeom& g) {
     c->results.reserve((size_t)std::max(g.T, 1) * sizeof(pctsea_type_result) + 64);
     if (g.T == 0) return;
     const int32_t Tpad = (int32_t)round_up(g.T, 32);
     c->obs_chain.reserve((size_t)g.Nu * g.T * sizeof(float2) + 64);
+    c->obs_misc.reserve((size_t)Tpad * 40 + 64);
+    c->obs_tiles.reserve((size_t)div_up(g.Nu, KSD_TILE) * g.Tc * 4 + 64);
+}
+
+void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st) {
+    reserve_ks_observed(c, g);
+    if (g.T == 0) return;
+    const int32_t Tpad = (int32_t)round_up(g.T, 32);
     // [2][Tpad] denominators | [Tpad] u64 supremum keys | [Tpad] u64 secondary keys | [Tpad] f64 KS D |
     // [Tpad] u32 last-negative indices | [Tpad] u32 secondary indices
     const size_t off_key = (size_t)2 * Tpad * 4, off_sec = off_key + (size_t)Tpad * 8, off_ksd = off_sec + (size_t)Tpad * 8,
@@ -872,756 +740,6 @@ void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* rep
                                                                    c->labels.as<uint16_t>() + (size_t)p0 * g.Nu_pad);
         count_launch(c);
     }
-    PCT_CUDA(cudaGetLastError());
-}
-
-FastPlan plan_fast(const EnrichGeom& g, int32_t Pc) {
-    // warp task = (permutation, segment of `seg` ranked positions). Enough tasks to fill 148 SMs several
-    // times over, but segments no shorter than 4096 positions so the per-CTA Feistel tables amortise.
-    FastPlan fp;
-    int64_t want_tasks = (int64_t)kNumSMs * 32 * 8;
-    int64_t k_target = std::max<int64_t>(1, div_up(want_tasks, std::max<int32_t>(Pc, 1)));
-    int64_t k_max = std::max<int64_t>(1, g.Nu / 4096);
-    int64_t K = std::min(k_target, k_max);
-    fp.seg = round_up(div_up(std::max<int64_t>(g.Nu, 1), K), 128);
-    fp.K = (int32_t)div_up(std::max<int64_t>(g.Nu, 1), fp.seg);
-    fp.label_row_bytes = (size_t)g.Nu_pad * g.lab_bytes;
-    // FAST "lane" path: one thread per segment, per-thread per-type state in shared memory ([Ts + 1][Kp]
-    // doubles). With too many cell types for at least 128 threads per permutation, the types are processed in
-    // slices of Ts <= 109 (256 threads), one full pass over the labels per slice.
-    fp.lane_path = false;
-    const char* force = std::getenv("PCTSEA_FAST_PATH");  // "coop" | "lane": testing aid
-    if (g.Nu >= 4096 && g.T >= 1 && !(force && std::string(force) == "coop")) {
-        auto threads_for = [](int types) {
-            const size_t budget = 220 * 1024 - (size_t)(types + 1) * 24 - 256;
-            const int kp = (int)std::min<size_t>(256, budget / ((size_t)(types + 1) * 8));
-            return (kp / 32) * 32;
-        };
-        int ts = g.T, kp = threads_for(g.T);
-        int min_kp = 128;
-        if (const char* e = std::getenv("PCTSEA_LANE_MIN_THREADS")) min_kp = std::atoi(e);   // tuning aid
-        if (kp < min_kp) {
-            const int n_slices = (int)div_up(g.T, 109);
-            ts = (int)div_up(g.T, n_slices);
-            kp = threads_for(ts);
-        }
-        fp.lane_path = true;
-        fp.Kp = kp;
-        fp.slice_T = ts;
-        fp.lane_seg = (int32_t)round_up(div_up(g.Nu, kp), 32);  // the lane kernel steps 32 positions (LANE_MS words) at a time
-        fp.label_row_bytes = (size_t)fp.lane_seg * kp * g.lab_bytes;
-    }
-    return fp;
-}
-
-struct FeistelParams {
-    uint32_t a, b;
-    int rounds;
-    uint64_t seed;
-};
-
-// Round tables for permutation p into shared memory: tab[j*a + v] in [0, mod_j).
-__device__ __forceinline__ void feistel_build_tables(uint16_t* tab, const FeistelParams& fp, uint32_t p, int tid,
-                                                     int nthreads) {
-    const uint32_t n4 = (fp.a + 3) >> 2;
-    const uint32_t total = (uint32_t)fp.rounds * n4;
-    for (uint32_t e = tid; e < total; e += nthreads) {
-        uint32_t j = e / n4, blk = e - j * n4;
-        uint32_t dom = (j & 1) ? fp.a : fp.b;
-        uint32_t mod = (j & 1) ? fp.b : fp.a;
-        if (blk * 4 >= dom) continue;
-        uint32_t o[4];
-        philox4x32_10(blk, j, p, 0x46454953u, (uint32_t)fp.seed, (uint32_t)(fp.seed >> 32), o);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t v = blk * 4 + q;
-            if (v < dom) tab[j * fp.a + v] = (uint16_t)__umulhi(o[q], mod);
-        }
-    }
-}
-
-template <int NR>
-__device__ __forceinline__ uint32_t feistel_apply(const uint16_t* __restrict__ tab, uint32_t a, uint32_t b, int rounds_rt,
-                                                  uint32_t L, uint32_t R, uint32_t n) {
-    const int rounds = NR > 0 ? NR : rounds_rt;
-    uint32_t y;
-    do {
-#pragma unroll
-        for (int j = 0; j < rounds; j += 2) {
-            L += tab[j * a + R];
-            L = min(L, L - a);   // unsigned: L - a wraps above L exactly when L < a
-            if (j + 1 < rounds) {
-                R += tab[(j + 1) * a + L];
-                R = min(R, R - b);
-            }
-        }
-        y = L * b + R;
-    } while (y >= n);  // cycle-walk: < a of the a*b points are out of range
-    return y;
-}
-
-// One CTA = one permutation x WPC consecutive segments; lanes take 4 (u8) or 2 (u16) consecutive positions
-// so that every warp store is a full 128-byte line of labels.
-template <typename LabT, int NR>
-__global__ void __launch_bounds__(WPC * 32) k_labels_philox(const LabT* __restrict__ lab_rank, int64_t Nu, int64_t Nu_pad,
-                                                           int32_t T, FeistelParams fp, int32_t perm_begin, int64_t seg,
-                                                           int32_t K, LabT* __restrict__ labels) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.y;
-    feistel_build_tables(tab, fp, (uint32_t)(perm_begin + p), threadIdx.x, WPC * 32);
-    __syncthreads();
-
-    const int k = blockIdx.x * WPC + warp;
-    if (k >= K) return;
-    const int64_t xbeg = (int64_t)k * seg;
-    const int64_t xend = min(xbeg + seg, Nu_pad);
-    LabT* out = labels + (size_t)p * Nu_pad;
-    constexpr int PER = (sizeof(LabT) == 1) ? 4 : 2;  // labels per 32-bit store
-    const uint32_t n = (uint32_t)Nu, a = fp.a, b = fp.b;
-
-    // (L, R) = (x / b, x % b) of this lane's first position, then advanced incrementally
-    int64_t x0 = xbeg + (int64_t)lane * PER;
-    uint32_t L0 = (uint32_t)(x0 / b), R0 = (uint32_t)(x0 - (int64_t)L0 * b);
-    for (; x0 < xend; x0 += 32 * PER) {
-        uint32_t packed = 0;
-        uint32_t L = L0, R = R0;
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            uint32_t cls = (uint32_t)T;
-            if (x0 + q < Nu) cls = (uint32_t)lab_rank[feistel_apply<NR>(tab, a, b, fp.rounds, L, R, n)];
-            packed |= cls << (q * 8 * (int)sizeof(LabT));
-            R++;
-            if (R >= b) { R = 0; L++; }
-        }
-        *reinterpret_cast<uint32_t*>(out + x0) = packed;
-        R0 += 32 * PER;
-        while (R0 >= b) { R0 -= b; L0++; }
-    }
-}
-
-// Same permutation, "lane" layout for the FAST lane kernel: thread k of a permutation owns the segment
-// [k*seg, (k+1)*seg) and writes one 32-bit word (4 labels) per step to labelsT[p][i4][k], so that the
-// consumer's thread k reads its own segment with fully coalesced loads.
-template <typename LabT> struct LanePack;   // four labels -> one word of the lane layout
-template <> struct LanePack<uint8_t> {
-    typedef uint32_t type;
-    static __device__ __forceinline__ uint32_t pack(const uint32_t c[4]) { return c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24); }
-};
-template <> struct LanePack<uint16_t> {
-    typedef uint2 type;
-    static __device__ __forceinline__ uint2 pack(const uint32_t c[4]) { return make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16)); }
-};
-
-// Labels in the "lane" layout of the FAST lane kernel: thread k of a permutation owns the segment
-// [k*seg, (k+1)*seg), and labelsT[p][i4][k] holds its positions 4*i4 .. 4*i4+3 (one word), so that the consumer's
-// thread k reads its own segment with fully coalesced loads. Persistent CTAs walk permutations p = blockIdx.x,
-// blockIdx.x + gridDim.x, ...; warp tasks are (32 consecutive segments, one word).
-// LAB_SMEM (rankings that fit on chip, 8-bit labels): one CTA per SM keeps the whole rank -> class array in shared
-// memory next to the round tables, so the label gather lab_rank[pi(x)] is a shared-memory read (a few wavefronts
-// per warp) instead of 32 divergent L1/L2 sectors. Otherwise the gather goes to L2 and two CTAs share an SM.
-template <typename LabT, int NR, bool LAB_SMEM>
-__global__ void __launch_bounds__(1024, LAB_SMEM ? 1 : 2) k_labels_philox_lane(
-    const LabT* __restrict__ lab_rank, int64_t Nu, int32_t T, FeistelParams fp, int32_t perm_begin, int32_t Pc, int32_t seg,
-    int32_t Kp, uint32_t lab_bytes, typename LanePack<LabT>::type* __restrict__ labelsT, int* __restrict__ ticket) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_p;
-    uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + (LAB_SMEM ? lab_bytes : 0u));   // [rounds][a]
-    const LabT* lab = lab_rank;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (LAB_SMEM) {
-        LabT* lab_s = reinterpret_cast<LabT*>(smem_raw);   // [Nu], padded to lab_bytes
-        const int64_t nbytes = Nu * (int64_t)sizeof(LabT);
-        const int n16 = (int)(nbytes >> 4);
-        const uint4* src = reinterpret_cast<const uint4*>(lab_rank);
-        uint4* dst = reinterpret_cast<uint4*>(lab_s);
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
-        for (int64_t i = ((int64_t)n16 << 4) / (int64_t)sizeof(LabT) + threadIdx.x; i < Nu; i += blockDim.x) lab_s[i] = lab_rank[i];
-        lab = lab_s;
-    }
-    const int seg4 = seg >> 2, groups = Kp >> 5;
-    const uint32_t n = (uint32_t)Nu, a = fp.a, b = fp.b;
-    const uint32_t step = 4u * (uint32_t)nwarps;   // positions between a warp's consecutive words (< b whenever
-                                                   // Nu >= 128^2, else the wrap loop below takes a few turns)
-    // Permutations are handed out by a ticket counter, not round-robin: the observed-statistics kernels run beside
-    // this kernel on some of the SMs (second stream), and a CTA that shares its SM with them simply takes fewer
-    // permutations. Which CTA writes a permutation does not matter: p alone fixes its content and its place.
-    for (;;) {
-        __syncthreads();   // the previous permutation's table readers are done (and lab_s is loaded)
-        if (threadIdx.x == 0) s_p = atomicAdd(ticket, 1);
-        __syncthreads();
-        const int p = s_p;
-        if (p >= Pc) break;
-        feistel_build_tables(tab, fp, (uint32_t)(perm_begin + p), threadIdx.x, blockDim.x);
-        __syncthreads();
-        typename LanePack<LabT>::type* out = labelsT + (size_t)p * seg4 * Kp;
-        // warp tasks (segment group kg, word i4) are dealt round-robin over the flattened index kg*seg4 + i4, but
-        // walked group by group so that (L, R) = (x / b, x % b) advances by a fixed step without divisions
-        for (int kg = 0; kg < groups; kg++) {
-            const int k = kg * 32 + lane;
-            const int first = (warp + nwarps - (int)(((int64_t)kg * seg4) % nwarps)) % nwarps;
-            if (first >= seg4) continue;
-            uint32_t x0 = (uint32_t)k * (uint32_t)seg + 4u * (uint32_t)first;
-            uint32_t L0 = x0 / b, R0 = x0 - L0 * b;
-            for (int i4 = first; i4 < seg4; i4 += nwarps) {
-                uint32_t L = L0, R = R0;
-                uint32_t cls[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    cls[q] = (uint32_t)T;
-                    if (x0 + q < n) cls[q] = (uint32_t)lab[feistel_apply<NR>(tab, a, b, fp.rounds, L, R, n)];
-                    R++;
-                    if (R >= b) { R = 0; L++; }
-                }
-                out[(size_t)i4 * Kp + k] = LanePack<LabT>::pack(cls);
-                x0 += step;
-                R0 += step;
-                while (R0 >= b) { R0 -= b; L0++; }
-            }
-        }
-    }
-}
-
-void launch_labels_philox(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc,
-                          int rounds, bool want_sums, const FastPlan& plan, cudaStream_t st, size_t label_off) {
-    if (Pc == 0 || g.Nu == 0) return;
-    unsigned char* lbase = c->labels.as<unsigned char>() + label_off;
-    FeistelParams fp;
-    feistel_dims(g.Nu, &fp.a, &fp.b);
-    PCT_REQUIRE(fp.a <= 65535, "too many ranked cells for the 16-bit Feistel tables");
-    fp.rounds = rounds;
-    fp.seed = seed;
-    const size_t smem = (((size_t)rounds * fp.a * 2 + 15) / 16) * 16;
-    PCT_REQUIRE(smem <= 227 * 1024, "Feistel tables exceed shared memory");
-    const bool lane = want_sums && plan.lane_path;  // want_sums == FAST arithmetic
-    for (int32_t p0 = 0; p0 < Pc; p0 += 32768) {
-        int32_t pc = std::min<int32_t>(32768, Pc - p0);
-        if (lane) {
-            const size_t lab_bytes = (size_t)round_up(g.Nu * (int64_t)g.lab_bytes, 16);
-            const char* lab_env = std::getenv("PCTSEA_LABELS_PATH");   // "gather": testing aid, keeps lab_rank in L2
-            const bool lab_smem = g.lab_bytes == 1 && lab_bytes + smem <= 226 * 1024 && !(lab_env && std::string(lab_env) == "gather");
-            const size_t smem_s = (lab_smem ? lab_bytes : 0) + smem;
-            const unsigned grid_s = (unsigned)std::min<int32_t>(pc, lab_smem ? kNumSMs : 2 * kNumSMs);
-            unsigned char* dst = lbase + (size_t)p0 * plan.label_row_bytes;
-            c->lab_ticket.reserve(64);
-            PCT_CUDA(cudaMemsetAsync(c->lab_ticket.p, 0, 4, st));
-#define PCT_LAUNCH_LAB_LANE(LT, NR, SM)                                                                                   \
-    do {                                                                                                                  \
-        ensure_dyn_smem(c, k_labels_philox_lane<LT, NR, SM>, (size_t)(smem_s)); \
-        k_labels_philox_lane<LT, NR, SM><<<grid_s, 1024, smem_s, st>>>(c->lab_rank.as<LT>(), g.Nu, g.T, fp, perm_begin + p0, pc, \
-                                                                       plan.lane_seg, plan.Kp, (uint32_t)lab_bytes,        \
-                                                                       reinterpret_cast<LanePack<LT>::type*>(dst),         \
-                                                                       c->lab_ticket.as<int>());                           \
-    } while (0)
-            // the round count is a template parameter for the two usual values (unrolled table look-ups)
-#define PCT_LAUNCH_LAB_LANE_R(LT, SM)                                                                                     \
-    do {                                                                                                                  \
-        if (rounds == 4) PCT_LAUNCH_LAB_LANE(LT, 4, SM); else if (rounds == 6) PCT_LAUNCH_LAB_LANE(LT, 6, SM);            \
-        else PCT_LAUNCH_LAB_LANE(LT, 0, SM);                                                                              \
-    } while (0)
-            if (lab_smem) PCT_LAUNCH_LAB_LANE_R(uint8_t, true);
-            else if (g.lab_bytes == 1) PCT_LAUNCH_LAB_LANE_R(uint8_t, false);
-            else PCT_LAUNCH_LAB_LANE_R(uint16_t, false);
-#undef PCT_LAUNCH_LAB_LANE_R
-#undef PCT_LAUNCH_LAB_LANE
-            count_launch(c);
-            continue;
-        }
-        dim3 grid((unsigned)div_up(plan.K, WPC), (unsigned)pc);
-#define PCT_LAUNCH_LAB(LT, NR)                                                                                         \
-    do {                                                                                                               \
-        ensure_dyn_smem(c, k_labels_philox<LT, NR>, (size_t)(smem)); \
-        k_labels_philox<LT, NR><<<grid, WPC * 32, smem, st>>>(c->lab_rank.as<LT>(), g.Nu, g.Nu_pad, g.T, fp,           \
-                                                                     perm_begin + p0, plan.seg, plan.K,                \
-                                                                     reinterpret_cast<LT*>(lbase) + (size_t)p0 * g.Nu_pad); \
-    } while (0)
-        if (g.lab_bytes == 1) { if (rounds == 4) PCT_LAUNCH_LAB(uint8_t, 4); else if (rounds == 6) PCT_LAUNCH_LAB(uint8_t, 6); else PCT_LAUNCH_LAB(uint8_t, 0); }
-        else                  { if (rounds == 4) PCT_LAUNCH_LAB(uint16_t, 4); else if (rounds == 6) PCT_LAUNCH_LAB(uint16_t, 6); else PCT_LAUNCH_LAB(uint16_t, 0); }
-#undef PCT_LAUNCH_LAB
-        count_launch(c);
-    }
-    PCT_CUDA(cudaGetLastError());
-}
-
-// ================================================================================================
-// FAST KS null: one CTA per permutation, one warp per segment of ranked positions, lanes = positions.
-//   phase 1  per-segment, per-type sums of the fixed-point scores (no atomics: the two dominant classes
-//            accumulate in registers, the others are reduced per same-type lane group by its lowest lane)
-//   phase 2  exclusive prefix over the segments -> each warp's starting sums; totals -> 1/denomA, 1/denomB
-//   phase 3  the supremum of |a - b| evaluated at every hit and pre-hit position: the running sum of a
-//            type at a lane = segment start + by-type prefix inside the warp step (full-warp scans for the
-//            two dominant classes, a short shuffle loop over same-type lower lanes for the rest)
-//   phase 4  decode the winning key -> null ES and dStat
-// All sums are integers (|fx| <= 2^25) carried exactly in int32/int64/fp64, so the result does not depend
-// on the segmentation, the lane grouping or the GPU count.
-// ================================================================================================
-constexpr int FAST_WARPS = 32;
-
-__device__ __forceinline__ uint32_t sup_key(float f) {
-    // larger |diff| wins; on equal |diff| the positive one wins — an order-independent rule
-    uint32_t b = (uint32_t)__float_as_int(f);
-    uint32_t ab = b & 0x7fffffffu;
-    if (ab == 0) return 0u;
-    return (ab << 1) | ((b >> 31) ^ 1u);
-}
-
-__device__ __forceinline__ int warp_incl_scan_i32(int v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-    }
-    return v;
-}
-
-// Sum of `f` over the other lanes of my group, for group leaders (lowest lane); 0 elsewhere.
-__device__ __forceinline__ int group_sum_others(unsigned members, int f, int lane) {
-    unsigned rem = members;
-    int sum = 0;
-    while (__any_sync(0xffffffffu, rem != 0u)) {
-        const int src = rem ? (__ffs(rem) - 1) : lane;
-        const int v = __shfl_sync(0xffffffffu, f, src);
-        if (rem) { sum += v; rem &= rem - 1u; }
-    }
-    return sum;
-}
-
-template <typename LabT>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 1) k_ks_fast(
-    const LabT* __restrict__ labels, const int* __restrict__ fx, const double* __restrict__ Sd, int64_t Nu,
-    int64_t Nu_pad, int32_t T, int64_t seg, const int32_t* __restrict__ peel, const int32_t* __restrict__ class_cnt,
-    float* __restrict__ null_ews, float* __restrict__ null_d, int32_t P_stride, int32_t p_off) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int Tc = T + 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x;
-    const int nwarps = blockDim.x >> 5;   // as many segments per permutation as the shared memory allows (<= 32)
-    double* numA_all = reinterpret_cast<double*>(smem_raw);              // [nwarps][Tc]
-    double* c1s = numA_all + (size_t)nwarps * Tc;                        // [Tc]
-    double* c2s = c1s + Tc;                                              // [Tc]
-    uint32_t* best = reinterpret_cast<uint32_t*>(c2s + Tc);              // [Tc]
-    double* numA = numA_all + (size_t)warp * Tc;
-    for (int i = threadIdx.x; i < nwarps * Tc; i += blockDim.x) numA_all[i] = 0.0;
-    for (int i = threadIdx.x; i < Tc; i += blockDim.x) best[i] = 0u;
-    __syncthreads();
-
-    const int peel0 = peel[0], peel1 = peel[1];
-    const LabT* lab = labels + (size_t)p * Nu_pad;
-    const int64_t xbeg = min((int64_t)warp * seg, Nu), xend = min(xbeg + seg, Nu);
-    const unsigned lt = (1u << lane) - 1u;
-
-    // ---- phase 1: segment sums
-    {
-        long long acc0 = 0, acc1 = 0;
-        for (int64_t xb = xbeg; xb < xend; xb += 32) {
-            const int64_t x = xb + lane;
-            const bool inb = x < xend;
-            const int t = inb ? (int)lab[x] : T;
-            const int f = inb ? fx[x] : 0;
-            acc0 += (t == peel0) ? f : 0;
-            acc1 += (t == peel1) ? f : 0;
-            const bool resid = (t < T) && (t != peel0) && (t != peel1);
-            if (__any_sync(0xffffffffu, resid)) {
-                const unsigned grp = __match_any_sync(0xffffffffu, resid ? t : (Tc + lane));
-                const bool leader = resid && ((grp & lt) == 0u);
-                const int others = group_sum_others(leader ? (grp & ~(1u << lane)) : 0u, f, lane);
-                if (leader) numA[t] += (double)(f + others);
-                __syncwarp();
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-        }
-        if (lane == 0) {
-            if (peel0 >= 0) numA[peel0] = (double)acc0;
-            if (peel1 >= 0) numA[peel1] = (double)acc1;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: exclusive prefix over segments, reciprocals of the denominators
-    {
-        const double Stot = Sd[Nu - 1];
-        for (int t = threadIdx.x; t < Tc; t += blockDim.x) {
-            double run = 0.0;
-            for (int w = 0; w < nwarps; w++) {
-                const double v = numA_all[(size_t)w * Tc + t];
-                numA_all[(size_t)w * Tc + t] = run;
-                run += v;
-            }
-            const double dA = run, dB = Stot - run;
-            // diff = numA/dA - (S - numA)/dB = numA * (1/dA + 1/dB) - S * (1/dB)
-            double c12 = 0.0, c2 = 0.0;
-            if (t < T && dA != 0.0 && dB != 0.0) {
-                c2 = __ddiv_rn(1.0, dB);
-                c12 = __dadd_rn(__ddiv_rn(1.0, dA), c2);
-            }
-            c1s[t] = c12;
-            c2s[t] = c2;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3: suprema
-    {
-        double base0 = (peel0 >= 0) ? numA[peel0] : 0.0, base1 = (peel1 >= 0) ? numA[peel1] : 0.0;
-        uint32_t bestp0 = 0u, bestp1 = 0u;
-        for (int64_t xb = xbeg; xb < xend; xb += 32) {
-            const int64_t x = xb + lane;
-            const bool inb = x < xend;
-            const int t = inb ? (int)lab[x] : T;
-            const bool active = t < T;
-            int f = 0;
-            double S = 0.0;
-            if (active) { f = fx[x]; S = Sd[x]; }
-            const bool is0 = (t == peel0), is1 = (t == peel1);
-            const int v0 = is0 ? f : 0, v1 = is1 ? f : 0;
-            const int incl0 = warp_incl_scan_i32(v0, lane), incl1 = warp_incl_scan_i32(v1, lane);
-            const int tot0 = __shfl_sync(0xffffffffu, incl0, 31), tot1 = __shfl_sync(0xffffffffu, incl1, 31);
-            int pre = is0 ? (incl0 - v0) : (is1 ? (incl1 - v1) : 0);
-            const bool resid = active && !is0 && !is1;
-            unsigned grp = 0u;
-            const bool any_resid = __any_sync(0xffffffffu, resid);
-            if (any_resid) {
-                grp = __match_any_sync(0xffffffffu, resid ? t : (Tc + lane));
-                // by-type prefix over the lower lanes of my group
-                unsigned rem = resid ? (grp & lt) : 0u;
-                while (__any_sync(0xffffffffu, rem != 0u)) {
-                    const int src = rem ? (__ffs(rem) - 1) : lane;
-                    const int v = __shfl_sync(0xffffffffu, f, src);
-                    if (rem) { pre += v; rem &= rem - 1u; }
-                }
-            }
-            double after = 0.0;
-            if (active) {
-                const double start = is0 ? base0 : (is1 ? base1 : numA[t]);
-                const double before = start + (double)pre;
-                after = before + (double)f;
-                const double c12 = c1s[t], c2 = c2s[t];
-                const double d1 = __fma_rn(after, c12, -__dmul_rn(S, c2));
-                uint32_t key = sup_key(__double2float_rn(d1));
-                if (x > 0) {
-                    const double Sp = S - (double)f;
-                    const double d0 = __fma_rn(before, c12, -__dmul_rn(Sp, c2));
-                    const uint32_t k0 = sup_key(__double2float_rn(d0));
-                    key = k0 > key ? k0 : key;
-                }
-                if (is0) bestp0 = key > bestp0 ? key : bestp0;
-                else if (is1) bestp1 = key > bestp1 ? key : bestp1;
-                else if (key) atomicMax(&best[t], key);
-            }
-            base0 += (double)tot0;
-            base1 += (double)tot1;
-            if (any_resid) {
-                __syncwarp();
-                if (resid && (grp >> lane) == 1u) numA[t] = after;  // highest lane of the group carries the state
-                __syncwarp();
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const uint32_t u0 = __shfl_xor_sync(0xffffffffu, bestp0, o), u1 = __shfl_xor_sync(0xffffffffu, bestp1, o);
-            bestp0 = u0 > bestp0 ? u0 : bestp0;
-            bestp1 = u1 > bestp1 ? u1 : bestp1;
-        }
-        if (lane == 0) {
-            if (peel0 >= 0 && bestp0) atomicMax(&best[peel0], bestp0);
-            if (peel1 >= 0 && bestp1) atomicMax(&best[peel1], bestp1);
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 4: decode
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        const int32_t nk = class_cnt[t];
-        const int32_t sizeb = (int32_t)(Nu - nk);
-        float v, d;
-        if (!(nk > 1 && sizeb > 1)) { v = __int_as_float(0x7fc00000); d = v; }
-        else {
-            const uint32_t key = best[t];
-            v = (key == 0u) ? 0.0f : __int_as_float((int)((key >> 1) | (((key & 1u) ^ 1u) << 31)));
-            d = dstat_of(v, nk, sizeb);
-        }
-        null_ews[(size_t)t * P_stride + p_off + p] = v;
-        null_d[(size_t)t * P_stride + p_off + p] = d;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// FAST, "lane" variant (small type counts): one CTA per permutation, one THREAD per segment. Every thread
-// walks its own segment sequentially and keeps its own per-type running sums in shared memory
-// (numA[t][k], k fastest => conflict-free), so there is no cross-lane grouping at all: ~1 warp-instruction
-// per (cell x permutation) instead of ~9. Same integer arithmetic as k_ks_fast => bit-identical results.
-// Inputs are laid out so that thread k's stream is coalesced: labelsT[p][i4][k] (4 labels per word),
-// fxT4[i4][k] (4 fixed-point scores per int4).
-// ------------------------------------------------------------------------------------------------
-__global__ void k_fx_transpose(const int* __restrict__ fx, int64_t Nu, int32_t seg, int32_t Kp, int4* __restrict__ fxT4) {
-    const int seg4 = seg >> 2;
-    int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= (int64_t)seg4 * Kp) return;
-    const int k = (int)(id % Kp), i4 = (int)(id / Kp);
-    const int64_t x = (int64_t)k * seg + 4 * i4;
-    int4 v;
-    v.x = (x + 0 < Nu) ? fx[x + 0] : 0;
-    v.y = (x + 1 < Nu) ? fx[x + 1] : 0;
-    v.z = (x + 2 < Nu) ? fx[x + 2] : 0;
-    v.w = (x + 3 < Nu) ? fx[x + 3] : 0;
-    fxT4[id] = v;
-}
-
-__device__ __forceinline__ uint32_t sup_key_fast(float f) {
-    // same order as sup_key, except that +0 maps to 1 instead of 0: it still loses to every non-zero
-    // difference and decodes to +0, so the winner is unchanged
-    const uint32_t b = (uint32_t)__float_as_int(f);
-    return __funnelshift_l(~b, b, 1);   // (b << 1) | (~b >> 31)
-}
-
-constexpr int LANE_MS = 8;   // label words (4 positions each) per macro step of the lane kernel
-
-// Label word of the lane layout: four consecutive positions of one thread's segment.
-template <typename LabT> struct LaneWord;
-template <> struct LaneWord<uint8_t> {
-    typedef uint32_t type;
-    static __device__ __forceinline__ uint32_t get(uint32_t w, int q) { return (w >> (8 * q)) & 0xffu; }
-};
-template <> struct LaneWord<uint16_t> {
-    typedef uint2 type;
-    static __device__ __forceinline__ uint32_t get(uint2 w, int q) { return ((q < 2 ? w.x : w.y) >> (16 * (q & 1))) & 0xffffu; }
-};
-
-// SLICED: more cell types than the per-thread shared-memory state can hold at once. The kernel then makes one
-// full pass (phases 1-4) per slice of Ts types, with every other type mapped to the slice's dummy column (Ts),
-// which takes the same read-modify-write but has zero constants, so it can never set a maximum.
-template <typename LabT, bool SLICED>
-__global__ void __launch_bounds__(256, 1) k_ks_fast_lane(
-    const typename LaneWord<LabT>::type* __restrict__ labelsT, const int4* __restrict__ fxT4, const double* __restrict__ Sd,
-    int64_t Nu, int32_t T_all, int32_t Ts, int32_t seg, const int32_t* __restrict__ class_cnt,
-    float* __restrict__ null_ews, float* __restrict__ null_d, int32_t P_stride, int32_t p_off) {
-    typedef typename LaneWord<LabT>::type Word;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int Tc = Ts + 1;
-    const int Kp = blockDim.x;
-    const int k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarp = Kp >> 5;
-    const int p = blockIdx.x;
-    double2* cs = reinterpret_cast<double2*>(smem_raw);                  // [Tc] (c12, c2)
-    double* numA = reinterpret_cast<double*>(cs + Tc);                   // [Tc][Kp]
-    uint32_t* best = reinterpret_cast<uint32_t*>(numA + (size_t)Tc * Kp);  // [Tc]
-    const int seg4 = seg >> 2;
-    const Word* lab = labelsT + (size_t)p * seg4 * Kp + k;
-    const int4* fxp = fxT4 + k;
-    // this thread's private column: type t lives at col + t * Kp (bank = k % 32 for every t: conflict-free)
-    double* col = numA + k;
-
-  for (int t0 = 0; t0 < T_all; t0 += Ts) {   // one iteration unless SLICED
-    const int T = min(Ts, T_all - t0);        // real types of this slice: local ids [0, T), dummy = Ts
-    // local type id of a label: slice members keep their offset, everything else goes to the dummy column
-    auto local_type = [&](uint32_t t) -> uint32_t {
-        if (!SLICED) return t;   // labels are already in [0, T_all] with T_all = Ts the padding / unknown class
-        const uint32_t tl = t - (uint32_t)t0;
-        return tl < (uint32_t)T ? tl : (uint32_t)Ts;
-    };
-    for (int t = 0; t < Tc; t++) col[(size_t)t * Kp] = 0.0;
-    for (int t = k; t < Tc; t += Kp) best[t] = 0u;
-    // (each thread only touches its own column until the barrier)
-
-    // ---- phase 1: per-segment, per-type sums: one shared-memory read-modify-write per position, in program
-    // order (same-type repeats see the previous store). 4 * LANE_MS positions per macro step with the next macro
-    // step's loads in flight. Padding positions carry type T and f = 0.
-    {
-        // the words of a macro step live in LANE_MS register sets; a set is refilled with the word of the next
-        // macro step as soon as its own word has been consumed (in place: no register rotation), so the loads run
-        // LANE_MS - 1 words ahead of their use
-        Word wc[LANE_MS];
-        int4 fc[LANE_MS];
-#pragma unroll
-        for (int u = 0; u < LANE_MS; u++) { wc[u] = lab[(size_t)u * Kp]; fc[u] = fxp[(size_t)u * Kp]; }
-        for (int i4 = 0; i4 < seg4; i4 += LANE_MS) {
-            const bool more = i4 + LANE_MS < seg4;   // seg4 is a multiple of LANE_MS
-#pragma unroll
-            for (int u = 0; u < LANE_MS; u++) {
-                const int fq[4] = { fc[u].x, fc[u].y, fc[u].z, fc[u].w };
-                const Word wcu = wc[u];
-                if (more) { wc[u] = lab[(size_t)(i4 + LANE_MS + u) * Kp]; fc[u] = fxp[(size_t)(i4 + LANE_MS + u) * Kp]; }
-                // two positions at a time: both columns are read up front and a same-type pair is chained in
-                // registers, which halves the load -> add -> store chain; pairs follow each other in program order
-#pragma unroll
-                for (int q = 0; q < 4; q += 2) {
-                    const uint32_t ta = local_type(LaneWord<LabT>::get(wcu, q)), tb = local_type(LaneWord<LabT>::get(wcu, q + 1));
-                    double* s0 = col + (size_t)ta * Kp;
-                    double* s1 = col + (size_t)tb * Kp;
-                    const double b0 = *s0, b1 = *s1;
-                    const double a0 = b0 + (double)fq[q];
-                    const double a1 = (ta == tb ? a0 : b1) + (double)fq[q + 1];
-                    *s0 = a0;
-                    *s1 = a1;   // same type: the second store wins
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: exclusive prefix over the segments (warp w scans types w, w + nwarp, ...), reciprocals
-    {
-        const double Stot = Sd[Nu - 1];
-        for (int t = warp; t < Tc; t += nwarp) {
-            double carry = 0.0;
-            for (int k0 = 0; k0 < Kp; k0 += 32) {
-                const double v = numA[(size_t)t * Kp + k0 + lane];
-                double incl = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double u = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += u;
-                }
-                numA[(size_t)t * Kp + k0 + lane] = carry + (incl - v);
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (lane == 0) {
-                const double dA = carry, dB = Stot - carry;
-                double c12 = 0.0, c2 = 0.0;
-                if (t < T && dA != 0.0 && dB != 0.0) {
-                    c2 = __ddiv_rn(1.0, dB);
-                    c12 = __dadd_rn(__ddiv_rn(1.0, dA), c2);
-                }
-                cs[t] = make_double2(c12, c2);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3: suprema at hit / pre-hit positions. Per group of 4 positions: the four running-sum
-    // updates in program order, then the eight candidate differences (independent arithmetic), then the
-    // shared-memory maxima. At the global position 0 the pre-hit candidate is exactly 0 and cannot win.
-    {
-        const int64_t x0 = (int64_t)k * seg;
-        double S = (x0 > 0 && x0 <= Nu) ? Sd[x0 - 1] : 0.0;   // exact prefix before my segment
-        Word wc[LANE_MS];   // register sets refilled in place, as in phase 1
-        int4 fc[LANE_MS];
-#pragma unroll
-        for (int u = 0; u < LANE_MS; u++) { wc[u] = lab[(size_t)u * Kp]; fc[u] = fxp[(size_t)u * Kp]; }
-        for (int i4 = 0; i4 < seg4; i4 += LANE_MS) {
-            const bool more = i4 + LANE_MS < seg4;
-#pragma unroll
-            for (int u = 0; u < LANE_MS; u++) {
-                const int fq[4] = { fc[u].x, fc[u].y, fc[u].z, fc[u].w };
-                const Word wcu = wc[u];
-                if (more) { wc[u] = lab[(size_t)(i4 + LANE_MS + u) * Kp]; fc[u] = fxp[(size_t)(i4 + LANE_MS + u) * Kp]; }
-                uint32_t t[4];
-                double f[4], b[4], a[4];
-#pragma unroll
-                for (int q = 0; q < 4; q += 2) {   // pairs, as in phase 1
-                    t[q] = local_type(LaneWord<LabT>::get(wcu, q));
-                    t[q + 1] = local_type(LaneWord<LabT>::get(wcu, q + 1));
-                    f[q] = (double)fq[q];
-                    f[q + 1] = (double)fq[q + 1];
-                    double* s0 = col + (size_t)t[q] * Kp;
-                    double* s1 = col + (size_t)t[q + 1] * Kp;
-                    b[q] = *s0;
-                    const double b1 = *s1;
-                    a[q] = b[q] + f[q];
-                    b[q + 1] = (t[q] == t[q + 1]) ? a[q] : b1;
-                    a[q + 1] = b[q + 1] + f[q + 1];
-                    *s0 = a[q];
-                    *s1 = a[q + 1];
-                }
-                // the current maxima first (plain reads, issued together so that their latency hides behind the
-                // candidate arithmetic): best[] only grows, so a candidate that does not beat the possibly stale
-                // value read here cannot beat the current one either. Record-setting candidates are rare and a
-                // shared-memory atomic costs one wavefront per active lane, so the atomics sit behind one branch
-                // per group of four positions.
-                uint32_t cur[4], key[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) cur[q] = reinterpret_cast<volatile uint32_t*>(best)[t[q]];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const double2 c = cs[t[q]];
-                    const double Sp = S;
-                    S += f[q];   // exact: integers below 2^53
-                    const uint32_t k1 = sup_key_fast(__double2float_rn(__fma_rn(a[q], c.x, -__dmul_rn(S, c.y))));
-                    const uint32_t k0 = sup_key_fast(__double2float_rn(__fma_rn(b[q], c.x, -__dmul_rn(Sp, c.y))));
-                    key[q] = k0 > k1 ? k0 : k1;
-                }
-                if ((key[0] > cur[0]) | (key[1] > cur[1]) | (key[2] > cur[2]) | (key[3] > cur[3])) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        if (key[q] > cur[q]) atomicMax(&best[t[q]], key[q]);
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 4: decode
-    for (int t = k; t < T; t += Kp) {
-        const int32_t nk = class_cnt[t0 + t];
-        const int32_t sizeb = (int32_t)(Nu - nk);
-        float v, d;
-        if (!(nk > 1 && sizeb > 1)) { v = __int_as_float(0x7fc00000); d = v; }
-        else {
-            const uint32_t key = best[t];
-            v = (key <= 1u) ? 0.0f : __int_as_float((int)((key >> 1) | (((key & 1u) ^ 1u) << 31)));
-            d = dstat_of(v, nk, sizeb);
-        }
-        null_ews[(size_t)(t0 + t) * P_stride + p_off + p] = v;
-        null_d[(size_t)(t0 + t) * P_stride + p_off + p] = d;
-    }
-    __syncthreads();   // the next slice reuses the state
-  }
-}
-
-// Once per enrich call, before the permutation chunks: the lane layout of the fixed-point scores.
-void launch_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const FastPlan& plan) {
-    if (!plan.lane_path || g.Nu == 0) return;
-    const int seg4 = plan.lane_seg >> 2;
-    c->fxT.reserve((size_t)seg4 * plan.Kp * 16 + 64);
-    k_fx_transpose<<<(unsigned)div_up((int64_t)seg4 * plan.Kp, 256), 256, 0, c->stream>>>(
-        c->fx.as<int>(), g.Nu, plan.lane_seg, plan.Kp, c->fxT.as<int4>());
-    count_launch(c);
-    PCT_CUDA(cudaGetLastError());
-}
-
-void launch_ks_fast_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, const FastPlan& plan, int32_t P_stride,
-                         int32_t p_off, size_t label_off) {
-    if (Pc == 0 || g.T == 0 || g.Nu == 0) return;
-    const int32_t* peel_dev = reinterpret_cast<const int32_t*>(c->counters.as<unsigned long long>() + 5);
-    unsigned char* lbase = c->labels.as<unsigned char>() + label_off;
-    if (plan.lane_path) {
-        const int32_t Ts = plan.slice_T;
-        const size_t smem_l = (size_t)(Ts + 1) * plan.Kp * 8 + (size_t)(Ts + 1) * 20 + 16;
-#define PCT_LAUNCH_LANE(LT, SL)                                                                                       \
-    do {                                                                                                              \
-        ensure_dyn_smem(c, k_ks_fast_lane<LT, SL>, (size_t)(smem_l)); \
-        k_ks_fast_lane<LT, SL><<<(unsigned)Pc, plan.Kp, smem_l, c->stream>>>(                                         \
-            reinterpret_cast<const LaneWord<LT>::type*>(lbase), c->fxT.as<int4>(), c->Sfx.as<double>(), g.Nu, g.T, Ts, \
-            plan.lane_seg, c->class_cnt.as<int32_t>(), c->null_ews.as<float>(), c->null_d.as<float>(), P_stride, p_off); \
-    } while (0)
-        if (g.lab_bytes == 2) PCT_LAUNCH_LANE(uint16_t, true);
-        else if (Ts < g.T) PCT_LAUNCH_LANE(uint8_t, true);
-        else PCT_LAUNCH_LANE(uint8_t, false);
-#undef PCT_LAUNCH_LANE
-        count_launch(c);
-        PCT_CUDA(cudaGetLastError());
-        return;
-    }
-    // segments (warps) per permutation: as many as the [warps][Tc] fp64 state allows, at most 32
-    int nw = (int)std::min<size_t>(FAST_WARPS, (225 * 1024 - (size_t)g.Tc * 20 - 16) / ((size_t)g.Tc * 8));
-    PCT_REQUIRE(nw >= 1, "too many cell types for the FAST kernel's shared-memory state");
-    const size_t smem = (size_t)nw * g.Tc * 8 + (size_t)g.Tc * 20 + 16;
-    const int64_t seg = round_up(div_up(g.Nu, nw), 32);
-    const int32_t* peel = reinterpret_cast<const int32_t*>(c->counters.as<unsigned long long>() + 5);
-#define PCT_LAUNCH_FAST(LT)                                                                                    \
-    do {                                                                                                       \
-        ensure_dyn_smem(c, k_ks_fast<LT>, (size_t)(smem)); \
-        k_ks_fast<LT><<<(unsigned)Pc, nw * 32, smem, c->stream>>>(                                     \
-            reinterpret_cast<LT*>(lbase), c->fx.as<int>(), c->Sfx.as<double>(), g.Nu, g.Nu_pad, g.T, seg, peel, \
-            c->class_cnt.as<int32_t>(), c->null_ews.as<float>(), c->null_d.as<float>(), P_stride, p_off);      \
-    } while (0)
-    if (g.lab_bytes == 1) PCT_LAUNCH_FAST(uint8_t); else PCT_LAUNCH_FAST(uint16_t);
-#undef PCT_LAUNCH_FAST
-    count_launch(c);
     PCT_CUDA(cudaGetLastError());
 }
 

@@ -1,0 +1,722 @@
+// null_fused.cu — the label-permutation null of stage 3 in FAST arithmetic: ONE kernel per call that generates the
+// permuted labels and evaluates the weighted-KS supremum of every cell type, permutation by permutation.
+//
+// Replaces (reference paths under pctsea-core/src/main/java/edu/scripps/yates/pctsea/):
+//   a9  PCTSEA.java:1390-1443 (permutation driver: Collections.shuffle of the ranked labels, P times)
+//   a8  utils/parallel/EnrichmentWeigthedScoreParallel.java:104-227 evaluated once per (type, permutation)
+//
+// Permutation (PCTSEA_PERM_PHILOX): position x of permutation p carries the class at index pi_p(x) of the
+// TYPE-SORTED arrangement of the ranked labels (a uniform permutation of any fixed arrangement of the same multiset
+// is a uniform arrangement). pi_p is a keyed Feistel bijection of [0,Nu) on Z_a x Z_b (a = ceil(sqrt Nu),
+// b = ceil(Nu/a), cycle-walking for the < a out-of-range points) with ARITHMETIC round functions
+//   F(v, key, mod) = umulhi(mix(v * M1 + key), mod),   one 32-bit Philox4x32-10 key per round and permutation,
+// so it lives entirely in registers: no tables, no shared memory, and "class of index j" is a look-up in a coarse
+// bucket table of the T+1 cumulative class counts. The round that is applied LAST modifies the high digit (the one
+// that decides the class); with the sorted arrangement the class of a position is a range test on that digit, which
+// exposes the unevenness of a random round FUNCTION after 3-4 rounds as a 2 % inflation of the null's standard
+// deviation (profiles/feistel_rounds_check.txt) — 5 rounds are the default, measured indistinguishable from
+// Collections.shuffle.
+//
+// Arithmetic (PCTSEA_KS_FAST, round 2 form): scores quantised to int32 fixed point with the sum of |fx| over the
+// ranking below 2^31, so every running sum is an exact int32 and the result cannot depend on the segmentation.
+// Every ranked position is a hit for exactly one type, so sup|a-b| of a type can only sit at one of its hits or just
+// before one, and there the two running sums are closed-form: numA from the per-(type, segment) state, the total
+// prefix S from a register. One candidate = one fp32 FMA of the converted sums (the oracle restates the same definition).
+//
+// Kernel: persistent CTAs take permutations from a ticket counter; thread k of a CTA owns the segment
+// [k*seg, (k+1)*seg) of the ranking and keeps its own per-type running sums in shared memory (numA[t][k], k fastest:
+// conflict-free), 4 bytes per (type, thread):
+//   phase 1  generate the labels of the segment (registers only), accumulate the per-type segment sums, park the
+//            labels (1 B per position) in a per-CTA scratch row that stays in L2
+//   phase 2  exclusive prefix over the segments per type; totals -> 1/denomA, 1/denomB
+//   phase 3  second walk: running sums continue from the prefix, two candidates per position, per-type maxima by
+//            shared-memory atomicMax behind a stale-read filter
+//   phase 4  decode -> null ES and dStat
+#include "common.cuh"
+
+namespace pctsea {
+
+// ================================================================================================
+// fixed-point scores
+// ================================================================================================
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+// F0 = 25 - e with maxabs < 2^e, so |llrint(s * 2^F0)| <= 2^25 (same rule as the oracle)
+__device__ __forceinline__ int fast_frac_bits0(unsigned long long maxabs_bits) {
+    const double maxabs = __longlong_as_double((long long)maxabs_bits);
+    int e = 0;
+    if (maxabs > 0.0) e = ilogb(maxabs) + 1;
+    const int F = 25 - e;
+    return F > 1000 ? 1000 : F;
+}
+
+// ... minus the smallest shift that makes ceil(sum|fx0| / 2^sh) + Nu fit an int32
+__device__ __forceinline__ int fast_frac_bits(unsigned long long maxabs_bits, unsigned long long sumabs0, int64_t Nu) {
+    int sh = 0;
+    while ((long long)((sumabs0 + ((1ull << sh) - 1ull)) >> sh) + (long long)Nu > 2147483647LL) sh++;
+    return fast_frac_bits0(maxabs_bits) - sh;
+}
+
+__device__ __forceinline__ double pow2_double(int F) {   // exact for the exponents that can occur (|F| <= 1000)
+    return __longlong_as_double((long long)(1023 + F) << 52);
+}
+
+// sum over the ranking of |llrint(s * 2^F0)|: exact integer, order-independent
+__global__ void __launch_bounds__(SC_THREADS) k_fx_abs_sum(const double* __restrict__ s_rank, int64_t Nu,
+                                                          const unsigned long long* __restrict__ maxabs_bits,
+                                                          unsigned long long* __restrict__ sumabs) {
+    const double scale = pow2_double(fast_frac_bits0(*maxabs_bits));
+    const int64_t base = (int64_t)blockIdx.x * SC_TILE;
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int r = 0; r < SC_ITEMS; r++) {
+        const int64_t i = base + r * SC_THREADS + threadIdx.x;
+        if (i < Nu) {
+            const long long v = __double2ll_rn(__dmul_rn(s_rank[i], scale));
+            sum += (unsigned long long)(v < 0 ? -v : v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(sumabs, sum);
+}
+
+// fx = llrint(s * 2^F) per ranked cell, plus the sum of every SC_TILE-sized tile for the prefix scan.
+__global__ void __launch_bounds__(SC_THREADS) k_fixed_point(const double* __restrict__ s_rank, int64_t Nu,
+                                                           const unsigned long long* __restrict__ maxabs_bits,
+                                                           const unsigned long long* __restrict__ sumabs,
+                                                           int* __restrict__ fx, int32_t* __restrict__ frac_out,
+                                                           int* __restrict__ tile_sum) {
+    __shared__ int ws[SC_THREADS / 32];
+    const int F = fast_frac_bits(*maxabs_bits, *sumabs, Nu);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *frac_out = F;
+    const double scale = pow2_double(F);
+    const int64_t base = (int64_t)blockIdx.x * SC_TILE;
+    int sum = 0;
+#pragma unroll
+    for (int r = 0; r < SC_ITEMS; r++) {
+        const int64_t i = base + r * SC_THREADS + threadIdx.x;
+        if (i < Nu) {
+            const int v = (int)__double2ll_rn(__dmul_rn(s_rank[i], scale));
+            fx[i] = v;
+            sum += v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < SC_THREADS / 32; w++) t += ws[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+__device__ __forceinline__ int warp_incl_scan_i32(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+// Exact int32 prefix sums of the fixed-point scores: every tile first adds up the sums of the tiles before it (a few
+// hundred values written by k_fixed_point), then scans its own items.
+__global__ void __launch_bounds__(SC_THREADS) k_tile_scan_i32(const int* __restrict__ in, int64_t n,
+                                                             const int* __restrict__ tile_sum, int* __restrict__ out) {
+    // thread t owns items [t*8, t*8+8) of the tile => contiguous, so the scan is in index order
+    __shared__ int ws[SC_THREADS / 32];
+    __shared__ int s_before;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        int b = 0;
+        for (int j = threadIdx.x; j < (int)blockIdx.x; j += SC_THREADS) b += tile_sum[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_down_sync(0xffffffffu, b, o);
+        if (lane == 0) ws[warp] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < SC_THREADS / 32; w++) t += ws[w];
+            s_before = t;
+        }
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    int v[SC_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int r = 0; r < SC_ITEMS; r++) { const int64_t i = base + r; v[r] = (i < n) ? in[i] : 0; s += v[r]; v[r] = s; }
+    const int incl = warp_incl_scan_i32(s, lane);
+    if (lane == 31) ws[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; w++) woff += ws[w];
+    const int off = s_before + woff + (incl - s);
+#pragma unroll
+    for (int r = 0; r < SC_ITEMS; r++) { const int64_t i = base + r; if (i < n) out[i] = v[r] + off; }
+}
+
+// Lane layout of the fixed-point scores: thread k of the null kernel owns [k*seg, (k+1)*seg), and fxT4[i4][k] holds
+// its positions 4*i4 .. 4*i4+3, so that every thread's stream is a coalesced load.
+__global__ void k_fx_transpose(const int* __restrict__ fx, int64_t Nu, int32_t seg, int32_t Kp, int4* __restrict__ fxT4) {
+    const int seg4 = seg >> 2;
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (int64_t)seg4 * Kp) return;
+    const int k = (int)(id % Kp), i4 = (int)(id / Kp);
+    const int64_t x = (int64_t)k * seg + 4 * i4;
+    int4 v;
+    v.x = (x + 0 < Nu) ? fx[x + 0] : 0;
+    v.y = (x + 1 < Nu) ? fx[x + 1] : 0;
+    v.z = (x + 2 < Nu) ? fx[x + 2] : 0;
+    v.w = (x + 3 < Nu) ? fx[x + 3] : 0;
+    fxT4[id] = v;
+}
+
+// ================================================================================================
+// class of an index of the type-sorted arrangement
+// ================================================================================================
+// cum[c] = number of ranked cells of a class below c (c = 0 .. Tc, Tc = T + 1 classes, the last one "unknown type");
+// class(j) = the c with cum[c] <= j < cum[c+1]. ctab[j >> shift] packs, per bucket of 2^shift indices,
+//   (class of the bucket's first index) << 16 | offset of the bucket's only class boundary,
+// 0xffff = no boundary inside, 0xfffe = several (or one that skips empty classes): walk cum[] from the first class.
+constexpr uint32_t CT_NONE = 0xffffu, CT_MULTI = 0xfffeu;
+
+__device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cum, uint32_t Tc, uint32_t j) {
+    uint32_t lo = 0, hi = Tc;   // invariant: cum[lo] <= j < cum[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cum[mid] <= j) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict__ class_cnt, int32_t Tc, int64_t Nu,
+                                                      int shift, int32_t nb, uint32_t* __restrict__ cum,
+                                                      uint32_t* __restrict__ ctab) {
+    // one CTA: exclusive scan of the class counts (thread t owns a contiguous chunk), then the bucket table
+    __shared__ uint32_t part[1024];
+    const int per = (Tc + 1023) / 1024;
+    const int c0 = threadIdx.x * per, c1 = min(c0 + per, (int)Tc);
+    uint32_t s = 0;
+    for (int c = c0; c < c1; c++) s += (uint32_t)class_cnt[c];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; i++) { const uint32_t v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (int c = c0; c < c1; c++) { cum[c] = run; run += (uint32_t)class_cnt[c]; }
+    if (threadIdx.x == 0) cum[Tc] = (uint32_t)Nu;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += 1024) {
+        const uint32_t start = (uint32_t)i << shift;
+        uint32_t e = 0xffffffffu;
+        if ((int64_t)start < Nu) {
+            const uint32_t last = (uint32_t)min((long long)start + (1ll << shift), (long long)Nu) - 1u;
+            const uint32_t ca = class_search(cum, (uint32_t)Tc, start), cb = class_search(cum, (uint32_t)Tc, last);
+            uint32_t off = CT_NONE;
+            if (cb == ca + 1u) off = cum[cb] - start;
+            else if (cb > ca + 1u) off = CT_MULTI;
+            e = (ca << 16) | off;
+        }
+        ctab[i] = e;
+    }
+}
+
+__device__ __forceinline__ uint32_t class_of(uint32_t j, const uint32_t* __restrict__ ctab_s, const uint32_t* __restrict__ cum,
+                                             int shift) {
+    const uint32_t e = ctab_s[j >> shift];
+    uint32_t c = e >> 16;
+    const uint32_t off = e & 0xffffu;
+    if (off == CT_MULTI) {
+        while (j >= cum[c + 1]) c++;   // ends: cum[Tc] = Nu > j
+    } else {
+        c += ((j & ((1u << shift) - 1u)) >= off) ? 1u : 0u;   // CT_NONE is above every in-bucket offset (shift <= 15)
+    }
+    return c;
+}
+
+// ================================================================================================
+// the keyed Feistel bijection
+// ================================================================================================
+struct FeistelParams {
+    uint32_t a, b;
+    int rounds;
+    uint64_t seed;
+};
+
+__host__ __device__ __forceinline__ uint32_t feistel_mix(uint32_t v, uint32_t key) {
+    uint32_t t = v * 0x9E3779B1u + key;
+    t ^= t >> 15;
+    t *= 0x2C1B3C6Du;
+    return t;
+}
+
+// round keys of permutation p: Philox4x32-10(ctr = {j / 4, 0, p, "FEIS"}, key = seed)[j % 4]
+template <int NR>
+__device__ __forceinline__ void feistel_keys(uint64_t seed, uint32_t p, uint32_t (&keys)[NR]) {
+#pragma unroll
+    for (int j0 = 0; j0 < NR; j0 += 4) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)(j0 >> 2), 0u, p, 0x46454953u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (j0 + q < NR) keys[j0 + q] = o[q];
+    }
+}
+
+// NR > 0: unrolled, keys in registers; NR == 0: `rounds` at run time, keys from memory.
+template <int NR, typename Keys>
+__device__ __forceinline__ uint32_t feistel_apply(const Keys& keys, uint32_t a, uint32_t b, int rounds_rt, uint32_t L,
+                                                  uint32_t R, uint32_t n) {
+    const int rounds = NR > 0 ? NR : rounds_rt;
+    uint32_t y;
+    do {
+#pragma unroll
+        for (int j = 0; j < rounds; j++) {
+            if (((rounds - 1 - j) & 1) == 0) {   // the last round modifies the high digit
+                L += __umulhi(feistel_mix(R, keys[j]), a);
+                L = min(L, L - a);   // unsigned: L - a wraps above L exactly when L < a
+            } else {
+                R += __umulhi(feistel_mix(L, keys[j]), b);
+                R = min(R, R - b);
+            }
+        }
+        y = L * b + R;
+    } while (y >= n);  // cycle-walk: < a of the a*b points are out of range
+    return y;
+}
+
+// Four labels of one thread's segment = one word of the lane layout.
+template <typename LabT> struct LaneWord;
+template <> struct LaneWord<uint8_t> {
+    typedef uint32_t type;
+    static __device__ __forceinline__ uint32_t get(uint32_t w, int q) { return (w >> (8 * q)) & 0xffu; }
+    static __device__ __forceinline__ uint32_t pack(const uint32_t c[4]) { return c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24); }
+};
+template <> struct LaneWord<uint16_t> {
+    typedef uint2 type;
+    static __device__ __forceinline__ uint32_t get(uint2 w, int q) { return ((q < 2 ? w.x : w.y) >> (16 * (q & 1))) & 0xffffu; }
+    static __device__ __forceinline__ uint2 pack(const uint32_t c[4]) { return make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16)); }
+};
+
+// Row-major permuted labels for the EXACT (validation) null: labels[p][x], one thread per position.
+template <typename LabT>
+__global__ void __launch_bounds__(256) k_labels_philox_rm(int64_t Nu, int64_t Nu_pad, int32_t T, FeistelParams fp,
+                                                         int32_t perm_begin, const uint32_t* __restrict__ cum,
+                                                         LabT* __restrict__ labels) {
+    __shared__ uint32_t keys[32];
+    const int p = blockIdx.y;
+    if (threadIdx.x < 8 && (int)threadIdx.x * 4 < fp.rounds) {
+        uint32_t o[4];
+        philox4x32_10(threadIdx.x, 0u, (uint32_t)(perm_begin + p), 0x46454953u, (uint32_t)fp.seed, (uint32_t)(fp.seed >> 32), o);
+#pragma unroll
+        for (int q = 0; q < 4; q++) keys[threadIdx.x * 4 + q] = o[q];
+    }
+    __syncthreads();
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= Nu_pad) return;
+    uint32_t cls = (uint32_t)T;
+    if (x < Nu) {
+        const uint32_t L = (uint32_t)(x / fp.b), R = (uint32_t)(x - (int64_t)L * fp.b);
+        const uint32_t j = feistel_apply<0>(keys, fp.a, fp.b, fp.rounds, L, R, (uint32_t)Nu);
+        cls = class_search(cum, (uint32_t)T + 1u, j);
+    }
+    labels[(size_t)p * Nu_pad + x] = (LabT)cls;
+}
+
+// ================================================================================================
+// the fused null kernel
+// ================================================================================================
+__device__ __forceinline__ float dstat_of_f(float sup, int32_t sizea, int32_t sizeb) {
+    // EnrichmentWeigthedScoreParallel.java:203-207: sizea*sizeb is an int32 multiply (wraps)
+    const int32_t prod = (int32_t)((uint32_t)sizea * (uint32_t)sizeb);
+    const int32_t sum = (int32_t)((uint32_t)sizea + (uint32_t)sizeb);
+    const float sq = (float)__dsqrt_rn(__ddiv_rn((double)prod, (double)sum));
+    return __fmul_rn(sup, sq);
+}
+
+__device__ __forceinline__ uint32_t sup_key_fast(float f) {
+    // larger |diff| wins; on equal |diff| the positive one wins (an order-independent rule). +0 maps to 1 and -0 to
+    // 0: both lose to every non-zero difference and decode to +0.
+    const uint32_t b = (uint32_t)__float_as_int(f);
+    return __funnelshift_l(~b, b, 1);   // (b << 1) | (~b >> 31)
+}
+
+constexpr int NF_PRE = 4;   // label / score words in flight per thread in the second walk
+
+struct NullArgs {
+    const int4* fxT4;            // [seg4][Kp] fixed-point scores, lane layout
+    const int* Sfx;              // [Nu] inclusive int32 prefix of the fixed-point scores
+    const int32_t* class_cnt;    // [Tc]
+    const uint32_t* cum;         // [Tc + 1]
+    const uint32_t* ctab;        // [nb]
+    void* scratch;               // [grid][seg4][Kp] label words
+    int* ticket;
+    float* null_ews;             // [T][P_stride]
+    float* null_d;
+    int64_t Nu;
+    int32_t T_all, Ts, seg, Pc, perm_begin, P_stride, p_off, nb, shift, cum_smem;
+    FeistelParams fp;
+};
+
+// SLICED: more cell types than the per-thread shared-memory state can hold at once. The labels are then generated
+// in a pass of their own, and phases 1-4 run once per slice of Ts types on the parked labels, with every other type
+// mapped to the slice's dummy column (Ts), which takes the same read-modify-write but has zero constants, so it can
+// never set a maximum.
+template <typename LabT, int NR, bool SLICED>
+__global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
+    typedef typename LaneWord<LabT>::type Word;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_p;
+    __shared__ uint32_t s_keys[32];
+    const int Ts = A.Ts, Tc = Ts + 1, T_all = A.T_all;
+    const int Kp = blockDim.x;
+    const int k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarp = Kp >> 5;
+    int* numA = reinterpret_cast<int*>(smem_raw);                               // [Tc][Kp]
+    float2* cs = reinterpret_cast<float2*>(numA + (size_t)Tc * Kp);             // [Tc] (c12, c2)
+    uint32_t* best = reinterpret_cast<uint32_t*>(cs + Tc);                      // [Tc]
+    uint32_t* ctab_s = best + Tc;                                               // [nb]
+    uint32_t* cum_s = ctab_s + A.nb;                                            // [T_all + 2] when it fits
+    const uint32_t* cum = A.cum_smem ? cum_s : A.cum;
+    for (int i = k; i < A.nb; i += Kp) ctab_s[i] = A.ctab[i];
+    if (A.cum_smem) for (int i = k; i < T_all + 2; i += Kp) cum_s[i] = A.cum[i];
+    const int seg = A.seg, seg4 = seg >> 2;
+    const uint32_t n = (uint32_t)A.Nu, a = A.fp.a, b = A.fp.b;
+    const int shift = A.shift;
+    Word* lab = reinterpret_cast<Word*>(A.scratch) + (size_t)blockIdx.x * seg4 * Kp + k;
+    const int4* fxp = A.fxT4 + k;
+    int* col = numA + k;   // this thread's private column: type t lives at col[t * Kp] (bank = k % 32 for every t)
+    const uint32_t x0 = (uint32_t)k * (uint32_t)seg;
+    const uint32_t L00 = x0 / b, R00 = x0 - L00 * b;
+    const int Stot = A.Sfx[A.Nu - 1];
+    const int S0 = (x0 > 0u && x0 <= n) ? A.Sfx[x0 - 1u] : 0;   // exact prefix before my segment
+
+    for (;;) {
+        __syncthreads();   // the previous permutation is done with the shared state (and the tables are loaded)
+        if (k == 0) s_p = atomicAdd(A.ticket, 1);
+        __syncthreads();
+        const int p = s_p;
+        if (p >= A.Pc) break;
+        uint32_t keys[NR > 0 ? NR : 1];
+        if (NR > 0) feistel_keys<(NR > 0 ? NR : 1)>(A.fp.seed, (uint32_t)(A.perm_begin + p), keys);
+        else {
+            if (k < 8 && k * 4 < A.fp.rounds) {
+                uint32_t o[4];
+                philox4x32_10((uint32_t)k, 0u, (uint32_t)(A.perm_begin + p), 0x46454953u, (uint32_t)A.fp.seed,
+                              (uint32_t)(A.fp.seed >> 32), o);
+#pragma unroll
+                for (int q = 0; q < 4; q++) s_keys[k * 4 + q] = o[q];
+            }
+            __syncthreads();
+        }
+        if (!SLICED) {
+            for (int t = 0; t < Tc; t++) col[(size_t)t * Kp] = 0;
+            for (int t = k; t < Tc; t += Kp) best[t] = 0u;
+        }
+
+        // ---- phase 1: labels of my segment + per-type segment sums (one shared-memory read-modify-write per
+        // position, in program order). Padding positions (x >= Nu) carry the unknown class and f = 0.
+        {
+            uint32_t L = L00, R = R00, x = x0;
+            int4 fn = fxp[0];
+            for (int i4 = 0; i4 < seg4; i4++) {
+                const int4 fc = fn;
+                if (i4 + 1 < seg4) fn = fxp[(size_t)(i4 + 1) * Kp];
+                const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
+                uint32_t cls[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    cls[q] = (uint32_t)T_all;
+                    if (x < n) {
+                        const uint32_t j = (NR > 0) ? feistel_apply<NR>(keys, a, b, NR, L, R, n)
+                                                    : feistel_apply<0>(s_keys, a, b, A.fp.rounds, L, R, n);
+                        cls[q] = class_of(j, ctab_s, cum, shift);
+                    }
+                    x++; R++;
+                    if (R >= b) { R = 0; L++; }
+                    if (!SLICED) col[(size_t)cls[q] * Kp] += fq[q];
+                }
+                lab[(size_t)i4 * Kp] = LaneWord<LabT>::pack(cls);
+            }
+        }
+
+      for (int t0 = 0; t0 < T_all; t0 += Ts) {   // one iteration unless SLICED
+        const int T = min(Ts, T_all - t0);        // real types of this slice: local ids [0, T), dummy = Ts
+        // local type id of a label: slice members keep their offset, everything else goes to the dummy column
+        auto local_type = [&](uint32_t t) -> uint32_t {
+            if (!SLICED) return t;   // labels are already in [0, T_all] with T_all = Ts the padding / unknown class
+            const uint32_t tl = t - (uint32_t)t0;
+            return tl < (uint32_t)T ? tl : (uint32_t)Ts;
+        };
+        if (SLICED) {
+            for (int t = 0; t < Tc; t++) col[(size_t)t * Kp] = 0;
+            for (int t = k; t < Tc; t += Kp) best[t] = 0u;
+            // phase 1 on the parked labels (each thread re-reads what it wrote itself: no barrier needed)
+            for (int i4 = 0; i4 < seg4; i4++) {
+                const Word w = lab[(size_t)i4 * Kp];
+                const int4 fc = fxp[(size_t)i4 * Kp];
+                const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
+#pragma unroll
+                for (int q = 0; q < 4; q++) col[(size_t)local_type(LaneWord<LabT>::get(w, q)) * Kp] += fq[q];
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: exclusive prefix over the segments (warp w scans types w, w + nwarp, ...), reciprocals
+        for (int t = warp; t < Tc; t += nwarp) {
+            int carry = 0;
+            for (int k0 = 0; k0 < Kp; k0 += 32) {
+                const int v = numA[(size_t)t * Kp + k0 + lane];
+                const int incl = warp_incl_scan_i32(v, lane);
+                numA[(size_t)t * Kp + k0 + lane] = carry + (incl - v);
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) {
+                const int dA = carry, dB = Stot - carry;
+                float c12 = 0.0f, c2 = 0.0f;
+                if (t < T && dA != 0 && dB != 0) {
+                    const double r2 = __ddiv_rn(1.0, (double)dB);
+                    c2 = __double2float_rn(r2);
+                    c12 = __double2float_rn(__dadd_rn(__ddiv_rn(1.0, (double)dA), r2));
+                }
+                cs[t] = make_float2(c12, c2);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: suprema at hit / pre-hit positions. At the global position 0 the pre-hit candidate is
+        // exactly 0 and cannot win.
+        {
+            int S = S0;
+            float Sf = __int2float_rn(S);
+            Word wc[NF_PRE];   // register sets refilled in place: the loads run NF_PRE - 1 words ahead of their use
+            int4 fc[NF_PRE];
+#pragma unroll
+            for (int u = 0; u < NF_PRE; u++)
+                if (u < seg4) { wc[u] = lab[(size_t)u * Kp]; fc[u] = fxp[(size_t)u * Kp]; }
+            for (int i4 = 0; i4 < seg4; i4 += NF_PRE) {
+#pragma unroll
+                for (int u = 0; u < NF_PRE; u++) {
+                    if (i4 + u >= seg4) break;
+                    const int fq[4] = { fc[u].x, fc[u].y, fc[u].z, fc[u].w };
+                    const Word wcu = wc[u];
+                    if (i4 + NF_PRE + u < seg4) {
+                        wc[u] = lab[(size_t)(i4 + NF_PRE + u) * Kp];
+                        fc[u] = fxp[(size_t)(i4 + NF_PRE + u) * Kp];
+                    }
+                    uint32_t t[4], cur[4], key[4];
+                    int bq[4], aq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {   // the four running-sum updates, in program order
+                        t[q] = local_type(LaneWord<LabT>::get(wcu, q));
+                        int* sp = col + (size_t)t[q] * Kp;
+                        bq[q] = *sp;
+                        aq[q] = bq[q] + fq[q];
+                        *sp = aq[q];
+                    }
+                    // the current maxima first (plain reads, issued together so that their latency hides behind
+                    // the candidate arithmetic): best[] only grows, so a candidate that does not beat the possibly
+                    // stale value read here cannot beat the current one either. Record-setting candidates are rare
+                    // and a shared-memory atomic costs one wavefront per active lane, so the atomics sit behind one
+                    // branch per group of four positions.
+#pragma unroll
+                    for (int q = 0; q < 4; q++) cur[q] = reinterpret_cast<volatile uint32_t*>(best)[t[q]];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float2 c = cs[t[q]];
+                        const float Spf = Sf;
+                        S += fq[q];   // exact: |S| <= sum |fx| < 2^31
+                        Sf = __int2float_rn(S);
+                        const uint32_t k1 = sup_key_fast(__fmaf_rn(__int2float_rn(aq[q]), c.x, -__fmul_rn(Sf, c.y)));
+                        const uint32_t k0 = sup_key_fast(__fmaf_rn(__int2float_rn(bq[q]), c.x, -__fmul_rn(Spf, c.y)));
+                        key[q] = k0 > k1 ? k0 : k1;
+                    }
+                    if ((key[0] > cur[0]) | (key[1] > cur[1]) | (key[2] > cur[2]) | (key[3] > cur[3])) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (key[q] > cur[q]) atomicMax(&best[t[q]], key[q]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 4: decode
+        for (int t = k; t < T; t += Kp) {
+            const int32_t nk = A.class_cnt[t0 + t];
+            const int32_t sizeb = (int32_t)(A.Nu - nk);
+            float v, d;
+            if (!(nk > 1 && sizeb > 1)) { v = __int_as_float(0x7fc00000); d = v; }
+            else {
+                const uint32_t key = best[t];
+                v = (key <= 1u) ? 0.0f : __int_as_float((int)((key >> 1) | (((key & 1u) ^ 1u) << 31)));
+                d = dstat_of_f(v, nk, sizeb);
+            }
+            A.null_ews[(size_t)(t0 + t) * A.P_stride + A.p_off + p] = v;
+            A.null_d[(size_t)(t0 + t) * A.P_stride + A.p_off + p] = d;
+        }
+        if (SLICED) __syncthreads();   // the next slice reuses the state
+      }
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+static void feistel_params(const EnrichGeom& g, uint64_t seed, int rounds, FeistelParams* fp) {
+    feistel_dims(g.Nu, &fp->a, &fp->b);
+    fp->rounds = rounds;
+    fp->seed = seed;
+}
+
+// Bucket table geometry: at most 1024 buckets of at most 2^15 indices.
+static void class_table_geom(int64_t Nu, int* shift, int32_t* nb) {
+    int s = 0;
+    while (((Nu - 1) >> s) + 1 > 1024) s++;
+    PCT_REQUIRE(s <= 15, "too many ranked cells for the permutation kernels' class table (limit 2^25)");
+    *shift = s;
+    *nb = (int32_t)(((Nu - 1) >> s) + 1);
+}
+
+NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
+    NullPlanFast pl;
+    class_table_geom(std::max<int64_t>(g.Nu, 1), &pl.shift, &pl.nb);
+    pl.cum_smem = (g.Tc + 1 <= 1024) ? 1 : 0;
+    const size_t smem_sm = (size_t)c->smem_per_sm, smem_cta_max = (size_t)c->smem_per_block_optin;
+    auto fixed = [&](int ts) { return (size_t)(ts + 1) * 12 + (size_t)pl.nb * 4 + (pl.cum_smem ? (size_t)(g.Tc + 1) * 4 : 0) + 64; };
+    auto threads_for = [&](int ts) {
+        const size_t f = fixed(ts);
+        if (f + (size_t)(ts + 1) * 4 * 32 > smem_cta_max) return 0;
+        const int kp = (int)std::min<size_t>(512, (smem_cta_max - f) / ((size_t)(ts + 1) * 4));
+        return (kp / 32) * 32;
+    };
+    int ts = std::max(g.T, 1), kp = threads_for(ts);
+    const int min_kp = c->opt_null_min_threads > 0 ? c->opt_null_min_threads : 192;
+    if (kp < min_kp) {
+        // slices of equal size, as few as give every slice at least 256 threads (or the maximum that fits)
+        int n_slices = 2;
+        for (;; n_slices++) {
+            ts = (int)div_up(g.T, n_slices);
+            kp = threads_for(ts);
+            if (kp >= 256 || ts == 1) break;
+        }
+        PCT_REQUIRE(kp >= 32, "shared memory too small for the null kernel's per-type state");
+    }
+    if (c->opt_null_threads > 0) kp = std::min(kp, (int)round_up(c->opt_null_threads, 32));
+    // short rankings: at least ~8 positions per thread
+    const int64_t want = std::max<int64_t>(32, round_up(div_up(std::max<int64_t>(g.Nu, 1), 8), 32));
+    kp = (int)std::min<int64_t>(kp, want);
+    pl.Kp = kp;
+    pl.Ts = ts;
+    pl.seg = (int32_t)round_up(div_up(std::max<int64_t>(g.Nu, 1), kp), 4);
+    pl.smem = (size_t)(ts + 1) * kp * 4 + fixed(ts);
+    int per_sm = (int)std::max<size_t>(1, smem_sm / (pl.smem + 1024));
+    per_sm = std::min(per_sm, std::max(1, 2048 / kp));
+    per_sm = std::min(per_sm, 4);
+    if (c->opt_null_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_null_ctas_per_sm);
+    pl.ctas_per_sm = per_sm;
+    pl.word_bytes = 4 * g.lab_bytes;
+    return pl;
+}
+
+// Once per enrich call (FAST arithmetic): fixed-point scores, their prefix and lane layout, class tables.
+void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl) {
+    if (g.Nu == 0) return;
+    unsigned long long* maxabs = c->counters.as<unsigned long long>() + 2;
+    unsigned long long* sumabs = c->counters.as<unsigned long long>() + 4;
+    int32_t* frac_dev = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 3);
+    c->fx.reserve((size_t)g.Nu * 4 + 64);
+    c->Sfx.reserve((size_t)g.Nu * 4 + 64);
+    const int n_tiles = (int)div_up(g.Nu, SC_TILE);
+    c->scan_tmp.reserve((size_t)n_tiles * 4 + 64);
+    k_fx_abs_sum<<<n_tiles, SC_THREADS, 0, c->stream>>>(c->s_rank.as<double>(), g.Nu, maxabs, sumabs);
+    k_fixed_point<<<n_tiles, SC_THREADS, 0, c->stream>>>(c->s_rank.as<double>(), g.Nu, maxabs, sumabs, c->fx.as<int>(),
+                                                         frac_dev, c->scan_tmp.as<int>());
+    k_tile_scan_i32<<<n_tiles, SC_THREADS, 0, c->stream>>>(c->fx.as<int>(), g.Nu, c->scan_tmp.as<int>(), c->Sfx.as<int>());
+    const int seg4 = pl.seg >> 2;
+    c->fxT.reserve((size_t)seg4 * pl.Kp * 16 + 64);
+    k_fx_transpose<<<(unsigned)div_up((int64_t)seg4 * pl.Kp, 256), 256, 0, c->stream>>>(c->fx.as<int>(), g.Nu, pl.seg, pl.Kp,
+                                                                                      c->fxT.as<int4>());
+    count_launch(c, 4);
+    PCT_CUDA(cudaGetLastError());
+}
+
+// cum[] (+ the bucket table when nb > 0) of the type-sorted arrangement; needs class_cnt (k_gather_ranked).
+void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb) {
+    c->cls_tab.reserve((size_t)(g.Tc + 1) * 4 + (size_t)std::max(nb, 1) * 4 + 64);
+    uint32_t* cum = c->cls_tab.as<uint32_t>();
+    uint32_t* ctab = cum + (g.Tc + 1);
+    k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift, nb, cum, ctab);
+    count_launch(c);
+    PCT_CUDA(cudaGetLastError());
+}
+
+void launch_labels_philox_rm(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc, int rounds) {
+    if (Pc == 0 || g.Nu == 0) return;
+    FeistelParams fp;
+    feistel_params(g, seed, rounds, &fp);
+    const uint32_t* cum = c->cls_tab.as<uint32_t>();
+    for (int32_t p0 = 0; p0 < Pc; p0 += 32768) {
+        const int32_t pc = std::min<int32_t>(32768, Pc - p0);
+        dim3 grid((unsigned)div_up(g.Nu_pad, 256), (unsigned)pc);
+        if (g.lab_bytes == 1)
+            k_labels_philox_rm<uint8_t><<<grid, 256, 0, c->stream>>>(g.Nu, g.Nu_pad, g.T, fp, perm_begin + p0, cum,
+                                                                     c->labels.as<uint8_t>() + (size_t)p0 * g.Nu_pad);
+        else
+            k_labels_philox_rm<uint16_t><<<grid, 256, 0, c->stream>>>(g.Nu, g.Nu_pad, g.T, fp, perm_begin + p0, cum,
+                                                                      c->labels.as<uint16_t>() + (size_t)p0 * g.Nu_pad);
+        count_launch(c);
+    }
+    PCT_CUDA(cudaGetLastError());
+}
+
+void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl, uint64_t seed, int32_t perm_begin,
+                       int32_t Pc, int rounds, int32_t P_stride, int32_t p_off) {
+    if (Pc == 0 || g.T == 0 || g.Nu == 0) return;
+    NullArgs A;
+    A.fxT4 = c->fxT.as<int4>();
+    A.Sfx = c->Sfx.as<int>();
+    A.class_cnt = c->class_cnt.as<int32_t>();
+    A.cum = c->cls_tab.as<uint32_t>();
+    A.ctab = A.cum + (g.Tc + 1);
+    const unsigned grid = (unsigned)std::min<int64_t>(Pc, (int64_t)pl.ctas_per_sm * c->num_sms);
+    const int seg4 = pl.seg >> 2;
+    c->labels.reserve((size_t)grid * seg4 * pl.Kp * pl.word_bytes + 64);
+    A.scratch = c->labels.p;
+    c->lab_ticket.reserve(64);
+    PCT_CUDA(cudaMemsetAsync(c->lab_ticket.p, 0, 4, c->stream));
+    A.ticket = c->lab_ticket.as<int>();
+    A.null_ews = c->null_ews.as<float>();
+    A.null_d = c->null_d.as<float>();
+    A.Nu = g.Nu;
+    A.T_all = g.T; A.Ts = pl.Ts; A.seg = pl.seg; A.Pc = Pc; A.perm_begin = perm_begin;
+    A.P_stride = P_stride; A.p_off = p_off; A.nb = pl.nb; A.shift = pl.shift; A.cum_smem = pl.cum_smem;
+    feistel_params(g, seed, rounds, &A.fp);
+    const bool sliced = pl.Ts < g.T;
+#define PCT_LAUNCH_NULL(LT, NR, SL)                                                          \
+    do {                                                                                     \
+        ensure_dyn_smem(c, k_null_fused<LT, NR, SL>, pl.smem);                               \
+        k_null_fused<LT, NR, SL><<<grid, pl.Kp, pl.smem, c->stream>>>(A);                    \
+    } while (0)
+#define PCT_LAUNCH_NULL_R(LT, SL)                                                            \
+    do {                                                                                     \
+        if (rounds == PCTSEA_DEFAULT_FEISTEL_ROUNDS) PCT_LAUNCH_NULL(LT, PCTSEA_DEFAULT_FEISTEL_ROUNDS, SL); \
+        else PCT_LAUNCH_NULL(LT, 0, SL);                                                     \
+    } while (0)
+    if (g.lab_bytes == 2) { if (sliced) PCT_LAUNCH_NULL_R(uint16_t, true); else PCT_LAUNCH_NULL_R(uint16_t, false); }
+    else                  { if (sliced) PCT_LAUNCH_NULL_R(uint8_t, true); else PCT_LAUNCH_NULL_R(uint8_t, false); }
+#undef PCT_LAUNCH_NULL_R
+#undef PCT_LAUNCH_NULL
+    count_launch(c);
+    PCT_CUDA(cudaGetLastError());
+}
+
+}  // namespace pctsea

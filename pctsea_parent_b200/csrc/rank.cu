@@ -280,7 +280,7 @@ void radix_sort_pairs(pctsea_ctx* c, int64_t n, uint64_t** keys, uint64_t** keys
     c->hist.reserve(8 * 256 * 4);
     c->pin_small.reserve(8 * 256 * 4 + 64);
     PCT_CUDA(cudaMemsetAsync(c->hist.p, 0, 8 * 256 * 4, c->stream));
-    int grid = (int)std::min<int64_t>(div_up(n, RS_THREADS), (int64_t)kNumSMs * 8);
+    int grid = (int)std::min<int64_t>(div_up(n, RS_THREADS), (int64_t)c->num_sms * 8);
     k_digit_hist<<<grid, RS_THREADS, 0, c->stream>>>(*keys, n, c->hist.as<uint32_t>(), ndig);
     count_launch(c);
     PCT_CUDA(cudaMemcpyAsync(c->pin_small.p, c->hist.p, 8 * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -319,7 +319,7 @@ void launch_type_counts(pctsea_ctx* c, int64_t N, const double* score_dev, const
     c->type_counts_T = T;
     if (N == 0) return;
     const int32_t hist_n = (n <= 8192) ? n : 0;
-    int grid = (int)std::min<int64_t>(div_up(N, 256), (int64_t)kNumSMs * 4);
+    int grid = (int)std::min<int64_t>(div_up(N, 256), (int64_t)c->num_sms * 4);
     k_type_counts<<<grid, 256, (size_t)hist_n * 4, c->stream>>>(score_dev, kept_dev, label_dev, N, min_score, T,
                                                                 c->type_counts.as<int32_t>(), hist_n);
     count_launch(c);
@@ -361,7 +361,7 @@ int64_t launch_rank(pctsea_ctx* c, int64_t N, const double* score_dev, const uin
     const int neg = (min_score < 0.0) ? 1 : 0;
     unsigned long long* ties = c->counters.as<unsigned long long>() + 1;
     if (neg) {
-        int grid = (int)std::min<int64_t>(div_up(Np, 256), (int64_t)kNumSMs * 4);
+        int grid = (int)std::min<int64_t>(div_up(Np, 256), (int64_t)c->num_sms * 4);
         k_count_top_ties<<<grid, 256, 0, c->stream>>>(k, Np, ties);
         count_launch(c);
     }

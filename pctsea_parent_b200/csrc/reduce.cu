@@ -232,7 +232,7 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
     k_red_rank<<<1, 1024, 0, c->stream>>>(T, results_dev, Rsorted, nobs, bins);
     if (n > 0) {
         const int use_smem = T <= 4096;
-        const int grid = (int)std::min<int64_t>(div_up(n, 256), (int64_t)kNumSMs * 8);
+        const int grid = (int)std::min<int64_t>(div_up(n, 256), (int64_t)c->num_sms * 8);
         k_red_count<<<grid, 256, use_smem ? ((size_t)2 * T + 2) * 4 : 0, c->stream>>>(null_dev, T, P, results_dev, expct, Rsorted,
                                                                                      nobs, bins, use_smem);
     }

@@ -524,7 +524,7 @@ int validate_csr(pctsea_ctx* c, const pctsea_matrix* m) {
     c->counters.reserve(64);
     int* bad = c->counters.as<int>();
     PCT_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
-    k_validate_csr<<<kNumSMs * 8, 256, 0, c->stream>>>(m->row_ptr, m->col, m->val, m->n_cells, m->n_genes, m->nnz, bad);
+    k_validate_csr<<<c->num_sms * 8, 256, 0, c->stream>>>(m->row_ptr, m->col, m->val, m->n_cells, m->n_genes, m->nnz, bad);
     PCT_CUDA(cudaGetLastError());
     int h = 0;
     PCT_CUDA(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -550,8 +550,7 @@ void launch_score_final(pctsea_ctx* c, const ScoreArgs& sa) {
 void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     const pctsea_matrix* m = sa.m;
     if (m->gm_mo && m->n_cells > 0) {   // the matrix carries its gene-major copy: lane-per-cell kernel (score_gm.cu)
-        const char* e = std::getenv("PCTSEA_SCORE_PATH");   // testing aid: "csr" forces the CSR scan
-        if (!(e && e[0] == 'c')) { launch_score_gm(c, sa); return; }
+        if (!c->opt_score_path) { launch_score_gm(c, sa); return; }   // PCTSEA_OPT_SCORE_PATH = 1 forces the CSR scan
     }
     const int64_t N = m->n_cells;
     const int32_t G = m->n_genes;
@@ -602,12 +601,12 @@ void launch_score(pctsea_ctx* c, const ScoreArgs& sa) {
     if (tab_bytes + rank_smem + pair_bytes > smem_limit)
         throw Error(PCTSEA_EINVAL, "input list too long for the on-chip pair buffer (L=" + std::to_string(sa.L) + ")");
     int maxw = kScoreMaxWarps;
-    if (const char* e = std::getenv("PCTSEA_SCORE_WARPS")) maxw = std::atoi(e);   // tuning aid
+    if (c->opt_score_warps > 0) maxw = c->opt_score_warps;   // PCTSEA_OPT_SCORE_WARPS (tuning aid)
     const int warps = (int)std::max<size_t>(1, std::min<size_t>(maxw, (smem_limit - tab_bytes - rank_smem) / pair_bytes));
     const size_t smem = tab_bytes + rank_smem + (size_t)warps * pair_bytes;
     ka.cap = cap;
     ka.tab_bytes = (int32_t)tab_bytes;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, div_up(N, kScoreCellBatch)));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(c->num_sms, div_up(N, kScoreCellBatch)));
 #define PCT_LAUNCH_SCORE2(B, W, AP)                                                                           \
     do {                                                                                                      \
         ensure_dyn_smem(c, k_score<B, W, 3, AP>, (size_t)(smem)); \

@@ -487,7 +487,7 @@ void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
     a.fix_list = c->gm_fix.as<int2>() + 8; a.fix_count = counters + 1;
     const unsigned grid = (unsigned)div_up(m->n_groups, 8);
     int unroll = 8;
-    if (const char* e = std::getenv("PCTSEA_GM_UNROLL")) unroll = std::atoi(e);   // tuning aid
+    if (c->opt_gm_unroll > 0) unroll = c->opt_gm_unroll;   // PCTSEA_OPT_GM_UNROLL (tuning aid)
     if (m->all_positive) {
         if (unroll >= 8) k_score_gm<true, 8><<<grid, 256, 0, c->stream>>>(a);
         else if (unroll >= 4) k_score_gm<true, 4><<<grid, 256, 0, c->stream>>>(a);
@@ -497,7 +497,7 @@ void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
     if (sa.prm.jitter_mode == PCTSEA_JITTER_PHILOX) {
-        k_score_gm_jitter<<<kNumSMs * 2, 256, 0, c->stream>>>(a);
+        k_score_gm_jitter<<<c->num_sms * 2, 256, 0, c->stream>>>(a);
         count_launch(c);
         PCT_CUDA(cudaGetLastError());
     }

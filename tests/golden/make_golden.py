@@ -62,7 +62,7 @@ def main():
     ne_f, nd_f = O.null(s_r, lab_r, cfg.n_types, 8, perm_mode=1, seed=42)
     red = O.reduce(res, ne_f)
     F = O.fast_frac_bits(s_r)
-    fast0 = O.ks_null_fast_one(s_r, lab_r[O.feistel_perm(42, 0, nu)], cfg.n_types, F)
+    fast0 = O.ks_null_fast_one(s_r, O.perm_labels(42, 0, lab_r, cfg.n_types), cfg.n_types, F)
     out["regression"] = {
         "config": "tiny", "n_pass": int(npass), "kept_sum": int(kept.sum()), "n_used_sum": int(used.sum()),
         "score_bits_first32_nonnan": bits64(sc[~np.isnan(sc)][:32]),

@@ -312,22 +312,21 @@ def test_null_philox_fast_matches_oracle_fast(ctx, oracle, n_used, T, Pn, simple
     res, ne, nd = ctx.enrich(s, order, lab, T, prm)
     F = oracle.fast_frac_bits(s)
     for p in range(Pn):
-        perm = oracle.feistel_perm(5, p, n_used)
-        exp = oracle.ks_null_fast_one(s, lab[perm], T, F)
+        exp = oracle.ks_null_fast_one(s, oracle.perm_labels(5, p, lab, T), T, F)
         assert_bits_equal_f32(ne[:, p], exp, f"fast null perm {p}")
 
 
-@pytest.mark.parametrize("rounds", [2, 5, 6, 7])
+@pytest.mark.parametrize("rounds", [2, 4, 6, 9])
 @pytest.mark.parametrize("n_used,T", [(5000, 12), (9000, 300), (500, 4)])
 def test_null_philox_explicit_round_counts(ctx, oracle, rounds, n_used, T):
-    """feistel_rounds other than the default (4): the unrolled 6-round kernels and the generic-loop ones, in the lane
-    layout (rankings >= 4096 cells, 8- and 16-bit labels) and the row-major layout."""
+    """feistel_rounds other than the default (5, unrolled): the generic-loop instantiation of the null kernel with 8- and
+    16-bit labels, and the row-major label kernel of the EXACT null."""
     s, lab, order = _ranked(n_used, T, seed=8)
     prm = ctx.null_params(3, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=31, feistel_rounds=rounds)
     res, ne, nd = ctx.enrich(s, order, lab, T, prm)
     F = oracle.fast_frac_bits(s)
     for p in range(3):
-        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(31, p, n_used, rounds)], T, F)
+        exp = oracle.ks_null_fast_one(s, oracle.perm_labels(31, p, lab, T, rounds), T, F)
         assert_bits_equal_f32(ne[:, p], exp, f"rounds {rounds} perm {p}")
     one, _ = oracle.null(s, lab, T, 2, perm_mode=1, seed=31, rounds=rounds)
     ex = ctx.enrich(s, order, lab, T, ctx.null_params(2, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=31, feistel_rounds=rounds))[1]
@@ -335,10 +334,11 @@ def test_null_philox_explicit_round_counts(ctx, oracle, rounds, n_used, T):
 
 
 def test_fast_vs_exact_tolerance(ctx):
-    # FAST (exact prefix sums) vs EXACT (the reference's fp32 running sums) on identical labels.
-    # Stated tolerance: ||ES_fast| - |ES_exact|| <= 2e-4 (ES in [-1,1]); the fp32 accumulators of the reference
-    # drift by ~1e-5 relative over 1e5 steps, the FAST value is the exactly-rounded one. The sign can differ only
-    # when the positive and the negative excursion are within that tolerance of each other.
+    # FAST (exact int32 fixed-point sums, fp32 candidates) vs EXACT (the reference's fp32 running sums) on identical
+    # labels. Stated tolerance: ||ES_fast| - |ES_exact|| <= 2e-4 (ES in [-1,1]) for rankings of up to 250 k cells;
+    # it is EXACT that carries the error (its fp32 accumulators drift by ~1e-5 relative over 1e5 steps, FAST stays
+    # within 2e-5 of the real-number value, tests/test_oracle_cpu.py). The sign can differ only when the positive
+    # and the negative excursion are within that tolerance of each other.
     n_used, T, Pn = 60_000, 40, 12
     s, lab, order = _ranked(n_used, T, seed=4)
     a = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=8))[1]
@@ -508,30 +508,58 @@ def test_full_size_properties(ctx):
         assert_bits_equal_f32(de[t], exp.astype(np.float32), "dStat")
 
 
-def test_fast_lane_and_cooperative_kernels_agree(ctx, oracle):
-    """The FAST null has two kernels (one thread per segment for small type counts, a warp-cooperative one
-    otherwise); both carry the same exact integer arithmetic, so they must agree bit for bit — and with the
-    oracle's restatement of the FAST definition."""
-    import os
+def test_fast_null_is_independent_of_the_kernel_geometry(ctx, oracle):
+    """The FAST null carries exact integer sums, so how the kernel splits the ranking into per-thread segments (threads
+    per permutation), how many CTAs share an SM and whether the cell types are processed in slices cannot change a
+    bit — and every geometry agrees with the oracle's restatement of the FAST definition."""
     n_used, T, Pn = 50_000, 30, 7
     s, lab, order = _ranked(n_used, T, seed=12)
     prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=21)
-    old = os.environ.get("PCTSEA_FAST_PATH")
+    outs = {}
     try:
-        os.environ["PCTSEA_FAST_PATH"] = "coop"
-        coop = ctx.enrich(s, order, lab, T, prm)[1]
-        os.environ["PCTSEA_FAST_PATH"] = "lane"
-        lane = ctx.enrich(s, order, lab, T, prm)[1]
+        for name, opts in (("default", {}), ("64 threads", {P.OPT_NULL_THREADS: 64}), ("160 threads, 1 CTA/SM", {P.OPT_NULL_THREADS: 160, P.OPT_NULL_CTAS_PER_SM: 1}),
+                           ("sliced", {P.OPT_NULL_MIN_THREADS: 512, P.OPT_NULL_THREADS: 256}), ("no overlap", {P.OPT_OBS_OVERLAP: 0})):
+            for o in (P.OPT_NULL_THREADS, P.OPT_NULL_CTAS_PER_SM, P.OPT_NULL_MIN_THREADS):
+                ctx.set_option(o, 0)
+            ctx.set_option(P.OPT_OBS_OVERLAP, 1)
+            for o, v in opts.items():
+                ctx.set_option(o, v)
+            outs[name] = ctx.enrich(s, order, lab, T, prm)
     finally:
-        if old is None:
-            os.environ.pop("PCTSEA_FAST_PATH", None)
-        else:
-            os.environ["PCTSEA_FAST_PATH"] = old
-    assert_bits_equal_f32(lane, coop, "lane vs cooperative FAST kernel")
+        for o in (P.OPT_NULL_THREADS, P.OPT_NULL_CTAS_PER_SM, P.OPT_NULL_MIN_THREADS):
+            ctx.set_option(o, 0)
+        ctx.set_option(P.OPT_OBS_OVERLAP, 1)
+    ref = outs["default"]
+    for name, (res, ne, nd) in outs.items():
+        assert_bits_equal_f32(ne, ref[1], f"null ES, geometry '{name}'")
+        assert_bits_equal_f32(nd, ref[2], f"null dStat, geometry '{name}'")
+        assert res.tobytes() == ref[0].tobytes(), f"results, geometry '{name}'"
     F = oracle.fast_frac_bits(s)
     for p in (0, Pn - 1):
-        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(21, p, n_used)], T, F)
-        assert_bits_equal_f32(lane[:, p], exp, f"lane kernel vs oracle, perm {p}")
+        exp = oracle.ks_null_fast_one(s, oracle.perm_labels(21, p, lab, T), T, F)
+        assert_bits_equal_f32(ref[1][:, p], exp, f"null kernel vs oracle, perm {p}")
+
+
+def test_exact_null_chunking_is_invisible(ctx):
+    """The EXACT (validation) null processes its permutations in chunks when the label matrix would not fit: chunk sizes
+    of 1, 7 and unchunked give bit-identical nulls, for generated and for replayed permutations."""
+    n_used, T, Pn = 6000, 15, 20
+    s, lab, order = _ranked(n_used, T, seed=6)
+    rng = np.random.default_rng(3)
+    replay = np.stack([rng.permutation(n_used).astype(np.int32) for _ in range(Pn)])
+    try:
+        for mode, rp in ((P.PERM_PHILOX, None), (P.PERM_REPLAY, replay)):
+            prm = ctx.null_params(Pn, perm_mode=mode, ks_mode=P.KS_EXACT, seed=3)
+            outs = []
+            for chunk in (0, 1, 7):
+                ctx.set_option(P.OPT_PERM_CHUNK, chunk)
+                outs.append(ctx.enrich(s, order, lab, T, prm, replay=rp))
+            for o in outs[1:]:
+                assert_bits_equal_f32(o[1], outs[0][1], "chunked null ES")
+                assert_bits_equal_f32(o[2], outs[0][2], "chunked null dStat")
+                assert o[0].tobytes() == outs[0][0].tobytes()
+    finally:
+        ctx.set_option(P.OPT_PERM_CHUNK, 0)
 
 
 def test_load_random_checkpoint(ctx, small, tmp_path):
@@ -613,7 +641,7 @@ def test_negative_threshold_mode(ctx, oracle):
     fast = ctx.enrich(score, order, label, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=4))[1]
     F = oracle.fast_frac_bits(s_r)
     for p in range(Pn):
-        exp = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(4, p, nu)], T, F)
+        exp = oracle.ks_null_fast_one(s_r, oracle.perm_labels(4, p, lab_r, T), T, F)
         assert_bits_equal_f32(fast[:, p], exp, f"fast null (negative scores) perm {p}")
 
 
@@ -634,7 +662,7 @@ def test_ties_zeros_and_many_types(ctx, oracle):
         assert_results_equal(res, oracle.reduce(ores, one), None, f"ties/zeros T={T}")
         fast = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, ks_mode=P.KS_FAST, seed=6))[1]
         F = oracle.fast_frac_bits(s)
-        exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(6, 1, n_used)], T, F)
+        exp = oracle.ks_null_fast_one(s, oracle.perm_labels(6, 1, lab, T), T, F)
         assert_bits_equal_f32(fast[:, 1], exp, f"fast null T={T}")
 
 
@@ -716,8 +744,7 @@ def test_stage3_random_shapes_sweep(ctx, oracle):
         assert_results_equal(res, ores, OBSERVED_FIELDS, f"observed n={n_used} T={T}")
         F = oracle.fast_frac_bits(s)
         for p in range(Pn):
-            perm = oracle.feistel_perm(n_used, p, n_used)
-            exp = oracle.ks_null_fast_one(s, lab[perm], T, F)
+            exp = oracle.ks_null_fast_one(s, oracle.perm_labels(n_used, p, lab, T), T, F)
             assert_bits_equal_f32(ne[:, p], exp, f"fast null n={n_used} T={T} perm {p}")
         ored = oracle.reduce(ores, ne)
         assert_results_equal(res, ored, ("norm_ews", "p_emp", "fdr"), f"reduce n={n_used} T={T}")
@@ -733,7 +760,7 @@ def test_two_contexts_on_one_device(ctx, oracle):
             prm = c.null_params(3, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=5)
             res, ne, nd = c.enrich(s, order, lab, T, prm)
             F = oracle.fast_frac_bits(s)
-            exp = oracle.ks_null_fast_one(s, lab[oracle.feistel_perm(5, 1, n_used)], T, F)
+            exp = oracle.ks_null_fast_one(s, oracle.perm_labels(5, 1, lab, T), T, F)
             assert_bits_equal_f32(ne[:, 1], exp, f"ctx {'A' if c is ctx else 'B'} Nu={n_used} T={T}")
     finally:
         other.close()
@@ -790,7 +817,7 @@ def test_analyze_batch_equals_single_analyses(ctx, oracle, small, gene_major):
     nu = npass - 1
     s_r, lab_r = sc[order[:nu]], d["label"][order[:nu]]
     F = oracle.fast_frac_bits(s_r)
-    one = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(9, p, nu)], cfg.n_types, F)
+    one = np.stack([oracle.ks_null_fast_one(s_r, oracle.perm_labels(9, p, lab_r, cfg.n_types), cfg.n_types, F)
                     for p in range(Pn)], axis=1)
     ores = oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), one)
     assert_bits_equal_f32(out["null"][3], one, "batch list 3 null vs oracle")
@@ -955,7 +982,7 @@ def test_baseline_config_A_end_to_end(ctx, oracle, gene_major):
     nprm = ctx.null_params(cfg.n_perm, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=7, min_pass=1000)
     fast = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm, want_null=True)
     F = oracle.fast_frac_bits(s_r)
-    exp = np.stack([oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(7, p, nu)], cfg.n_types, F)
+    exp = np.stack([oracle.ks_null_fast_one(s_r, oracle.perm_labels(7, p, lab_r, cfg.n_types), cfg.n_types, F)
                     for p in range(cfg.n_perm)], axis=1)
     assert_bits_equal_f32(fast["null"], exp, "PHILOX FAST null")
     assert_results_equal(fast["results"], oracle.reduce(oracle.ks_observed(s_r, lab_r, cfg.n_types), exp), None,

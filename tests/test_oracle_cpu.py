@@ -109,7 +109,7 @@ def test_regression_fixture(oracle, tiny):
     assert red["fdr"].view(np.uint64).tolist() == g["fdr_bits"]
     assert oracle.feistel_perm(42, 0, nu)[:16].tolist() == g["feistel_perm_seed42_p0_first16"]
     assert oracle.fast_frac_bits(s_r) == g["fast_frac_bits"]
-    fast0 = oracle.ks_null_fast_one(s_r, lab_r[oracle.feistel_perm(42, 0, nu)], cfg.n_types, g["fast_frac_bits"])
+    fast0 = oracle.ks_null_fast_one(s_r, oracle.perm_labels(42, 0, lab_r, cfg.n_types), cfg.n_types, g["fast_frac_bits"])
     assert fast0.view(np.uint32).tolist() == g["fast_null_p0_bits"]
 
 
@@ -281,13 +281,13 @@ def test_fast_definition_close_to_exact(oracle):
     # FAST = exact prefix sums at hit / pre-hit positions; EXACT = the reference's fp32 running sums
     s, lab = synth.synthetic_ranked(20_000, 12, seed=7)
     F = oracle.fast_frac_bits(s)
-    assert F == 25  # max score in [0.5, 1)
+    assert F == 17  # largest F with sum |llrint(s * 2^F)| < 2^31 (20 000 scores around 0.6)
     for p in range(3):
-        lp = lab[oracle.feistel_perm(1, p, s.size)]
+        lp = oracle.perm_labels(1, p, lab, 12)
         e, _ = oracle.ks_null_one(s, lp, 12)
         f = oracle.ks_null_fast_one(s, lp, 12, F)
         ok = ~np.isnan(e)
-        assert np.array_equal(np.isnan(e), np.isnan(f)) and np.max(np.abs(np.abs(e[ok]) - np.abs(f[ok]))) < 2e-4
+        assert np.array_equal(np.isnan(e), np.isnan(f)) and np.max(np.abs(np.abs(e[ok]) - np.abs(f[ok]))) < 2e-5
 
 
 def test_reduce_semantics(oracle):
