@@ -47,8 +47,7 @@ extern "C" {
                                    TYPE-SORTED arrangement of the ranked labels (types ascending, unknown-type cells
                                    last); pi_p = keyed Feistel bijection of [0, n_used) with arithmetic round
                                    functions, one Philox4x32-10 key per round and permutation. A pure function of
-                                   (seed, global permutation index, x): identical for any GPU count or slicing.
-                                   Needs n_used <= 2^25. */
+                                   (seed, global permutation index, x): identical for any GPU count or slicing. */
 
 /* Rounds of the keyed Feistel bijection behind PCTSEA_PERM_PHILOX. The class of a position is a range test on the
  * high digit of pi_p(x), which exposes the unevenness of a random round function: measured on the null of the

@@ -147,16 +147,22 @@ double orc_jitter_uniform(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t i
 }
 
 static void feistel_dims(int64_t n, int64_t* a_out, int64_t* b_out) {
-    int64_t a = (int64_t)floor(sqrt((double)n));
-    while (a * a < n) a++;
-    while (a > 1 && (a - 1) * (a - 1) >= n) a--;
-    if (a < 1) a = 1;
-    *a_out = a;
-    *b_out = (n + a - 1) / a;
+    /* a0 = ceil(sqrt n); the a in [a0, a0 + a0/16] with the fewest out-of-range points a*ceil(n/a) - n (first on ties) */
+    int64_t a0 = (int64_t)floor(sqrt((double)n));
+    while (a0 * a0 < n) a0++;
+    while (a0 > 1 && (a0 - 1) * (a0 - 1) >= n) a0--;
+    if (a0 < 1) a0 = 1;
+    int64_t best_a = a0, best_w = a0 * ((n + a0 - 1) / a0) - n;
+    for (int64_t a = a0 + 1; a <= a0 + a0 / 16 && best_w > 0; a++) {
+        int64_t w = a * ((n + a - 1) / a) - n;
+        if (w < best_w) { best_w = w; best_a = a; }
+    }
+    *a_out = best_a;
+    *b_out = (n + best_a - 1) / best_a;
 }
 
-/* PHILOX-mode permutation, round 2 definition: a keyed Feistel bijection of [0,n) on Z_a x Z_b (a = ceil(sqrt n),
- * b = ceil(n / a); cycle-walking for the < a out-of-range points) whose round functions are ARITHMETIC:
+/* PHILOX-mode permutation, round 2 definition: a keyed Feistel bijection of [0,n) on Z_a x Z_b (a near sqrt n,
+ * b = ceil(n / a), see feistel_dims; cycle-walking for the few out-of-range points) whose round functions are ARITHMETIC:
  *   F(v, key, mod) = floor(mix(v, key) * mod / 2^32),  mix = multiply - xorshift - multiply hash of v and the round key,
  * with one 32-bit key per round from Philox4x32-10(ctr = {j / 4, 0, p, "FEIS"}, key = seed)[j % 4]. No tables:
  * the GPU evaluates it in registers inside the null kernel. Round j modifies the high digit L iff (rounds-1-j) is
@@ -165,8 +171,14 @@ static void feistel_dims(int64_t n, int64_t* a_out, int64_t* b_out) {
  * of the enrichment score (profiles/feistel_rounds_check.txt): 3 and 4 rounds inflate its standard deviation by 2 %
  * (the value histogram of a random round FUNCTION is uneven, and with the sorted arrangement that unevenness reaches
  * the class counts of long prefixes of the ranking); 5 and more rounds are indistinguishable. Default 5. */
+static int g_mix_variant = 1; /* EXPERIMENT */
+void orc_set_mix_variant(int v) { g_mix_variant = v; }
 static inline uint32_t feistel_mix(uint32_t v, uint32_t key) {
     uint32_t t = v * 0x9E3779B1u + key;
+    if (g_mix_variant == 3) return t * t;
+    if (g_mix_variant == 4) return t * (t >> 16);
+    if (g_mix_variant == 5) { t ^= t >> 15; return t * t; }
+    if (g_mix_variant == 6) { return (t | 1u) * (t >> 15); }
     t ^= t >> 15;
     t *= 0x2C1B3C6Du;
     return t;

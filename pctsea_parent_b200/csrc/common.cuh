@@ -170,14 +170,21 @@ __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// Feistel geometry shared by host and device: a = ceil(sqrt(n)), b = ceil(n / a).
+// Feistel geometry: digits (L, R) in Z_a x Z_b with a * b >= n. Starting from a0 = ceil(sqrt(n)), the a in
+// [a0, a0 + a0/16] with the fewest out-of-range points a * ceil(n / a) - n is taken (first one on ties): every such
+// point costs a cycle-walk, and one walking lane stalls its warp.
 inline void feistel_dims(int64_t n, uint32_t* a_out, uint32_t* b_out) {
-    int64_t a = (int64_t)std::floor(std::sqrt((double)n));
-    while (a * a < n) a++;
-    while (a > 1 && (a - 1) * (a - 1) >= n) a--;
-    if (a < 1) a = 1;
-    *a_out = (uint32_t)a;
-    *b_out = (uint32_t)((n + a - 1) / a);
+    int64_t a0 = (int64_t)std::floor(std::sqrt((double)n));
+    while (a0 * a0 < n) a0++;
+    while (a0 > 1 && (a0 - 1) * (a0 - 1) >= n) a0--;
+    if (a0 < 1) a0 = 1;
+    int64_t best_a = a0, best_w = a0 * ((n + a0 - 1) / a0) - n;
+    for (int64_t a = a0 + 1; a <= a0 + a0 / 16 && best_w > 0; a++) {
+        const int64_t w = a * ((n + a - 1) / a) - n;
+        if (w < best_w) { best_w = w; best_a = a; }
+    }
+    *a_out = (uint32_t)best_a;
+    *b_out = (uint32_t)((n + best_a - 1) / best_a);
 }
 
 inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }

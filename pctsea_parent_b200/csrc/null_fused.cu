@@ -181,10 +181,11 @@ __global__ void k_fx_transpose(const int* __restrict__ fx, int64_t Nu, int32_t s
 // class of an index of the type-sorted arrangement
 // ================================================================================================
 // cum[c] = number of ranked cells of a class below c (c = 0 .. Tc, Tc = T + 1 classes, the last one "unknown type");
-// class(j) = the c with cum[c] <= j < cum[c+1]. ctab[j >> shift] packs, per bucket of 2^shift indices,
-//   (class of the bucket's first index) << 16 | offset of the bucket's only class boundary,
-// 0xffff = no boundary inside, 0xfffe = several (or one that skips empty classes): walk cum[] from the first class.
-constexpr uint32_t CT_NONE = 0xffffu, CT_MULTI = 0xfffeu;
+// class(j) = the c with cum[c] <= j < cum[c+1]. ctab[j >> shift] holds, per bucket of 2^shift indices,
+//   .x = index of the bucket's only class boundary (0xffffffff: none inside), .y = class of the bucket's first index,
+// so that class(j) = .y + (j >= .x): one 8-byte shared-memory read, a compare and an add. A bucket with several
+// boundaries (or one that skips empty classes) has bit 31 of .y set: walk cum[] from class .y & 0x7fffffff.
+constexpr uint32_t CT_MULTI = 0x80000000u;
 
 __device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cum, uint32_t Tc, uint32_t j) {
     uint32_t lo = 0, hi = Tc;   // invariant: cum[lo] <= j < cum[hi]
@@ -197,7 +198,7 @@ __device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cu
 
 __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict__ class_cnt, int32_t Tc, int64_t Nu,
                                                       int shift, int32_t nb, uint32_t* __restrict__ cum,
-                                                      uint32_t* __restrict__ ctab) {
+                                                      uint2* __restrict__ ctab) {
     // one CTA: exclusive scan of the class counts (thread t owns a contiguous chunk), then the bucket table
     __shared__ uint32_t part[1024];
     const int per = (Tc + 1023) / 1024;
@@ -216,31 +217,36 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
     if (threadIdx.x == 0) cum[Tc] = (uint32_t)Nu;
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += 1024) {
-        const uint32_t start = (uint32_t)i << shift;
-        uint32_t e = 0xffffffffu;
-        if ((int64_t)start < Nu) {
-            const uint32_t last = (uint32_t)min((long long)start + (1ll << shift), (long long)Nu) - 1u;
-            const uint32_t ca = class_search(cum, (uint32_t)Tc, start), cb = class_search(cum, (uint32_t)Tc, last);
-            uint32_t off = CT_NONE;
-            if (cb == ca + 1u) off = cum[cb] - start;
-            else if (cb > ca + 1u) off = CT_MULTI;
-            e = (ca << 16) | off;
+        const long long start = (long long)i << shift;
+        uint2 e = make_uint2(0xffffffffu, 0u);
+        if (start < Nu) {
+            const uint32_t last = (uint32_t)(min(start + (1ll << shift), (long long)Nu) - 1);
+            const uint32_t ca = class_search(cum, (uint32_t)Tc, (uint32_t)start), cb = class_search(cum, (uint32_t)Tc, last);
+            e.y = ca;
+            if (cb == ca + 1u) e.x = cum[cb];
+            else if (cb > ca + 1u) e.y = ca | CT_MULTI;
         }
         ctab[i] = e;
     }
 }
 
-__device__ __forceinline__ uint32_t class_of(uint32_t j, const uint32_t* __restrict__ ctab_s, const uint32_t* __restrict__ cum,
-                                             int shift) {
-    const uint32_t e = ctab_s[j >> shift];
-    uint32_t c = e >> 16;
-    const uint32_t off = e & 0xffffu;
-    if (off == CT_MULTI) {
-        while (j >= cum[c + 1]) c++;   // ends: cum[Tc] = Nu > j
-    } else {
-        c += ((j & ((1u << shift) - 1u)) >= off) ? 1u : 0u;   // CT_NONE is above every in-bucket offset (shift <= 15)
+// Classes of four indices; the several-boundaries case is checked once for the four.
+__device__ __forceinline__ void class_of4(const uint32_t (&j)[4], const uint2* __restrict__ ctab_s,
+                                          const uint32_t* __restrict__ cum, int shift, uint32_t (&c)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint2 e = ctab_s[j[q] >> shift];
+        c[q] = e.y + (j[q] >= e.x ? 1u : 0u);
     }
-    return c;
+    if ((c[0] | c[1] | c[2] | c[3]) & CT_MULTI) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (c[q] & CT_MULTI) {
+                uint32_t cc = c[q] & ~CT_MULTI;
+                while (j[q] >= cum[cc + 1]) cc++;   // ends: cum[Tc] = Nu > j
+                c[q] = cc;
+            }
+    }
 }
 
 // ================================================================================================
@@ -272,23 +278,35 @@ __device__ __forceinline__ void feistel_keys(uint64_t seed, uint32_t p, uint32_t
     }
 }
 
-// NR > 0: unrolled, keys in registers; NR == 0: `rounds` at run time, keys from memory.
+__device__ __forceinline__ uint32_t mad_hi_u32(uint32_t x, uint32_t y, uint32_t z) {   // hi32(x * y) + z, one IMAD.HI
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(y), "r"(z));
+    return d;
+}
+
+// One pass of the rounds over the digits (L, R). NR > 0: unrolled, keys in registers; NR == 0: `rounds` at run time,
+// keys from memory.
+template <int NR, typename Keys>
+__device__ __forceinline__ void feistel_rounds(const Keys& keys, uint32_t a, uint32_t b, int rounds_rt, uint32_t& L, uint32_t& R) {
+    const int rounds = NR > 0 ? NR : rounds_rt;
+#pragma unroll
+    for (int j = 0; j < rounds; j++) {
+        if (((rounds - 1 - j) & 1) == 0) {   // the last round modifies the high digit
+            L = mad_hi_u32(feistel_mix(R, keys[j]), a, L);
+            L = min(L, L - a);   // unsigned: L - a wraps above L exactly when L < a
+        } else {
+            R = mad_hi_u32(feistel_mix(L, keys[j]), b, R);
+            R = min(R, R - b);
+        }
+    }
+}
+
 template <int NR, typename Keys>
 __device__ __forceinline__ uint32_t feistel_apply(const Keys& keys, uint32_t a, uint32_t b, int rounds_rt, uint32_t L,
                                                   uint32_t R, uint32_t n) {
-    const int rounds = NR > 0 ? NR : rounds_rt;
     uint32_t y;
     do {
-#pragma unroll
-        for (int j = 0; j < rounds; j++) {
-            if (((rounds - 1 - j) & 1) == 0) {   // the last round modifies the high digit
-                L += __umulhi(feistel_mix(R, keys[j]), a);
-                L = min(L, L - a);   // unsigned: L - a wraps above L exactly when L < a
-            } else {
-                R += __umulhi(feistel_mix(L, keys[j]), b);
-                R = min(R, R - b);
-            }
-        }
+        feistel_rounds<NR>(keys, a, b, rounds_rt, L, R);
         y = L * b + R;
     } while (y >= n);  // cycle-walk: < a of the a*b points are out of range
     return y;
@@ -298,8 +316,10 @@ __device__ __forceinline__ uint32_t feistel_apply(const Keys& keys, uint32_t a, 
 template <typename LabT> struct LaneWord;
 template <> struct LaneWord<uint8_t> {
     typedef uint32_t type;
-    static __device__ __forceinline__ uint32_t get(uint32_t w, int q) { return (w >> (8 * q)) & 0xffu; }
-    static __device__ __forceinline__ uint32_t pack(const uint32_t c[4]) { return c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24); }
+    static __device__ __forceinline__ uint32_t get(uint32_t w, int q) { return __byte_perm(w, 0u, 0x4440u + (uint32_t)q); }   // one PRMT
+    static __device__ __forceinline__ uint32_t pack(const uint32_t c[4]) {
+        return __byte_perm(__byte_perm(c[0], c[1], 0x0040u), __byte_perm(c[2], c[3], 0x0040u), 0x5410u);
+    }
 };
 template <> struct LaneWord<uint16_t> {
     typedef uint2 type;
@@ -352,12 +372,28 @@ __device__ __forceinline__ uint32_t sup_key_fast(float f) {
 
 constexpr int NF_PRE = 4;   // label / score words in flight per thread in the second walk
 
+struct __align__(16) TypeConst {   // per cell type and permutation: the two constants of the candidate and the running maximum
+    float c12, c2;
+    uint32_t best;
+    uint32_t pad;
+};
+
+// 16-byte shared-memory read that is re-issued every time (the maxima change under the reader); saddr = address in
+// the shared window
+__device__ __forceinline__ uint4 lds128_volatile(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(saddr));
+    return v;
+}
+
 struct NullArgs {
     const int4* fxT4;            // [seg4][Kp] fixed-point scores, lane layout
     const int* Sfx;              // [Nu] inclusive int32 prefix of the fixed-point scores
     const int32_t* class_cnt;    // [Tc]
     const uint32_t* cum;         // [Tc + 1]
-    const uint32_t* ctab;        // [nb]
+    const uint2* ctab;           // [nb]
     void* scratch;               // [grid][seg4][Kp] label words
     int* ticket;
     float* null_ews;             // [T][P_stride]
@@ -381,21 +417,25 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     const int Kp = blockDim.x;
     const int k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarp = Kp >> 5;
     int* numA = reinterpret_cast<int*>(smem_raw);                               // [Tc][Kp]
-    float2* cs = reinterpret_cast<float2*>(numA + (size_t)Tc * Kp);             // [Tc] (c12, c2)
-    uint32_t* best = reinterpret_cast<uint32_t*>(cs + Tc);                      // [Tc]
-    uint32_t* ctab_s = best + Tc;                                               // [nb]
-    uint32_t* cum_s = ctab_s + A.nb;                                            // [T_all + 2] when it fits
+    TypeConst* cb = reinterpret_cast<TypeConst*>(numA + (size_t)Tc * Kp);       // [Tc]
+    uint2* ctab_s = reinterpret_cast<uint2*>(cb + Tc);                          // [nb]
+    uint32_t* cum_s = reinterpret_cast<uint32_t*>(ctab_s + A.nb);               // [T_all + 2] when it fits
     const uint32_t* cum = A.cum_smem ? cum_s : A.cum;
+    const uint32_t cb_saddr = (uint32_t)__cvta_generic_to_shared(cb);
     for (int i = k; i < A.nb; i += Kp) ctab_s[i] = A.ctab[i];
     if (A.cum_smem) for (int i = k; i < T_all + 2; i += Kp) cum_s[i] = A.cum[i];
-    const int seg = A.seg, seg4 = seg >> 2;
+    const int seg = A.seg;
     const uint32_t n = (uint32_t)A.Nu, a = A.fp.a, b = A.fp.b;
     const int shift = A.shift;
-    Word* lab = reinterpret_cast<Word*>(A.scratch) + (size_t)blockIdx.x * seg4 * Kp + k;
+    Word* lab = reinterpret_cast<Word*>(A.scratch) + (size_t)blockIdx.x * (seg >> 2) * Kp + k;
     const int4* fxp = A.fxT4 + k;
     int* col = numA + k;   // this thread's private column: type t lives at col[t * Kp] (bank = k % 32 for every t)
     const uint32_t x0 = (uint32_t)k * (uint32_t)seg;
     const uint32_t L00 = x0 / b, R00 = x0 - L00 * b;
+    // my positions: nv valid ones = nfull whole words + possibly one partial word; nothing behind them is visited
+    // (the fixed-point scores are zero-padded, the labels of a partial word's tail are the unknown class)
+    const int nv = x0 < n ? (int)min((uint32_t)seg, n - x0) : 0;
+    const int nfull = nv >> 2, nw = (nv + 3) >> 2;
     const int Stot = A.Sfx[A.Nu - 1];
     const int S0 = (x0 > 0u && x0 <= n) ? A.Sfx[x0 - 1u] : 0;   // exact prefix before my segment
 
@@ -406,7 +446,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
         const int p = s_p;
         if (p >= A.Pc) break;
         uint32_t keys[NR > 0 ? NR : 1];
-        if (NR > 0) feistel_keys<(NR > 0 ? NR : 1)>(A.fp.seed, (uint32_t)(A.perm_begin + p), keys);
+        if constexpr (NR > 0) feistel_keys<NR>(A.fp.seed, (uint32_t)(A.perm_begin + p), keys);
         else {
             if (k < 8 && k * 4 < A.fp.rounds) {
                 uint32_t o[4];
@@ -417,34 +457,73 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             }
             __syncthreads();
         }
+        auto rounds = [&](uint32_t& L, uint32_t& R) {
+            if constexpr (NR > 0) feistel_rounds<NR>(keys, a, b, NR, L, R);
+            else feistel_rounds<0>(s_keys, a, b, A.fp.rounds, L, R);
+        };
         if (!SLICED) {
-            for (int t = 0; t < Tc; t++) col[(size_t)t * Kp] = 0;
-            for (int t = k; t < Tc; t += Kp) best[t] = 0u;
+            for (int t = 0; t < Tc; t++) col[t * Kp] = 0;
+            for (int t = k; t < Tc; t += Kp) cb[t].best = 0u;
         }
 
         // ---- phase 1: labels of my segment + per-type segment sums (one shared-memory read-modify-write per
-        // position, in program order). Padding positions (x >= Nu) carry the unknown class and f = 0.
+        // position, in program order). Four positions at a time: four independent round chains, no per-position tests.
         {
-            uint32_t L = L00, R = R00, x = x0;
-            int4 fn = fxp[0];
-            for (int i4 = 0; i4 < seg4; i4++) {
+            uint32_t L = L00, R = R00;
+            const int4* fptr = fxp;
+            Word* lptr = lab;
+            int4 fn = nw > 0 ? *fptr : make_int4(0, 0, 0, 0);
+            for (int i4 = 0; i4 < nw; i4++) {
                 const int4 fc = fn;
-                if (i4 + 1 < seg4) fn = fxp[(size_t)(i4 + 1) * Kp];
+                fptr += Kp;
+                if (i4 + 1 < nw) fn = *fptr;
                 const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
-                uint32_t cls[4];
+                uint32_t y[4], cls[4];
+                if (i4 < nfull) {
+                    uint32_t Lq[4], Rq[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    cls[q] = (uint32_t)T_all;
-                    if (x < n) {
-                        const uint32_t j = (NR > 0) ? feistel_apply<NR>(keys, a, b, NR, L, R, n)
-                                                    : feistel_apply<0>(s_keys, a, b, A.fp.rounds, L, R, n);
-                        cls[q] = class_of(j, ctab_s, cum, shift);
+                    for (int q = 0; q < 4; q++) {
+                        // digits of position x + q, branch-free across a row boundary (lanes cross rows at different words)
+                        const uint32_t r = R + (uint32_t)q;
+                        Lq[q] = L + (r >= b ? 1u : 0u);
+                        Rq[q] = min(r, r - b);
+                        rounds(Lq[q], Rq[q]);
+                        y[q] = Lq[q] * b + Rq[q];
                     }
-                    x++; R++;
-                    if (R >= b) { R = 0; L++; }
-                    if (!SLICED) col[(size_t)cls[q] * Kp] += fq[q];
+                    R += 4u;
+                    if (R >= b) { R -= b; L++; }
+                    if (max(max(y[0], y[1]), max(y[2], y[3])) >= n) {   // cycle-walk: rare
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            while (y[q] >= n) { rounds(Lq[q], Rq[q]); y[q] = Lq[q] * b + Rq[q]; }
+                    }
+                    class_of4(y, ctab_s, cum, shift, cls);
+                } else {   // the partial last word of the ranking
+                    y[0] = y[1] = y[2] = y[3] = 0xffffffffu;
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++) {
+                        if (i4 * 4 + q < nv) {
+                            uint32_t Lc = L, Rc = R, yy;
+                            do { rounds(Lc, Rc); yy = Lc * b + Rc; } while (yy >= n);
+                            y[0] = q == 0 ? yy : y[0]; y[1] = q == 1 ? yy : y[1];   // (no dynamic indexing: y[] stays in registers)
+                            y[2] = q == 2 ? yy : y[2]; y[3] = q == 3 ? yy : y[3];
+                        }
+                        R++;
+                        if (R >= b) { R = 0u; L++; }
+                    }
+                    uint32_t jj[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) jj[q] = min(y[q], n - 1u);
+                    class_of4(jj, ctab_s, cum, shift, cls);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) cls[q] = (y[q] == 0xffffffffu) ? (uint32_t)T_all : cls[q];
                 }
-                lab[(size_t)i4 * Kp] = LaneWord<LabT>::pack(cls);
+                if (!SLICED) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) col[cls[q] * (uint32_t)Kp] += fq[q];
+                }
+                *lptr = LaneWord<LabT>::pack(cls);
+                lptr += Kp;
             }
         }
 
@@ -457,15 +536,15 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             return tl < (uint32_t)T ? tl : (uint32_t)Ts;
         };
         if (SLICED) {
-            for (int t = 0; t < Tc; t++) col[(size_t)t * Kp] = 0;
-            for (int t = k; t < Tc; t += Kp) best[t] = 0u;
+            for (int t = 0; t < Tc; t++) col[t * Kp] = 0;
+            for (int t = k; t < Tc; t += Kp) cb[t].best = 0u;
             // phase 1 on the parked labels (each thread re-reads what it wrote itself: no barrier needed)
-            for (int i4 = 0; i4 < seg4; i4++) {
+            for (int i4 = 0; i4 < nw; i4++) {
                 const Word w = lab[(size_t)i4 * Kp];
                 const int4 fc = fxp[(size_t)i4 * Kp];
                 const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
 #pragma unroll
-                for (int q = 0; q < 4; q++) col[(size_t)local_type(LaneWord<LabT>::get(w, q)) * Kp] += fq[q];
+                for (int q = 0; q < 4; q++) col[local_type(LaneWord<LabT>::get(w, q)) * (uint32_t)Kp] += fq[q];
             }
         }
         __syncthreads();
@@ -474,9 +553,9 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
         for (int t = warp; t < Tc; t += nwarp) {
             int carry = 0;
             for (int k0 = 0; k0 < Kp; k0 += 32) {
-                const int v = numA[(size_t)t * Kp + k0 + lane];
+                const int v = numA[t * Kp + k0 + lane];
                 const int incl = warp_incl_scan_i32(v, lane);
-                numA[(size_t)t * Kp + k0 + lane] = carry + (incl - v);
+                numA[t * Kp + k0 + lane] = carry + (incl - v);
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
             if (lane == 0) {
@@ -487,7 +566,8 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     c2 = __double2float_rn(r2);
                     c12 = __double2float_rn(__dadd_rn(__ddiv_rn(1.0, (double)dA), r2));
                 }
-                cs[t] = make_float2(c12, c2);
+                cb[t].c12 = c12;
+                cb[t].c2 = c2;
             }
         }
         __syncthreads();
@@ -499,50 +579,53 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             float Sf = __int2float_rn(S);
             Word wc[NF_PRE];   // register sets refilled in place: the loads run NF_PRE - 1 words ahead of their use
             int4 fc[NF_PRE];
+            const Word* lptr = lab;
+            const int4* fptr = fxp;
 #pragma unroll
-            for (int u = 0; u < NF_PRE; u++)
-                if (u < seg4) { wc[u] = lab[(size_t)u * Kp]; fc[u] = fxp[(size_t)u * Kp]; }
-            for (int i4 = 0; i4 < seg4; i4 += NF_PRE) {
+            for (int u = 0; u < NF_PRE; u++) {
+                if (u < nw) { wc[u] = *lptr; fc[u] = *fptr; }
+                lptr += Kp; fptr += Kp;
+            }
+            for (int i4 = 0; i4 < nw; i4 += NF_PRE) {
 #pragma unroll
                 for (int u = 0; u < NF_PRE; u++) {
-                    if (i4 + u >= seg4) break;
+                    if (i4 + u >= nw) break;
                     const int fq[4] = { fc[u].x, fc[u].y, fc[u].z, fc[u].w };
                     const Word wcu = wc[u];
-                    if (i4 + NF_PRE + u < seg4) {
-                        wc[u] = lab[(size_t)(i4 + NF_PRE + u) * Kp];
-                        fc[u] = fxp[(size_t)(i4 + NF_PRE + u) * Kp];
-                    }
-                    uint32_t t[4], cur[4], key[4];
+                    if (i4 + NF_PRE + u < nw) { wc[u] = *lptr; fc[u] = *fptr; }
+                    lptr += Kp; fptr += Kp;
+                    uint32_t t[4], key[4];
                     int bq[4], aq[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {   // the four running-sum updates, in program order
                         t[q] = local_type(LaneWord<LabT>::get(wcu, q));
-                        int* sp = col + (size_t)t[q] * Kp;
+                        int* sp = col + t[q] * (uint32_t)Kp;
                         bq[q] = *sp;
                         aq[q] = bq[q] + fq[q];
                         *sp = aq[q];
                     }
-                    // the current maxima first (plain reads, issued together so that their latency hides behind
-                    // the candidate arithmetic): best[] only grows, so a candidate that does not beat the possibly
-                    // stale value read here cannot beat the current one either. Record-setting candidates are rare
-                    // and a shared-memory atomic costs one wavefront per active lane, so the atomics sit behind one
-                    // branch per group of four positions.
+                    // the constants and the current maximum of each type in one 16-byte read (issued together so
+                    // that their latency hides behind the candidate arithmetic): best only grows, so a candidate
+                    // that does not beat the possibly stale value read here cannot beat the current one either.
+                    // Record-setting candidates are rare and a shared-memory atomic costs one wavefront per active
+                    // lane, so the atomics sit behind one branch per group of four positions.
+                    uint4 cq[4];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) cur[q] = reinterpret_cast<volatile uint32_t*>(best)[t[q]];
+                    for (int q = 0; q < 4; q++) cq[q] = lds128_volatile(cb_saddr + t[q] * 16u);
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const float2 c = cs[t[q]];
+                        const float c12 = __uint_as_float(cq[q].x), c2 = __uint_as_float(cq[q].y);
                         const float Spf = Sf;
                         S += fq[q];   // exact: |S| <= sum |fx| < 2^31
                         Sf = __int2float_rn(S);
-                        const uint32_t k1 = sup_key_fast(__fmaf_rn(__int2float_rn(aq[q]), c.x, -__fmul_rn(Sf, c.y)));
-                        const uint32_t k0 = sup_key_fast(__fmaf_rn(__int2float_rn(bq[q]), c.x, -__fmul_rn(Spf, c.y)));
+                        const uint32_t k1 = sup_key_fast(__fmaf_rn(__int2float_rn(aq[q]), c12, -__fmul_rn(Sf, c2)));
+                        const uint32_t k0 = sup_key_fast(__fmaf_rn(__int2float_rn(bq[q]), c12, -__fmul_rn(Spf, c2)));
                         key[q] = k0 > k1 ? k0 : k1;
                     }
-                    if ((key[0] > cur[0]) | (key[1] > cur[1]) | (key[2] > cur[2]) | (key[3] > cur[3])) {
+                    if ((key[0] > cq[0].z) | (key[1] > cq[1].z) | (key[2] > cq[2].z) | (key[3] > cq[3].z)) {
 #pragma unroll
                         for (int q = 0; q < 4; q++)
-                            if (key[q] > cur[q]) atomicMax(&best[t[q]], key[q]);
+                            if (key[q] > cq[q].z) atomicMax(&cb[t[q]].best, key[q]);
                     }
                 }
             }
@@ -556,7 +639,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             float v, d;
             if (!(nk > 1 && sizeb > 1)) { v = __int_as_float(0x7fc00000); d = v; }
             else {
-                const uint32_t key = best[t];
+                const uint32_t key = cb[t].best;
                 v = (key <= 1u) ? 0.0f : __int_as_float((int)((key >> 1) | (((key & 1u) ^ 1u) << 31)));
                 d = dstat_of_f(v, nk, sizeb);
             }
@@ -577,11 +660,10 @@ static void feistel_params(const EnrichGeom& g, uint64_t seed, int rounds, Feist
     fp->seed = seed;
 }
 
-// Bucket table geometry: at most 1024 buckets of at most 2^15 indices.
+// Bucket table geometry: at most 1024 buckets.
 static void class_table_geom(int64_t Nu, int* shift, int32_t* nb) {
     int s = 0;
     while (((Nu - 1) >> s) + 1 > 1024) s++;
-    PCT_REQUIRE(s <= 15, "too many ranked cells for the permutation kernels' class table (limit 2^25)");
     *shift = s;
     *nb = (int32_t)(((Nu - 1) >> s) + 1);
 }
@@ -591,7 +673,7 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
     class_table_geom(std::max<int64_t>(g.Nu, 1), &pl.shift, &pl.nb);
     pl.cum_smem = (g.Tc + 1 <= 1024) ? 1 : 0;
     const size_t smem_sm = (size_t)c->smem_per_sm, smem_cta_max = (size_t)c->smem_per_block_optin;
-    auto fixed = [&](int ts) { return (size_t)(ts + 1) * 12 + (size_t)pl.nb * 4 + (pl.cum_smem ? (size_t)(g.Tc + 1) * 4 : 0) + 64; };
+    auto fixed = [&](int ts) { return (size_t)(ts + 1) * 16 + (size_t)pl.nb * 8 + (pl.cum_smem ? (size_t)(g.Tc + 1) * 4 : 0) + 64; };
     auto threads_for = [&](int ts) {
         const size_t f = fixed(ts);
         if (f + (size_t)(ts + 1) * 4 * 32 > smem_cta_max) return 0;
@@ -651,9 +733,10 @@ void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlan
 
 // cum[] (+ the bucket table when nb > 0) of the type-sorted arrangement; needs class_cnt (k_gather_ranked).
 void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb) {
-    c->cls_tab.reserve((size_t)(g.Tc + 1) * 4 + (size_t)std::max(nb, 1) * 4 + 64);
+    const size_t cum_bytes = (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16);
+    c->cls_tab.reserve(cum_bytes + (size_t)std::max(nb, 1) * 8 + 64);
     uint32_t* cum = c->cls_tab.as<uint32_t>();
-    uint32_t* ctab = cum + (g.Tc + 1);
+    uint2* ctab = reinterpret_cast<uint2*>(c->cls_tab.as<unsigned char>() + cum_bytes);
     k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift, nb, cum, ctab);
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
@@ -686,7 +769,7 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
     A.Sfx = c->Sfx.as<int>();
     A.class_cnt = c->class_cnt.as<int32_t>();
     A.cum = c->cls_tab.as<uint32_t>();
-    A.ctab = A.cum + (g.Tc + 1);
+    A.ctab = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16));
     const unsigned grid = (unsigned)std::min<int64_t>(Pc, (int64_t)pl.ctas_per_sm * c->num_sms);
     const int seg4 = pl.seg >> 2;
     c->labels.reserve((size_t)grid * seg4 * pl.Kp * pl.word_bytes + 64);

@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Time the label + null KS stages alone on a synthetic ranked list: python profiles/time_null.py N_USED T P"""
+"""Time the null stage alone on a synthetic ranked list, over kernel geometries:
+    python profiles/time_null.py N_USED T P [threads,ctas_per_sm,min_threads,overlap ...]
+Each geometry argument sets the ctx options OPT_NULL_THREADS, OPT_NULL_CTAS_PER_SM, OPT_NULL_MIN_THREADS,
+OPT_OBS_OVERLAP (0 = library default for the first three)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,13 +10,21 @@ import pctsea_parent_b200 as P
 from pctsea_parent_b200 import synth
 from pctsea_parent_b200._lib import Context
 n_used, T, Pn = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-s, lab = synth.synthetic_ranked(n_used + 1, T, seed=1)
+geoms = [tuple(int(v) for v in a.split(",")) for a in sys.argv[4:]] or [(0, 0, 0, 1)]
+s, lab = synth.synthetic_ranked(n_used + 1, T, seed=1, simple=bool(int(os.environ.get("SIMPLE", "0"))))
 order = np.arange(n_used + 1, dtype=np.int32)
 ctx = Context(0)
 prm = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=3)
-out = []
-for _ in range(4):
-    ctx.enrich(s, order, lab, T, prm, want_null=False)
-    t = ctx.timings()
-    out.append((t["labels_ms"], t["null_ms"], t["observed_ms"]))
-print(f"Nu={n_used} T={T} P={Pn}: labels {out[-1][0]:.3f} ms  null {out[-1][1]:.3f} ms  observed {out[-1][2]:.3f} ms")
+for g in geoms:
+    thr, ctas, minthr, ov = (list(g) + [0, 0, 0, 1])[:4] if len(g) < 4 else g
+    ctx.set_option(P.OPT_NULL_THREADS, thr)
+    ctx.set_option(P.OPT_NULL_CTAS_PER_SM, ctas)
+    ctx.set_option(P.OPT_NULL_MIN_THREADS, minthr)
+    ctx.set_option(P.OPT_OBS_OVERLAP, ov)
+    out = []
+    for _ in range(4):
+        ctx.enrich(s, order, lab, T, prm, want_null=False)
+        t = ctx.timings()
+        out.append((t["null_ms"], t["observed_ms"], t["total_ms"]))
+    print(f"Nu={n_used} T={T} P={Pn} threads={thr} ctas/SM={ctas} min_threads={minthr} overlap={ov}: "
+          f"null {out[-1][0]:.3f} ms  observed {out[-1][1]:.3f} ms  total {out[-1][2]:.3f} ms", flush=True)
