@@ -182,9 +182,9 @@ __global__ void k_fx_transpose(const int* __restrict__ fx, int64_t Nu, int32_t s
 // ================================================================================================
 // cum[c] = number of ranked cells of a class below c (c = 0 .. Tc, Tc = T + 1 classes, the last one "unknown type");
 // class(j) = the c with cum[c] <= j < cum[c+1]. ctab[j >> shift] holds, per bucket of 2^shift indices,
-//   .x = index of the bucket's only class boundary (0xffffffff: none inside), .y = class of the bucket's first index,
-// so that class(j) = .y + (j >= .x): one 8-byte shared-memory read, a compare and an add. A bucket with several
-// boundaries (or one that skips empty classes) has bit 31 of .y set: walk cum[] from class .y & 0x7fffffff.
+//   .x = index of the bucket's only class boundary (0xffffffff: none inside), .y = class of the bucket's first index + 1,
+// so that class(j) = .y - (j < .x): one 8-byte shared-memory read and a subtract with borrow. A bucket with several
+// boundaries (or one that skips empty classes) has .x = 0xffffffff and bit 31 of .y set: walk cum[] from the class.
 constexpr uint32_t CT_MULTI = 0x80000000u;
 
 __device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cum, uint32_t Tc, uint32_t j) {
@@ -218,25 +218,28 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += 1024) {
         const long long start = (long long)i << shift;
-        uint2 e = make_uint2(0xffffffffu, 0u);
+        uint2 e = make_uint2(0xffffffffu, 1u);
         if (start < Nu) {
             const uint32_t last = (uint32_t)(min(start + (1ll << shift), (long long)Nu) - 1);
             const uint32_t ca = class_search(cum, (uint32_t)Tc, (uint32_t)start), cb = class_search(cum, (uint32_t)Tc, last);
-            e.y = ca;
+            e.y = ca + 1u;   // indices below .x borrow: class ca; the others: ca + 1
             if (cb == ca + 1u) e.x = cum[cb];
-            else if (cb > ca + 1u) e.y = ca | CT_MULTI;
+            else if (cb > ca + 1u) e.y = (ca + 1u) | CT_MULTI;
         }
         ctab[i] = e;
     }
 }
 
-// Classes of four indices; the several-boundaries case is checked once for the four.
-__device__ __forceinline__ void class_of4(const uint32_t (&j)[4], const uint2* __restrict__ ctab_s,
-                                          const uint32_t* __restrict__ cum, int shift, uint32_t (&c)[4]) {
+// Classes of four indices; the several-boundaries case is checked once for the four. ctab_saddr = address of the
+// bucket table in the shared window.
+__device__ __forceinline__ void class_of4(const uint32_t (&j)[4], uint32_t ctab_saddr, const uint32_t* __restrict__ cum,
+                                          int shift, uint32_t (&c)[4]) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const uint2 e = ctab_s[j[q] >> shift];
-        c[q] = e.y + (j[q] >= e.x ? 1u : 0u);
+        uint32_t ex, ey;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(ctab_saddr + ((j[q] >> shift) << 3)));
+        // c = ey - (j < ex): .y holds the class of the bucket's first index PLUS ONE; the borrow of j - ex takes it back
+        asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.u32 %0, %3, 0;\n\t}" : "=r"(c[q]) : "r"(j[q]), "r"(ex), "r"(ey));
     }
     if ((c[0] | c[1] | c[2] | c[3]) & CT_MULTI) {
 #pragma unroll
@@ -372,11 +375,46 @@ __device__ __forceinline__ uint32_t sup_key_fast(float f) {
 
 constexpr int NF_PRE = 4;   // label / score words in flight per thread in the second walk
 
-struct __align__(16) TypeConst {   // per cell type and permutation: the two constants of the candidate and the running maximum
-    float c12, c2;
-    uint32_t best;
-    uint32_t pad;
+struct __align__(16) TypeConst {   // per cell type and permutation
+    float c12, c2;     // the two constants of a candidate difference
+    uint32_t best;     // ordering key of the running supremum (sup_key_fast)
+    uint32_t top;      // float bits of its magnitude; +inf for a type that cannot have a supremum (zero constants)
 };
+
+// Shared-memory accesses by address in the shared window (32-bit address arithmetic, no generic-pointer conversion in
+// the loops).
+__device__ __forceinline__ int lds_i32(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_i32(uint32_t saddr, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+
+// Four read-modify-writes col[t[q]] += f[q] in program order with the four reads issued together: a repeated type
+// takes the running value of its earlier occurrence from a register instead of waiting for the store (one
+// shared-memory latency per four positions instead of four). bq / aq = value before / after each update.
+__device__ __forceinline__ void rmw4(uint32_t col_saddr, uint32_t stride_bytes, const uint32_t (&t)[4], const int (&f)[4],
+                                     int (&bq)[4], int (&aq)[4]) {
+    uint32_t ad[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { ad[q] = col_saddr + t[q] * stride_bytes; bq[q] = lds_i32(ad[q]); }
+    aq[0] = bq[0] + f[0];
+    bq[1] = (t[1] == t[0]) ? aq[0] : bq[1];
+    aq[1] = bq[1] + f[1];
+    bq[2] = (t[2] == t[1]) ? aq[1] : ((t[2] == t[0]) ? aq[0] : bq[2]);
+    aq[2] = bq[2] + f[2];
+    bq[3] = (t[3] == t[2]) ? aq[2] : ((t[3] == t[1]) ? aq[1] : ((t[3] == t[0]) ? aq[0] : bq[3]));
+    aq[3] = bq[3] + f[3];
+#pragma unroll
+    for (int q = 0; q < 4; q++) sts_i32(ad[q], aq[q]);   // same address: the later store carries the later value
+}
 
 // 16-byte shared-memory read that is re-issued every time (the maxima change under the reader); saddr = address in
 // the shared window
@@ -422,6 +460,9 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     uint32_t* cum_s = reinterpret_cast<uint32_t*>(ctab_s + A.nb);               // [T_all + 2] when it fits
     const uint32_t* cum = A.cum_smem ? cum_s : A.cum;
     const uint32_t cb_saddr = (uint32_t)__cvta_generic_to_shared(cb);
+    const uint32_t ctab_saddr = (uint32_t)__cvta_generic_to_shared(ctab_s);
+    const uint32_t col_saddr = (uint32_t)__cvta_generic_to_shared(numA) + 4u * (uint32_t)threadIdx.x;
+    const uint32_t Kp4 = 4u * (uint32_t)blockDim.x;
     for (int i = k; i < A.nb; i += Kp) ctab_s[i] = A.ctab[i];
     if (A.cum_smem) for (int i = k; i < T_all + 2; i += Kp) cum_s[i] = A.cum[i];
     const int seg = A.seg;
@@ -497,7 +538,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                         for (int q = 0; q < 4; q++)
                             while (y[q] >= n) { rounds(Lq[q], Rq[q]); y[q] = Lq[q] * b + Rq[q]; }
                     }
-                    class_of4(y, ctab_s, cum, shift, cls);
+                    class_of4(y, ctab_saddr, cum, shift, cls);
                 } else {   // the partial last word of the ranking
                     y[0] = y[1] = y[2] = y[3] = 0xffffffffu;
 #pragma unroll 1
@@ -514,13 +555,13 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     uint32_t jj[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) jj[q] = min(y[q], n - 1u);
-                    class_of4(jj, ctab_s, cum, shift, cls);
+                    class_of4(jj, ctab_saddr, cum, shift, cls);
 #pragma unroll
                     for (int q = 0; q < 4; q++) cls[q] = (y[q] == 0xffffffffu) ? (uint32_t)T_all : cls[q];
                 }
                 if (!SLICED) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) col[cls[q] * (uint32_t)Kp] += fq[q];
+                    int bq[4], aq[4];
+                    rmw4(col_saddr, Kp4, cls, fq, bq, aq);
                 }
                 *lptr = LaneWord<LabT>::pack(cls);
                 lptr += Kp;
@@ -543,8 +584,11 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                 const Word w = lab[(size_t)i4 * Kp];
                 const int4 fc = fxp[(size_t)i4 * Kp];
                 const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
+                uint32_t t[4];
+                int bq[4], aq[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) col[local_type(LaneWord<LabT>::get(w, q)) * (uint32_t)Kp] += fq[q];
+                for (int q = 0; q < 4; q++) t[q] = local_type(LaneWord<LabT>::get(w, q));
+                rmw4(col_saddr, Kp4, t, fq, bq, aq);
             }
         }
         __syncthreads();
@@ -568,6 +612,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                 }
                 cb[t].c12 = c12;
                 cb[t].c2 = c2;
+                cb[t].top = (c12 != 0.0f || c2 != 0.0f) ? 0u : 0x7f800000u;
             }
         }
         __syncthreads();
@@ -594,38 +639,42 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     const Word wcu = wc[u];
                     if (i4 + NF_PRE + u < nw) { wc[u] = *lptr; fc[u] = *fptr; }
                     lptr += Kp; fptr += Kp;
-                    uint32_t t[4], key[4];
+                    uint32_t t[4];
                     int bq[4], aq[4];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {   // the four running-sum updates, in program order
-                        t[q] = local_type(LaneWord<LabT>::get(wcu, q));
-                        int* sp = col + t[q] * (uint32_t)Kp;
-                        bq[q] = *sp;
-                        aq[q] = bq[q] + fq[q];
-                        *sp = aq[q];
-                    }
-                    // the constants and the current maximum of each type in one 16-byte read (issued together so
-                    // that their latency hides behind the candidate arithmetic): best only grows, so a candidate
-                    // that does not beat the possibly stale value read here cannot beat the current one either.
-                    // Record-setting candidates are rare and a shared-memory atomic costs one wavefront per active
-                    // lane, so the atomics sit behind one branch per group of four positions.
+                    for (int q = 0; q < 4; q++) t[q] = local_type(LaneWord<LabT>::get(wcu, q));
+                    // the constants and the current maximum of each type in one 16-byte read, issued together with
+                    // the running-sum reads so that their latency hides behind each other
                     uint4 cq[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) cq[q] = lds128_volatile(cb_saddr + t[q] * 16u);
+                    rmw4(col_saddr, Kp4, t, fq, bq, aq);
+                    // Two candidates per position, compared as floats against the largest |diff| of the type so far
+                    // (.w; it only grows, so a candidate that does not reach the possibly stale value read here
+                    // cannot beat the current one either). Record-setting candidates are rare: the exact ordering
+                    // keys and the shared-memory atomics sit behind one branch per group of four positions.
+                    float d0[4], d1[4];
+                    bool rec = false;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const float c12 = __uint_as_float(cq[q].x), c2 = __uint_as_float(cq[q].y);
+                        const float c12 = __uint_as_float(cq[q].x), c2 = __uint_as_float(cq[q].y), top = __uint_as_float(cq[q].w);
                         const float Spf = Sf;
                         S += fq[q];   // exact: |S| <= sum |fx| < 2^31
                         Sf = __int2float_rn(S);
-                        const uint32_t k1 = sup_key_fast(__fmaf_rn(__int2float_rn(aq[q]), c12, -__fmul_rn(Sf, c2)));
-                        const uint32_t k0 = sup_key_fast(__fmaf_rn(__int2float_rn(bq[q]), c12, -__fmul_rn(Spf, c2)));
-                        key[q] = k0 > k1 ? k0 : k1;
+                        d1[q] = __fmaf_rn(__int2float_rn(aq[q]), c12, -__fmul_rn(Sf, c2));
+                        d0[q] = __fmaf_rn(__int2float_rn(bq[q]), c12, -__fmul_rn(Spf, c2));
+                        rec = rec || (fabsf(d1[q]) >= top) || (fabsf(d0[q]) >= top);
                     }
-                    if ((key[0] > cq[0].z) | (key[1] > cq[1].z) | (key[2] > cq[2].z) | (key[3] > cq[3].z)) {
+                    if (rec) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (key[q] > cq[q].z) atomicMax(&cb[t[q]].best, key[q]);
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t k1 = sup_key_fast(d1[q]), k0 = sup_key_fast(d0[q]);
+                            const uint32_t key = k0 > k1 ? k0 : k1;
+                            if (key > cq[q].z) {
+                                atomicMax(&cb[t[q]].best, key);
+                                atomicMax(&cb[t[q]].top, key >> 1);   // the bits of |diff|: non-negative floats order as integers
+                            }
+                        }
                     }
                 }
             }
