@@ -237,7 +237,7 @@ void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* rep
 // Geometry of the fused null kernel (null_fused.cu) for one ranking.
 struct NullPlanFast {
     int32_t Kp = 0;           // threads (segments) per permutation
-    int32_t seg = 0;          // positions per thread (multiple of 4)
+    int32_t seg = 0;          // positions per thread (multiple of 16)
     int32_t Ts = 0;           // cell types per pass (== T unless sliced)
     int32_t ctas_per_sm = 1;
     int32_t nb = 0;           // buckets of the class table

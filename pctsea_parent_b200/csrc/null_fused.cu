@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     // my positions: nv valid ones = nfull whole words + possibly one partial word; nothing behind them is visited
     // (the fixed-point scores are zero-padded, the labels of a partial word's tail are the unknown class)
     const int nv = x0 < n ? (int)min((uint32_t)seg, n - x0) : 0;
-    const int nfull = nv >> 2, nw = (nv + 3) >> 2;
+    const int nfull = nv >> 2, nw = (nv + 3) >> 2, nwp = (nw + NF_PRE - 1) / NF_PRE * NF_PRE;   // seg / 4 is a multiple of NF_PRE
     const int Stot = A.Sfx[A.Nu - 1];
     const int S0 = (x0 > 0u && x0 <= n) ? A.Sfx[x0 - 1u] : 0;   // exact prefix before my segment
 
@@ -511,13 +511,11 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
         // position, in program order). Four positions at a time: four independent round chains, no per-position tests.
         {
             uint32_t L = L00, R = R00;
-            const int4* fptr = fxp;
-            Word* lptr = lab;
-            int4 fn = nw > 0 ? *fptr : make_int4(0, 0, 0, 0);
+            uint32_t idx = 0;   // i4 * Kp: the same index addresses the label word and the score quad of (i4, k)
+            int4 fn = nw > 0 ? fxp[0] : make_int4(0, 0, 0, 0);
             for (int i4 = 0; i4 < nw; i4++) {
                 const int4 fc = fn;
-                fptr += Kp;
-                if (i4 + 1 < nw) fn = *fptr;
+                if (i4 + 1 < nw) fn = fxp[idx + (uint32_t)Kp];
                 const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
                 uint32_t y[4], cls[4];
                 if (i4 < nfull) {
@@ -563,9 +561,12 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     int bq[4], aq[4];
                     rmw4(col_saddr, Kp4, cls, fq, bq, aq);
                 }
-                *lptr = LaneWord<LabT>::pack(cls);
-                lptr += Kp;
+                lab[idx] = LaneWord<LabT>::pack(cls);
+                idx += (uint32_t)Kp;
             }
+            // pad my words to a whole number of NF_PRE groups (unknown class, zero scores): the second walk has no tail
+            const uint32_t dummy[4] = { (uint32_t)T_all, (uint32_t)T_all, (uint32_t)T_all, (uint32_t)T_all };
+            for (int i4 = nw; i4 < nwp; i4++) { lab[idx] = LaneWord<LabT>::pack(dummy); idx += (uint32_t)Kp; }
         }
 
       for (int t0 = 0; t0 < T_all; t0 += Ts) {   // one iteration unless SLICED
@@ -581,8 +582,8 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             for (int t = k; t < Tc; t += Kp) cb[t].best = 0u;
             // phase 1 on the parked labels (each thread re-reads what it wrote itself: no barrier needed)
             for (int i4 = 0; i4 < nw; i4++) {
-                const Word w = lab[(size_t)i4 * Kp];
-                const int4 fc = fxp[(size_t)i4 * Kp];
+                const Word w = lab[(uint32_t)i4 * (uint32_t)Kp];
+                const int4 fc = fxp[(uint32_t)i4 * (uint32_t)Kp];
                 const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
                 uint32_t t[4];
                 int bq[4], aq[4];
@@ -593,17 +594,31 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
         }
         __syncthreads();
 
-        // ---- phase 2: exclusive prefix over the segments (warp w scans types w, w + nwarp, ...), reciprocals
-        for (int t = warp; t < Tc; t += nwarp) {
-            int carry = 0;
-            for (int k0 = 0; k0 < Kp; k0 += 32) {
-                const int v = numA[t * Kp + k0 + lane];
-                const int incl = warp_incl_scan_i32(v, lane);
-                numA[t * Kp + k0 + lane] = carry + (incl - v);
-                carry += __shfl_sync(0xffffffffu, incl, 31);
+        // ---- phase 2: exclusive prefix over the segments (warp w scans types w, w + nwarp, ...: 128 segments per step,
+        // four per lane), then the reciprocals, one type per lane
+        for (int base = 0; base < Tc; base += 32 * nwarp) {   // one pass unless Tc > 32 * nwarp
+            int mytot = 0;
+            for (int i = 0; i < 32; i++) {
+                const int t = base + warp + i * nwarp;
+                if (t >= Tc) break;
+                int* row = numA + t * Kp;
+                int carry = 0;
+                for (int k0 = 0; k0 < Kp; k0 += 128) {
+                    const int kk = k0 + 4 * lane;
+                    const bool in = kk < Kp;   // Kp is a multiple of 32
+                    int4 v = make_int4(0, 0, 0, 0);
+                    if (in) v = *reinterpret_cast<int4*>(row + kk);
+                    const int s1 = v.x, s2 = s1 + v.y, s3 = s2 + v.z, s4 = s3 + v.w;
+                    const int incl = warp_incl_scan_i32(s4, lane);
+                    const int ex = carry + (incl - s4);
+                    if (in) *reinterpret_cast<int4*>(row + kk) = make_int4(ex, ex + s1, ex + s2, ex + s3);
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == i) mytot = carry;
             }
-            if (lane == 0) {
-                const int dA = carry, dB = Stot - carry;
+            const int t = base + warp + lane * nwarp;
+            if (t < Tc) {
+                const int dA = mytot, dB = Stot - mytot;
                 float c12 = 0.0f, c2 = 0.0f;
                 if (t < T && dA != 0 && dB != 0) {
                     const double r2 = __ddiv_rn(1.0, (double)dB);
@@ -624,21 +639,20 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             float Sf = __int2float_rn(S);
             Word wc[NF_PRE];   // register sets refilled in place: the loads run NF_PRE - 1 words ahead of their use
             int4 fc[NF_PRE];
-            const Word* lptr = lab;
-            const int4* fptr = fxp;
+            const uint32_t Kpu = (uint32_t)Kp;
+            uint32_t idx = 0;   // index of the group's first word
+            if (nwp > 0) {
 #pragma unroll
-            for (int u = 0; u < NF_PRE; u++) {
-                if (u < nw) { wc[u] = *lptr; fc[u] = *fptr; }
-                lptr += Kp; fptr += Kp;
+                for (int u = 0; u < NF_PRE; u++) { wc[u] = lab[idx + u * Kpu]; fc[u] = fxp[idx + u * Kpu]; }
             }
-            for (int i4 = 0; i4 < nw; i4 += NF_PRE) {
+            for (int i4 = 0; i4 < nwp; i4 += NF_PRE) {
+                const bool more = i4 + NF_PRE < nwp;
+                idx += NF_PRE * Kpu;
 #pragma unroll
                 for (int u = 0; u < NF_PRE; u++) {
-                    if (i4 + u >= nw) break;
                     const int fq[4] = { fc[u].x, fc[u].y, fc[u].z, fc[u].w };
                     const Word wcu = wc[u];
-                    if (i4 + NF_PRE + u < nw) { wc[u] = *lptr; fc[u] = *fptr; }
-                    lptr += Kp; fptr += Kp;
+                    if (more) { wc[u] = lab[idx + u * Kpu]; fc[u] = fxp[idx + u * Kpu]; }
                     uint32_t t[4];
                     int bq[4], aq[4];
 #pragma unroll
@@ -747,7 +761,7 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
     kp = (int)std::min<int64_t>(kp, want);
     pl.Kp = kp;
     pl.Ts = ts;
-    pl.seg = (int32_t)round_up(div_up(std::max<int64_t>(g.Nu, 1), kp), 4);
+    pl.seg = (int32_t)round_up(div_up(std::max<int64_t>(g.Nu, 1), kp), 4 * NF_PRE);
     pl.smem = (size_t)(ts + 1) * kp * 4 + fixed(ts);
     int per_sm = (int)std::max<size_t>(1, smem_sm / (pl.smem + 1024));
     per_sm = std::min(per_sm, std::max(1, 2048 / kp));
