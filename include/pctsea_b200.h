@@ -12,8 +12,10 @@
  * returns a message valid until the next call on that ctx. All pointers are HOST pointers unless the
  * parameter name ends in _dev. Caller allocates every output buffer. No C++ exceptions cross the ABI.
  * There is NO CPU fallback: without a CUDA device pctsea_create fails with PCTSEA_ECUDA.
- * A ctx is bound to one device and is not re-entrant; multi-GPU = one ctx (one process) per GPU, each
- * computing a slice of the permutations (pctsea_null_params.perm_begin/perm_count).
+ * A ctx is bound to one device and is not re-entrant; multi-GPU = one ctx (one process or thread) per GPU joined
+ * by pctsea_comm_init_rank: pctsea_analyze then shards the permutations over the ranks and all-gathers the null
+ * slices with NCCL inside the call. (A host that prefers its own collective leaves the communicator out and
+ * passes explicit slices in pctsea_null_params.perm_begin/perm_count.)
  */
 #ifndef PCTSEA_B200_H
 #define PCTSEA_B200_H
@@ -24,12 +26,12 @@
 extern "C" {
 #endif
 
-#define PCTSEA_ABI_VERSION 1
+#define PCTSEA_ABI_VERSION 2
 
 #define PCTSEA_OK         0
 #define PCTSEA_EINVAL    (-1)
 #define PCTSEA_ECUDA     (-2)
-#define PCTSEA_ENCCL     (-3)  /* reserved: collectives live in the host plumbing (torch.distributed) */
+#define PCTSEA_ENCCL     (-3)  /* libnccl could not be loaded, or an NCCL call failed (pctsea_comm_*, multi-GPU pctsea_analyze) */
 #define PCTSEA_ETOOFEW   (-4)  /* fewer than min_pass cells pass the score threshold, PCTSEA.java:389-395 */
 #define PCTSEA_EMINGENES (-5)  /* min_genes_cells > list size, model/SingleCell.java:347-352 */
 #define PCTSEA_ENOMEM    (-6)
@@ -127,6 +129,8 @@ typedef struct pctsea_timings {
     int64_t launches;     /* kernels launched by the call */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    float   gather_ms;    /* multi-GPU: NCCL all-gather of the null slices + reorder (0 without a communicator) */
+    float   reserved0;
 } pctsea_timings;
 
 int         pctsea_abi_version(void);
@@ -254,8 +258,28 @@ int pctsea_last_type_counts(pctsea_ctx* ctx, int32_t n_types, int32_t* n_cells_o
  * type's first cell. n_used must be the n_used of that call. */
 int pctsea_last_observed_curve(pctsea_ctx* ctx, int32_t type_id, int64_t n_used, float* a_out, float* b_out);
 
+/* ---- multi-GPU: permutations shard over the GPUs of one box; the null slices are the only data exchanged
+ * (SURVEY.md §8 e; the reference is single-process, PCTSEA.java:1398-1429 runs all permutations in one JVM).
+ * One ctx per GPU (one process per GPU, or one thread per GPU inside one JVM). Rank 0 obtains an id with
+ * pctsea_comm_unique_id and hands the 128 bytes to the other ranks by any means the host has (a socket, a file,
+ * MPI, torch.distributed); then EVERY rank calls pctsea_comm_init_rank (collective, blocks until all ranks joined).
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls return PCTSEA_ENCCL and everything else works.
+ *
+ * With a communicator attached, pctsea_analyze must be called by all ranks with the same list and parameters,
+ * perm_begin = 0 and perm_count = 0 ("all n_perm permutations"): rank r computes the r-th contiguous share of the
+ * global permutation indices (sizes differ by at most one), the slices are all-gathered over NVLink on the ctx
+ * stream, and a10-a12 run on the complete null on every rank — out[], null_out and nullD_out ([n_types][n_perm])
+ * are bit-identical on every rank to what a single-GPU call returns. pctsea_analyze_batch, pctsea_enrich and the
+ * stage calls stay per-rank (independent lists shard without a collective). */
+#define PCTSEA_COMM_ID_BYTES 128
+int pctsea_comm_unique_id(void* id_out /*[PCTSEA_COMM_ID_BYTES]*/);
+int pctsea_comm_init_rank(pctsea_ctx* ctx, int32_t nranks, int32_t rank, const void* id /*[PCTSEA_COMM_ID_BYTES]*/);
+int pctsea_comm_destroy(pctsea_ctx* ctx);   /* also done by pctsea_destroy */
+
 /* Device pointers of the null slice left by the last pctsea_analyze / pctsea_enrich on this ctx:
- * [n_types][perm_count] fp32 each. Valid until the next call on the ctx. For NCCL all-gathers. */
+ * [n_types][perm_count] fp32 each. Valid until the next call on the ctx (for a host that runs its own collective).
+ * After a multi-GPU pctsea_analyze: the complete null [n_types][n_perm] (nullD_dev is NULL unless that call was
+ * given a nullD_out). */
 int pctsea_last_null_dev(pctsea_ctx* ctx, float** null_dev, float** nullD_dev, int32_t* n_types,
                          int32_t* perm_count);
 

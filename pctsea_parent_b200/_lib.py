@@ -31,8 +31,9 @@ EXPORTS = [
     "pctsea_stream", "pctsea_matrix_load_csr", "pctsea_matrix_wrap_device", "pctsea_matrix_set_labels", "pctsea_matrix_build_gene_index",
     "pctsea_matrix_free", "pctsea_score", "pctsea_rank", "pctsea_enrich", "pctsea_reduce_null",
     "pctsea_reduce_null_dev", "pctsea_analyze", "pctsea_analyze_batch", "pctsea_last_null_dev", "pctsea_last_type_counts",
-    "pctsea_last_observed_curve",
+    "pctsea_last_observed_curve", "pctsea_comm_unique_id", "pctsea_comm_init_rank", "pctsea_comm_destroy",
 ]
+COMM_ID_BYTES = 128   # PCTSEA_COMM_ID_BYTES
 
 
 class PctseaError(RuntimeError):
@@ -64,7 +65,8 @@ class Timings(C.Structure):
     _fields_ = [("setup_ms", C.c_float), ("score_ms", C.c_float), ("rank_ms", C.c_float),
                 ("observed_ms", C.c_float), ("labels_ms", C.c_float), ("null_ms", C.c_float),
                 ("reduce_ms", C.c_float), ("total_ms", C.c_float), ("n_pass", C.c_int64), ("n_used", C.c_int64),
-                ("launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("gather_ms", C.c_float), ("reserved0", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -115,6 +117,9 @@ def load_library() -> C.CDLL:
     L.pctsea_last_null_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.pctsea_last_type_counts.argtypes = [vp, i32, vp, vp, C.POINTER(i64)]
     L.pctsea_last_observed_curve.argtypes = [vp, i32, i64, vp, vp]
+    L.pctsea_comm_unique_id.argtypes = [vp]
+    L.pctsea_comm_init_rank.argtypes = [vp, i32, i32, vp]
+    L.pctsea_comm_destroy.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("pctsea_last_error", "pctsea_stream"):
             getattr(L, name).restype = C.c_int
@@ -191,6 +196,27 @@ class Context:
         """Testing / tuning switch of this ctx (OPT_* constants; none is needed in production)."""
         self._check(self.L.pctsea_ctx_set_option(self.h, int(option), int(value)))
 
+    # ---- multi-GPU: one Context per GPU, joined by an NCCL communicator inside the library
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes from rank 0 (ncclGetUniqueId); hand them to every rank, then call comm_init_rank everywhere."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load_library().pctsea_comm_unique_id(buf)
+        if rc != 0:
+            raise PctseaError(rc, "pctsea_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
+        """Collective over the ranks. Afterwards analyze() shards the permutations over the ranks and returns the
+        complete results (and null) on every rank."""
+        assert len(unique_id) == COMM_ID_BYTES
+        self._check(self.L.pctsea_comm_init_rank(self.h, int(nranks), int(rank), C.c_char_p(unique_id)))
+        self.comm_nranks, self.comm_rank = int(nranks), int(rank)
+
+    def comm_destroy(self):
+        self._check(self.L.pctsea_comm_destroy(self.h))
+        self.comm_nranks, self.comm_rank = 1, 0
+
     def stream(self) -> int:
         return int(self.L.pctsea_stream(self.h) or 0)
 
@@ -265,7 +291,7 @@ class Context:
         gene_idx, abundance = _c(gene_idx, np.int32), _c(abundance, np.float32)
         label = None if label is None else _c(label, np.int32)
         replay = None if replay is None else _c(replay, np.int32)
-        cnt = nprm.perm_count or (nprm.n_perm - nprm.perm_begin)
+        cnt = nprm.perm_count or (nprm.n_perm - nprm.perm_begin)   # with a communicator: the complete null, n_perm
         n = m.n_cells
         res = np.zeros(n_types, TYPE_RESULT_DTYPE)
         ne = np.empty((n_types, cnt), np.float32) if want_null else None

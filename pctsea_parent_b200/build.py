@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpctsea_b200.so")
-SOURCES = ["abi.cu", "score.cu", "score_gm.cu", "rank.cu", "enrich.cu", "null_fused.cu", "reduce.cu"]
+SOURCES = ["abi.cu", "score.cu", "score_gm.cu", "rank.cu", "enrich.cu", "null_fused.cu", "reduce.cu", "comm.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "pctsea_b200.h")]
 
 NVCC_FLAGS = [
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"--- nvcc {s} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc(), "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    link = [nvcc(), "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
     subprocess.check_call(link)
     return SO
 

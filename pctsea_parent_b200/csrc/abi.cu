@@ -123,6 +123,10 @@ struct NullPlan {
     int32_t P = 0, begin = 0, count = 0;
     bool full = false;
     int rounds = PCTSEA_DEFAULT_FEISTEL_ROUNDS;
+    // multi-GPU call (communicator attached): this rank computes [begin, begin + count), the slices are all-gathered
+    // into the pooled null [T][P]; stride = permutations per row of the local slice buffers (the widest rank's count)
+    bool pooled = false, pool_dstat = false;
+    int32_t stride = 0;
 };
 
 NullPlan validate_null_params(const pctsea_null_params* p) {
@@ -138,7 +142,23 @@ NullPlan validate_null_params(const pctsea_null_params* p) {
     np.full = (np.begin == 0 && np.count == np.P);
     np.rounds = p->feistel_rounds == 0 ? PCTSEA_DEFAULT_FEISTEL_ROUNDS : p->feistel_rounds;
     PCT_REQUIRE(np.rounds >= 2 && np.rounds <= 32, "feistel_rounds out of range [2,32]");
+    np.stride = np.count;
     return np;
+}
+
+// With a communicator: the call covers all n_perm permutations, this rank takes its contiguous share.
+void shard_over_ranks(const pctsea_ctx* c, const pctsea_null_params* p, NullPlan* np, bool want_dstat) {
+    if (!c->comm) return;
+    PCT_REQUIRE(np->full, "with a communicator attached pctsea_analyze covers all permutations: perm_begin = perm_count = 0");
+    PCT_REQUIRE(p->perm_mode == PCTSEA_PERM_PHILOX, "multi-GPU analysis generates its permutations (perm_mode PHILOX)");
+    int64_t b = 0, n = 0;
+    comm_share(np->P, c->comm_nranks, c->comm_rank, &b, &n);
+    np->begin = (int32_t)b;
+    np->count = (int32_t)n;
+    np->stride = (int32_t)div_up(np->P, c->comm_nranks);
+    np->pooled = true;
+    np->pool_dstat = want_dstat;
+    np->full = false;
 }
 
 // Stage 3 on device-resident score / label / order. Leaves results in c->results, the null slice in
@@ -160,13 +180,14 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     if (fast && !philox) throw Error(PCTSEA_EINVAL, "REPLAY permutations are a validation mode: use ks_mode EXACT");
     launch_prepare_ranked(c, N, score_dev, label_dev, order_dev, g);
     const int32_t Pc_all = np.count;
+    const int32_t Pstride = np.stride;   // == Pc_all unless the slices of a multi-GPU call differ in size
     const bool want_null = Pc_all > 0 && T > 0;
     // Everything the call will allocate is reserved here, before any memory budget is taken (the grow-only buffers
     // over-allocate by 1/8): the observed accumulator history first, then the null.
     c->results.reserve((size_t)std::max(T, 1) * sizeof(pctsea_type_result) + 64);
     reserve_ks_observed(c, g);
-    c->null_ews.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
-    c->null_d.reserve((size_t)std::max(T, 1) * std::max(Pc_all, 1) * 4 + 64);
+    c->null_ews.reserve((size_t)std::max(T, 1) * std::max(Pstride, 1) * 4 + 64);
+    c->null_d.reserve((size_t)std::max(T, 1) * std::max(Pstride, 1) * 4 + 64);
     NullPlanFast plan;
     if (want_null && philox) {
         plan = plan_null_fast(c, g);
@@ -200,7 +221,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     if (want_null && fast) {
         // FAST arithmetic: one fused kernel generates the labels and evaluates them; nothing of size P x Nu exists
         cudaEvent_t e0 = et.mark(c->stream);
-        launch_null_fused(c, g, plan, prm->seed, np.begin, Pc_all, np.rounds, Pc_all, 0);
+        launch_null_fused(c, g, plan, prm->seed, np.begin, Pc_all, np.rounds, Pstride, 0);
         cudaEvent_t e1 = et.mark(c->stream);
         if (obs_overlap) queue_observed_aux();   // after the null launch: the big kernel gets its SMs first
         null_spans.push_back({ e0, e1 });
@@ -235,7 +256,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
             }
             cudaEvent_t e1 = et.mark(c->stream);
             if (obs_overlap && !obs_queued) queue_observed_aux();
-            launch_ks_exact_null(c, g, pc, Pc_all, p0, 0);
+            launch_ks_exact_null(c, g, pc, Pstride, p0, 0);
             cudaEvent_t e2 = et.mark(c->stream);
             lab_spans.push_back({ e0, e1 });
             null_spans.push_back({ e1, e2 });
@@ -244,8 +265,17 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     if (obs_overlap && !obs_queued) queue_observed_aux();
     if (obs_queued) PCT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_obs[2], 0));
     rec(c, EV_NULL);
-    if (np.full && T > 0) launch_reduce(c, T, np.P, c->null_ews.as<float>(), prm->mean_policy,
-                                        c->results.as<pctsea_type_result>());
+    c->last_pool_P = 0;
+    if (np.pooled && T > 0) {
+        // the one exchange step of the path: all ranks' slices -> the complete null, in global permutation order
+        comm_pool_null(c, T, np.P, Pstride, np.pool_dstat);
+        c->last_pool_P = np.P;
+        c->last_pool_dstat = np.pool_dstat;
+        rec(c, EV_GATHER);
+        launch_reduce(c, T, np.P, c->null_pool.as<float>(), prm->mean_policy, c->results.as<pctsea_type_result>());
+    } else if (np.full && T > 0) {
+        launch_reduce(c, T, np.P, c->null_ews.as<float>(), prm->mean_policy, c->results.as<pctsea_type_result>());
+    }
     rec(c, EV_REDUCE);
 }
 
@@ -260,7 +290,8 @@ void finish_timings(pctsea_ctx* c, const std::vector<std::pair<cudaEvent_t, cuda
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c->ev_obs[1], c->ev_obs[2]) == cudaSuccess) c->tm.observed_ms = ms;
     }
-    c->tm.reduce_ms = between(c, EV_NULL, EV_REDUCE);
+    c->tm.gather_ms = between(c, EV_NULL, EV_GATHER);
+    c->tm.reduce_ms = between(c, c->ev_rec[EV_GATHER] ? EV_GATHER : EV_NULL, EV_REDUCE);
     c->tm.total_ms = between(c, EV_BEGIN, EV_END);
     float lm = 0, nm = 0;
     for (auto& s : lab_spans) { float ms = 0; if (cudaEventElapsedTime(&ms, s.first, s.second) == cudaSuccess) lm += ms; }
@@ -347,8 +378,13 @@ void analyze_core(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32_
     enrich_device(c, N, c->score.as<double>(), label_dev, c->order.as<int32_t>(), Nu, n_types, nprm, np, replay_perm,
                   et, &lm, &nm, ls, ns);
     d2h(c, out, c->results.p, (size_t)n_types * sizeof(pctsea_type_result));
-    if (null_out) d2h(c, null_out, c->null_ews.p, (size_t)n_types * np.count * 4);
-    if (nullD_out) d2h(c, nullD_out, c->null_d.p, (size_t)n_types * np.count * 4);
+    if (np.pooled) {
+        if (null_out) d2h(c, null_out, c->null_pool.p, (size_t)n_types * np.P * 4);
+        if (nullD_out) d2h(c, nullD_out, c->null_pool_d.p, (size_t)n_types * np.P * 4);
+    } else {
+        if (null_out) d2h(c, null_out, c->null_ews.p, (size_t)n_types * np.count * 4);
+        if (nullD_out) d2h(c, nullD_out, c->null_d.p, (size_t)n_types * np.count * 4);
+    }
     rec(c, EV_END);
     finish_timings(c, ls, ns);
     c->tm.n_pass = Np;
@@ -406,10 +442,11 @@ int pctsea_destroy(pctsea_ctx* c) {
     if (!c) return PCTSEA_EINVAL;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    comm_destroy(c);
     DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->list_rank, &c->score_sums, &c->score, &c->nused, &c->nnzc, &c->kept, &c->gm_fix,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
                        &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels, &c->lab_ticket, &c->cls_tab,
-                       &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->results, &c->red_tmp,
+                       &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->null_gather, &c->null_pool, &c->null_pool_d, &c->results, &c->red_tmp,
                        &c->red_misc };
     for (DevBuf* b : bufs) b->release();
     c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
@@ -493,6 +530,10 @@ int pctsea_matrix_load_csr(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, cons
             pctsea_matrix_free(c, m);
             throw Error(PCTSEA_EINVAL, "col_idx entries must lie in [0, n_genes)");
         }
+        if (bad & 8) {
+            pctsea_matrix_free(c, m);
+            throw Error(PCTSEA_EINVAL, "a row stores the same column twice: one value per (cell, gene) (model/SingleCell.java:80)");
+        }
         *out = m;
     });
 }
@@ -519,6 +560,7 @@ int pctsea_matrix_wrap_device(pctsea_ctx* c, int64_t n_cells, int32_t n_genes, c
             m->all_positive = !(bad & 4);
             if (bad & 1) throw Error(PCTSEA_EINVAL, "row_ptr_dev must start at 0 and be non-decreasing");
             if (bad & 2) throw Error(PCTSEA_EINVAL, "col_idx_dev entries must lie in [0, n_genes)");
+            if (bad & 8) throw Error(PCTSEA_EINVAL, "a row stores the same column twice: one value per (cell, gene) (model/SingleCell.java:80)");
         } catch (...) { delete m; throw; }
         *out = m;
     });
@@ -677,7 +719,8 @@ int pctsea_analyze(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32
                    int32_t* order_out, int64_t* n_pass_out) {
     return guarded(c, [&] {
         PCT_REQUIRE(m != nullptr && out != nullptr, "matrix / out are NULL");
-        const NullPlan np = validate_analysis(m, min_score, label, n_types, nprm);
+        NullPlan np = validate_analysis(m, min_score, label, n_types, nprm);
+        shard_over_ranks(c, nprm, &np, nullD_out != nullptr);
         rec(c, EV_BEGIN);
         const int32_t* label_dev = resident_labels(c, m, label);
         analyze_core(c, m, L, gene_idx, abundance, sprm, min_score, label_dev, n_types, nprm, np, replay_perm, out,
@@ -776,8 +819,30 @@ int pctsea_last_observed_curve(pctsea_ctx* c, int32_t type_id, int64_t n_used, f
     });
 }
 
+int pctsea_comm_unique_id(void* id_out) {
+    if (!id_out) return PCTSEA_EINVAL;
+    try { comm_unique_id(id_out); return PCTSEA_OK; }
+    catch (const Error& e) { return e.code; }
+    catch (...) { return PCTSEA_ENCCL; }
+}
+
+int pctsea_comm_init_rank(pctsea_ctx* c, int32_t nranks, int32_t rank, const void* id) {
+    return guarded(c, [&] { comm_init_rank(c, nranks, rank, id); });
+}
+
+int pctsea_comm_destroy(pctsea_ctx* c) {
+    return guarded(c, [&] { comm_destroy(c); });
+}
+
 int pctsea_last_null_dev(pctsea_ctx* c, float** null_dev, float** nullD_dev, int32_t* n_types, int32_t* perm_count) {
     if (!c) return PCTSEA_EINVAL;
+    if (c->last_pool_P > 0) {   // multi-GPU analysis: the complete null, identical on every rank
+        if (null_dev) *null_dev = c->null_pool.as<float>();
+        if (nullD_dev) *nullD_dev = c->last_pool_dstat ? c->null_pool_d.as<float>() : nullptr;
+        if (n_types) *n_types = c->last_T;
+        if (perm_count) *perm_count = c->last_pool_P;
+        return PCTSEA_OK;
+    }
     if (null_dev) *null_dev = c->null_ews.as<float>();
     if (nullD_dev) *nullD_dev = c->null_d.as<float>();
     if (n_types) *n_types = c->last_T;

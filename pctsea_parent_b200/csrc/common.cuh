@@ -71,7 +71,7 @@ struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum Ev { EV_BEGIN = 0, EV_SETUP, EV_SCORE, EV_RANK, EV_OBS, EV_LABELS, EV_NULL, EV_REDUCE, EV_END, EV_COUNT };
+enum Ev { EV_BEGIN = 0, EV_SETUP, EV_SCORE, EV_RANK, EV_OBS, EV_LABELS, EV_NULL, EV_GATHER, EV_REDUCE, EV_END, EV_COUNT };
 
 }  // namespace pctsea
 
@@ -144,6 +144,13 @@ struct pctsea_ctx {
     pctsea::DevBuf red_tmp, red_misc;  // reduce: staged null of pctsea_reduce_null; expected values, sorted scores, bins
     pctsea::PinnedBuf pin_in, pin_out, pin_small;
     int32_t last_T = 0, last_Pc = 0;
+    // multi-GPU (comm.cu): NCCL communicator attached by pctsea_comm_init_rank; one ctx = one rank
+    void* comm = nullptr;                                       // ncclComm_t
+    int32_t comm_nranks = 1, comm_rank = 0;
+    pctsea::DevBuf null_gather;                                 // [nranks][T][width] all-gathered null slices (x2 with dStat)
+    pctsea::DevBuf null_pool, null_pool_d;                      // [T][P] complete null in global permutation order
+    int32_t last_pool_P = 0;                                    // P of the resident pooled null, 0 = none
+    bool last_pool_dstat = false;
     int64_t last_obs_Nu = -1;   // n_used of the resident observed accumulator history (obs_chain), -1 = none
 };
 
@@ -203,8 +210,8 @@ void launch_list_lookup(pctsea_ctx* c, const ScoreArgs& a);   // by-gene abundan
 void launch_score_final(pctsea_ctx* c, const ScoreArgs& a);   // centred sums -> getR() + thresholds
 void launch_score_gm(pctsea_ctx* c, const ScoreArgs& a);      // score_gm.cu
 void build_gene_index(pctsea_ctx* c, pctsea_matrix* m);       // score_gm.cu; syncs the stream
-// One pass over a device CSR: bit 0 = row_ptr not 0-based / non-decreasing / not ending at nnz, bit 1 = a column
-// outside [0, n_genes). Syncs the stream.
+// Checks a device CSR: bit 0 = row_ptr not 0-based / non-decreasing / not ending at nnz, bit 1 = a column outside
+// [0, n_genes), bit 2 = some stored value is not > 0 (informational), bit 3 = a row repeats a column. Syncs the stream.
 int validate_csr(pctsea_ctx* c, const pctsea_matrix* m);
 
 // Threshold + stable radix sort; writes c->order ([Np]); returns Np (syncs the stream once).
@@ -256,6 +263,14 @@ void launch_ks_exact_null(pctsea_ctx* c, const EnrichGeom& g, int32_t Pc, int32_
                           size_t label_off);
 void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, int mean_policy,
                    pctsea_type_result* results_dev);
+
+// comm.cu — NCCL bound at run time
+void comm_unique_id(void* id_out);
+void comm_init_rank(pctsea_ctx* c, int32_t nranks, int32_t rank, const void* id_bytes);
+void comm_destroy(pctsea_ctx* c);
+void comm_share(int64_t n, int32_t nranks, int32_t rank, int64_t* begin, int64_t* count);
+// all-gather of c->null_ews (and c->null_d) [T][width] over the ranks, reordered into c->null_pool[_d] [T][P]
+void comm_pool_null(pctsea_ctx* c, int32_t T, int32_t P, int32_t width, bool with_dstat);
 
 inline void count_launch(pctsea_ctx* c, int n = 1) { c->launches += n; }
 

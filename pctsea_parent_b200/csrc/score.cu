@@ -517,6 +517,35 @@ __global__ void k_validate_csr(const int64_t* __restrict__ row_ptr, const int32_
     if (b) atomicOr(bad, b);
 }
 
+// Bit 3: some row stores a column twice. The reference keeps ONE value per (cell, gene) (model/SingleCell.java:80, the
+// last one written), the two scoring kernels would each do something else with a repeated column (the CSR scan pairs
+// it twice, the gene-major build collapses it into one mask bit and races on the value), so such a matrix is
+// rejected. One warp per row, any storage order: the row's columns are marked in the warp's bitmap of G bits in
+// shared memory (atomicOr returns the previous word), then the same walk clears them again.
+__global__ void __launch_bounds__(256) k_validate_unique_cols(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                              int64_t N, int32_t G, int words, int* __restrict__ bad) {
+    extern __shared__ unsigned s_bits[];   // [warps][words]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned* bits = s_bits + (size_t)warp * words;
+    for (int w = lane; w < words; w += 32) bits[w] = 0u;
+    __syncwarp();
+    bool dup = false;
+    for (int64_t i = (int64_t)blockIdx.x * nwarps + warp; i < N; i += (int64_t)gridDim.x * nwarps) {
+        const int64_t b = row_ptr[i], e = row_ptr[i + 1];
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const unsigned g = (unsigned)col[k];
+            if (g < (unsigned)G) dup |= (atomicOr(&bits[g >> 5], 1u << (g & 31)) >> (g & 31)) & 1u;
+        }
+        __syncwarp();
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const unsigned g = (unsigned)col[k];
+            if (g < (unsigned)G) bits[g >> 5] = 0u;
+        }
+        __syncwarp();
+    }
+    if (dup) atomicOr(bad, 8);
+}
+
 // Checks the device CSR once when a matrix is loaded or wrapped: the scoring kernel indexes its shared-memory
 // membership table with the stored columns and trusts the row bounds. Bit 2 of the result is informational: some
 // stored value is not > 0 (the scoring kernel then keeps its per-step test for such values).
@@ -526,6 +555,23 @@ int validate_csr(pctsea_ctx* c, const pctsea_matrix* m) {
     PCT_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
     k_validate_csr<<<c->num_sms * 8, 256, 0, c->stream>>>(m->row_ptr, m->col, m->val, m->n_cells, m->n_genes, m->nnz, bad);
     PCT_CUDA(cudaGetLastError());
+    {
+        int h0 = 0;   // the uniqueness pass walks the rows: only behind valid row bounds
+        PCT_CUDA(cudaMemcpyAsync(&h0, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PCT_CUDA(cudaStreamSynchronize(c->stream));
+        if (!(h0 & 1) && m->n_cells > 0 && m->nnz > 0) {
+            const int words = (int)div_up(std::max(m->n_genes, 1), 32);
+            int warps = 8;
+            while (warps > 1 && (size_t)warps * words * 4 > (size_t)c->smem_per_block_optin) warps >>= 1;
+            const size_t smem = (size_t)warps * words * 4;
+            PCT_REQUIRE(smem <= (size_t)c->smem_per_block_optin, "n_genes too large for the duplicate-column check");
+            ensure_dyn_smem(c, k_validate_unique_cols, smem);
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)c->smem_per_sm / (smem + 1024)));
+            k_validate_unique_cols<<<c->num_sms * per_sm, warps * 32, smem, c->stream>>>(m->row_ptr, m->col, m->n_cells,
+                                                                                         m->n_genes, words, bad);
+            PCT_CUDA(cudaGetLastError());
+        }
+    }
     int h = 0;
     PCT_CUDA(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PCT_CUDA(cudaStreamSynchronize(c->stream));

@@ -62,6 +62,17 @@ def all_gather_null(local: torch.Tensor, n_perm: int) -> torch.Tensor:
     return torch.cat([p[:, :c] for p, c in zip(parts, counts)], dim=1).contiguous()
 
 
+def attach_communicator(ctx) -> None:
+    """Join `ctx` (this rank's pctsea Context) to an NCCL communicator INSIDE libpctsea_b200.so, using the default
+    torch.distributed group only to hand rank 0's unique id to the other ranks (any backend; a Java host would use a
+    socket). Afterwards ctx.analyze() is the whole multi-GPU path: permutations sharded over the ranks, null slices
+    all-gathered over NVLink on the library's own stream, complete results on every rank."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init_rank(world, rank, box[0])
+
+
 class DevicePointer:
     """Zero-copy view of a raw device pointer (the ABI's pctsea_last_null_dev) for torch.as_tensor."""
 

@@ -191,6 +191,20 @@ def test_matrix_validation(ctx):
     with pytest.raises(P.PctseaError) as e:   # row_ptr not monotone
         ctx.load_csr(np.array([0, 3, 2], np.int64), np.array([0, 1, 2], np.int32), val[:3], 5)
     assert e.value.code == -1
+    # a row that stores a column twice (adjacent, or apart in an unsorted row): the reference holds one value per
+    # (cell, gene), model/SingleCell.java:80, and the two scoring kernels would disagree on such a row
+    for cols in ([0, 1, 3, 3], [4, 1, 4, 2]):
+        with pytest.raises(P.PctseaError) as e:
+            ctx.load_csr(np.array([0, 1, 4], np.int64), np.array(cols, np.int32), val, 5)
+        assert e.value.code == -1 and "twice" in e.value.msg
+    rng = np.random.default_rng(5)
+    rp, col, v = _random_csr(rng, 300, 70_000, 40, unsorted_rows=True)   # unsorted rows, many genes: accepted
+    ctx.load_csr(rp, col, v, 70_000).free()
+    col2 = col.copy()
+    col2[rp[200] + 3] = col2[rp[200]]   # one repeated column deep inside the matrix
+    if rp[201] - rp[200] > 3:
+        with pytest.raises(P.PctseaError):
+            ctx.load_csr(rp, col2, v, 70_000)
     m = ctx.load_csr(row_ptr, np.array([0, 1, 2, 4], np.int32), val, 5)   # the context still works afterwards
     m.free()
 
@@ -1018,3 +1032,118 @@ def test_scoring_paths_agree_at_scale(ctx):
     assert npass == int(np.count_nonzero((b[3] == 1) & (b[0] >= 0.0)))
     assert np.all((s[:-1] > s[1:]) | ((s[:-1] == s[1:]) & (order[:-1] < order[1:])))
     m.free()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at FULL size against the oracle (the configurations the published numbers are quoted on)
+# ---------------------------------------------------------------------------------------------------
+def _device_dataset(ctx, cfg, gene_index=True):
+    """Config generated in HBM (as bench.py does), wrapped as a resident matrix; host copy for the oracle."""
+    import torch
+    ds = synth.make_dataset(cfg, torch.device("cuda", 0))
+    d = ds.numpy()
+    m = ctx.wrap_device_csr(ds.row_ptr.data_ptr(), ds.col.data_ptr(), ds.val.data_ptr(), cfg.n_cells, cfg.n_genes, keepalive=ds)
+    m.set_labels(d["label"], cfg.n_types)
+    if gene_index:
+        m.build_gene_index()
+    return ds, d, m
+
+
+@pytest.fixture(scope="module")
+def config_B(ctx):
+    cfg = synth.CONFIGS["B"]
+    ds, d, m = _device_dataset(ctx, cfg)
+    yield cfg, ds, d, m
+    m.free()
+
+
+def _score_kw(cfg, seed):
+    return dict(method=cfg.method, min_genes_cells=cfg.min_genes_cells, min_corr=cfg.min_corr, has_min_corr=True,
+                jitter_mode=1, seed=seed)
+
+
+def test_baseline_config_B_full_size_vs_oracle(ctx, oracle, config_B):
+    """BASELINE configs[1] exactly as bench.py runs it — 600 000 cells x 25 000 genes (~5 %), 100 cell types,
+    1000-protein list, PEARSONS_CORRELATION, -perm 1000, gene-major scoring, PHILOX permutations, FAST arithmetic —
+    against the oracle at full size: scores of all 600 000 cells bit for bit (canonical form of the gene-major kernel)
+    and <= 1e-9 relative to the sequential SimpleRegression restatement on 2000 cells, the ranking, every observed
+    field, the FAST null of permutations 0, 1, 500 and 999 bit for bit, and a10-a12 recomputed from the GPU's null."""
+    from tests.parity import check_analysis
+    cfg, ds, d, m = config_B
+    sprm = P.ScoreParams(cfg.method, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 1)
+    nprm = ctx.null_params(cfg.n_perm, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=20261019, min_pass=1000)
+    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm,
+                      want_null=True, want_scores=True, want_order=True)
+    rep, _ = check_analysis(oracle, d, cfg.n_genes, cfg.n_types, out, score_params=_score_kw(cfg, 1),
+                            min_score=cfg.min_score, canonical=2, seed=20261019,
+                            perm_indices=(0, 1, 500, cfg.n_perm - 1), what="config B")
+    assert rep["n_used"] > 200_000 and rep["max_rel_vs_sequential"] <= 1e-9
+
+
+def test_baseline_config_B_csr_scan_and_exact_null_vs_oracle(ctx, oracle, config_B):
+    """The same matrix through the CSR-scan scoring kernel (north_star's warp-per-cell kernel; canonical form 1) and
+    the validation arithmetic (PHILOX permutations, EXACT fp32/fp64 recurrence) for 3 permutations, at full size."""
+    from tests.parity import check_analysis
+    cfg, ds, d, m = config_B
+    ctx.set_option(P.OPT_SCORE_PATH, 1)
+    try:
+        sprm = P.ScoreParams(cfg.method, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 1)
+        nprm = ctx.null_params(3, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=5, min_pass=1000)
+        out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm,
+                          want_null=True, want_scores=True, want_order=True)
+    finally:
+        ctx.set_option(P.OPT_SCORE_PATH, 0)
+    check_analysis(oracle, d, cfg.n_genes, cfg.n_types, out, score_params=_score_kw(cfg, 1), min_score=cfg.min_score,
+                   canonical=1, seed=5, perm_indices=(0, 1, 2), ks_fast=False, sequential_sample=0,
+                   what="config B, CSR scan + EXACT")
+
+
+def test_baseline_config_E_batch_lists_vs_oracle(ctx, oracle, config_B):
+    """BASELINE configs[4]'s shape: several input lists against the resident 600 000-cell matrix through
+    pctsea_analyze_batch, -perm 1000 each. Three of the lists are checked in full against the oracle (scores through
+    a single analysis of the same list — the batch must equal it bit for bit —, observed fields, FAST null columns,
+    a10-a12)."""
+    from tests.parity import check_analysis
+    cfg, ds, d, m = config_B
+    lists = [tuple(t.cpu().numpy() for t in synth.make_list(cfg, "cpu", list_seed=s)) for s in range(1, 6)]
+    sprm = P.ScoreParams(cfg.method, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 1)
+    nprm = ctx.null_params(cfg.n_perm, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=77, min_pass=1000)
+    batch = ctx.analyze_batch(m, lists, sprm, cfg.min_score, cfg.n_types, nprm, want_null=True)
+    for i in (0, 2, 4):
+        if batch["status"][i] != 0:
+            assert batch["status"][i] == -4   # PCTSEA_ETOOFEW: the oracle must agree that fewer than 1000 cells pass
+            sc, used, nz, kept = oracle.score(d["row_ptr"], d["col"], d["val"], cfg.n_genes, lists[i][0], lists[i][1],
+                                              canonical=2, **_score_kw(cfg, 1))
+            assert oracle.rank(sc, kept, cfg.min_score)[1] < 1000
+            continue
+        one = ctx.analyze(m, lists[i][0], lists[i][1], sprm, cfg.min_score, cfg.n_types, nprm,
+                          want_null=True, want_scores=True, want_order=True)
+        assert one["n_pass"] == batch["n_pass"][i]
+        assert_bits_equal_f32(batch["null"][i], one["null"], f"list {i}: batch null vs single analysis")
+        assert_results_equal(batch["results"][i], one["results"], None, f"list {i}: batch vs single analysis")
+        di = dict(d, gene_idx=lists[i][0], abundance=lists[i][1])
+        check_analysis(oracle, di, cfg.n_genes, cfg.n_types, one, score_params=_score_kw(cfg, 1),
+                       min_score=cfg.min_score, canonical=2, seed=77, perm_indices=(0, 333, cfg.n_perm - 1),
+                       sequential_sample=0, what=f"config E, list {i}")
+
+
+def test_baseline_config_D_shape_full_size_vs_oracle(ctx, oracle):
+    """BASELINE configs[3]'s shape: 30 000 genes, 300 cell types (16-bit labels, the null kernel's type-sliced form),
+    SIMPLE_SCORE, ~1.2 M ranked cells (60 % of D's 2 M cells: the host copy the oracle needs stays at 14 GB) —
+    everything against the oracle as for config B."""
+    import dataclasses
+    from tests.parity import check_analysis
+    cfg = dataclasses.replace(synth.CONFIGS["D"], n_cells=1_200_000, n_perm=64)
+    ds, d, m = _device_dataset(ctx, cfg)
+    try:
+        sprm = P.ScoreParams(cfg.method, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 3)
+        nprm = ctx.null_params(cfg.n_perm, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=4, min_pass=1000)
+        out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm,
+                          want_null=True, want_scores=True, want_order=True)
+    finally:
+        m.free()
+    del ds
+    rep, _ = check_analysis(oracle, d, cfg.n_genes, cfg.n_types, out, score_params=_score_kw(cfg, 3),
+                            min_score=cfg.min_score, canonical=2, seed=4, perm_indices=(0, 31, cfg.n_perm - 1),
+                            what="config D shape")
+    assert rep["n_used"] >= 1_000_000

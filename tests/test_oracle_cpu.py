@@ -354,7 +354,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert lib.pctsea_abi_version() == 1
+    assert lib.pctsea_abi_version() == 2
 
 
 def test_no_gpu_means_error_not_fallback():
@@ -370,7 +370,7 @@ def test_no_gpu_means_error_not_fallback():
 def test_struct_layouts_match_header():
     from pctsea_parent_b200 import _lib
     assert ctypes.sizeof(_lib.TypeResult) == 72 and ctypes.sizeof(_lib.ScoreParams) == 32
-    assert ctypes.sizeof(_lib.NullParams) == 40 and ctypes.sizeof(_lib.Timings) == 72
+    assert ctypes.sizeof(_lib.NullParams) == 40 and ctypes.sizeof(_lib.Timings) == 80
     assert _lib.TYPE_RESULT_DTYPE.fields["norm_supX"][1] == 16 and _lib.TYPE_RESULT_DTYPE.fields["fdr"][1] == 48
 
 
