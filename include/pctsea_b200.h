@@ -141,7 +141,8 @@ int         pctsea_get_timings(pctsea_ctx* ctx, pctsea_timings* out);
 
 /* Testing and tuning switches of a ctx (none is needed in production; results never depend on them except where
  * noted). Returns PCTSEA_EINVAL for an unknown option or a value out of range. */
-#define PCTSEA_OPT_OBS_OVERLAP       1  /* 1 (default): observed-statistics kernels run on a second stream beside the null */
+#define PCTSEA_OPT_OBS_OVERLAP       1  /* observed-statistics kernels: 0 = on the main stream before the null; on a second
+                                           stream beside the null, queued 1 = behind / 2 (default) = ahead of the null kernel */
 #define PCTSEA_OPT_SCORE_PATH        2  /* 0 (default): gene-major kernel when the matrix has its index; 1: always the CSR
                                            scan (the two differ in the last bits of a score, see build_gene_index) */
 #define PCTSEA_OPT_GM_UNROLL         3  /* value loads in flight per lane of the gene-major kernel: 1, 2, 4, 8 (0 = default) */

@@ -188,22 +188,18 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     reserve_ks_observed(c, g);
     c->null_ews.reserve((size_t)std::max(T, 1) * std::max(Pstride, 1) * 4 + 64);
     c->null_d.reserve((size_t)std::max(T, 1) * std::max(Pstride, 1) * 4 + 64);
-    NullPlanFast plan;
-    if (want_null && philox) {
-        plan = plan_null_fast(c, g);
-        launch_class_tables(c, g, plan.shift, plan.nb);
-        if (fast) launch_null_fast_prepare(c, g, plan);
-    }
-    rec(c, EV_RANK);
-    // The observed statistics and the permutation null both depend only on the ranked arrays. The observed
-    // kernels are small, latency-bound launches of 512-thread CTAs with ~40 registers, so by default they go to the
-    // auxiliary stream and run in the shadow of the null stage; the reduction waits for both.
-    // PCTSEA_OPT_OBS_OVERLAP = 0 keeps them on the main stream. With the overlap observed_ms is the span of the
-    // observed kernels on their own stream, not a share of total_ms.
-    const bool obs_overlap = c->opt_obs_overlap && want_null && philox;
+    // The observed statistics and the permutation null both depend only on the ranked arrays. The observed stage is
+    // a dependent chain of small, latency-bound launches (k_obs_chain: one 512-thread CTA per cell type walking the
+    // ranking), so by default it goes to the auxiliary high-priority stream and runs beside the null stage; the
+    // reduction waits for both. PCTSEA_OPT_OBS_OVERLAP: 0 keeps the observed kernels on the main stream (before the
+    // null), 1 queues them behind the launch of the null kernel, 2 (default) queues them BEFORE it: the null kernel is
+    // persistent and fills every SM it is given for the whole stage, so the chain has to be resident first — its
+    // CTAs then share their SMs with one null CTA each, the null CTAs that found no room start as the chain's CTAs
+    // retire, and the ticket counter of the null kernel balances the work whatever the start order was. With the
+    // overlap observed_ms is the span of the observed kernels on their own stream, not a share of total_ms.
+    const int obs_mode = (want_null && philox) ? c->opt_obs_overlap : 0;
+    const bool obs_overlap = obs_mode != 0;
     c->obs_span_valid = false;
-    if (obs_overlap) PCT_CUDA(cudaEventRecord(c->ev_obs[0], c->stream));   // ranked arrays are ready
-    else launch_ks_observed(c, g, c->stream);
     bool obs_queued = false;
     auto queue_observed_aux = [&]() {
         PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, c->ev_obs[0], 0));
@@ -213,6 +209,18 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
         c->obs_span_valid = true;
         obs_queued = true;
     };
+    if (obs_overlap) {
+        PCT_CUDA(cudaEventRecord(c->ev_obs[0], c->stream));   // ranked arrays and class counts are ready
+        if (obs_mode == 2) queue_observed_aux();
+    }
+    NullPlanFast plan;
+    if (want_null && philox) {
+        plan = plan_null_fast(c, g);
+        launch_class_tables(c, g, plan.shift, plan.nb);
+        if (fast) launch_null_fast_prepare(c, g, plan);
+    }
+    rec(c, EV_RANK);
+    if (!obs_overlap) launch_ks_observed(c, g, c->stream);
     c->last_obs_Nu = T > 0 ? Nu : -1;
     rec(c, EV_OBS);
 
@@ -223,7 +231,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
         cudaEvent_t e0 = et.mark(c->stream);
         launch_null_fused(c, g, plan, prm->seed, np.begin, Pc_all, np.rounds, Pstride, 0);
         cudaEvent_t e1 = et.mark(c->stream);
-        if (obs_overlap) queue_observed_aux();   // after the null launch: the big kernel gets its SMs first
+        if (obs_overlap && !obs_queued) queue_observed_aux();   // mode 1: behind the null launch
         null_spans.push_back({ e0, e1 });
     } else if (want_null) {
         if (!philox) PCT_REQUIRE(replay_host != nullptr, "REPLAY mode needs replay_perm");
@@ -468,7 +476,7 @@ int pctsea_ctx_set_option(pctsea_ctx* c, int32_t option, int64_t value) {
     if (value < 0 || value > (1 << 20)) return bad("value out of range");
     const int v = (int)value;
     switch (option) {
-        case PCTSEA_OPT_OBS_OVERLAP: if (v > 1) return bad("0 or 1"); c->opt_obs_overlap = v; break;
+        case PCTSEA_OPT_OBS_OVERLAP: if (v > 2) return bad("0, 1 or 2"); c->opt_obs_overlap = v; break;
         case PCTSEA_OPT_SCORE_PATH: if (v > 1) return bad("0 or 1"); c->opt_score_path = v; break;
         case PCTSEA_OPT_GM_UNROLL: if (v > 8) return bad("at most 8"); c->opt_gm_unroll = v; break;
         case PCTSEA_OPT_SCORE_WARPS: if (v > 32) return bad("at most 32"); c->opt_score_warps = v; break;

@@ -101,7 +101,7 @@ struct pctsea_ctx {
     int smem_per_sm = 0;             // bytes of shared memory per SM
     int smem_per_block_optin = 0;    // largest dynamic shared memory a CTA may opt in to
     // pctsea_ctx_set_option (testing and tuning; none is needed in production)
-    int opt_obs_overlap = 1;         // observed-statistics kernels on the auxiliary stream beside the null
+    int opt_obs_overlap = 2;         // observed-statistics kernels on the auxiliary stream beside the null (2: queued before it)
     int opt_score_path = 0;          // 1 = CSR scan even when the matrix has its gene-major index
     int opt_gm_unroll = 0;           // value loads in flight per lane of the gene-major kernel (0 = default)
     int opt_score_warps = 0;         // warps per CTA of the CSR-scan kernel (0 = as many as fit)

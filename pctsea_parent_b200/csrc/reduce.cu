@@ -24,17 +24,22 @@ __device__ __forceinline__ uint32_t java_orderable_f32(float f) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// One warp per type. Counts are warp-parallel (ballots); the fp32 / fp64 running sums of a11 keep the
-// permutation order (the Maths.mean policy) by replaying each coalesced 32-value chunk lane by lane.
+// One THREAD per type: a10's counts and a11's running sums in one sequential walk over the type's row of the null.
+// The fp32 / fp64 running sums of a11 must keep the permutation order (the Maths.mean policy), so the walk is a
+// dependent chain of P additions whatever the layout; a thread per type runs the T chains side by side with nothing
+// between two additions but the add itself (the loads are independent of the chain and are issued eight values
+// ahead; a warp-per-type version that broadcast each value by shuffle spent 49 cycles per value on the shuffle ->
+// select -> add round trip: 202 us at P = 8000, 87 % of the whole reduction).
 __global__ void __launch_bounds__(32) k_red_type(const float* __restrict__ null_ews, int32_t T, int32_t P,
                                                  int mean_policy, pctsea_type_result* __restrict__ res,
                                                  float* __restrict__ expct_out) {
-    const int t = blockIdx.x, lane = threadIdx.x;
+    const int t = blockIdx.x * 32 + threadIdx.x;
+    if (t >= T) return;
     const float real = res[t].ews;
     const double dnan = __longlong_as_double(0x7ff8000000000000LL);
     const float fnan = __int_as_float(0x7fc00000);
     if (real != real) {
-        if (lane == 0) { res[t].p_emp = dnan; res[t].norm_ews = fnan; res[t].fdr = dnan; expct_out[t] = fnan; }
+        res[t].p_emp = dnan; res[t].norm_ews = fnan; res[t].fdr = dnan; expct_out[t] = fnan;
         return;
     }
     const float* nl = null_ews + (size_t)t * P;
@@ -42,38 +47,31 @@ __global__ void __launch_bounds__(32) k_red_type(const float* __restrict__ null_
     float fsum_pos = 0.0f, fsum_neg = 0.0f;
     double dsum_pos = 0.0, dsum_neg = 0.0;
     const bool pos_side = real >= 0.0f;
-    for (int32_t p0 = 0; p0 < P; p0 += 32) {
-        const int32_t p = p0 + lane;
-        const bool in = p < P;
-        const float v = in ? nl[p] : fnan;
-        // a10: NaNs dropped, zeros excluded, strict comparisons
-        const bool side = in && (v == v) && (pos_side ? !(v <= 0.0f) : !(v >= 0.0f));
-        total += __popc(__ballot_sync(0xffffffffu, side));
-        cnt += __popc(__ballot_sync(0xffffffffu, side && (pos_side ? (v > real) : (v < real))));
-        // a11: zeros go with the positives
-        npos += __popc(__ballot_sync(0xffffffffu, in && v >= 0.0f));
-        nneg += __popc(__ballot_sync(0xffffffffu, in && v < 0.0f));
-        const int n = min(32, P - p0);
-        // only the accumulator of the selected mean policy: the two sequential chains (positives, negatives) are
-        // what bounds this kernel
-        if (mean_policy) {
-            for (int j = 0; j < n; j++) {
-                const float vj = __shfl_sync(0xffffffffu, v, j);
+    constexpr int U = 8;
+    for (int32_t p0 = 0; p0 < P; p0 += U) {
+        float v[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) v[j] = (p0 + j < P) ? __ldg(nl + p0 + j) : fnan;
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const float vj = v[j];   // the padding NaNs fail every test below
+            // a10: NaNs dropped, zeros excluded, strict comparisons
+            const bool side = (vj == vj) && (pos_side ? !(vj <= 0.0f) : !(vj >= 0.0f));
+            total += side ? 1 : 0;
+            cnt += (side && (pos_side ? (vj > real) : (vj < real))) ? 1 : 0;
+            // a11: zeros go with the positives
+            npos += (vj >= 0.0f) ? 1 : 0;
+            nneg += (vj < 0.0f) ? 1 : 0;
+            if (mean_policy) {
                 if (vj >= 0.0f) dsum_pos = __dadd_rn(dsum_pos, (double)vj);
                 else if (vj < 0.0f) dsum_neg = __dadd_rn(dsum_neg, (double)vj);
-            }
-        } else {
-#pragma unroll 8
-            for (int j = 0; j < n; j++) {
-                const float vj = __shfl_sync(0xffffffffu, v, j);
-                // adding -0.0f leaves any fp32 accumulator bit-unchanged (also a -0.0f one), so the two chains can
-                // be branch-free
+            } else {
+                // adding -0.0f leaves any fp32 accumulator bit-unchanged (also a -0.0f one): branch-free chains
                 fsum_pos = __fadd_rn(fsum_pos, (vj >= 0.0f) ? vj : -0.0f);
                 fsum_neg = __fadd_rn(fsum_neg, (vj < 0.0f) ? vj : -0.0f);
             }
         }
     }
-    if (lane != 0) return;
     res[t].p_emp = __ddiv_rn(__dmul_rn(1.0, (double)cnt), (double)total);  // 0/0 -> NaN
     float mean_pos = mean_policy ? __double2float_rn(__ddiv_rn(dsum_pos, (double)npos)) : __fdiv_rn(fsum_pos, (float)npos);
     float mean_neg = mean_policy ? __double2float_rn(__ddiv_rn(dsum_neg, (double)nneg)) : __fdiv_rn(fsum_neg, (float)nneg);
@@ -179,12 +177,23 @@ __global__ void __launch_bounds__(1024) k_red_fdr(int32_t T, pctsea_type_result*
     __shared__ long long s_nnull;
     const int32_t nobs = *nobs_p;
     const int nb = 2 * nobs + 1;
-    // exclusive prefix of the bins in place (nb is a few hundred to a few thousand): one thread, sequential
-    if (threadIdx.x == 0) {
+    // exclusive prefix of the bins in place (nb is a few hundred to a few thousand): one warp, 32 bins per step
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         long long run = 0;
-        for (int i = 0; i < nb; i++) { const unsigned int v = bins[i]; bins[i] = (unsigned int)run; run += v; }
-        bins[nb] = (unsigned int)run;
-        s_nnull = run;
+        for (int base = 0; base < nb; base += 32) {
+            const int i = base + lane;
+            const unsigned int v = i < nb ? bins[i] : 0u;
+            unsigned int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (i < nb) bins[i] = (unsigned int)run + (incl - v);
+            run += (long long)__shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) { bins[nb] = (unsigned int)run; s_nnull = run; }
     }
     __syncthreads();
     const long long nnull = s_nnull;
@@ -228,7 +237,7 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
     int32_t* nobs = reinterpret_cast<int32_t*>(base + off_n);
     unsigned int* bins = reinterpret_cast<unsigned int*>(base + off_b);
 
-    k_red_type<<<(unsigned)T, 32, 0, c->stream>>>(null_dev, T, P, mean_policy, results_dev, expct);
+    k_red_type<<<(unsigned)div_up(T, 32), 32, 0, c->stream>>>(null_dev, T, P, mean_policy, results_dev, expct);
     k_red_rank<<<1, 1024, 0, c->stream>>>(T, results_dev, Rsorted, nobs, bins);
     if (n > 0) {
         const int use_smem = T <= 4096;

@@ -504,3 +504,30 @@ def test_cell_type_file_writers(tmp_path):
     assert h.read_text().splitlines()[1:] == ["# genes\t4\t2", "# genes\t7\t1", "# genes\t9\t3",
                                               "# genes or more\t4\t6", "# genes or more\t7\t4", "# genes or more\t9\t3"]
     assert api.get_output_txt_file_name("T_ews", "run1", api.ScoringMethod.PEARSONS_CORRELATION).startswith("run1_")
+
+
+def test_jni_shim_covers_every_native_method_and_abi_entry(tmp_path):
+    """java/jni/pctsea_b200_jni.c is the C side of java/src/.../PctseaB200.java. No JDK exists in this image, so the
+    shim is compiled against a minimal stand-in for jni.h (java/test/jni_mock: same type names and prototypes, NOT
+    the JVM's table layout) and linked against the real libpctsea_b200.so: every `native` method of the Java class
+    has its Java_<class>_<method> export, every host-pointer entry point of include/pctsea_b200.h is called, and
+    the prototypes the shim assumes match the header (a mismatch is a compile error)."""
+    import subprocess
+    from pctsea_parent_b200 import build as B
+    B.build()
+    so = tmp_path / "libjni_check.so"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-shared", "-fPIC",
+                           "-I" + os.path.join(ROOT, "java", "test", "jni_mock"), "-I" + os.path.join(ROOT, "include"),
+                           "-o", str(so), os.path.join(ROOT, "java", "jni", "pctsea_b200_jni.c"),
+                           "-L" + os.path.join(ROOT, "pctsea_parent_b200"), "-lpctsea_b200"])
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", str(so)], text=True)
+    exported = set(re.findall(r"Java_edu_scripps_yates_pctsea_gpu_PctseaB200_(\w+)", syms))
+    java = open(os.path.join(ROOT, "java", "src", "edu", "scripps", "yates", "pctsea", "gpu", "PctseaB200.java")).read()
+    natives = set(re.findall(r"private static native [\w\[\].]+ (\w+)\(", java))
+    assert natives and natives == exported, (natives ^ exported)
+    shim = open(os.path.join(ROOT, "java", "jni", "pctsea_b200_jni.c")).read()
+    hdr = open(os.path.join(ROOT, "include", "pctsea_b200.h")).read()
+    declared = set(re.findall(r"\b(pctsea_[a-z_0-9]+)\s*\(", hdr))
+    device_pointer_only = {"pctsea_stream", "pctsea_matrix_wrap_device", "pctsea_reduce_null_dev", "pctsea_last_null_dev"}
+    for name in sorted(declared - device_pointer_only):
+        assert re.search(r"\b" + name + r"\(", shim), f"{name} has no JNI method"
