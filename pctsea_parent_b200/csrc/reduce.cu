@@ -24,44 +24,77 @@ __device__ __forceinline__ uint32_t java_orderable_f32(float f) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// One THREAD per type: a10's counts and a11's running sums in one sequential walk over the type's row of the null.
-// The fp32 / fp64 running sums of a11 must keep the permutation order (the Maths.mean policy), so the walk is a
-// dependent chain of P additions whatever the layout; a thread per type runs the T chains side by side with nothing
-// between two additions but the add itself (the loads are independent of the chain and are issued eight values
-// ahead; a warp-per-type version that broadcast each value by shuffle spent 49 cycles per value on the shuffle ->
-// select -> add round trip: 202 us at P = 8000, 87 % of the whole reduction).
-__global__ void __launch_bounds__(32) k_red_type(const float* __restrict__ null_ews, int32_t T, int32_t P,
-                                                 int mean_policy, pctsea_type_result* __restrict__ res,
-                                                 float* __restrict__ expct_out) {
-    const int t = blockIdx.x * 32 + threadIdx.x;
-    if (t >= T) return;
+// a10 / a11 in three small kernels.
+//   k_red_counts     one warp per type: the four counts of a10 / a11 by ballots over coalesced 32-value chunks
+//   k_red_transpose  null [T][P] -> nullT [P][Tpad] (32 x 32 tiles through shared memory)
+//   k_red_chain      one THREAD per type: the fp32 / fp64 running sums of a11. They must keep the permutation order
+//                    (the Maths.mean policy), so each is a dependent chain of P additions whatever the layout. On
+//                    the transposed copy lane = type reads one coalesced 128-byte line per permutation, the loads
+//                    are independent of the chain (16 in flight), and nothing stands between two additions but the
+//                    add itself. (A warp-per-type version that broadcast each value by shuffle spent 49 cycles per
+//                    value: 202 us at P = 8000, 87 % of the whole reduction; a thread-per-type walk over the
+//                    untransposed rows waits one L2 round trip per 8 values: 0.6 ms.)
+struct RedCounts { int32_t total, cnt, npos, nneg; };
+
+__global__ void __launch_bounds__(32) k_red_counts(const float* __restrict__ null_ews, int32_t T, int32_t P,
+                                                   const pctsea_type_result* __restrict__ res, RedCounts* __restrict__ counts) {
+    const int t = blockIdx.x, lane = threadIdx.x;
     const float real = res[t].ews;
-    const double dnan = __longlong_as_double(0x7ff8000000000000LL);
     const float fnan = __int_as_float(0x7fc00000);
-    if (real != real) {
-        res[t].p_emp = dnan; res[t].norm_ews = fnan; res[t].fdr = dnan; expct_out[t] = fnan;
-        return;
-    }
     const float* nl = null_ews + (size_t)t * P;
     int32_t total = 0, cnt = 0, npos = 0, nneg = 0;
+    const bool pos_side = real >= 0.0f;
+    for (int32_t p0 = 0; p0 < P; p0 += 32) {
+        const int32_t p = p0 + lane;
+        const bool in = p < P;
+        const float v = in ? nl[p] : fnan;
+        // a10: NaNs dropped, zeros excluded, strict comparisons
+        const bool side = in && (v == v) && (pos_side ? !(v <= 0.0f) : !(v >= 0.0f));
+        total += __popc(__ballot_sync(0xffffffffu, side));
+        cnt += __popc(__ballot_sync(0xffffffffu, side && (pos_side ? (v > real) : (v < real))));
+        // a11: zeros go with the positives
+        npos += __popc(__ballot_sync(0xffffffffu, in && v >= 0.0f));
+        nneg += __popc(__ballot_sync(0xffffffffu, in && v < 0.0f));
+    }
+    if (lane == 0) counts[t] = RedCounts{ total, cnt, npos, nneg };
+}
+
+__global__ void __launch_bounds__(256) k_red_transpose(const float* __restrict__ in, int32_t T, int32_t P, int32_t Tpad,
+                                                       float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int p0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    const float fnan = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int t = t0 + r, p = p0 + tx;
+        tile[r][tx] = (t < T && p < P) ? in[(size_t)t * P + p] : fnan;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int p = p0 + r, t = t0 + tx;
+        if (p < P && t < Tpad) out[(size_t)p * Tpad + t] = tile[tx][r];
+    }
+}
+
+__global__ void __launch_bounds__(32) k_red_chain(const float* __restrict__ nullT, int32_t T, int32_t P, int32_t Tpad,
+                                                  int mean_policy, const RedCounts* __restrict__ counts,
+                                                  pctsea_type_result* __restrict__ res, float* __restrict__ expct_out) {
+    const int t = blockIdx.x * 32 + threadIdx.x;   // t < Tpad: padding lanes walk NaN columns and write nothing
+    const float* col = nullT + t;
     float fsum_pos = 0.0f, fsum_neg = 0.0f;
     double dsum_pos = 0.0, dsum_neg = 0.0;
-    const bool pos_side = real >= 0.0f;
-    constexpr int U = 8;
-    for (int32_t p0 = 0; p0 < P; p0 += U) {
-        float v[U];
+    constexpr int U = 16;
+    float v[U];
 #pragma unroll
-        for (int j = 0; j < U; j++) v[j] = (p0 + j < P) ? __ldg(nl + p0 + j) : fnan;
+    for (int j = 0; j < U; j++) v[j] = (j < P) ? col[(size_t)j * Tpad] : __int_as_float(0x7fc00000);
+    for (int32_t p0 = 0; p0 < P; p0 += U) {
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            const float vj = v[j];   // the padding NaNs fail every test below
-            // a10: NaNs dropped, zeros excluded, strict comparisons
-            const bool side = (vj == vj) && (pos_side ? !(vj <= 0.0f) : !(vj >= 0.0f));
-            total += side ? 1 : 0;
-            cnt += (side && (pos_side ? (vj > real) : (vj < real))) ? 1 : 0;
-            // a11: zeros go with the positives
-            npos += (vj >= 0.0f) ? 1 : 0;
-            nneg += (vj < 0.0f) ? 1 : 0;
+            const float vj = v[j];   // NaNs (real ones and the padding) fail both tests
+            const int32_t pn = p0 + U + j;
+            v[j] = (pn < P) ? col[(size_t)pn * Tpad] : __int_as_float(0x7fc00000);
             if (mean_policy) {
                 if (vj >= 0.0f) dsum_pos = __dadd_rn(dsum_pos, (double)vj);
                 else if (vj < 0.0f) dsum_neg = __dadd_rn(dsum_neg, (double)vj);
@@ -72,9 +105,19 @@ __global__ void __launch_bounds__(32) k_red_type(const float* __restrict__ null_
             }
         }
     }
-    res[t].p_emp = __ddiv_rn(__dmul_rn(1.0, (double)cnt), (double)total);  // 0/0 -> NaN
-    float mean_pos = mean_policy ? __double2float_rn(__ddiv_rn(dsum_pos, (double)npos)) : __fdiv_rn(fsum_pos, (float)npos);
-    float mean_neg = mean_policy ? __double2float_rn(__ddiv_rn(dsum_neg, (double)nneg)) : __fdiv_rn(fsum_neg, (float)nneg);
+    if (t >= T) return;
+    const float real = res[t].ews;
+    const double dnan = __longlong_as_double(0x7ff8000000000000LL);
+    const float fnan = __int_as_float(0x7fc00000);
+    if (real != real) {
+        res[t].p_emp = dnan; res[t].norm_ews = fnan; res[t].fdr = dnan; expct_out[t] = fnan;
+        return;
+    }
+    const RedCounts c = counts[t];
+    const bool pos_side = real >= 0.0f;
+    res[t].p_emp = __ddiv_rn(__dmul_rn(1.0, (double)c.cnt), (double)c.total);  // 0/0 -> NaN
+    float mean_pos = mean_policy ? __double2float_rn(__ddiv_rn(dsum_pos, (double)c.npos)) : __fdiv_rn(fsum_pos, (float)c.npos);
+    float mean_neg = mean_policy ? __double2float_rn(__ddiv_rn(dsum_neg, (double)c.nneg)) : __fdiv_rn(fsum_neg, (float)c.nneg);
     float expct = pos_side ? fabsf(mean_pos) : fabsf(mean_neg);
     res[t].norm_ews = __fdiv_rn(real, expct);
     expct_out[t] = expct;
@@ -227,17 +270,27 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
     if (T == 0) return;
     const int64_t n = (int64_t)T * P;
     if (n > 0x7fffffffll) throw Error(PCTSEA_EINVAL, "pooled null larger than a Java int");
-    // [T] expected values | [T] sorted observed keys | nobs | [2T + 2] bins
+    // [T] expected values | [T] sorted observed keys | nobs | [2T + 2] bins | [T] counts | [P][Tpad] transposed null
+    const int32_t Tpad = (int32_t)round_up(T, 32);
     const size_t off_r = (size_t)round_up((int64_t)T * 4, 16), off_n = off_r + (size_t)round_up((int64_t)T * 4, 16),
-                 off_b = off_n + 16, total = off_b + ((size_t)2 * T + 2) * 4;
+                 off_b = off_n + 16, off_c = (size_t)round_up((int64_t)(off_b + ((size_t)2 * T + 2) * 4), 16),
+                 off_t = off_c + (size_t)T * sizeof(RedCounts), total = off_t + (size_t)std::max(P, 1) * Tpad * 4;
     c->red_misc.reserve(total + 64);
     unsigned char* base = c->red_misc.as<unsigned char>();
     float* expct = reinterpret_cast<float*>(base);
     uint32_t* Rsorted = reinterpret_cast<uint32_t*>(base + off_r);
     int32_t* nobs = reinterpret_cast<int32_t*>(base + off_n);
     unsigned int* bins = reinterpret_cast<unsigned int*>(base + off_b);
+    RedCounts* counts = reinterpret_cast<RedCounts*>(base + off_c);
+    float* nullT = reinterpret_cast<float*>(base + off_t);
 
-    k_red_type<<<(unsigned)div_up(T, 32), 32, 0, c->stream>>>(null_dev, T, P, mean_policy, results_dev, expct);
+    k_red_counts<<<(unsigned)T, 32, 0, c->stream>>>(null_dev, T, P, results_dev, counts);
+    if (P > 0) {
+        dim3 tg((unsigned)div_up(P, 32), (unsigned)(Tpad / 32));
+        k_red_transpose<<<tg, 256, 0, c->stream>>>(null_dev, T, P, Tpad, nullT);
+    }
+    k_red_chain<<<(unsigned)(Tpad / 32), 32, 0, c->stream>>>(nullT, T, P, Tpad, mean_policy, counts, results_dev, expct);
+    count_launch(c, P > 0 ? 2 : 1);
     k_red_rank<<<1, 1024, 0, c->stream>>>(T, results_dev, Rsorted, nobs, bins);
     if (n > 0) {
         const int use_smem = T <= 4096;

@@ -70,6 +70,57 @@ class CSRDataset:
         z = np.load(path, allow_pickle=True)
         return cls(z["row_ptr"], z["col"], z["val"], list(z["gene_names"]), list(z["cell_names"]), list(z["cell_types"]))
 
+    # ---- the binary dump shared with the Java side (java/src/.../gpu/MongoToCsr.java writes it from the reference's
+    # MongoDB, GpuDataset.java reads it): "<base>.csr" little endian = magic "PCTSEACSR1\0\0" | nCells i64 | nGenes i32 |
+    # nTypes i32 | nnz i64 | rowPtr i64[nCells+1] | col i32[nnz] | val f32[nnz] | label i32[nCells], plus
+    # "<base>.genes.txt" / ".types.txt" / ".cells.txt" with one name per line (line i = column / label id / row i).
+    MAGIC = b"PCTSEACSR1\0\0"
+
+    def labels(self):
+        """(label int32[nCells], type names): ids in order of first appearance, -1 for a cell without a type."""
+        ids: Dict[str, int] = {}
+        lab = np.empty(len(self.cell_types), np.int32)
+        for i, t in enumerate(self.cell_types):
+            if t is None or t == "":
+                lab[i] = -1
+            else:
+                lab[i] = ids.setdefault(t, len(ids))
+        return lab, list(ids.keys())
+
+    def save_binary(self, base: str):
+        lab, types = self.labels()
+        n_cells, n_genes = self.shape
+        with open(base + ".csr", "wb") as fh:
+            fh.write(self.MAGIC)
+            fh.write(np.array([n_cells], "<i8").tobytes())
+            fh.write(np.array([n_genes, len(types)], "<i4").tobytes())
+            fh.write(np.array([len(self.col)], "<i8").tobytes())
+            fh.write(np.ascontiguousarray(self.row_ptr, "<i8").tobytes())
+            fh.write(np.ascontiguousarray(self.col, "<i4").tobytes())
+            fh.write(np.ascontiguousarray(self.val, "<f4").tobytes())
+            fh.write(np.ascontiguousarray(lab, "<i4").tobytes())
+        for suffix, names in ((".genes.txt", self.gene_names), (".types.txt", types), (".cells.txt", self.cell_names)):
+            with open(base + suffix, "w") as fh:
+                fh.writelines(str(n) + "\n" for n in names)
+
+    @classmethod
+    def load_binary(cls, base: str) -> "CSRDataset":
+        with open(base + ".csr", "rb") as fh:
+            if fh.read(12) != cls.MAGIC:
+                raise ValueError(f"{base}.csr is not a PCTSEA CSR dump")
+            n_cells = int(np.frombuffer(fh.read(8), "<i8")[0])
+            n_genes, n_types = (int(v) for v in np.frombuffer(fh.read(8), "<i4"))
+            nnz = int(np.frombuffer(fh.read(8), "<i8")[0])
+            row_ptr = np.frombuffer(fh.read(8 * (n_cells + 1)), "<i8").astype(np.int64)
+            col = np.frombuffer(fh.read(4 * nnz), "<i4").astype(np.int32)
+            val = np.frombuffer(fh.read(4 * nnz), "<f4").astype(np.float32)
+            lab = np.frombuffer(fh.read(4 * n_cells), "<i4")
+        read = lambda suffix: [ln.rstrip("\n") for ln in open(base + suffix)]
+        genes, types, cells = read(".genes.txt"), read(".types.txt"), read(".cells.txt")
+        if len(genes) != n_genes or len(types) != n_types or len(cells) != n_cells or int(row_ptr[-1]) != nnz:
+            raise ValueError(f"{base}: name files do not match the CSR header")
+        return cls(row_ptr, col, val, genes, cells, [types[t] if t >= 0 else "" for t in lab])
+
 
 def read_hcl_expression_files(files: Sequence[str], annotations: Optional[Dict[str, Tuple[str, str]]] = None) -> CSRDataset:
     cell_index: Dict[str, int] = {}

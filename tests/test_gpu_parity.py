@@ -268,6 +268,26 @@ def test_observed_bit_exact(ctx, oracle, n_used, T):
     assert_results_equal(res, ores, OBSERVED_FIELDS, "observed")
 
 
+def test_hand_derived_vectors(ctx):
+    """The CUDA library against results worked out on paper from the reference's lines (tests/helpers.py)."""
+    from tests import helpers as H
+    from tests.test_oracle_cpu import _check_observed
+    prm = ctx.null_params(0, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT)
+    for make in (H.hand_vector_secondary, H.hand_vector_secondary_index_zero):
+        s, lab, T, exp = make()
+        res, _, _ = ctx.enrich(s, np.arange(s.size, dtype=np.int32), lab, T, prm)
+        _check_observed(res, 0, exp, make.__name__)
+    ews, null, exp = H.hand_vector_fdr_duplicates()
+    res = np.zeros(3, P.TYPE_RESULT_DTYPE)
+    res["ews"] = ews
+    red = ctx.reduce_null(res, null)
+    assert np.array_equal(red["norm_ews"], exp["norm_ews"]) and np.array_equal(red["p_emp"], exp["p_emp"])
+    assert np.array_equal(red["fdr"], exp["fdr"]), red["fdr"]
+    for score, thr, order in H.hand_vectors_rank():
+        got, npass = ctx.rank(score, None, thr)
+        assert npass == len(order) and got.tolist() == order, (thr, got)
+
+
 def test_observed_survey_micro_vector(ctx):
     # SURVEY.md Appendix B.1 (hand-derived bit patterns)
     s = np.array([0.9, 0.85, 0.8, 0.75, 0.7, 0.65, 0.6, 0.55, 0.5, 0.45])
