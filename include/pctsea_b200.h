@@ -152,6 +152,8 @@ int         pctsea_get_timings(pctsea_ctx* ctx, pctsea_timings* out);
 #define PCTSEA_OPT_NULL_CTAS_PER_SM  7  /* resident CTAs per SM of the null kernel (0 = as many as fit) */
 #define PCTSEA_OPT_NULL_MIN_THREADS  8  /* cell types are processed in slices when fewer threads would fit (0 = 192) */
 #define PCTSEA_OPT_DEBUG_GAPS        9  /* 1: report idle gaps between the stages on stderr */
+#define PCTSEA_OPT_SHARD_SCORE      10  /* multi-GPU pctsea_analyze with the gene-major index: 1 (default) every rank scores
+                                           1 / nranks of the cells and the scores are all-gathered; 0: every rank scores all */
 int         pctsea_ctx_set_option(pctsea_ctx* ctx, int32_t option, int64_t value);
 /* cudaStream_t the ctx launches on (so a caller can time or order against it). */
 void*       pctsea_stream(pctsea_ctx* ctx);
@@ -269,7 +271,8 @@ int pctsea_last_observed_curve(pctsea_ctx* ctx, int32_t type_id, int64_t n_used,
  * With a communicator attached, pctsea_analyze must be called by all ranks with the same list and parameters,
  * perm_begin = 0 and perm_count = 0 ("all n_perm permutations"): rank r computes the r-th contiguous share of the
  * global permutation indices (sizes differ by at most one), the slices are all-gathered over NVLink on the ctx
- * stream, and a10-a12 run on the complete null on every rank — out[], null_out and nullD_out ([n_types][n_perm])
+ * stream, and a10-a12 run on the complete null on every rank (with the gene-major index stage 1 shards over the
+ * ranks too: every rank scores 1 / nranks of the cells, 16 bytes per cell are all-gathered) — out[], null_out and nullD_out ([n_types][n_perm])
  * are bit-identical on every rank to what a single-GPU call returns. pctsea_analyze_batch, pctsea_enrich and the
  * stage calls stay per-rank (independent lists shard without a collective). */
 #define PCTSEA_COMM_ID_BYTES 128

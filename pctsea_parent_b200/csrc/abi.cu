@@ -6,6 +6,8 @@
 #include <cstring>
 #include <limits>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: the calls are no-ops unless a profiler injects itself (nsys, ncu)
+
 using namespace pctsea;
 
 namespace {
@@ -27,9 +29,28 @@ struct EvTimer {
     }
 };
 
+// Stage boundary: a CUDA event on the ctx stream (pctsea_timings) and an NVTX range on the calling thread, so that a
+// timeline shows the path as setup | score | rank | enrich (observed + null) | reduce | results.
+void nvtx_close(pctsea_ctx* c) {
+    if (c->nvtx_open) { nvtxRangePop(); c->nvtx_open = false; }
+}
 void rec(pctsea_ctx* c, int which) {
     PCT_CUDA(cudaEventRecord(c->ev[which], c->stream));
     c->ev_rec[which] = true;
+    const char* next = nullptr;
+    switch (which) {
+        case EV_BEGIN: next = "pctsea:setup"; break;
+        case EV_SETUP: next = "pctsea:score"; break;
+        case EV_SCORE: next = "pctsea:rank"; break;
+        case EV_RANK: next = "pctsea:enrich (observed + null)"; break;
+        case EV_NULL: next = "pctsea:reduce"; break;
+        case EV_REDUCE: next = "pctsea:results"; break;
+        case EV_END: nvtx_close(c); return;
+        default: return;   // EV_OBS, EV_GATHER: inside a stage
+    }
+    nvtx_close(c);
+    nvtxRangePushA(next);
+    c->nvtx_open = true;
 }
 
 float between(pctsea_ctx* c, int a, int b) {
@@ -41,6 +62,7 @@ float between(pctsea_ctx* c, int a, int b) {
 
 void begin_call(pctsea_ctx* c) {
     PCT_CUDA(cudaSetDevice(c->device));
+    nvtx_close(c);                         // open only if a previous call failed half-way
     cudaStreamSynchronize(c->stream_aux);  // idle unless a previous call failed half-way
     c->err.clear();
     memset(&c->tm, 0, sizeof c->tm);
@@ -454,7 +476,7 @@ int pctsea_destroy(pctsea_ctx* c) {
     DevBuf* bufs[] = { &c->list_gene, &c->list_abund, &c->ybg, &c->bitmap, &c->list_rank, &c->score_sums, &c->score, &c->nused, &c->nnzc, &c->kept, &c->gm_fix,
                        &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->tile_hist, &c->scan_tmp, &c->counters,
                        &c->order, &c->type_counts, &c->label_tmp, &c->obs_chain, &c->obs_misc, &c->obs_tiles, &c->s_rank, &c->lab_rank, &c->fx, &c->Sfx, &c->class_cnt, &c->labels, &c->lab_ticket, &c->cls_tab,
-                       &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->null_gather, &c->null_pool, &c->null_pool_d, &c->results, &c->red_tmp,
+                       &c->replay, &c->fxT, &c->null_ews, &c->null_d, &c->null_gather, &c->null_pool, &c->null_pool_d, &c->score_pack, &c->results, &c->red_tmp,
                        &c->red_misc };
     for (DevBuf* b : bufs) b->release();
     c->pin_in.release(); c->pin_out.release(); c->pin_small.release();
@@ -485,6 +507,7 @@ int pctsea_ctx_set_option(pctsea_ctx* c, int32_t option, int64_t value) {
         case PCTSEA_OPT_NULL_CTAS_PER_SM: if (v > 4) return bad("at most 4"); c->opt_null_ctas_per_sm = v; break;
         case PCTSEA_OPT_NULL_MIN_THREADS: if (v > 512) return bad("at most 512"); c->opt_null_min_threads = v; break;
         case PCTSEA_OPT_DEBUG_GAPS: if (v > 1) return bad("0 or 1"); c->opt_debug_gaps = v; break;
+        case PCTSEA_OPT_SHARD_SCORE: if (v > 1) return bad("0 or 1"); c->opt_shard_score = v; break;
         default: return bad("unknown option");
     }
     return PCTSEA_OK;
@@ -731,6 +754,10 @@ int pctsea_analyze(pctsea_ctx* c, const pctsea_matrix* m, int32_t L, const int32
         shard_over_ranks(c, nprm, &np, nullD_out != nullptr);
         rec(c, EV_BEGIN);
         const int32_t* label_dev = resident_labels(c, m, label);
+        // stage 1 shards over the ranks as well (gene-major kernel): every rank scores 1 / nranks of the cells and the
+        // scores are all-gathered, instead of every rank scoring all of them
+        struct Guard { pctsea_ctx* c; ~Guard() { c->shard_score = false; } } guard{ c };
+        c->shard_score = np.pooled && c->comm_nranks > 1 && c->opt_shard_score;
         analyze_core(c, m, L, gene_idx, abundance, sprm, min_score, label_dev, n_types, nprm, np, replay_perm, out,
                      null_out, nullD_out, score_out, n_genes_used_out, kept_out, order_out, n_pass_out);
     });

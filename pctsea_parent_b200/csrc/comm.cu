@@ -116,6 +116,15 @@ void comm_share(int64_t n, int32_t nranks, int32_t rank, int64_t* begin, int64_t
     *count = base + (rank < rem ? 1 : 0);
 }
 
+// In-place all-gather of `bytes_per_rank` bytes per rank on the ctx stream: rank r's block sits at buf + r * bytes_per_rank.
+void comm_all_gather_in_place(pctsea_ctx* c, void* buf, size_t bytes_per_rank) {
+    NcclApi& a = nccl_or_throw();
+    PCT_REQUIRE(c->comm != nullptr, "no communicator");
+    if (bytes_per_rank == 0) return;
+    PCT_NCCL(a.AllGather(static_cast<char*>(buf) + (size_t)c->comm_rank * bytes_per_rank, buf, bytes_per_rank, ncclChar,
+                         reinterpret_cast<ncclComm_t>(c->comm), c->stream));
+}
+
 // gathered[r][t][width] (rank r's slice in its first count_r columns) -> pooled[t][P], permutations in global order
 __global__ void k_pool_null(const float* __restrict__ gathered, int32_t T, int32_t P, int32_t width, int32_t nranks,
                             float* __restrict__ pooled) {

@@ -109,6 +109,7 @@ struct pctsea_ctx {
     int opt_null_threads = 0;        // threads (segments) per permutation of the fused null kernel (0 = as many as fit)
     int opt_null_ctas_per_sm = 0;    // resident CTAs per SM of the fused null kernel (0 = as many as fit)
     int opt_null_min_threads = 0;    // below this many threads per permutation the cell types are sliced (0 = 192)
+    int opt_shard_score = 1;         // multi-GPU analysis: stage 1 sharded over the ranks (0: every rank scores all cells)
     int opt_debug_gaps = 0;          // print a line to stderr when the stream sat idle between stages
     cudaStream_t stream = nullptr;
     std::string err;
@@ -121,6 +122,7 @@ struct pctsea_ctx {
     bool ev_rec[pctsea::EV_COUNT];
     pctsea_timings tm;
     int64_t launches = 0;
+    bool nvtx_open = false;   // an NVTX stage range is open on the calling thread
 
     // workspaces (grow-only)
     pctsea::DevBuf list_gene, list_abund, ybg, bitmap, list_rank, score_sums;  // stage 1 lookup + per-cell centred sums
@@ -149,6 +151,9 @@ struct pctsea_ctx {
     int32_t comm_nranks = 1, comm_rank = 0;
     pctsea::DevBuf null_gather;                                 // [nranks][T][width] all-gathered null slices (x2 with dStat)
     pctsea::DevBuf null_pool, null_pool_d;                      // [T][P] complete null in global permutation order
+    bool shard_score = false;                                   // set for the duration of a multi-GPU pctsea_analyze: stage 1
+                                                                // (gene-major kernel) scores every nranks-th tile + all-gather
+    pctsea::DevBuf score_pack;                                  // [nranks][tiles per rank][256] {score, nused, kept} in tile order
     int32_t last_pool_P = 0;                                    // P of the resident pooled null, 0 = none
     bool last_pool_dstat = false;
     int64_t last_obs_Nu = -1;   // n_used of the resident observed accumulator history (obs_chain), -1 = none
@@ -271,6 +276,7 @@ void comm_destroy(pctsea_ctx* c);
 void comm_share(int64_t n, int32_t nranks, int32_t rank, int64_t* begin, int64_t* count);
 // all-gather of c->null_ews (and c->null_d) [T][width] over the ranks, reordered into c->null_pool[_d] [T][P]
 void comm_pool_null(pctsea_ctx* c, int32_t T, int32_t P, int32_t width, bool with_dstat);
+void comm_all_gather_in_place(pctsea_ctx* c, void* buf, size_t bytes_per_rank);
 
 inline void count_launch(pctsea_ctx* c, int n = 1) { c->launches += n; }
 

@@ -26,14 +26,15 @@ __device__ __forceinline__ uint32_t java_orderable_f32(float f) {
 
 // a10 / a11 in three small kernels.
 //   k_red_counts     one warp per type: the four counts of a10 / a11 by ballots over coalesced 32-value chunks
-//   k_red_transpose  null [T][P] -> nullT [P][Tpad] (32 x 32 tiles through shared memory)
+//   k_red_transpose  null [T][P] -> nullT [T / 32][P][32] (32 x 32 tiles through shared memory)
 //   k_red_chain      one THREAD per type: the fp32 / fp64 running sums of a11. They must keep the permutation order
-//                    (the Maths.mean policy), so each is a dependent chain of P additions whatever the layout. On
-//                    the transposed copy lane = type reads one coalesced 128-byte line per permutation, the loads
-//                    are independent of the chain (16 in flight), and nothing stands between two additions but the
-//                    add itself. (A warp-per-type version that broadcast each value by shuffle spent 49 cycles per
-//                    value: 202 us at P = 8000, 87 % of the whole reduction; a thread-per-type walk over the
-//                    untransposed rows waits one L2 round trip per 8 values: 0.6 ms.)
+//                    (the Maths.mean policy), so each is a dependent chain of P additions whatever the layout. In
+//                    the transposed copy the 32 types of a warp form one contiguous stream, which lane 0 brings into
+//                    a shared-memory ring with bulk asynchronous copies (TMA, completion on mbarriers): nothing
+//                    stands between two additions but a conflict-free shared-memory read and the add itself. (A
+//                    warp-per-type version that broadcast each value by shuffle spent 49 cycles per value: 202 us
+//                    at P = 8000, 87 % of the whole reduction; thread-per-type walks with plain global loads wait one
+//                    L2 round trip per batch of loads in flight: 0.55 - 0.6 ms.)
 struct RedCounts { int32_t total, cnt, npos, nneg; };
 
 __global__ void __launch_bounds__(32) k_red_counts(const float* __restrict__ null_ews, int32_t T, int32_t P,
@@ -59,7 +60,9 @@ __global__ void __launch_bounds__(32) k_red_counts(const float* __restrict__ nul
     if (lane == 0) counts[t] = RedCounts{ total, cnt, npos, nneg };
 }
 
-__global__ void __launch_bounds__(256) k_red_transpose(const float* __restrict__ in, int32_t T, int32_t P, int32_t Tpad,
+// null [T][P] -> nullT [T / 32][P][32]: the 32 types of one chain warp are one contiguous stream of 128-byte lines
+// (padding types and nothing else hold NaN), 32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) k_red_transpose(const float* __restrict__ in, int32_t T, int32_t P,
                                                        float* __restrict__ out) {
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -71,38 +74,94 @@ __global__ void __launch_bounds__(256) k_red_transpose(const float* __restrict__
         tile[r][tx] = (t < T && p < P) ? in[(size_t)t * P + p] : fnan;
     }
     __syncthreads();
+    float* dst = out + (size_t)blockIdx.y * P * 32;
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
-        const int p = p0 + r, t = t0 + tx;
-        if (p < P && t < Tpad) out[(size_t)p * Tpad + t] = tile[tx][r];
+        const int p = p0 + r;
+        if (p < P) dst[(size_t)p * 32 + tx] = tile[tx][r];
     }
 }
 
-__global__ void __launch_bounds__(32) k_red_chain(const float* __restrict__ nullT, int32_t T, int32_t P, int32_t Tpad,
+// ---- bulk asynchronous copies (TMA, 1-D) into a shared-memory ring, completion through mbarriers ----------------
+__device__ __forceinline__ void mbar_init(uint32_t bar_saddr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_saddr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_saddr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(bar_saddr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar_saddr) : "memory");
+}
+
+constexpr int RC_STAGE_PERMS = 128;                       // permutations per ring stage: 128 x 128 B = 16 KB
+constexpr int RC_STAGES = 6;                              // 96 KB in flight per chain warp (dynamic shared memory)
+
+// One warp per 32 types, lane = type. The warp's stream nullT[tb][P][32] is contiguous, so lane 0 keeps RC_STAGES bulk
+// copies of 16 KB in flight (cp.async.bulk + mbarrier complete_tx) and every lane walks its own column of the stage
+// that has landed: conflict-free shared-memory reads, no global-load latency anywhere near the dependent adds.
+__global__ void __launch_bounds__(32) k_red_chain(const float* __restrict__ nullT, int32_t T, int32_t P,
                                                   int mean_policy, const RedCounts* __restrict__ counts,
                                                   pctsea_type_result* __restrict__ res, float* __restrict__ expct_out) {
-    const int t = blockIdx.x * 32 + threadIdx.x;   // t < Tpad: padding lanes walk NaN columns and write nothing
-    const float* col = nullT + t;
+    extern __shared__ __align__(128) float ring_dyn[];   // [RC_STAGES][RC_STAGE_PERMS * 32]
+    float (*ring)[RC_STAGE_PERMS * 32] = reinterpret_cast<float (*)[RC_STAGE_PERMS * 32]>(ring_dyn);
+    __shared__ __align__(8) unsigned long long bars[RC_STAGES];
+    const int lane = threadIdx.x;
+    const int t = blockIdx.x * 32 + lane;
+    const float* src = nullT + (size_t)blockIdx.x * P * 32;
+    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(&ring[0][0]);
+    const uint32_t bar_saddr = (uint32_t)__cvta_generic_to_shared(&bars[0]);
+    const int n_stage = (P + RC_STAGE_PERMS - 1) / RC_STAGE_PERMS;
+    auto stage_perms = [&](int k) { return min(RC_STAGE_PERMS, P - k * RC_STAGE_PERMS); };
+    if (lane == 0) {
+        for (int k = 0; k < RC_STAGES; k++) mbar_init(bar_saddr + 8u * k, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int k = 0; k < RC_STAGES && k < n_stage; k++) {
+            const uint32_t bytes = (uint32_t)stage_perms(k) * 128u;
+            mbar_expect_tx(bar_saddr + 8u * k, bytes);
+            bulk_g2s(ring_saddr + (uint32_t)k * RC_STAGE_PERMS * 128u, src + (size_t)k * RC_STAGE_PERMS * 32, bytes, bar_saddr + 8u * k);
+        }
+    }
     float fsum_pos = 0.0f, fsum_neg = 0.0f;
     double dsum_pos = 0.0, dsum_neg = 0.0;
-    constexpr int U = 16;
-    float v[U];
-#pragma unroll
-    for (int j = 0; j < U; j++) v[j] = (j < P) ? col[(size_t)j * Tpad] : __int_as_float(0x7fc00000);
-    for (int32_t p0 = 0; p0 < P; p0 += U) {
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const float vj = v[j];   // NaNs (real ones and the padding) fail both tests
-            const int32_t pn = p0 + U + j;
-            v[j] = (pn < P) ? col[(size_t)pn * Tpad] : __int_as_float(0x7fc00000);
-            if (mean_policy) {
+    for (int k = 0; k < n_stage; k++) {
+        const int slot = k % RC_STAGES;
+        mbar_wait(bar_saddr + 8u * slot, (uint32_t)((k / RC_STAGES) & 1));
+        const float* col = &ring[slot][lane];
+        const int np = stage_perms(k);
+        if (mean_policy) {
+            for (int j = 0; j < np; j++) {
+                const float vj = col[j * 32];   // NaNs (real ones and the padding types) fail both tests
                 if (vj >= 0.0f) dsum_pos = __dadd_rn(dsum_pos, (double)vj);
                 else if (vj < 0.0f) dsum_neg = __dadd_rn(dsum_neg, (double)vj);
-            } else {
+            }
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < np; j++) {
+                const float vj = col[j * 32];
                 // adding -0.0f leaves any fp32 accumulator bit-unchanged (also a -0.0f one): branch-free chains
                 fsum_pos = __fadd_rn(fsum_pos, (vj >= 0.0f) ? vj : -0.0f);
                 fsum_neg = __fadd_rn(fsum_neg, (vj < 0.0f) ? vj : -0.0f);
             }
+        }
+        __syncwarp();   // every lane is done with the slot before it is refilled
+        if (lane == 0 && k + RC_STAGES < n_stage) {
+            const int kn = k + RC_STAGES;
+            const uint32_t bytes = (uint32_t)stage_perms(kn) * 128u;
+            mbar_expect_tx(bar_saddr + 8u * slot, bytes);
+            bulk_g2s(ring_saddr + (uint32_t)slot * RC_STAGE_PERMS * 128u, src + (size_t)kn * RC_STAGE_PERMS * 32, bytes, bar_saddr + 8u * slot);
         }
     }
     if (t >= T) return;
@@ -270,11 +329,11 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
     if (T == 0) return;
     const int64_t n = (int64_t)T * P;
     if (n > 0x7fffffffll) throw Error(PCTSEA_EINVAL, "pooled null larger than a Java int");
-    // [T] expected values | [T] sorted observed keys | nobs | [2T + 2] bins | [T] counts | [P][Tpad] transposed null
+    // [T] expected values | [T] sorted observed keys | nobs | [2T + 2] bins | [T] counts | [Tpad / 32][P][32] transposed null
     const int32_t Tpad = (int32_t)round_up(T, 32);
     const size_t off_r = (size_t)round_up((int64_t)T * 4, 16), off_n = off_r + (size_t)round_up((int64_t)T * 4, 16),
                  off_b = off_n + 16, off_c = (size_t)round_up((int64_t)(off_b + ((size_t)2 * T + 2) * 4), 16),
-                 off_t = off_c + (size_t)T * sizeof(RedCounts), total = off_t + (size_t)std::max(P, 1) * Tpad * 4;
+                 off_t = (size_t)round_up((int64_t)(off_c + (size_t)T * sizeof(RedCounts)), 128), total = off_t + (size_t)std::max(P, 1) * Tpad * 4;
     c->red_misc.reserve(total + 64);
     unsigned char* base = c->red_misc.as<unsigned char>();
     float* expct = reinterpret_cast<float*>(base);
@@ -287,9 +346,11 @@ void launch_reduce(pctsea_ctx* c, int32_t T, int32_t P, const float* null_dev, i
     k_red_counts<<<(unsigned)T, 32, 0, c->stream>>>(null_dev, T, P, results_dev, counts);
     if (P > 0) {
         dim3 tg((unsigned)div_up(P, 32), (unsigned)(Tpad / 32));
-        k_red_transpose<<<tg, 256, 0, c->stream>>>(null_dev, T, P, Tpad, nullT);
+        k_red_transpose<<<tg, 256, 0, c->stream>>>(null_dev, T, P, nullT);
     }
-    k_red_chain<<<(unsigned)(Tpad / 32), 32, 0, c->stream>>>(nullT, T, P, Tpad, mean_policy, counts, results_dev, expct);
+    const size_t ring_bytes = (size_t)RC_STAGES * RC_STAGE_PERMS * 128;
+    ensure_dyn_smem(c, k_red_chain, ring_bytes);
+    k_red_chain<<<(unsigned)(Tpad / 32), 32, ring_bytes, c->stream>>>(nullT, T, P, mean_policy, counts, results_dev, expct);
     count_launch(c, P > 0 ? 2 : 1);
     k_red_rank<<<1, 1024, 0, c->stream>>>(T, results_dev, Rsorted, nobs, bins);
     if (n > 0) {

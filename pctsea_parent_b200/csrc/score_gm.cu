@@ -172,6 +172,8 @@ struct GmArgs {
     int32_t* nused;
     int32_t* nnzc;
     uint8_t* kept;
+    int64_t tile_begin, tile_stride;   // CTA b scores tile tile_begin + b * tile_stride (a tile = the 8 groups of one CTA):
+                                       // all tiles on one GPU; rank, rank + nranks, ... when stage 1 is sharded
     int2* fix_list;   // slots whose pairs have zero variance (jitter mode PHILOX): {slot, bit 0 = list vector constant, bit 1 = cell vector constant}
     int* fix_count;
 };
@@ -237,7 +239,7 @@ __device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
 template <bool ALL_POSITIVE, int U>
 __global__ void __launch_bounds__(256, 4) k_score_gm(const GmArgs a) {
     const int lane = threadIdx.x & 31;
-    const int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t grp = (a.tile_begin + (int64_t)blockIdx.x * a.tile_stride) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (grp >= a.n_groups) return;
     const int64_t cell = a.slot_cell[grp * 32 + lane];
     const float* gv = a.gval + a.grp_base[grp];
@@ -375,6 +377,41 @@ __global__ void __launch_bounds__(256) k_score_gm_jitter(const GmArgs a) {
     }
 }
 
+// ---- stage 1 sharded over the ranks of a communicator (multi-GPU pctsea_analyze) --------------------------------
+// Rank r scores the tiles r, r + R, ... (interleaved: the tiles are ordered by cell type and row length, so any
+// contiguous range would be a biased sample of the work). Its results travel in tile order: pack[(r * tpr + j) * 256 + s]
+// is slot s of tile j * R + r; one in-place all-gather; every rank scatters all records back to cell order.
+struct __align__(16) ScoreRec { double score; int32_t nused; int32_t kept; };
+
+__global__ void k_score_pack(const double* __restrict__ score, const int32_t* __restrict__ nused, const uint8_t* __restrict__ kept,
+                             const int32_t* __restrict__ slot_cell, int64_t n_slots, int64_t tiles_per_rank, int32_t R, int32_t r,
+                             ScoreRec* __restrict__ pack) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (j, s)
+    if (id >= tiles_per_rank * 256) return;
+    const int64_t j = id >> 8, s = id & 255, slot = (j * R + r) * 256 + s;
+    ScoreRec rec;
+    rec.score = __longlong_as_double(0x7ff8000000000000LL); rec.nused = 0; rec.kept = -1;   // kept -1: no cell here
+    if (slot < n_slots) {
+        const int32_t cell = slot_cell[slot];
+        if (cell >= 0) { rec.score = score[cell]; rec.nused = nused[cell]; rec.kept = kept[cell]; }
+    }
+    pack[(int64_t)r * tiles_per_rank * 256 + id] = rec;
+}
+
+__global__ void k_score_unpack(const ScoreRec* __restrict__ pack, const int32_t* __restrict__ slot_cell, int64_t n_slots,
+                               int64_t tiles_per_rank, int32_t R, double* __restrict__ score, int32_t* __restrict__ nused,
+                               uint8_t* __restrict__ kept) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (rr, j, s)
+    if (id >= (int64_t)R * tiles_per_rank * 256) return;
+    const int64_t per = tiles_per_rank * 256, rr = id / per, rem = id - rr * per, j = rem >> 8, s = rem & 255;
+    const int64_t slot = (j * R + rr) * 256 + s;
+    if (slot >= n_slots) return;
+    const int32_t cell = slot_cell[slot];
+    if (cell < 0) return;
+    const ScoreRec rec = pack[id];
+    score[cell] = rec.score; nused[cell] = rec.nused; kept[cell] = (uint8_t)rec.kept;
+}
+
 }  // namespace
 
 // Which cells share a group is free (cells are independent), and it matters: a chunk of the list costs a group as
@@ -485,10 +522,16 @@ void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
     a.sums = c->score_sums.as<double>(); a.nused = c->nused.as<int32_t>(); a.nnzc = c->nnzc.as<int32_t>();
     a.kept = c->kept.as<uint8_t>();
     a.fix_list = c->gm_fix.as<int2>() + 8; a.fix_count = counters + 1;
-    const unsigned grid = (unsigned)div_up(m->n_groups, 8);
+    // multi-GPU analysis: this rank scores every R-th tile, the results are all-gathered below
+    const int32_t R = c->shard_score ? c->comm_nranks : 1, r = c->shard_score ? c->comm_rank : 0;
+    const int64_t n_tiles = div_up(m->n_groups, 8);
+    a.tile_begin = r; a.tile_stride = R;
+    const unsigned grid = (unsigned)std::max<int64_t>((n_tiles - r + R - 1) / R, 0);
+    // (a rank can be left without tiles when the matrix has fewer tiles than the communicator has ranks)
     int unroll = 8;
     if (c->opt_gm_unroll > 0) unroll = c->opt_gm_unroll;   // PCTSEA_OPT_GM_UNROLL (tuning aid)
-    if (m->all_positive) {
+    if (grid == 0) {
+    } else if (m->all_positive) {
         if (unroll >= 8) k_score_gm<true, 8><<<grid, 256, 0, c->stream>>>(a);
         else if (unroll >= 4) k_score_gm<true, 4><<<grid, 256, 0, c->stream>>>(a);
         else if (unroll <= 1) k_score_gm<true, 1><<<grid, 256, 0, c->stream>>>(a);
@@ -501,7 +544,21 @@ void launch_score_gm(pctsea_ctx* c, const ScoreArgs& sa) {
         count_launch(c);
         PCT_CUDA(cudaGetLastError());
     }
-    launch_score_final(c, sa);
+    launch_score_final(c, sa);   // over all cells: the scores of the tiles of other ranks are overwritten below
+    if (R > 1) {
+        const int64_t tpr = div_up(n_tiles, R), n_slots = m->n_groups * 32;
+        const size_t rank_bytes = (size_t)tpr * 256 * sizeof(ScoreRec);
+        c->score_pack.reserve(rank_bytes * R + 64);
+        ScoreRec* pack = c->score_pack.as<ScoreRec>();
+        k_score_pack<<<(unsigned)div_up(tpr * 256, 256), 256, 0, c->stream>>>(c->score.as<double>(), c->nused.as<int32_t>(),
+                                                                             c->kept.as<uint8_t>(), m->gm_slot_cell, n_slots, tpr, R, r, pack);
+        comm_all_gather_in_place(c, pack, rank_bytes);
+        k_score_unpack<<<(unsigned)div_up((int64_t)R * tpr * 256, 256), 256, 0, c->stream>>>(pack, m->gm_slot_cell, n_slots, tpr, R,
+                                                                                            c->score.as<double>(), c->nused.as<int32_t>(),
+                                                                                            c->kept.as<uint8_t>());
+        count_launch(c, 2);
+        PCT_CUDA(cudaGetLastError());
+    }
 }
 
 }  // namespace pctsea

@@ -1167,3 +1167,72 @@ def test_baseline_config_D_shape_full_size_vs_oracle(ctx, oracle):
                             min_score=cfg.min_score, canonical=2, seed=4, perm_indices=(0, 31, cfg.n_perm - 1),
                             what="config D shape")
     assert rep["n_used"] >= 1_000_000
+
+
+def test_philox_null_matches_jdk_shuffle_null_at_config_B_size(ctx, oracle):
+    """north_star: 'in the Philox mode [nulls] must be within a stated statistical tolerance (KS test on the null
+    distributions)'. At config B's size (219 530 ranked cells, 100 cell types), 2000 permutations each, all on the GPU:
+        A  REPLAY of java.util.Collections.shuffle index arrays (the reference's permutation source) + EXACT arithmetic
+        B  PHILOX (keyed Feistel on the type-sorted arrangement)                                    + EXACT arithmetic
+        C  PHILOX                                                                                    + FAST arithmetic
+    Stated tolerance, per cell type with Bonferroni over the types: two-sample KS statistic below the alpha = 0.001
+    critical value; the 99th and 99.9th percentiles of |ES| of B and C inside the 4.5-sigma binomial rank interval of
+    A's order statistics (p-values and FDR live in that tail); and the empirical p-value of the observed score from
+    B / C within 4 * sqrt(2 p (1 - p) / P) + 1 / P of the one from A."""
+    n_used, T, Pn = 219_530, 100, 2000
+    s, lab, order = _ranked(n_used, T, seed=5)
+    rng_seed = 424242
+    replay = np.empty((Pn, n_used), np.int32)
+    ident = np.arange(n_used, dtype=np.int32)
+    jr = oracle.JRandom(rng_seed)          # one Random for all permutations, as PCTSEA.java:1398-1405
+    for p in range(Pn):
+        replay[p] = jr.shuffle(ident)
+    prmA = ctx.null_params(Pn, perm_mode=P.PERM_REPLAY, ks_mode=P.KS_EXACT)
+    resA, nullA, _ = ctx.enrich(s, order, lab, T, prmA, replay=replay)
+    del replay
+    prmB = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=99)
+    resB, nullB, _ = ctx.enrich(s, order, lab, T, prmB)
+    prmC = ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=99)
+    resC, nullC, _ = ctx.enrich(s, order, lab, T, prmC)
+    # spot check of A against the oracle's own walk of the same shuffled labels (first and last permutation)
+    jr = oracle.JRandom(rng_seed)
+    first = jr.shuffle(ident)
+    assert_bits_equal_f32(nullA[:, 0], oracle.ks_null_one(s, lab[first], T)[0], "REPLAY null, permutation 0")
+
+    alpha = 0.001 / T
+    d_crit = np.sqrt(-np.log(alpha / 2.0) / 2.0) * np.sqrt(2.0 / Pn)
+    z = 4.5
+
+    def rank_interval(q):
+        k = Pn * (1.0 - q)                                  # expected number of values above the quantile
+        sd = np.sqrt(Pn * q * (1.0 - q))
+        lo = int(np.clip(np.floor(Pn - k - z * sd), 0, Pn - 1))
+        hi = int(np.clip(np.ceil(Pn - k + z * sd), 0, Pn - 1))
+        return lo, hi
+
+    worst = {"ks": 0.0, "dp": 0.0}
+    for t in range(T):
+        a = np.sort(nullA[t][~np.isnan(nullA[t])])
+        if a.size < Pn:
+            continue
+        for name, other in (("PHILOX+EXACT", nullB[t]), ("PHILOX+FAST", nullC[t])):
+            b = np.sort(other)
+            allv = np.concatenate([a, b])
+            d = np.max(np.abs(np.searchsorted(a, allv, side="right") / a.size - np.searchsorted(b, allv, side="right") / b.size))
+            worst["ks"] = max(worst["ks"], d)
+            assert d < d_crit, f"type {t} {name}: two-sample KS {d:.4f} >= {d_crit:.4f}"
+            aa, bb = np.sort(np.abs(a)), np.sort(np.abs(b))
+            for q in (0.99, 0.999):
+                lo, hi = rank_interval(q)
+                v = bb[int(np.ceil(q * Pn)) - 1]
+                assert aa[lo] <= v <= aa[hi], f"type {t} {name}: {q} quantile of |ES| {v} outside [{aa[lo]}, {aa[hi]}]"
+            # empirical p of the observed score (a10: positive side, strict comparisons)
+            real = resA["ews"][t]
+            if real == real and real >= 0:
+                pa = np.count_nonzero(a > real) / max(np.count_nonzero(a > 0), 1)
+                pb = np.count_nonzero(b > real) / max(np.count_nonzero(b > 0), 1)
+                pm = 0.5 * (pa + pb)
+                worst["dp"] = max(worst["dp"], abs(pa - pb))
+                assert abs(pa - pb) <= 4.0 * np.sqrt(2.0 * pm * (1.0 - pm) / Pn) + 1.0 / Pn, f"type {t} {name}: p_emp {pa} vs {pb}"
+    assert_results_equal(resA, resB, OBSERVED_FIELDS, "observed fields do not depend on the permutation source")
+    print(f"worst two-sample KS {worst['ks']:.4f} (critical {d_crit:.4f}), worst |dp| {worst['dp']:.4f}")

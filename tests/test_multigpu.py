@@ -22,7 +22,8 @@ def _analysis(ctx, d, cfg, n_perm, ks_mode, **kw):
     m.build_gene_index()
     sprm = P.ScoreParams(0, cfg.min_genes_cells, cfg.min_corr, 1, P.JITTER_PHILOX, 1)
     nprm = ctx.null_params(n_perm, perm_mode=P.PERM_PHILOX, ks_mode=ks_mode, seed=9, min_pass=100, **kw)
-    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm, want_null=True)
+    out = ctx.analyze(m, d["gene_idx"], d["abundance"], sprm, cfg.min_score, cfg.n_types, nprm, want_null=True,
+                      want_scores=True, want_order=True)
     tm = ctx.timings()
     m.free()
     return out, tm
@@ -67,7 +68,8 @@ def _rank_main(rank, world, uid_q, res_q, n_perm):
         uid = uid_q.get(timeout=120)
     ctx.comm_init_rank(world, rank, uid)
     out, tm = _analysis(ctx, d, cfg, n_perm, PP.KS_FAST)
-    res_q.put((rank, out["null"], out["nullD"], out["results"], tm["gather_ms"]))
+    res_q.put((rank, out["null"], out["nullD"], out["results"], tm["gather_ms"], out["score"], out["n_genes_used"], out["kept"],
+               out["order"]))
     ctx.close()
 
 
@@ -87,8 +89,11 @@ def test_two_rank_analysis_equals_single_gpu(ctx, small, n_perm):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, null, nullD, res, gather_ms in got:
+    for rank, null, nullD, res, gather_ms, score, used, kept, order in got:
         assert gather_ms > 0.0
+        # stage 1 was sharded over the two ranks (every second tile of 256 cells each) and all-gathered
+        assert np.array_equal(score.view(np.uint64), ref["score"].view(np.uint64)), f"rank {rank}: scores"
+        assert np.array_equal(used, ref["n_genes_used"]) and np.array_equal(kept, ref["kept"]) and np.array_equal(order, ref["order"])
         assert_bits_equal_f32(null, ref["null"], f"rank {rank}: pooled null")
         assert_bits_equal_f32(nullD, ref["nullD"], f"rank {rank}: pooled null dStat")
         assert_results_equal(res, ref["results"], None, f"rank {rank}")
