@@ -32,9 +32,9 @@ ALGO_BYTES_PER_UNIT = 10.0  # 8 B fp64 score + 2 B label per (
 
 def profiled_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full
-    capture of this same command (profiles/r1_traffic.json); None if that kernel was not captured."""
+    capture of this same command (profiles/r2_traffic.json); None if that kernel was not captured."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["kernels"]
         return float(d[kernel]["dram_bytes"]) if kernel in d else None
     except Exception:
         return None
@@ -238,6 +238,23 @@ def run_ours(args):
                   "ms_device": s_dev,
                   "stage_ms": {k: float(tm_s[k]) for k in ("score_ms", "rank_ms", "observed_ms", "null_ms", "gather_ms", "reduce_ms")}}
 
+    # ---- the dominant kernel alone: in the timed steps the observed-statistics kernels run beside the null kernel on a
+    # second stream (that is what makes the step short), so the CUDA events around the null launch also span their
+    # interference. For the roofline the same steps are repeated with the observed kernels kept on the main stream
+    # (PCTSEA_OPT_OBS_OVERLAP = 0): the events then bracket k_null_fused and nothing else.
+    iso_null_ms, iso_total_ms = [], []
+    ctx.set_option(P.OPT_OBS_OVERLAP, 0)
+    try:
+        for i in range(3 + min(args.steps, 10)):
+            flush.zero_()
+            _, tm_i = step()
+            if i >= 3:
+                iso_null_ms.append(tm_i["null_ms"])
+                iso_total_ms.append(tm_i["total_ms"] - tm_i["setup_ms"])
+    finally:
+        ctx.set_option(P.OPT_OBS_OVERLAP, 2)
+    barrier()
+
     parity = None if args.no_parity else parity_gate(ctx, m, ds, cfg, sprm, nprm, gene_idx, abundance, args, rank, world,
                                                      P_per_gpu, P_total)
 
@@ -256,17 +273,14 @@ def run_ours(args):
         mean = lambda k: float(np.mean([t[k] for t in tms]))
         lab_ms, null_ms = mean("labels_ms"), mean("null_ms")
         ks_name = "k_null_fused" if ks_mode == P.KS_FAST else "k_ks_exact"
-        # the kernel with the largest share of a step in the committed launch list (profiles/r1_launches.txt) is the
-        # null KS kernel; the label kernel's span inside a step also contains the observed-statistics kernels that
-        # run beside it on the second stream, so its span is reported (labels_kernel_ms) but is not a kernel time
-        dom_name, dom_ms = ks_name, null_ms
+        # the kernel with the largest share of a step (profiles/r2_launches.txt): the fused null kernel, which generates
+        # the permuted labels and evaluates them (the label kernel and the KS kernel of round 1 in one)
+        kernel_ms = float(np.mean(iso_null_ms)) + (0.0 if ks_mode == P.KS_FAST else lab_ms)
         units_gpu = float(nu) * float(P_per_gpu)
-        ach = ALGO_BYTES_PER_UNIT * units_gpu / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        overl_ms = lab_ms + null_ms
-        stage_ach = ALGO_BYTES_PER_UNIT * units_gpu / (overl_ms * 1e-3) / 1e9 if overl_ms > 0 else 0.0
+        ach = ALGO_BYTES_PER_UNIT * units_gpu / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
         nnz = ds.nnz
-        score_bytes = 8.0 * nnz + 16.0 * cfg.n_cells + 17.0 * cfg.n_cells + 8.0 * cfg.list_len
         score_ms = mean("score_ms")
+        score_dram = profiled_traffic("k_score_gm" if args.gene_index else "k_score") if cfg.name == "B" else None
         line = {
             "metric": "cells x permutations KS-scored per second", "value": units / (dev_ms * 1e-3),
             "unit": "cell-permutations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -275,7 +289,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_string(cfg, P_per_gpu, P_total),
                        "nnz": nnz, "Np": int(tms[-1]["n_pass"]), "Nu": int(nu), "n_perm_total": P_total,
-                       "perm_mode": "PHILOX", "ks_mode": args.ks.upper(), "parallelism": f"perm-shard x{world}",
+                       "perm_mode": "PHILOX", "ks_mode": args.ks.upper(), "parallelism": f"perm-shard x{world}" + (" + stage-1 cell-shard" if world > 1 and args.gene_index else ""),
                        "score_path": "gene-major index" if args.gene_index else "csr-scan",
                        "l2": "256 MiB flush between timed steps; CSR inputs (>= 6 GB) exceed the 126 MB L2"},
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "cell-permutations/s",
@@ -283,24 +297,28 @@ def run_ours(args):
                     "analysis_seconds": e2e_ms * 1e-3},
             "gpu_launches": int(sum(t["launches"] for t in tms)),
             "stage_ms": {k: mean(k) for k in ("setup_ms", "score_ms", "rank_ms", "observed_ms", "labels_ms", "null_ms", "gather_ms", "reduce_ms", "total_ms")},
-            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": profiled_traffic(dom_name) if cfg.name == "B" and P_per_gpu == 1000 else None,
-                         "traffic_note": "DRAM bytes of one launch from profiles/r1_top_kernels.txt (ncu --set full, config B); the "
-                                         "kernel's inputs (ranked scores, labels of the resident permutations) are L2-resident by "
-                                         "design, so DRAM traffic is far below the notional 10 B/unit stream",
+            "roofline": {"bound": "hbm", "kernel": ks_name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak,
+                         "traffic": profiled_traffic(ks_name) if cfg.name == "B" and P_per_gpu == 1000 else None,
+                         "traffic_note": "DRAM bytes of one launch (ncu --set full, config B, profiles/r2_traffic.json): the kernel's "
+                                         "inputs (fixed-point scores in lane layout, class tables) and its per-CTA label scratch "
+                                         "are L2-resident by design, so DRAM traffic is far below the notional 10 B/unit stream; "
+                                         "the kernel is bound by instruction issue (ALU pipe), not by HBM",
                          "algorithmic_bytes": ALGO_BYTES_PER_UNIT * units_gpu, "peak_source": peak_src,
-                         "kernel_ms": dom_ms, "labels_kernel_ms": lab_ms, "ks_kernel_ms": null_ms,
-                         "null_stage_ms": overl_ms,
-                         "null_stage_achieved": stage_ach, "null_stage_frac": stage_ach / peak,
-                         "score_path": "gene-major index (k_score_gm): reads the list's genes only" if args.gene_index
-                                       else "CSR scan (k_score)",
-                         "score_stage_ms": score_ms,
-                         "score_kernel_achieved": score_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else None,
-                         "score_kernel_frac": score_bytes / (score_ms * 1e-3) / 1e9 / peak if score_ms > 0 else None,
-                         "score_note": "achieved/frac are SURVEY 8(d)'s algorithmic bytes of stage 1 (8 B x nnz + 33 B x N: the "
-                                       "whole CSR once) over the stage time; the gene-major kernel does not read the CSR "
-                                       "(its own DRAM traffic is in profiles/), so its figure is an equivalent rate, "
-                                       "comparable with the CSR scan's, not a bandwidth"},
+                         "kernel_ms": kernel_ms,
+                         "kernel_ms_note": "CUDA events around the kernel's launch on the library stream, observed-statistics "
+                                           "kernels kept off the GPU meanwhile (separate pass after the timed steps, same inputs)",
+                         "kernel_ms_in_step": null_ms + (0.0 if ks_mode == P.KS_FAST else lab_ms),
+                         "step_ms_without_overlap": float(np.mean(iso_total_ms)),
+                         "null_stage_frac": ach / peak,
+                         "score": {"kernel": "k_score_gm" if args.gene_index else "k_score", "stage_ms": score_ms,
+                                   "dram_bytes": score_dram,
+                                   "dram_gbs": score_dram / (score_ms * 1e-3) / 1e9 if score_dram and score_ms > 0 else None,
+                                   "dram_frac_of_peak": score_dram / (score_ms * 1e-3) / 1e9 / peak if score_dram and score_ms > 0 else None,
+                                   "csr_bytes_not_read": 8.0 * nnz,
+                                   "note": "the gene-major kernel reads the list's genes only (entries + short value runs: every "
+                                           "run costs at least a 32-byte sector), not the CSR; dram_bytes is the ncu measurement of "
+                                           "one launch (stage time here also covers the list lookup and the final-score kernels)"}},
             "clocks": clocks,
             "per_step_total_ms": [round(t["total_ms"], 3) for t in tms],
             "setup": {"generate_s": gen_s, "gene_index_s": index_s},

@@ -154,6 +154,8 @@ int         pctsea_get_timings(pctsea_ctx* ctx, pctsea_timings* out);
 #define PCTSEA_OPT_DEBUG_GAPS        9  /* 1: report idle gaps between the stages on stderr */
 #define PCTSEA_OPT_SHARD_SCORE      10  /* multi-GPU pctsea_analyze with the gene-major index: 1 (default) every rank scores
                                            1 / nranks of the cells and the scores are all-gathered; 0: every rank scores all */
+#define PCTSEA_OPT_OBS_CHAIN_MB     11  /* device memory for the observed accumulator history in MiB (0 = 1024): 8 bytes per
+                                           (ranked cell, type); the types go through it in slices when they do not fit */
 int         pctsea_ctx_set_option(pctsea_ctx* ctx, int32_t option, int64_t value);
 /* cudaStream_t the ctx launches on (so a caller can time or order against it). */
 void*       pctsea_stream(pctsea_ctx* ctx);

@@ -508,6 +508,7 @@ int pctsea_ctx_set_option(pctsea_ctx* c, int32_t option, int64_t value) {
         case PCTSEA_OPT_NULL_MIN_THREADS: if (v > 512) return bad("at most 512"); c->opt_null_min_threads = v; break;
         case PCTSEA_OPT_DEBUG_GAPS: if (v > 1) return bad("0 or 1"); c->opt_debug_gaps = v; break;
         case PCTSEA_OPT_SHARD_SCORE: if (v > 1) return bad("0 or 1"); c->opt_shard_score = v; break;
+        case PCTSEA_OPT_OBS_CHAIN_MB: c->opt_obs_chain_mb = v; break;
         default: return bad("unknown option");
     }
     return PCTSEA_OK;

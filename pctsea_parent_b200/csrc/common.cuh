@@ -109,6 +109,7 @@ struct pctsea_ctx {
     int opt_null_threads = 0;        // threads (segments) per permutation of the fused null kernel (0 = as many as fit)
     int opt_null_ctas_per_sm = 0;    // resident CTAs per SM of the fused null kernel (0 = as many as fit)
     int opt_null_min_threads = 0;    // below this many threads per permutation the cell types are sliced (0 = 192)
+    int opt_obs_chain_mb = 0;        // budget of the observed accumulator history in MiB (0 = 1024); more types than fit go in slices
     int opt_shard_score = 1;         // multi-GPU analysis: stage 1 sharded over the ranks (0: every rank scores all cells)
     int opt_debug_gaps = 0;          // print a line to stderr when the stream sat idle between stages
     cudaStream_t stream = nullptr;
@@ -156,6 +157,8 @@ struct pctsea_ctx {
     pctsea::DevBuf score_pack;                                  // [nranks][tiles per rank][256] {score, nused, kept} in tile order
     int32_t last_pool_P = 0;                                    // P of the resident pooled null, 0 = none
     bool last_pool_dstat = false;
+    int32_t obs_slice_t0 = 0, obs_slice_n = 0;   // cell types whose accumulator history is resident in obs_chain
+    int last_lab_bytes = 1;                      // label width of the resident ranked arrays
     int64_t last_obs_Nu = -1;   // n_used of the resident observed accumulator history (obs_chain), -1 = none
 };
 

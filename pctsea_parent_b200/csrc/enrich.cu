@@ -61,6 +61,7 @@ void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, co
     (void)N;
     g.Tc = g.T + 1;
     g.lab_bytes = (g.Tc <= 256) ? 1 : 2;
+    c->last_lab_bytes = g.lab_bytes;
     g.Nu_pad = round_up(std::max<int64_t>(g.Nu, 1), 128);
     c->s_rank.reserve((size_t)g.Nu_pad * 8 + 64);
     c->lab_rank.reserve((size_t)g.Nu_pad * g.lab_bytes + 64);
@@ -247,15 +248,15 @@ constexpr int OBS_STEP = OBS_THREADS * OBS_V;     // positions per block step
 
 template <typename LabT>
 __global__ void __launch_bounds__(OBS_THREADS) k_obs_chain(const double* __restrict__ s_rank, const LabT* __restrict__ lab,
-                                                           int64_t Nu, int32_t Tpad, float2* __restrict__ chainT,
+                                                           int64_t Nu, int32_t Tpad, int32_t t0, float2* __restrict__ chainT,
                                                            float* __restrict__ denom /*[2][Tpad]*/) {
     __shared__ uint32_t scratch[64];
     __shared__ float st_acc[2];   // accumulators A, B
     __shared__ int st_any[2];     // touched yet?
     __shared__ int st_first;
-    const int t = blockIdx.x;
+    const int t = t0 + blockIdx.x;   // the history buffer holds the types of one slice: row = t - t0
     const int tid = threadIdx.x;
-    float2* out = chainT + (size_t)t * Nu;
+    float2* out = chainT + (size_t)blockIdx.x * Nu;
     const float neg0 = __int_as_float((int)0x80000000);
     if (tid == 0) { st_acc[0] = 0.0f; st_acc[1] = 0.0f; st_any[0] = 0; st_any[1] = 0; }
     __syncthreads();
@@ -370,12 +371,12 @@ __device__ __forceinline__ float obs_diff(float2 v, float dA, float dB) {
 constexpr int OBS_TILE = 2048;  // positions per CTA (256 threads x 8)
 
 __global__ void __launch_bounds__(256) k_obs_sup(const float2* __restrict__ chainT, const float* __restrict__ denom,
-                                                 const int32_t* __restrict__ class_cnt, int64_t Nu, int32_t Tpad,
+                                                 const int32_t* __restrict__ class_cnt, int64_t Nu, int32_t Tpad, int32_t t0,
                                                  unsigned long long* __restrict__ supkey) {
     __shared__ unsigned long long wbest[8];
-    const int t = blockIdx.y;
+    const int t = t0 + blockIdx.y;
     const float dA = denom[t], dB = denom[Tpad + t];
-    const float2* row = chainT + (size_t)t * Nu;
+    const float2* row = chainT + (size_t)blockIdx.y * Nu;
     unsigned long long best = 0ull;
     const int64_t i_beg = (int64_t)blockIdx.x * OBS_TILE, i_end = min(i_beg + OBS_TILE, Nu);
     for (int64_t i = i_beg + threadIdx.x; i < i_end; i += 256) {
@@ -404,17 +405,17 @@ __global__ void __launch_bounds__(256) k_obs_sup(const float2* __restrict__ chai
 // :492-512) and, for the secondary supremum, lookForSecondaryEnrichmentIndex (:514-533): the largest
 // i < supX-1 with diff[i] > 0 and diff[i+1] < 0 (0 = none, also when the only such i is 0).
 __global__ void __launch_bounds__(256) k_obs_neg(const float2* __restrict__ chainT, const float* __restrict__ denom,
-                                                 int64_t Nu, int32_t Tpad, const unsigned long long* __restrict__ supkey,
+                                                 int64_t Nu, int32_t Tpad, int32_t t0, const unsigned long long* __restrict__ supkey,
                                                  unsigned int* __restrict__ lastneg /* index+1, 0 = none */,
                                                  unsigned int* __restrict__ secidx) {
-    const int t = blockIdx.y;
+    const int t = t0 + blockIdx.y;
     const unsigned long long key = supkey[t];
     if (key == 0ull) return;
     const int64_t supX = (int64_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) + 1;  // 1-based
     const int64_t i_beg = (int64_t)blockIdx.x * OBS_TILE, i_end = min(min(i_beg + OBS_TILE, Nu), supX);
     if (i_beg >= i_end) return;
     const float dA = denom[t], dB = denom[Tpad + t];
-    const float2* row = chainT + (size_t)t * Nu;
+    const float2* row = chainT + (size_t)blockIdx.y * Nu;
     unsigned int best = 0, bsec = 0;
     for (int64_t i = i_beg + threadIdx.x; i < i_end; i += 256) {
         const float d = obs_diff(row[i], dA, dB);
@@ -530,17 +531,17 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_ksd(const double* __restric
 // Second walk over [0, secidx]: with |score| numerators and the same denominators a' = +-a, b' = +-b (all
 // ranked scores share a sign), so the candidates are e = +-diff > 0; first position of the largest one.
 __global__ void __launch_bounds__(256) k_obs_sec_sup(const float2* __restrict__ chainT, const float* __restrict__ denom,
-                                                     const double* __restrict__ s_rank, int64_t Nu, int32_t Tpad,
+                                                     const double* __restrict__ s_rank, int64_t Nu, int32_t Tpad, int32_t t0,
                                                      const unsigned int* __restrict__ secidx,
                                                      unsigned long long* __restrict__ seckey) {
-    const int t = blockIdx.y;
+    const int t = t0 + blockIdx.y;
     const unsigned int sidx = secidx[t];
     if (sidx == 0u) return;
     const int64_t i_beg = (int64_t)blockIdx.x * OBS_TILE, i_end = min(min(i_beg + OBS_TILE, Nu), (int64_t)sidx + 1);
     if (i_beg >= i_end) return;
     const bool neg_mode = (s_rank[Nu - 1] < 0.0) && (s_rank[0] <= 0.0);
     const float dA = denom[t], dB = denom[Tpad + t];
-    const float2* row = chainT + (size_t)t * Nu;
+    const float2* row = chainT + (size_t)blockIdx.y * Nu;
     unsigned long long best = 0ull;
     for (int64_t i = i_beg + threadIdx.x; i < i_end; i += 256) {
         float e = obs_diff(row[i], dA, dB);
@@ -557,12 +558,12 @@ __global__ void __launch_bounds__(256) k_obs_sec_sup(const float2* __restrict__ 
 }
 
 __global__ void k_obs_finish(const float2* __restrict__ chainT, const float* __restrict__ denom,
-                             const int32_t* __restrict__ class_cnt, int64_t Nu, int32_t T, int32_t Tpad,
+                             const int32_t* __restrict__ class_cnt, int64_t Nu, int32_t T, int32_t Tpad, int32_t t0, int32_t t1,
                              const unsigned long long* __restrict__ supkey, const unsigned int* __restrict__ lastneg,
                              const unsigned long long* __restrict__ seckey,
                              const unsigned long long* __restrict__ ksd_sup, pctsea_type_result* __restrict__ results) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
+    const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;   // the types [t0, t1) of the resident history slice
+    if (t >= t1 || t >= T) return;
     const float qnan = __int_as_float(0x7fc00000);
     const double dnan = __longlong_as_double(0x7ff8000000000000LL);
     pctsea_type_result r;
@@ -576,7 +577,7 @@ __global__ void k_obs_finish(const float2* __restrict__ chainT, const float* __r
         return;
     }
     const float dA = denom[t], dB = denom[Tpad + t];
-    const float2* row = chainT + (size_t)t * Nu;
+    const float2* row = chainT + (size_t)(t - t0) * Nu;
     const unsigned long long key = supkey[t];
     float sup = 0.0f;
     int32_t supX = 0;
@@ -604,14 +605,29 @@ __global__ void k_obs_finish(const float2* __restrict__ chainT, const float* __r
     results[t] = r;
 }
 
+// The accumulator history is kept for a slice of the cell types at a time: as many types as fit obs_chain_budget bytes
+// (1 GiB unless PCTSEA_OPT_OBS_CHAIN_MB says otherwise). Config B's 100 types x 219 530 cells are 176 MB and go in one
+// slice; an atlas-scale ranking (2 M cells x 300 types = 4.8 GB) takes five.
+static int32_t obs_types_per_slice(const pctsea_ctx* c, const EnrichGeom& g) {
+    const size_t budget = c->opt_obs_chain_mb > 0 ? (size_t)c->opt_obs_chain_mb << 20 : (size_t)1 << 30;
+    const size_t per_type = (size_t)std::max<int64_t>(g.Nu, 1) * sizeof(float2);
+    return (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)std::max(g.T, 1), budget / per_type));
+}
+
 // Workspaces of the observed stage, reserved up front (before the null takes its memory budget).
 void reserve_ks_observed(pctsea_ctx* c, const EnrichGeom& g) {
     c->results.reserve((size_t)std::max(g.T, 1) * sizeof(pctsea_type_result) + 64);
     if (g.T == 0) return;
     const int32_t Tpad = (int32_t)round_up(g.T, 32);
-    c->obs_chain.reserve((size_t)g.Nu * g.T * sizeof(float2) + 64);
+    c->obs_chain.reserve((size_t)g.Nu * obs_types_per_slice(c, g) * sizeof(float2) + 64);
     c->obs_misc.reserve((size_t)Tpad * 40 + 64);
     c->obs_tiles.reserve((size_t)div_up(g.Nu, KSD_TILE) * g.Tc * 4 + 64);
+}
+
+template <typename LabT>
+static void launch_obs_chain_slice(pctsea_ctx* c, const EnrichGeom& g, int32_t Tpad, int32_t t0, int32_t nt, cudaStream_t st) {
+    k_obs_chain<LabT><<<nt, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<LabT>(), g.Nu, Tpad, t0,
+                                                 c->obs_chain.as<float2>(), c->obs_misc.as<float>());
 }
 
 void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st) {
@@ -638,28 +654,33 @@ void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st) {
     int32_t* tiles = c->obs_tiles.as<int32_t>();
     dim3 kgrid((unsigned)n_tiles, (unsigned)g.T);
     if (g.lab_bytes == 1) {
-        k_obs_chain<uint8_t><<<g.T, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint8_t>(), g.Nu,
-                                                                 Tpad, chain, denom);
         k_obs_tilecnt<uint8_t><<<n_tiles, OBS_THREADS, (size_t)g.Tc * 4, st>>>(c->lab_rank.as<uint8_t>(), g.Nu, g.Tc, tiles);
         k_obs_tilescan<<<(unsigned)div_up(g.Tc, 128), 128, 0, st>>>(tiles, n_tiles, g.Tc);
         k_obs_ksd<uint8_t><<<kgrid, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint8_t>(), g.Nu, g.Tc,
                                                                  cnt, tiles, ksd);
     } else {
-        k_obs_chain<uint16_t><<<g.T, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint16_t>(), g.Nu,
-                                                                  Tpad, chain, denom);
         ensure_dyn_smem(c, k_obs_tilecnt<uint16_t>, (size_t)(((size_t)g.Tc * 4)));
         k_obs_tilecnt<uint16_t><<<n_tiles, OBS_THREADS, (size_t)g.Tc * 4, st>>>(c->lab_rank.as<uint16_t>(), g.Nu, g.Tc, tiles);
         k_obs_tilescan<<<(unsigned)div_up(g.Tc, 128), 128, 0, st>>>(tiles, n_tiles, g.Tc);
         k_obs_ksd<uint16_t><<<kgrid, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint16_t>(), g.Nu, g.Tc,
                                                                   cnt, tiles, ksd);
     }
-    dim3 grid((unsigned)div_up(g.Nu, OBS_TILE), (unsigned)g.T);
-    k_obs_sup<<<grid, 256, 0, st>>>(chain, denom, cnt, g.Nu, Tpad, supkey);
-    k_obs_neg<<<grid, 256, 0, st>>>(chain, denom, g.Nu, Tpad, supkey, lastneg, secidx);
-    k_obs_sec_sup<<<grid, 256, 0, st>>>(chain, denom, c->s_rank.as<double>(), g.Nu, Tpad, secidx, seckey);
-    k_obs_finish<<<(unsigned)div_up(g.T, 128), 128, 0, st>>>(chain, denom, cnt, g.Nu, g.T, Tpad, supkey, lastneg,
-                                                                   seckey, ksd, c->results.as<pctsea_type_result>());
-    count_launch(c, 8);
+    count_launch(c, 3);
+    const int32_t Ts = obs_types_per_slice(c, g);
+    for (int32_t t0 = 0; t0 < g.T; t0 += Ts) {
+        const int32_t nt = std::min(Ts, g.T - t0);
+        if (g.lab_bytes == 1) launch_obs_chain_slice<uint8_t>(c, g, Tpad, t0, nt, st);
+        else launch_obs_chain_slice<uint16_t>(c, g, Tpad, t0, nt, st);
+        dim3 grid((unsigned)div_up(g.Nu, OBS_TILE), (unsigned)nt);
+        k_obs_sup<<<grid, 256, 0, st>>>(chain, denom, cnt, g.Nu, Tpad, t0, supkey);
+        k_obs_neg<<<grid, 256, 0, st>>>(chain, denom, g.Nu, Tpad, t0, supkey, lastneg, secidx);
+        k_obs_sec_sup<<<grid, 256, 0, st>>>(chain, denom, c->s_rank.as<double>(), g.Nu, Tpad, t0, secidx, seckey);
+        k_obs_finish<<<(unsigned)div_up(nt, 128), 128, 0, st>>>(chain, denom, cnt, g.Nu, g.T, Tpad, t0, t0 + nt, supkey, lastneg,
+                                                                seckey, ksd, c->results.as<pctsea_type_result>());
+        count_launch(c, 5);
+        c->obs_slice_t0 = t0;
+        c->obs_slice_n = nt;
+    }
     PCT_CUDA(cudaGetLastError());
 }
 
@@ -680,8 +701,20 @@ void launch_obs_curve(pctsea_ctx* c, int32_t type_id, int64_t Nu, int32_t T, flo
     PCT_CUDA(cudaMemcpyAsync(&d[0], denom + type_id, 4, cudaMemcpyDeviceToHost, c->stream));
     PCT_CUDA(cudaMemcpyAsync(&d[1], denom + Tpad + type_id, 4, cudaMemcpyDeviceToHost, c->stream));
     PCT_CUDA(cudaStreamSynchronize(c->stream));
-    k_obs_curve<<<(unsigned)div_up(Nu, 256), 256, 0, c->stream>>>(c->obs_chain.as<float2>() + (size_t)type_id * Nu, d[0], d[1],
-                                                                 Nu, a_dev, b_dev);
+    if (type_id < c->obs_slice_t0 || type_id >= c->obs_slice_t0 + c->obs_slice_n) {
+        // not in the resident history slice (rankings whose history went through several slices): walk this one type
+        // again (the ranked arrays of the last call are still there; the walk rewrites the type's two denominators
+        // with the same values)
+        EnrichGeom g;
+        g.Nu = Nu; g.T = T;
+        if (c->last_lab_bytes == 1) launch_obs_chain_slice<uint8_t>(c, g, Tpad, type_id, 1, c->stream);
+        else launch_obs_chain_slice<uint16_t>(c, g, Tpad, type_id, 1, c->stream);
+        count_launch(c);
+        c->obs_slice_t0 = type_id;
+        c->obs_slice_n = 1;
+    }
+    k_obs_curve<<<(unsigned)div_up(Nu, 256), 256, 0, c->stream>>>(c->obs_chain.as<float2>() + (size_t)(type_id - c->obs_slice_t0) * Nu,
+                                                                 d[0], d[1], Nu, a_dev, b_dev);
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
 }
