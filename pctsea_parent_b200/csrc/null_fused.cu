@@ -184,8 +184,15 @@ __global__ void k_fx_transpose(const int* __restrict__ fx, int64_t Nu, int32_t s
 // class(j) = the c with cum[c] <= j < cum[c+1]. ctab[j >> shift] holds, per bucket of 2^shift indices,
 //   .x = index of the bucket's only class boundary (0xffffffff: none inside), .y = class of the bucket's first index + 1,
 // so that class(j) = .y - (j < .x): one 8-byte shared-memory read and a subtract with borrow. A bucket with several
-// boundaries (or one that skips empty classes) has .x = 0xffffffff and bit 31 of .y set: walk cum[] from the class.
+// boundaries (or one that skips empty classes) points to a second-level table instead: .y = CT_SUB | slot, and
+// sub[slot][(j >> shift2) & (CT_NSUB - 1)] is an entry of the same form for one of the bucket's CT_NSUB sub-buckets
+// (real cell-type size distributions are long-tailed: config B's ranking has 100 types with a median of 87 cells
+// next to buckets of 256 indices, so most words of four labels touch such a bucket; walking cum[] for them cost 18 %
+// more warp instructions than a ranking without small types). A sub-bucket that still holds several boundaries
+// (types of a dozen cells, empty types) has bit 31 of .y set: walk cum[] from the class.
 constexpr uint32_t CT_MULTI = 0x80000000u;
+constexpr uint32_t CT_SUB = 0x40000000u;
+constexpr int CT_NSUB_LOG2 = 5, CT_NSUB = 1 << CT_NSUB_LOG2;
 
 __device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cum, uint32_t Tc, uint32_t j) {
     uint32_t lo = 0, hi = Tc;   // invariant: cum[lo] <= j < cum[hi]
@@ -196,9 +203,23 @@ __device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cu
     return lo;
 }
 
+__device__ __forceinline__ uint2 class_entry(const uint32_t* __restrict__ cum, uint32_t Tc, long long start, long long width,
+                                             long long Nu, bool* several) {
+    uint2 e = make_uint2(0xffffffffu, 1u);
+    *several = false;
+    if (start < Nu) {
+        const uint32_t last = (uint32_t)(min(start + width, Nu) - 1);
+        const uint32_t ca = class_search(cum, Tc, (uint32_t)start), cb = class_search(cum, Tc, last);
+        e.y = ca + 1u;   // indices below .x borrow: class ca; the others: ca + 1
+        if (cb == ca + 1u) e.x = cum[cb];
+        else if (cb > ca + 1u) { e.y = (ca + 1u) | CT_MULTI; *several = true; }
+    }
+    return e;
+}
+
 __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict__ class_cnt, int32_t Tc, int64_t Nu,
                                                       int shift, int32_t nb, uint32_t* __restrict__ cum,
-                                                      uint2* __restrict__ ctab) {
+                                                      uint2* __restrict__ ctab, uint2* __restrict__ sub) {
     // one CTA: exclusive scan of the class counts (thread t owns a contiguous chunk), then the bucket table
     __shared__ uint32_t part[1024];
     const int per = (Tc + 1023) / 1024;
@@ -216,15 +237,29 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
     for (int c = c0; c < c1; c++) { cum[c] = run; run += (uint32_t)class_cnt[c]; }
     if (threadIdx.x == 0) cum[Tc] = (uint32_t)Nu;
     __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += 1024) {
-        const long long start = (long long)i << shift;
-        uint2 e = make_uint2(0xffffffffu, 1u);
-        if (start < Nu) {
-            const uint32_t last = (uint32_t)(min(start + (1ll << shift), (long long)Nu) - 1);
-            const uint32_t ca = class_search(cum, (uint32_t)Tc, (uint32_t)start), cb = class_search(cum, (uint32_t)Tc, last);
-            e.y = ca + 1u;   // indices below .x borrow: class ca; the others: ca + 1
-            if (cb == ca + 1u) e.x = cum[cb];
-            else if (cb > ca + 1u) e.y = (ca + 1u) | CT_MULTI;
+    // first level: nb <= 1024 buckets, one per thread; the buckets with several boundaries get a slot of the second level
+    const int i = threadIdx.x;
+    bool several = false;
+    uint2 e = make_uint2(0xffffffffu, 1u);
+    if (i < nb) e = class_entry(cum, (uint32_t)Tc, (long long)i << shift, 1ll << shift, Nu, &several);
+    part[i] = several ? 1u : 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t r2 = 0;
+        for (int k = 0; k < 1024; k++) { const uint32_t v = part[k]; part[k] = r2; r2 += v; }
+    }
+    __syncthreads();
+    if (i < nb) {
+        const int sub_log2 = min(CT_NSUB_LOG2, shift);   // a bucket of fewer than CT_NSUB indices: one index per sub-bucket
+        const int shift2 = shift - sub_log2;
+        if (several) {
+            const uint32_t slot = part[i];
+            for (int k = 0; k < (1 << sub_log2); k++) {
+                bool sev2;
+                sub[(size_t)slot * CT_NSUB + k] = class_entry(cum, (uint32_t)Tc, ((long long)i << shift) + ((long long)k << shift2),
+                                                              1ll << shift2, Nu, &sev2);
+            }
+            e = make_uint2(0xffffffffu, CT_SUB | slot);
         }
         ctab[i] = e;
     }
@@ -232,14 +267,24 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
 
 // Classes of four indices; the several-boundaries case is checked once for the four. ctab_saddr = address of the
 // bucket table in the shared window.
-__device__ __forceinline__ void class_of4(const uint32_t (&j)[4], uint32_t ctab_saddr, const uint32_t* __restrict__ cum,
-                                          int shift, uint32_t (&c)[4]) {
+__device__ __forceinline__ void class_of4(const uint32_t (&j)[4], uint32_t ctab_saddr, const uint2* __restrict__ sub,
+                                          const uint32_t* __restrict__ cum, int shift, int shift2, uint32_t (&c)[4]) {
+    uint32_t ex[4], ey[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex[q]), "=r"(ey[q]) : "r"(ctab_saddr + ((j[q] >> shift) << 3)));
+    if ((ey[0] | ey[1] | ey[2] | ey[3]) & CT_SUB) {   // some index of the four sits in a bucket with several boundaries
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (ey[q] & CT_SUB) {
+                const uint2 e2 = __ldg(sub + (((size_t)(ey[q] & (CT_SUB - 1u)) << CT_NSUB_LOG2) + ((j[q] >> shift2) & (uint32_t)(CT_NSUB - 1))));
+                ex[q] = e2.x; ey[q] = e2.y;
+            }
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        uint32_t ex, ey;
-        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(ctab_saddr + ((j[q] >> shift) << 3)));
         // c = ey - (j < ex): .y holds the class of the bucket's first index PLUS ONE; the borrow of j - ex takes it back
-        asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.u32 %0, %3, 0;\n\t}" : "=r"(c[q]) : "r"(j[q]), "r"(ex), "r"(ey));
+        asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.u32 %0, %3, 0;\n\t}" : "=r"(c[q]) : "r"(j[q]), "r"(ex[q]), "r"(ey[q]));
     }
     if ((c[0] | c[1] | c[2] | c[3]) & CT_MULTI) {
 #pragma unroll
@@ -432,6 +477,7 @@ struct NullArgs {
     const int32_t* class_cnt;    // [Tc]
     const uint32_t* cum;         // [Tc + 1]
     const uint2* ctab;           // [nb]
+    const uint2* sub;            // [<= nb][CT_NSUB] second level of the buckets with several class boundaries
     void* scratch;               // [grid][seg4][Kp] label words
     int* ticket;
     float* null_ews;             // [T][P_stride]
@@ -467,7 +513,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     if (A.cum_smem) for (int i = k; i < T_all + 2; i += Kp) cum_s[i] = A.cum[i];
     const int seg = A.seg;
     const uint32_t n = (uint32_t)A.Nu, a = A.fp.a, b = A.fp.b;
-    const int shift = A.shift;
+    const int shift = A.shift, shift2 = A.shift - min(CT_NSUB_LOG2, A.shift);
     Word* lab = reinterpret_cast<Word*>(A.scratch) + (size_t)blockIdx.x * (seg >> 2) * Kp + k;
     const int4* fxp = A.fxT4 + k;
     int* col = numA + k;   // this thread's private column: type t lives at col[t * Kp] (bank = k % 32 for every t)
@@ -536,7 +582,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                         for (int q = 0; q < 4; q++)
                             while (y[q] >= n) { rounds(Lq[q], Rq[q]); y[q] = Lq[q] * b + Rq[q]; }
                     }
-                    class_of4(y, ctab_saddr, cum, shift, cls);
+                    class_of4(y, ctab_saddr, A.sub, cum, shift, shift2, cls);
                 } else {   // the partial last word of the ranking
                     y[0] = y[1] = y[2] = y[3] = 0xffffffffu;
 #pragma unroll 1
@@ -553,7 +599,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     uint32_t jj[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) jj[q] = min(y[q], n - 1u);
-                    class_of4(jj, ctab_saddr, cum, shift, cls);
+                    class_of4(jj, ctab_saddr, A.sub, cum, shift, shift2, cls);
 #pragma unroll
                     for (int q = 0; q < 4; q++) cls[q] = (y[q] == 0xffffffffu) ? (uint32_t)T_all : cls[q];
                 }
@@ -809,12 +855,16 @@ void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlan
 }
 
 // cum[] (+ the bucket table when nb > 0) of the type-sorted arrangement; needs class_cnt (k_gather_ranked).
+static size_t class_tab_cum_bytes(const EnrichGeom& g) { return (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16); }
+static size_t class_tab_sub_offset(const EnrichGeom& g, int32_t nb) { return class_tab_cum_bytes(g) + (size_t)round_up((int64_t)std::max(nb, 1) * 8, 16); }
+
 void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb) {
-    const size_t cum_bytes = (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16);
-    c->cls_tab.reserve(cum_bytes + (size_t)std::max(nb, 1) * 8 + 64);
+    const size_t cum_bytes = class_tab_cum_bytes(g), sub_off = class_tab_sub_offset(g, nb);
+    c->cls_tab.reserve(sub_off + (size_t)std::max(nb, 1) * CT_NSUB * 8 + 64);
     uint32_t* cum = c->cls_tab.as<uint32_t>();
     uint2* ctab = reinterpret_cast<uint2*>(c->cls_tab.as<unsigned char>() + cum_bytes);
-    k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift, nb, cum, ctab);
+    uint2* sub = reinterpret_cast<uint2*>(c->cls_tab.as<unsigned char>() + sub_off);
+    k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift, nb, cum, ctab, sub);
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
 }
@@ -846,7 +896,8 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
     A.Sfx = c->Sfx.as<int>();
     A.class_cnt = c->class_cnt.as<int32_t>();
     A.cum = c->cls_tab.as<uint32_t>();
-    A.ctab = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16));
+    A.ctab = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + class_tab_cum_bytes(g));
+    A.sub = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + class_tab_sub_offset(g, pl.nb));
     const unsigned grid = (unsigned)std::min<int64_t>(Pc, (int64_t)pl.ctas_per_sm * c->num_sms);
     const int seg4 = pl.seg >> 2;
     c->labels.reserve((size_t)grid * seg4 * pl.Kp * pl.word_bytes + 64);
