@@ -462,11 +462,20 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_tilecnt(const LabT* __restr
     for (int j = threadIdx.x; j < Tc; j += OBS_THREADS) tilecnt[(size_t)blockIdx.x * Tc + j] = sh_cnt[j];
 }
 
-__global__ void k_obs_tilescan(int32_t* __restrict__ tilecnt, int32_t n_tiles, int32_t Tc) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// exclusive scan over the tiles, one warp per class (32 tiles per step)
+__global__ void __launch_bounds__(128) k_obs_tilescan(int32_t* __restrict__ tilecnt, int32_t n_tiles, int32_t Tc) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (t >= Tc) return;
     int32_t run = 0;
-    for (int32_t k = 0; k < n_tiles; k++) { const int32_t v = tilecnt[(size_t)k * Tc + t]; tilecnt[(size_t)k * Tc + t] = run; run += v; }
+    for (int32_t k0 = 0; k0 < n_tiles; k0 += 32) {
+        const int32_t k = k0 + lane;
+        const int32_t v = k < n_tiles ? tilecnt[(size_t)k * Tc + t] : 0;
+        int32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (k < n_tiles) tilecnt[(size_t)k * Tc + t] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
 }
 
 template <typename LabT>
@@ -655,13 +664,13 @@ void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st) {
     dim3 kgrid((unsigned)n_tiles, (unsigned)g.T);
     if (g.lab_bytes == 1) {
         k_obs_tilecnt<uint8_t><<<n_tiles, OBS_THREADS, (size_t)g.Tc * 4, st>>>(c->lab_rank.as<uint8_t>(), g.Nu, g.Tc, tiles);
-        k_obs_tilescan<<<(unsigned)div_up(g.Tc, 128), 128, 0, st>>>(tiles, n_tiles, g.Tc);
+        k_obs_tilescan<<<(unsigned)div_up(g.Tc, 4), 128, 0, st>>>(tiles, n_tiles, g.Tc);
         k_obs_ksd<uint8_t><<<kgrid, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint8_t>(), g.Nu, g.Tc,
                                                                  cnt, tiles, ksd);
     } else {
         ensure_dyn_smem(c, k_obs_tilecnt<uint16_t>, (size_t)(((size_t)g.Tc * 4)));
         k_obs_tilecnt<uint16_t><<<n_tiles, OBS_THREADS, (size_t)g.Tc * 4, st>>>(c->lab_rank.as<uint16_t>(), g.Nu, g.Tc, tiles);
-        k_obs_tilescan<<<(unsigned)div_up(g.Tc, 128), 128, 0, st>>>(tiles, n_tiles, g.Tc);
+        k_obs_tilescan<<<(unsigned)div_up(g.Tc, 4), 128, 0, st>>>(tiles, n_tiles, g.Tc);
         k_obs_ksd<uint16_t><<<kgrid, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint16_t>(), g.Nu, g.Tc,
                                                                   cnt, tiles, ksd);
     }

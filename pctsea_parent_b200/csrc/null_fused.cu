@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
 // Classes of four indices; the several-boundaries case is checked once for the four. ctab_saddr = address of the
 // bucket table in the shared window.
 __device__ __forceinline__ void class_of4(const uint32_t (&j)[4], uint32_t ctab_saddr, const uint2* __restrict__ sub,
-                                          const uint32_t* __restrict__ cum, int shift, int shift2, uint32_t (&c)[4]) {
+                                          const uint32_t* __restrict__ cum, int shift, int shift2, uint32_t sub_mask, uint32_t (&c)[4]) {
     uint32_t ex[4], ey[4];
 #pragma unroll
     for (int q = 0; q < 4; q++)
@@ -277,7 +277,7 @@ __device__ __forceinline__ void class_of4(const uint32_t (&j)[4], uint32_t ctab_
 #pragma unroll
         for (int q = 0; q < 4; q++)
             if (ey[q] & CT_SUB) {
-                const uint2 e2 = __ldg(sub + (((size_t)(ey[q] & (CT_SUB - 1u)) << CT_NSUB_LOG2) + ((j[q] >> shift2) & (uint32_t)(CT_NSUB - 1))));
+                const uint2 e2 = __ldg(sub + (((size_t)(ey[q] & (CT_SUB - 1u)) << CT_NSUB_LOG2) + ((j[q] >> shift2) & sub_mask)));
                 ex[q] = e2.x; ey[q] = e2.y;
             }
     }
@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     const int seg = A.seg;
     const uint32_t n = (uint32_t)A.Nu, a = A.fp.a, b = A.fp.b;
     const int shift = A.shift, shift2 = A.shift - min(CT_NSUB_LOG2, A.shift);
+    const uint32_t sub_mask = (1u << min(CT_NSUB_LOG2, A.shift)) - 1u;   // a bucket narrower than CT_NSUB indices has one index per sub-bucket
     Word* lab = reinterpret_cast<Word*>(A.scratch) + (size_t)blockIdx.x * (seg >> 2) * Kp + k;
     const int4* fxp = A.fxT4 + k;
     int* col = numA + k;   // this thread's private column: type t lives at col[t * Kp] (bank = k % 32 for every t)
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                         for (int q = 0; q < 4; q++)
                             while (y[q] >= n) { rounds(Lq[q], Rq[q]); y[q] = Lq[q] * b + Rq[q]; }
                     }
-                    class_of4(y, ctab_saddr, A.sub, cum, shift, shift2, cls);
+                    class_of4(y, ctab_saddr, A.sub, cum, shift, shift2, sub_mask, cls);
                 } else {   // the partial last word of the ranking
                     y[0] = y[1] = y[2] = y[3] = 0xffffffffu;
 #pragma unroll 1
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     uint32_t jj[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) jj[q] = min(y[q], n - 1u);
-                    class_of4(jj, ctab_saddr, A.sub, cum, shift, shift2, cls);
+                    class_of4(jj, ctab_saddr, A.sub, cum, shift, shift2, sub_mask, cls);
 #pragma unroll
                     for (int q = 0; q < 4; q++) cls[q] = (y[q] == 0xffffffffu) ? (uint32_t)T_all : cls[q];
                 }
