@@ -262,6 +262,14 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
     for (int c = c0; c < c1; c++) { cum[c] = run; run += (uint32_t)class_cnt[c]; }
     if (threadIdx.x == 0) cum[Tc] = (uint32_t)Nu;
     __syncthreads();
+    // the binary searches below run on a shared-memory copy of the cumulative counts when it fits (it does up to
+    // 2047 classes): ~70 dependent look-ups per thread, and this single CTA sits on the critical path of every analysis
+    __shared__ uint32_t s_cum[2048];
+    if (Tc + 1 <= 2048) {
+        for (int c = threadIdx.x; c <= Tc; c += 1024) s_cum[c] = cum[c];
+        __syncthreads();
+        cum = s_cum;
+    }
     // first level: nb <= 1024 buckets, one per thread; the buckets with several boundaries get a slot of the second level
     const int i = threadIdx.x;
     bool several = false;
@@ -274,19 +282,24 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
         for (int k = 0; k < 1024; k++) { const uint32_t v = part[k]; part[k] = r2; r2 += v; }
     }
     __syncthreads();
+    __shared__ int s_multi[1024];   // bucket of every second-level slot
+    __shared__ int s_nmulti;
     if (i < nb) {
-        const int sub_log2 = min(CT_NSUB_LOG2, shift);   // a bucket of fewer than CT_NSUB indices: one index per sub-bucket
-        const int shift2 = shift - sub_log2;
         if (several) {
-            const uint32_t slot = part[i];
-            for (int k = 0; k < (1 << sub_log2); k++) {
-                bool sev2;
-                sub[(size_t)slot * CT_NSUB + k] = class_entry(cum, (uint32_t)Tc, ((long long)i << shift) + ((long long)k << shift2),
-                                                              1ll << shift2, Nu, &sev2);
-            }
-            e = make_uint2(0xffffffffu, CT_SUB | slot);
+            s_multi[part[i]] = i;
+            e = make_uint2(0xffffffffu, CT_SUB | part[i]);
         }
         ctab[i] = e;
+    }
+    if (i == 1023) s_nmulti = (int)part[1023] + (several ? 1 : 0);
+    __syncthreads();
+    const int sub_log2 = min(CT_NSUB_LOG2, shift);   // a bucket of fewer than CT_NSUB indices: one index per sub-bucket
+    const int shift2 = shift - sub_log2, nsub = 1 << sub_log2;
+    for (int w = threadIdx.x; w < s_nmulti * nsub; w += 1024) {   // one sub-bucket per thread
+        const int slot = w >> sub_log2, k = w & (nsub - 1), bkt = s_multi[slot];
+        bool sev2;
+        sub[(size_t)slot * CT_NSUB + k] = class_entry(cum, (uint32_t)Tc, ((long long)bkt << shift) + ((long long)k << shift2),
+                                                      1ll << shift2, Nu, &sev2);
     }
 }
 
