@@ -156,6 +156,10 @@ int         pctsea_get_timings(pctsea_ctx* ctx, pctsea_timings* out);
                                            1 / nranks of the cells and the scores are all-gathered; 0: every rank scores all */
 #define PCTSEA_OPT_OBS_CHAIN_MB     11  /* device memory for the observed accumulator history in MiB (0 = 1024): 8 bytes per
                                            (ranked cell, type); the types go through it in slices when they do not fit */
+#define PCTSEA_OPT_NULL_FINE_ENTRIES 12 /* null kernel's class table: at most value - 1 fine entries for the small classes
+                                           (0 = as many as fit the CTA's shared memory; 1 = none: every bucket coarse) */
+#define PCTSEA_OPT_SHARD_OBSERVED   13  /* multi-GPU pctsea_analyze: 1 (default) every rank computes the observed statistics of
+                                           1 / nranks of the cell types and the records are all-gathered; 0: every rank all */
 int         pctsea_ctx_set_option(pctsea_ctx* ctx, int32_t option, int64_t value);
 /* cudaStream_t the ctx launches on (so a caller can time or order against it). */
 void*       pctsea_stream(pctsea_ctx* ctx);

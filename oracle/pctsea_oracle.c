@@ -147,23 +147,27 @@ double orc_jitter_uniform(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t i
 }
 
 static void feistel_dims(int64_t n, int64_t* a_out, int64_t* b_out) {
-    /* a0 = ceil(sqrt n); the a in [a0, a0 + a0/16] with the fewest out-of-range points a*ceil(n/a) - n (first on ties) */
+    /* a0 = ceil(sqrt n); b(a) = ceil(n/a) rounded up to a multiple of 4; the a in [a0, a0 + max(a0/16, 8)] with the
+     * fewest out-of-range points a*b(a) - n (first on ties) */
     int64_t a0 = (int64_t)floor(sqrt((double)n));
     while (a0 * a0 < n) a0++;
     while (a0 > 1 && (a0 - 1) * (a0 - 1) >= n) a0--;
     if (a0 < 1) a0 = 1;
-    int64_t best_a = a0, best_w = a0 * ((n + a0 - 1) / a0) - n;
-    for (int64_t a = a0 + 1; a <= a0 + a0 / 16 && best_w > 0; a++) {
-        int64_t w = a * ((n + a - 1) / a) - n;
+#define ORC_FEISTEL_B(a) (((n + (a) - 1) / (a) + 3) / 4 * 4)
+    int64_t best_a = a0, best_w = a0 * ORC_FEISTEL_B(a0) - n;
+    int64_t span = a0 / 16 > 8 ? a0 / 16 : 8;
+    for (int64_t a = a0 + 1; a <= a0 + span && best_w > 0; a++) {
+        int64_t w = a * ORC_FEISTEL_B(a) - n;
         if (w < best_w) { best_w = w; best_a = a; }
     }
     *a_out = best_a;
-    *b_out = (n + best_a - 1) / best_a;
+    *b_out = ORC_FEISTEL_B(best_a);
+#undef ORC_FEISTEL_B
 }
 
 /* PHILOX-mode permutation, round 2 definition: a keyed Feistel bijection of [0,n) on Z_a x Z_b (a near sqrt n,
  * b = ceil(n / a), see feistel_dims; cycle-walking for the few out-of-range points) whose round functions are ARITHMETIC:
- *   F(v, key, mod) = floor(mix(v, key) * mod / 2^32),  mix = multiply - xorshift - multiply hash of v and the round key,
+ *   F(v, key, mod) = floor(mix(v, key) * mod / 2^32),  mix = multiply - shift - multiply hash of v and the round key,
  * with one 32-bit key per round from Philox4x32-10(ctr = {j / 4, 0, p, "FEIS"}, key = seed)[j % 4]. No tables:
  * the GPU evaluates it in registers inside the null kernel. Round j modifies the high digit L iff (rounds-1-j) is
  * even, i.e. the LAST round always does: the class of a position is a range test on pi(x) (orc_perm_labels), decided
@@ -171,17 +175,16 @@ static void feistel_dims(int64_t n, int64_t* a_out, int64_t* b_out) {
  * of the enrichment score (profiles/feistel_rounds_check.txt): 3 and 4 rounds inflate its standard deviation by 2 %
  * (the value histogram of a random round FUNCTION is uneven, and with the sorted arrangement that unevenness reaches
  * the class counts of long prefixes of the ranking); 5 and more rounds are indistinguishable. Default 5. */
-static int g_mix_variant = 1; /* EXPERIMENT */
+/* mix: t = v * M + key spreads the digit over the word, t * (t >> 16) folds its high half back in non-linearly (three
+ * GPU instructions). g_mix_variant selects other hashes for profiles/feistel_mix_check.py only (1: the multiply -
+ * xorshift - multiply hash this replaced, statistically equivalent; 3: t * t, which fails on short rankings). */
+static int g_mix_variant = 0;
 void orc_set_mix_variant(int v) { g_mix_variant = v; }
 static inline uint32_t feistel_mix(uint32_t v, uint32_t key) {
     uint32_t t = v * 0x9E3779B1u + key;
+    if (g_mix_variant == 1) { t ^= t >> 15; return t * 0x2C1B3C6Du; }
     if (g_mix_variant == 3) return t * t;
-    if (g_mix_variant == 4) return t * (t >> 16);
-    if (g_mix_variant == 5) { t ^= t >> 15; return t * t; }
-    if (g_mix_variant == 6) { return (t | 1u) * (t >> 15); }
-    t ^= t >> 15;
-    t *= 0x2C1B3C6Du;
-    return t;
+    return t * (t >> 16);
 }
 
 void orc_feistel_keys(uint64_t seed, uint32_t p, int rounds, uint32_t* keys_out) {
@@ -215,23 +218,38 @@ void orc_feistel_perm(uint64_t seed, uint32_t p, int64_t n, int rounds, int32_t*
     }
 }
 
-/* Permuted labels of PHILOX mode: position x carries the class at index pi_p(x) of the TYPE-SORTED arrangement of
- * the ranked labels (types 0..T-1 ascending, unknown-type cells last). A uniform permutation applied to any fixed
+/* Permuted labels of PHILOX mode: position x carries the class at index pi_p(x) of the SIZE-SORTED arrangement of
+ * the ranked labels: the T+1 classes (types 0..T-1 and the unknown-type class T) in ascending order of their number
+ * of ranked cells, ties by class id, every class one contiguous run. A uniform permutation applied to any fixed
  * arrangement of the same multiset is a uniform arrangement, so which arrangement is permuted does not matter for
- * the null; the sorted one turns "class of index j" into a search in the T+1 cumulative class counts. */
+ * the null; a sorted one turns "class of index j" into a search in the T+1 cumulative class counts, and sorting by
+ * size puts all the small classes (the ones that need a fine-grained look-up table) into one short prefix. */
+void orc_size_sorted_classes(const int64_t* cnt, int32_t Tc, int32_t* order_out) {
+    /* order_out[s] = class at sorted position s: rank by (count, id), O(Tc^2) like the device table builder */
+    for (int32_t c = 0; c < Tc; c++) {
+        int32_t r = 0;
+        for (int32_t d = 0; d < Tc; d++) r += (cnt[d] < cnt[c] || (cnt[d] == cnt[c] && d < c)) ? 1 : 0;
+        order_out[r] = c;
+    }
+}
+
 void orc_perm_labels(uint64_t seed, uint32_t p, int64_t Nu, const int32_t* lab, int32_t T, int rounds,
                      int32_t* lab_perm_out) {
     if (Nu <= 0) return;
-    int64_t* cum = (int64_t*)calloc((size_t)T + 2, sizeof(int64_t));
-    for (int64_t i = 0; i < Nu; i++) { int32_t c = (lab[i] < 0 || lab[i] >= T) ? T : lab[i]; cum[c + 1]++; }
-    for (int32_t c = 0; c <= T; c++) cum[c + 1] += cum[c];
+    int64_t* cnt = (int64_t*)calloc((size_t)T + 1, sizeof(int64_t));
+    for (int64_t i = 0; i < Nu; i++) { int32_t c = (lab[i] < 0 || lab[i] >= T) ? T : lab[i]; cnt[c]++; }
+    int32_t* order = (int32_t*)malloc(((size_t)T + 1) * sizeof(int32_t));
+    orc_size_sorted_classes(cnt, T + 1, order);
     int32_t* sorted = (int32_t*)malloc((size_t)Nu * sizeof(int32_t));
-    for (int32_t c = 0; c <= T; c++)
-        for (int64_t j = cum[c]; j < cum[c + 1]; j++) sorted[j] = (c == T) ? -1 : c;
+    int64_t j = 0;
+    for (int32_t s = 0; s <= T; s++) {
+        const int32_t c = order[s];
+        for (int64_t i = 0; i < cnt[c]; i++) sorted[j++] = (c == T) ? -1 : c;
+    }
     int32_t* idx = (int32_t*)malloc((size_t)Nu * sizeof(int32_t));
     orc_feistel_perm(seed, p, Nu, rounds, idx);
     for (int64_t x = 0; x < Nu; x++) lab_perm_out[x] = sorted[idx[x]];
-    free(cum); free(sorted); free(idx);
+    free(cnt); free(order); free(sorted); free(idx);
 }
 
 /* ============================================================================================

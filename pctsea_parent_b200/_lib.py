@@ -23,7 +23,7 @@ DEFAULT_FEISTEL_ROUNDS = 5   # PCTSEA_DEFAULT_FEISTEL_ROUNDS of include/pctsea_b
 
 # pctsea_ctx_set_option: testing / tuning switches (include/pctsea_b200.h)
 (OPT_OBS_OVERLAP, OPT_SCORE_PATH, OPT_GM_UNROLL, OPT_SCORE_WARPS, OPT_PERM_CHUNK, OPT_NULL_THREADS, OPT_NULL_CTAS_PER_SM,
- OPT_NULL_MIN_THREADS, OPT_DEBUG_GAPS, OPT_SHARD_SCORE, OPT_OBS_CHAIN_MB) = range(1, 12)
+ OPT_NULL_MIN_THREADS, OPT_DEBUG_GAPS, OPT_SHARD_SCORE, OPT_OBS_CHAIN_MB, OPT_NULL_FINE_ENTRIES, OPT_SHARD_OBSERVED) = range(1, 14)
 
 EXPORTS = [
     "pctsea_abi_version", "pctsea_create", "pctsea_destroy", "pctsea_last_error", "pctsea_get_timings",

@@ -206,7 +206,14 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     const bool want_null = Pc_all > 0 && T > 0;
     // Everything the call will allocate is reserved here, before any memory budget is taken (the grow-only buffers
     // over-allocate by 1/8): the observed accumulator history first, then the null.
-    c->results.reserve((size_t)std::max(T, 1) * sizeof(pctsea_type_result) + 64);
+    // A multi-GPU analysis shards the observed statistics by cell type (every type is an independent walk of the
+    // ranking): rank r walks the r-th block of ceil(T / R) types, and the result records are all-gathered in place
+    // next to the null (PCTSEA_OPT_SHARD_OBSERVED 0: every rank walks all types).
+    const bool shard_obs = np.pooled && c->comm_nranks > 1 && T > 0 && c->opt_shard_observed;
+    const int32_t obs_w = shard_obs ? (int32_t)div_up(T, c->comm_nranks) : T;
+    const int32_t obs_tb = shard_obs ? std::min(T, c->comm_rank * obs_w) : 0;
+    const int32_t obs_te = shard_obs ? std::min(T, obs_tb + obs_w) : T;
+    c->results.reserve((size_t)std::max(shard_obs ? obs_w * c->comm_nranks : T, 1) * sizeof(pctsea_type_result) + 64);
     reserve_ks_observed(c, g);
     c->null_ews.reserve((size_t)std::max(T, 1) * std::max(Pstride, 1) * 4 + 64);
     c->null_d.reserve((size_t)std::max(T, 1) * std::max(Pstride, 1) * 4 + 64);
@@ -226,7 +233,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     auto queue_observed_aux = [&]() {
         PCT_CUDA(cudaStreamWaitEvent(c->stream_aux, c->ev_obs[0], 0));
         PCT_CUDA(cudaEventRecord(c->ev_obs[1], c->stream_aux));
-        launch_ks_observed(c, g, c->stream_aux);
+        launch_ks_observed(c, g, c->stream_aux, obs_tb, obs_te);
         PCT_CUDA(cudaEventRecord(c->ev_obs[2], c->stream_aux));
         c->obs_span_valid = true;
         obs_queued = true;
@@ -238,11 +245,11 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     NullPlanFast plan;
     if (want_null && philox) {
         plan = plan_null_fast(c, g);
-        launch_class_tables(c, g, plan.shift, plan.nb);
+        launch_class_tables(c, g, plan.shift, plan.nb, plan.nA_cap);
         if (fast) launch_null_fast_prepare(c, g, plan);
     }
     rec(c, EV_RANK);
-    if (!obs_overlap) launch_ks_observed(c, g, c->stream);
+    if (!obs_overlap) launch_ks_observed(c, g, c->stream, obs_tb, obs_te);
     c->last_obs_Nu = T > 0 ? Nu : -1;
     rec(c, EV_OBS);
 
@@ -298,6 +305,8 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     c->last_pool_P = 0;
     if (np.pooled && T > 0) {
         // the one exchange step of the path: all ranks' slices -> the complete null, in global permutation order
+        // (and the observed statistics of the other ranks' cell types)
+        if (shard_obs) comm_all_gather_in_place(c, c->results.p, (size_t)obs_w * sizeof(pctsea_type_result));
         comm_pool_null(c, T, np.P, Pstride, np.pool_dstat);
         c->last_pool_P = np.P;
         c->last_pool_dstat = np.pool_dstat;
@@ -509,6 +518,8 @@ int pctsea_ctx_set_option(pctsea_ctx* c, int32_t option, int64_t value) {
         case PCTSEA_OPT_DEBUG_GAPS: if (v > 1) return bad("0 or 1"); c->opt_debug_gaps = v; break;
         case PCTSEA_OPT_SHARD_SCORE: if (v > 1) return bad("0 or 1"); c->opt_shard_score = v; break;
         case PCTSEA_OPT_OBS_CHAIN_MB: c->opt_obs_chain_mb = v; break;
+        case PCTSEA_OPT_NULL_FINE_ENTRIES: c->opt_null_fine_entries = v - 1; break;
+        case PCTSEA_OPT_SHARD_OBSERVED: if (v > 1) return bad("0 or 1"); c->opt_shard_observed = v; break;
         default: return bad("unknown option");
     }
     return PCTSEA_OK;

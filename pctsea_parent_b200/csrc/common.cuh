@@ -109,6 +109,8 @@ struct pctsea_ctx {
     int opt_null_threads = 0;        // threads (segments) per permutation of the fused null kernel (0 = as many as fit)
     int opt_null_ctas_per_sm = 0;    // resident CTAs per SM of the fused null kernel (0 = as many as fit)
     int opt_null_min_threads = 0;    // below this many threads per permutation the cell types are sliced (0 = 192)
+    int opt_shard_observed = 1;      // multi-GPU analysis: observed statistics sharded by cell type over the ranks
+    int opt_null_fine_entries = -1;  // cap on the fine (region A) entries of the null kernel's class table (-1 = what fits)
     int opt_obs_chain_mb = 0;        // budget of the observed accumulator history in MiB (0 = 1024); more types than fit go in slices
     int opt_shard_score = 1;         // multi-GPU analysis: stage 1 sharded over the ranks (0: every rank scores all cells)
     int opt_debug_gaps = 0;          // print a line to stderr when the stream sat idle between stages
@@ -139,7 +141,8 @@ struct pctsea_ctx {
     pctsea::DevBuf obs_chain, obs_misc, obs_tiles;                       // observed KS: accumulator history [Nu][Tpad]
     pctsea::DevBuf labels;                                      // EXACT null: [Pc][Nu_pad] permuted labels; fused null: per-CTA label scratch
     pctsea::DevBuf lab_ticket;                                  // permutation ticket counter of the fused null kernel
-    pctsea::DevBuf cls_tab;                                     // cumulative class counts [Tc+1] + bucket table of the sorted arrangement
+    pctsea::DevBuf cls_tab;                                     // size-sorted classes: cumulative counts, order, header, bucket table (null_fused.cu)
+    int32_t cls_tab_nb = 0, cls_tab_nA_cap = 0;                 // geometry cls_tab was last built for
     pctsea::DevBuf replay;                                      // [Pc][Nu] int32
     pctsea::DevBuf fxT;                                         // FAST mode: lane layout of the fixed-point scores
     pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
@@ -185,21 +188,24 @@ __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// Feistel geometry: digits (L, R) in Z_a x Z_b with a * b >= n. Starting from a0 = ceil(sqrt(n)), the a in
-// [a0, a0 + a0/16] with the fewest out-of-range points a * ceil(n / a) - n is taken (first one on ties): every such
+// Feistel geometry: digits (L, R) in Z_a x Z_b with a * b >= n and b a multiple of 4 (the null kernel generates four
+// consecutive positions at a time from segments that start at multiples of 4: with such rows the four share their
+// high digit and no per-position row-wrap arithmetic is needed). Starting from a0 = ceil(sqrt(n)), the a in
+// [a0, a0 + max(a0/16, 8)] with the fewest out-of-range points a * b - n is taken (first one on ties): every such
 // point costs a cycle-walk, and one walking lane stalls its warp.
 inline void feistel_dims(int64_t n, uint32_t* a_out, uint32_t* b_out) {
     int64_t a0 = (int64_t)std::floor(std::sqrt((double)n));
     while (a0 * a0 < n) a0++;
     while (a0 > 1 && (a0 - 1) * (a0 - 1) >= n) a0--;
     if (a0 < 1) a0 = 1;
-    int64_t best_a = a0, best_w = a0 * ((n + a0 - 1) / a0) - n;
-    for (int64_t a = a0 + 1; a <= a0 + a0 / 16 && best_w > 0; a++) {
-        const int64_t w = a * ((n + a - 1) / a) - n;
+    auto b_of = [n](int64_t a) { return ((n + a - 1) / a + 3) / 4 * 4; };   // rows of a multiple of 4 positions
+    int64_t best_a = a0, best_w = a0 * b_of(a0) - n;
+    for (int64_t a = a0 + 1; a <= a0 + std::max<int64_t>(a0 / 16, 8) && best_w > 0; a++) {
+        const int64_t w = a * b_of(a) - n;
         if (w < best_w) { best_w = w; best_a = a; }
     }
     *a_out = (uint32_t)best_a;
-    *b_out = (uint32_t)((n + best_a - 1) / best_a);
+    *b_out = (uint32_t)b_of(best_a);
 }
 
 inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -245,7 +251,7 @@ struct EnrichGeom {
 void launch_prepare_ranked(pctsea_ctx* c, int64_t N, const double* score_dev, const int32_t* label_dev,
                            const int32_t* order_dev, EnrichGeom& g);
 void reserve_ks_observed(pctsea_ctx* c, const EnrichGeom& g);
-void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st);
+void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st, int32_t type_begin = 0, int32_t type_end = -1);
 // a / b series of one type from the resident accumulator history into two device arrays of Nu floats
 void launch_obs_curve(pctsea_ctx* c, int32_t type_id, int64_t Nu, int32_t T, float* a_dev, float* b_dev);
 void launch_labels_replay(pctsea_ctx* c, const EnrichGeom& g, const int32_t* replay_dev, int32_t Pc);
@@ -255,15 +261,16 @@ struct NullPlanFast {
     int32_t seg = 0;          // positions per thread (multiple of 16)
     int32_t Ts = 0;           // cell types per pass (== T unless sliced)
     int32_t ctas_per_sm = 1;
-    int32_t nb = 0;           // buckets of the class table
-    int shift = 0;            // log2 of the bucket width
+    int32_t nb = 0;           // coarse (region B) buckets of the class table
+    int32_t nA_cap = 0;       // capacity of its fine region A
+    int shift = 0;            // log2 of the coarse bucket width
     int cum_smem = 0;         // cumulative class counts held in shared memory
     int word_bytes = 4;       // bytes of one label word (4 positions)
     size_t smem = 0;          // dynamic shared memory per CTA
 };
 NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g);
 void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl);
-void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb);
+void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb, int32_t nA_cap);
 void launch_labels_philox_rm(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc, int rounds);
 void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl, uint64_t seed, int32_t perm_begin,
                        int32_t Pc, int rounds, int32_t P_stride, int32_t p_off);

@@ -481,11 +481,11 @@ __global__ void __launch_bounds__(128) k_obs_tilescan(int32_t* __restrict__ tile
 template <typename LabT>
 __global__ void __launch_bounds__(OBS_THREADS) k_obs_ksd(const double* __restrict__ s_rank, const LabT* __restrict__ lab,
                                                          int64_t Nu, int32_t Tc, const int32_t* __restrict__ class_cnt,
-                                                         const int32_t* __restrict__ tilebase,
+                                                         const int32_t* __restrict__ tilebase, int32_t t_first,
                                                          unsigned long long* __restrict__ ksd_sup) {
     __shared__ int wtot[32];
     __shared__ unsigned long long wbest[32];
-    const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = t_first + blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n = class_cnt[t], m = Nu - n;
     const int64_t i0 = (int64_t)blockIdx.x * KSD_TILE + (int64_t)tid * KSD_V;
     bool hit[KSD_V];
@@ -639,9 +639,14 @@ static void launch_obs_chain_slice(pctsea_ctx* c, const EnrichGeom& g, int32_t T
                                                  c->obs_chain.as<float2>(), c->obs_misc.as<float>());
 }
 
-void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st) {
+// Observed statistics of the cell types [tb, te) (all of them unless a multi-GPU analysis shards the types over its
+// ranks: every type is an independent walk of the ranking).
+void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st, int32_t tb, int32_t te) {
     reserve_ks_observed(c, g);
-    if (g.T == 0) return;
+    if (te < 0) te = g.T;
+    c->obs_slice_t0 = 0;
+    c->obs_slice_n = 0;
+    if (g.T == 0 || te <= tb) return;
     const int32_t Tpad = (int32_t)round_up(g.T, 32);
     // [2][Tpad] denominators | [Tpad] u64 supremum keys | [Tpad] u64 secondary keys | [Tpad] f64 KS D |
     // [Tpad] u32 last-negative indices | [Tpad] u32 secondary indices
@@ -661,23 +666,23 @@ void launch_ks_observed(pctsea_ctx* c, const EnrichGeom& g, cudaStream_t st) {
     const int32_t n_tiles = (int32_t)div_up(g.Nu, KSD_TILE);
     c->obs_tiles.reserve((size_t)n_tiles * g.Tc * 4 + 64);
     int32_t* tiles = c->obs_tiles.as<int32_t>();
-    dim3 kgrid((unsigned)n_tiles, (unsigned)g.T);
+    dim3 kgrid((unsigned)n_tiles, (unsigned)(te - tb));
     if (g.lab_bytes == 1) {
         k_obs_tilecnt<uint8_t><<<n_tiles, OBS_THREADS, (size_t)g.Tc * 4, st>>>(c->lab_rank.as<uint8_t>(), g.Nu, g.Tc, tiles);
         k_obs_tilescan<<<(unsigned)div_up(g.Tc, 4), 128, 0, st>>>(tiles, n_tiles, g.Tc);
         k_obs_ksd<uint8_t><<<kgrid, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint8_t>(), g.Nu, g.Tc,
-                                                                 cnt, tiles, ksd);
+                                                                 cnt, tiles, tb, ksd);
     } else {
         ensure_dyn_smem(c, k_obs_tilecnt<uint16_t>, (size_t)(((size_t)g.Tc * 4)));
         k_obs_tilecnt<uint16_t><<<n_tiles, OBS_THREADS, (size_t)g.Tc * 4, st>>>(c->lab_rank.as<uint16_t>(), g.Nu, g.Tc, tiles);
         k_obs_tilescan<<<(unsigned)div_up(g.Tc, 4), 128, 0, st>>>(tiles, n_tiles, g.Tc);
         k_obs_ksd<uint16_t><<<kgrid, OBS_THREADS, 0, st>>>(c->s_rank.as<double>(), c->lab_rank.as<uint16_t>(), g.Nu, g.Tc,
-                                                                  cnt, tiles, ksd);
+                                                                  cnt, tiles, tb, ksd);
     }
     count_launch(c, 3);
     const int32_t Ts = obs_types_per_slice(c, g);
-    for (int32_t t0 = 0; t0 < g.T; t0 += Ts) {
-        const int32_t nt = std::min(Ts, g.T - t0);
+    for (int32_t t0 = tb; t0 < te; t0 += Ts) {
+        const int32_t nt = std::min(Ts, te - t0);
         if (g.lab_bytes == 1) launch_obs_chain_slice<uint8_t>(c, g, Tpad, t0, nt, st);
         else launch_obs_chain_slice<uint16_t>(c, g, Tpad, t0, nt, st);
         dim3 grid((unsigned)div_up(g.Nu, OBS_TILE), (unsigned)nt);
@@ -707,13 +712,10 @@ void launch_obs_curve(pctsea_ctx* c, int32_t type_id, int64_t Nu, int32_t T, flo
     const int32_t Tpad = (int32_t)round_up(T, 32);
     float d[2];
     const float* denom = c->obs_misc.as<float>();
-    PCT_CUDA(cudaMemcpyAsync(&d[0], denom + type_id, 4, cudaMemcpyDeviceToHost, c->stream));
-    PCT_CUDA(cudaMemcpyAsync(&d[1], denom + Tpad + type_id, 4, cudaMemcpyDeviceToHost, c->stream));
-    PCT_CUDA(cudaStreamSynchronize(c->stream));
     if (type_id < c->obs_slice_t0 || type_id >= c->obs_slice_t0 + c->obs_slice_n) {
-        // not in the resident history slice (rankings whose history went through several slices): walk this one type
-        // again (the ranked arrays of the last call are still there; the walk rewrites the type's two denominators
-        // with the same values)
+        // not in the resident history slice (rankings whose history went through several slices, or a type that
+        // another rank of a multi-GPU analysis walked): walk this one type again (the ranked arrays of the last call
+        // are still there; the walk writes the type's two denominators)
         EnrichGeom g;
         g.Nu = Nu; g.T = T;
         if (c->last_lab_bytes == 1) launch_obs_chain_slice<uint8_t>(c, g, Tpad, type_id, 1, c->stream);
@@ -722,6 +724,9 @@ void launch_obs_curve(pctsea_ctx* c, int32_t type_id, int64_t Nu, int32_t T, flo
         c->obs_slice_t0 = type_id;
         c->obs_slice_n = 1;
     }
+    PCT_CUDA(cudaMemcpyAsync(&d[0], denom + type_id, 4, cudaMemcpyDeviceToHost, c->stream));
+    PCT_CUDA(cudaMemcpyAsync(&d[1], denom + Tpad + type_id, 4, cudaMemcpyDeviceToHost, c->stream));
+    PCT_CUDA(cudaStreamSynchronize(c->stream));
     k_obs_curve<<<(unsigned)div_up(Nu, 256), 256, 0, c->stream>>>(c->obs_chain.as<float2>() + (size_t)(type_id - c->obs_slice_t0) * Nu,
                                                                  d[0], d[1], Nu, a_dev, b_dev);
     count_launch(c);

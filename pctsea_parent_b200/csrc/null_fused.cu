@@ -178,26 +178,36 @@ __global__ void k_fx_transpose(const int* __restrict__ fx, int64_t Nu, int32_t s
 }
 
 // ================================================================================================
-// class of an index of the type-sorted arrangement
+// class of an index of the size-sorted arrangement
 // ================================================================================================
-// cum[c] = number of ranked cells of a class below c (c = 0 .. Tc, Tc = T + 1 classes, the last one "unknown type");
-// class(j) = the c with cum[c] <= j < cum[c+1]. ctab[j >> shift] holds, per bucket of 2^shift indices,
+// The arrangement that is permuted lists the Tc = T + 1 classes (the last id = "unknown type") in ascending order of
+// their number of ranked cells, ties by id; sorder[s] = id of the class at SORTED POSITION s, and
+// cum[s] = number of ranked cells at sorted positions below s (s = 0 .. Tc). The null kernel works in sorted positions
+// throughout (its per-type columns, the parked labels) and maps back to ids when it writes its results.
+//   class(j) = the s with cum[s] <= j < cum[s+1].
+// Look-up: one 8-byte shared-memory entry per bucket of indices,
 //   .x = index of the bucket's only class boundary (0xffffffff: none inside), .y = class of the bucket's first index + 1,
-// so that class(j) = .y - (j < .x): one 8-byte shared-memory read and a subtract with borrow. A bucket with several
-// boundaries (or one that skips empty classes) points to a second-level table instead: .y = CT_SUB | slot, and
-// sub[slot][(j >> shift2) & (CT_NSUB - 1)] is an entry of the same form for one of the bucket's CT_NSUB sub-buckets
-// (real cell-type size distributions are long-tailed: config B's ranking has 100 types with a median of 87 cells
-// next to buckets of 256 indices, so most words of four labels touch such a bucket; walking cum[] for them cost 18 %
-// more warp instructions than a ranking without small types). A sub-bucket that still holds several boundaries
-// (types of a dozen cells, empty types) has bit 31 of .y set: walk cum[] from the class.
+// so that class(j) = .y - (j < .x): one read and a subtract with borrow. Real cell-type size distributions are
+// long-tailed (config B's ranking: 100 types with a median of 87 cells next to buckets of 256 indices), and a bucket
+// that holds several boundaries needs more than that. Because the arrangement is sorted by size, all classes narrower
+// than a bucket sit in one short prefix [0, X) of the indices: that prefix gets its own, finer buckets (region A,
+// 2^shiftA indices each, as fine as the table's capacity allows), everything behind it the coarse ones (region B,
+// 2^shiftB indices, at most one boundary each by construction). Which region an index belongs to is one compare and
+// two selects, no divergence. (Round 2's first form resolved the several-boundary buckets through a second-level
+// table in global memory: only 2 % of the indices took that path, but some lane of almost every warp did — 12 % of
+// the kernel's warp instructions.) A region-A bucket that still holds several boundaries (classes of a handful of
+// cells) has bit 31 of .y set: walk cum[] from the class.
 constexpr uint32_t CT_MULTI = 0x80000000u;
-constexpr uint32_t CT_SUB = 0x40000000u;
-constexpr int CT_NSUB_LOG2 = 5, CT_NSUB = 1 << CT_NSUB_LOG2;
+
+struct ClassHdr {     // written by k_class_tables, read by the kernels that use the tables
+    uint32_t X;       // indices below X use region A
+    uint32_t shiftA;  // log2 of region A's bucket width
+    uint32_t su;      // sorted position of the unknown-type class
+    uint32_t nA;      // region A entries in use (<= the capacity the tables were built for)
+};
 
 // Global loads with a cache policy. The kernel streams its fixed-point scores and parked labels through L1 (every
-// byte is used once per walk), while the few KB of second-level class-table entries are touched by some lane of
-// almost every word: the streams do not allocate in L1, the table entries are kept there (before this the table
-// loads missed L1 — 3.6 % hit rate — and the first use of a class entry was the hottest stall of the kernel).
+// byte is used once per walk): the streams do not allocate there.
 __device__ __forceinline__ int4 ld_stream(const int4* p) {
     int4 v;
     asm("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -213,14 +223,9 @@ __device__ __forceinline__ uint2 ld_stream(const uint2* p) {
     asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint2 ld_keep(const uint2* p) {
-    uint2 v;
-    asm("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
 
 __device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cum, uint32_t Tc, uint32_t j) {
-    uint32_t lo = 0, hi = Tc;   // invariant: cum[lo] <= j < cum[hi]
+    uint32_t lo = 0, hi = Tc;   // invariant: cum[lo] <= j < cum[hi]; empty classes (equal counts) are skipped
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (cum[mid] <= j) lo = mid; else hi = mid;
@@ -229,107 +234,114 @@ __device__ __forceinline__ uint32_t class_search(const uint32_t* __restrict__ cu
 }
 
 __device__ __forceinline__ uint2 class_entry(const uint32_t* __restrict__ cum, uint32_t Tc, long long start, long long width,
-                                             long long Nu, bool* several) {
+                                             long long Nu) {
     uint2 e = make_uint2(0xffffffffu, 1u);
-    *several = false;
     if (start < Nu) {
         const uint32_t last = (uint32_t)(min(start + width, Nu) - 1);
         const uint32_t ca = class_search(cum, Tc, (uint32_t)start), cb = class_search(cum, Tc, last);
         e.y = ca + 1u;   // indices below .x borrow: class ca; the others: ca + 1
         if (cb == ca + 1u) e.x = cum[cb];
-        else if (cb > ca + 1u) { e.y = (ca + 1u) | CT_MULTI; *several = true; }
+        else if (cb > ca + 1u) e.y = (ca + 1u) | CT_MULTI;
     }
     return e;
 }
 
+// One CTA: sorted order of the classes, their cumulative counts, the two-region bucket table.
+// ctab = [nA_cap region-A entries][nb region-B entries, indexed by j >> shiftB over the whole ranking].
 __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict__ class_cnt, int32_t Tc, int64_t Nu,
-                                                      int shift, int32_t nb, uint32_t* __restrict__ cum,
-                                                      uint2* __restrict__ ctab, uint2* __restrict__ sub) {
-    // one CTA: exclusive scan of the class counts (thread t owns a contiguous chunk), then the bucket table
+                                                      int shiftB, int32_t nb, int32_t nA_cap, uint32_t* __restrict__ cum,
+                                                      int32_t* __restrict__ sorder, ClassHdr* __restrict__ hdr,
+                                                      uint2* __restrict__ ctab) {
     __shared__ uint32_t part[1024];
+    __shared__ uint32_t s_buf[2048];   // class counts by id, later the cumulative counts, when they fit
+    __shared__ uint32_t s_small, s_X, s_shiftA, s_nA;
+    const bool fits = Tc + 1 <= 2048;
+    if (threadIdx.x == 0) s_small = 0u;
+    if (fits) for (int c = threadIdx.x; c < Tc; c += 1024) s_buf[c] = (uint32_t)class_cnt[c];
+    __syncthreads();
+    // sorted position of a class = number of classes that come before it in (count, id) order; the unsorted counts
+    // land in cum[1 ..] at their sorted positions
+    const uint32_t W = 1u << shiftB;
+    for (int c = threadIdx.x; c < Tc; c += 1024) {
+        const uint32_t mine = fits ? s_buf[c] : (uint32_t)class_cnt[c];
+        uint32_t r = 0;
+        for (int d = 0; d < Tc; d++) {
+            const uint32_t o = fits ? s_buf[d] : (uint32_t)class_cnt[d];
+            r += (o < mine || (o == mine && d < c)) ? 1u : 0u;
+        }
+        sorder[r] = c;
+        cum[r + 1] = mine;
+        if (c == Tc - 1) hdr->su = r;
+        if (mine < W) atomicAdd(&s_small, 1u);
+    }
+    __syncthreads();
+    // inclusive scan of cum[1 .. Tc] in place (thread t owns a contiguous chunk)
     const int per = (Tc + 1023) / 1024;
-    const int c0 = threadIdx.x * per, c1 = min(c0 + per, (int)Tc);
-    uint32_t s = 0;
-    for (int c = c0; c < c1; c++) s += (uint32_t)class_cnt[c];
-    part[threadIdx.x] = s;
+    const int c0 = 1 + threadIdx.x * per, c1 = min(c0 + per, (int)Tc + 1);
+    uint32_t sum = 0;
+    for (int c = c0; c < c1; c++) sum += cum[c];
+    part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
         for (int i = 0; i < 1024; i++) { const uint32_t v = part[i]; part[i] = run; run += v; }
+        cum[0] = 0u;
     }
     __syncthreads();
     uint32_t run = part[threadIdx.x];
-    for (int c = c0; c < c1; c++) { cum[c] = run; run += (uint32_t)class_cnt[c]; }
-    if (threadIdx.x == 0) cum[Tc] = (uint32_t)Nu;
+    for (int c = c0; c < c1; c++) { run += cum[c]; cum[c] = run; }
     __syncthreads();
-    // the binary searches below run on a shared-memory copy of the cumulative counts when it fits (it does up to
-    // 2047 classes): ~70 dependent look-ups per thread, and this single CTA sits on the critical path of every analysis
-    __shared__ uint32_t s_cum[2048];
-    if (Tc + 1 <= 2048) {
-        for (int c = threadIdx.x; c <= Tc; c += 1024) s_cum[c] = cum[c];
+    // the binary searches below run on a shared-memory copy of the cumulative counts when it fits: ~40 dependent
+    // look-ups per thread, and this single CTA sits on the critical path of every analysis
+    if (fits) {
+        for (int c = threadIdx.x; c <= Tc; c += 1024) s_buf[c] = cum[c];
         __syncthreads();
-        cum = s_cum;
+        cum = s_buf;
     }
-    // first level: nb <= 1024 buckets, one per thread; the buckets with several boundaries get a slot of the second level
-    const int i = threadIdx.x;
-    bool several = false;
-    uint2 e = make_uint2(0xffffffffu, 1u);
-    if (i < nb) e = class_entry(cum, (uint32_t)Tc, (long long)i << shift, 1ll << shift, Nu, &several);
-    part[i] = several ? 1u : 0u;
-    __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t r2 = 0;
-        for (int k = 0; k < 1024; k++) { const uint32_t v = part[k]; part[k] = r2; r2 += v; }
+        // region A = [0, X): the classes narrower than a region-B bucket (they are the first s_small sorted
+        // positions), up to the next bucket boundary; as fine as nA_cap entries allow
+        const unsigned long long raw = cum[s_small];
+        unsigned long long X = (raw + W - 1) / W * W;
+        const unsigned long long cover = min(X, (unsigned long long)Nu);
+        uint32_t sA = 0;
+        while (nA_cap > 0 && ((cover + (1ull << sA) - 1) >> sA) > (unsigned long long)nA_cap) sA++;
+        if (nA_cap <= 0 || (int)sA >= shiftB || raw == 0) { X = 0; sA = 0; }   // no finer than region B: not worth a region
+        s_X = (uint32_t)min(X, 0xffffffffull);
+        s_shiftA = sA;
+        s_nA = X ? (uint32_t)((cover + (1ull << sA) - 1) >> sA) : 0u;
+        hdr->X = s_X; hdr->shiftA = sA; hdr->nA = s_nA;
     }
     __syncthreads();
-    __shared__ int s_multi[1024];   // bucket of every second-level slot
-    __shared__ int s_nmulti;
-    if (i < nb) {
-        if (several) {
-            s_multi[part[i]] = i;
-            e = make_uint2(0xffffffffu, CT_SUB | part[i]);
-        }
-        ctab[i] = e;
-    }
-    if (i == 1023) s_nmulti = (int)part[1023] + (several ? 1 : 0);
-    __syncthreads();
-    const int sub_log2 = min(CT_NSUB_LOG2, shift);   // a bucket of fewer than CT_NSUB indices: one index per sub-bucket
-    const int shift2 = shift - sub_log2, nsub = 1 << sub_log2;
-    for (int w = threadIdx.x; w < s_nmulti * nsub; w += 1024) {   // one sub-bucket per thread
-        const int slot = w >> sub_log2, k = w & (nsub - 1), bkt = s_multi[slot];
-        bool sev2;
-        sub[(size_t)slot * CT_NSUB + k] = class_entry(cum, (uint32_t)Tc, ((long long)bkt << shift) + ((long long)k << shift2),
-                                                      1ll << shift2, Nu, &sev2);
-    }
+    const uint32_t sA = s_shiftA, nA = s_nA;
+    for (int i = threadIdx.x; i < nA_cap; i += 1024)
+        ctab[i] = (uint32_t)i < nA ? class_entry(cum, (uint32_t)Tc, (long long)i << sA, 1ll << sA, Nu) : make_uint2(0xffffffffu, 1u);
+    for (int i = threadIdx.x; i < nb; i += 1024)
+        ctab[nA_cap + i] = class_entry(cum, (uint32_t)Tc, (long long)i << shiftB, 1ll << shiftB, Nu);
 }
 
-// Classes of four indices; the several-boundaries case is checked once for the four. ctab_saddr = address of the
-// bucket table in the shared window.
-__device__ __forceinline__ void class_of4(const uint32_t (&j)[4], uint32_t ctab_saddr, const uint2* __restrict__ sub,
-                                          const uint32_t* __restrict__ cum, int shift, int shift2, uint32_t sub_mask, uint32_t (&c)[4]) {
+// Sorted positions (classes) of four indices. saddrA / saddrB = addresses of the two regions of the bucket table in
+// the shared window.
+__device__ __forceinline__ void class_of4(const uint32_t (&j)[4], uint32_t saddrA, uint32_t saddrB, uint32_t X, uint32_t shiftA,
+                                          uint32_t shiftB, const uint32_t* __restrict__ cum, uint32_t (&c)[4]) {
     uint32_t ex[4], ey[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex[q]), "=r"(ey[q]) : "r"(ctab_saddr + ((j[q] >> shift) << 3)));
-    if ((ey[0] | ey[1] | ey[2] | ey[3]) & CT_SUB) {   // some index of the four sits in a bucket with several boundaries
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (ey[q] & CT_SUB) {
-                const uint2 e2 = ld_keep(sub + (((ey[q] & (CT_SUB - 1u)) << CT_NSUB_LOG2) + ((j[q] >> shift2) & sub_mask)));
-                ex[q] = e2.x; ey[q] = e2.y;
-            }
+    for (int q = 0; q < 4; q++) {
+        const bool inA = j[q] < X;
+        const uint32_t base = inA ? saddrA : saddrB, sh = inA ? shiftA : shiftB;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex[q]), "=r"(ey[q]) : "r"(base + ((j[q] >> sh) << 3)));
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         // c = ey - (j < ex): .y holds the class of the bucket's first index PLUS ONE; the borrow of j - ex takes it back
         asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.u32 %0, %3, 0;\n\t}" : "=r"(c[q]) : "r"(j[q]), "r"(ex[q]), "r"(ey[q]));
     }
-    if ((c[0] | c[1] | c[2] | c[3]) & CT_MULTI) {
+    if ((c[0] | c[1] | c[2] | c[3]) & CT_MULTI) {   // a bucket of region A with several boundaries: rare
 #pragma unroll
         for (int q = 0; q < 4; q++)
             if (c[q] & CT_MULTI) {
-                uint32_t cc = c[q] & ~CT_MULTI;
-                while (j[q] >= cum[cc + 1]) cc++;   // ends: cum[Tc] = Nu > j
+                uint32_t cc = (ey[q] & ~CT_MULTI) - 1u;   // class of the bucket's first index
+                while (j[q] >= cum[cc + 1]) cc++;          // ends: cum[Tc] = Nu > j
                 c[q] = cc;
             }
     }
@@ -344,11 +356,13 @@ struct FeistelParams {
     uint64_t seed;
 };
 
+// multiply - shift - multiply: t = v * M + key spreads the digit over the word, t * (t >> 16) folds its high half back
+// in non-linearly (without that the round function is affine in the digit and neighbouring positions correlate).
+// Three instructions, one of them on the ALU pipe; the multiply - xorshift - multiply hash it replaces took four
+// (two on the ALU pipe, the kernel's busiest) and gives the same null (profiles/feistel_mix_check.txt).
 __host__ __device__ __forceinline__ uint32_t feistel_mix(uint32_t v, uint32_t key) {
-    uint32_t t = v * 0x9E3779B1u + key;
-    t ^= t >> 15;
-    t *= 0x2C1B3C6Du;
-    return t;
+    const uint32_t t = v * 0x9E3779B1u + key;
+    return t * (t >> 16);
 }
 
 // round keys of permutation p: Philox4x32-10(ctr = {j / 4, 0, p, "FEIS"}, key = seed)[j % 4]
@@ -417,7 +431,7 @@ template <> struct LaneWord<uint16_t> {
 template <typename LabT>
 __global__ void __launch_bounds__(256) k_labels_philox_rm(int64_t Nu, int64_t Nu_pad, int32_t T, FeistelParams fp,
                                                          int32_t perm_begin, const uint32_t* __restrict__ cum,
-                                                         LabT* __restrict__ labels) {
+                                                         const int32_t* __restrict__ sorder, LabT* __restrict__ labels) {
     __shared__ uint32_t keys[32];
     const int p = blockIdx.y;
     if (threadIdx.x < 8 && (int)threadIdx.x * 4 < fp.rounds) {
@@ -433,7 +447,7 @@ __global__ void __launch_bounds__(256) k_labels_philox_rm(int64_t Nu, int64_t Nu
     if (x < Nu) {
         const uint32_t L = (uint32_t)(x / fp.b), R = (uint32_t)(x - (int64_t)L * fp.b);
         const uint32_t j = feistel_apply<0>(keys, fp.a, fp.b, fp.rounds, L, R, (uint32_t)Nu);
-        cls = class_search(cum, (uint32_t)T + 1u, j);
+        cls = (uint32_t)sorder[class_search(cum, (uint32_t)T + 1u, j)];   // sorted position -> class id
     }
     labels[(size_t)p * Nu_pad + x] = (LabT)cls;
 }
@@ -513,46 +527,52 @@ struct NullArgs {
     const int4* fxT4;            // [seg4][Kp] fixed-point scores, lane layout
     const int* Sfx;              // [Nu] inclusive int32 prefix of the fixed-point scores
     const int32_t* class_cnt;    // [Tc]
-    const uint32_t* cum;         // [Tc + 1]
-    const uint2* ctab;           // [nb]
-    const uint2* sub;            // [<= nb][CT_NSUB] second level of the buckets with several class boundaries
+    const uint32_t* cum;         // [Tc + 1] cumulative counts of the size-sorted classes
+    const int32_t* sorder;       // [Tc] class id at every sorted position
+    const ClassHdr* hdr;
+    const uint2* ctab;           // [nA_cap + nb]
     void* scratch;               // [grid][seg4][Kp] label words
     int* ticket;
     float* null_ews;             // [T][P_stride]
     float* null_d;
     int64_t Nu;
-    int32_t T_all, Ts, seg, Pc, perm_begin, P_stride, p_off, nb, shift, cum_smem;
+    int32_t T_all, Ts, seg, Pc, perm_begin, P_stride, p_off, nb, nA_cap, shift, cum_smem;
     FeistelParams fp;
 };
 
-// SLICED: more cell types than the per-thread shared-memory state can hold at once. The labels are then generated
-// in a pass of their own, and phases 1-4 run once per slice of Ts types on the parked labels, with every other type
-// mapped to the slice's dummy column (Ts), which takes the same read-modify-write but has zero constants, so it can
-// never set a maximum.
+// Classes are sorted positions of the size-sorted arrangement everywhere inside the kernel (columns of the per-thread
+// state, parked labels); sorder[] maps back to type ids when the results are written. The unknown-type class (sorted
+// position su) has a column like every other class but zero constants, so it can never set a maximum; padding
+// positions carry it with zero scores.
+// SLICED: more classes than the per-thread shared-memory state can hold at once. The labels are then generated
+// in a pass of their own, and phases 1-4 run once per slice of Ts sorted positions on the parked labels, with every
+// other class mapped to the slice's dummy column (Ts), which takes the same read-modify-write but has zero constants.
 template <typename LabT, int NR, bool SLICED>
 __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     typedef typename LaneWord<LabT>::type Word;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_p;
     __shared__ uint32_t s_keys[32];
-    const int Ts = A.Ts, Tc = Ts + 1, T_all = A.T_all;
+    const int Ts = A.Ts, T_all = A.T_all, Tc_all = T_all + 1;
+    const int Tc = SLICED ? Ts + 1 : Tc_all;   // columns: the slice + its dummy, or every class
     const int Kp = blockDim.x;
     const int k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarp = Kp >> 5;
     int* numA = reinterpret_cast<int*>(smem_raw);                               // [Tc][Kp]
     TypeConst* cb = reinterpret_cast<TypeConst*>(numA + (size_t)Tc * Kp);       // [Tc]
-    uint2* ctab_s = reinterpret_cast<uint2*>(cb + Tc);                          // [nb]
-    uint32_t* cum_s = reinterpret_cast<uint32_t*>(ctab_s + A.nb);               // [T_all + 2] when it fits
+    uint2* ctab_s = reinterpret_cast<uint2*>(cb + Tc);                          // [nA_cap + nb]
+    uint32_t* cum_s = reinterpret_cast<uint32_t*>(ctab_s + A.nA_cap + A.nb);    // [T_all + 2] when it fits
     const uint32_t* cum = A.cum_smem ? cum_s : A.cum;
     const uint32_t cb_saddr = (uint32_t)__cvta_generic_to_shared(cb);
     const uint32_t ctab_saddr = (uint32_t)__cvta_generic_to_shared(ctab_s);
     const uint32_t col_saddr = (uint32_t)__cvta_generic_to_shared(numA) + 4u * (uint32_t)threadIdx.x;
     const uint32_t Kp4 = 4u * (uint32_t)blockDim.x;
-    for (int i = k; i < A.nb; i += Kp) ctab_s[i] = A.ctab[i];
+    for (int i = k; i < A.nA_cap + A.nb; i += Kp) ctab_s[i] = A.ctab[i];
+    const uint32_t ctabB_saddr = ctab_saddr + 8u * (uint32_t)A.nA_cap;
+    const uint32_t X = A.hdr->X, shiftA = A.hdr->shiftA, shiftB = (uint32_t)A.shift;
+    const int su = (int)A.hdr->su;
     if (A.cum_smem) for (int i = k; i < T_all + 2; i += Kp) cum_s[i] = A.cum[i];
     const int seg = A.seg;
     const uint32_t n = (uint32_t)A.Nu, a = A.fp.a, b = A.fp.b;
-    const int shift = A.shift, shift2 = A.shift - min(CT_NSUB_LOG2, A.shift);
-    const uint32_t sub_mask = (1u << min(CT_NSUB_LOG2, A.shift)) - 1u;   // a bucket narrower than CT_NSUB indices has one index per sub-bucket
     Word* lab = reinterpret_cast<Word*>(A.scratch) + (size_t)blockIdx.x * (seg >> 2) * Kp + k;
     const int4* fxp = A.fxT4 + k;
     int* col = numA + k;   // this thread's private column: type t lives at col[t * Kp] (bank = k % 32 for every t)
@@ -607,21 +627,21 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     uint32_t Lq[4], Rq[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        // digits of position x + q, branch-free across a row boundary (lanes cross rows at different words)
-                        const uint32_t r = R + (uint32_t)q;
-                        Lq[q] = L + (r >= b ? 1u : 0u);
-                        Rq[q] = min(r, r - b);
+                        // digits of position x + q: rows are a multiple of 4 positions long and x is a multiple of 4, so
+                        // the four positions of a word share their row
+                        Lq[q] = L;
+                        Rq[q] = R + (uint32_t)q;
                         rounds(Lq[q], Rq[q]);
                         y[q] = Lq[q] * b + Rq[q];
                     }
                     R += 4u;
-                    if (R >= b) { R -= b; L++; }
+                    if (R == b) { R = 0u; L++; }
                     if (max(max(y[0], y[1]), max(y[2], y[3])) >= n) {   // cycle-walk: rare
 #pragma unroll
                         for (int q = 0; q < 4; q++)
                             while (y[q] >= n) { rounds(Lq[q], Rq[q]); y[q] = Lq[q] * b + Rq[q]; }
                     }
-                    class_of4(y, ctab_saddr, A.sub, cum, shift, shift2, sub_mask, cls);
+                    class_of4(y, ctab_saddr, ctabB_saddr, X, shiftA, shiftB, cum, cls);
                 } else {   // the partial last word of the ranking
                     y[0] = y[1] = y[2] = y[3] = 0xffffffffu;
 #pragma unroll 1
@@ -638,9 +658,9 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     uint32_t jj[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) jj[q] = min(y[q], n - 1u);
-                    class_of4(jj, ctab_saddr, A.sub, cum, shift, shift2, sub_mask, cls);
+                    class_of4(jj, ctab_saddr, ctabB_saddr, X, shiftA, shiftB, cum, cls);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) cls[q] = (y[q] == 0xffffffffu) ? (uint32_t)T_all : cls[q];
+                    for (int q = 0; q < 4; q++) cls[q] = (y[q] == 0xffffffffu) ? (uint32_t)su : cls[q];
                 }
                 if (!SLICED) {
                     int bq[4], aq[4];
@@ -650,15 +670,15 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                 idx += (uint32_t)Kp;
             }
             // pad my words to a whole number of NF_PRE groups (unknown class, zero scores): the second walk has no tail
-            const uint32_t dummy[4] = { (uint32_t)T_all, (uint32_t)T_all, (uint32_t)T_all, (uint32_t)T_all };
+            const uint32_t dummy[4] = { (uint32_t)su, (uint32_t)su, (uint32_t)su, (uint32_t)su };
             for (int i4 = nw; i4 < nwp; i4++) { lab[idx] = LaneWord<LabT>::pack(dummy); idx += (uint32_t)Kp; }
         }
 
-      for (int t0 = 0; t0 < T_all; t0 += Ts) {   // one iteration unless SLICED
-        const int T = min(Ts, T_all - t0);        // real types of this slice: local ids [0, T), dummy = Ts
-        // local type id of a label: slice members keep their offset, everything else goes to the dummy column
+      for (int t0 = 0; t0 < Tc_all; t0 += (SLICED ? Ts : Tc_all)) {   // one iteration unless SLICED
+        const int T = SLICED ? min(Ts, Tc_all - t0) : Tc_all;   // classes of this slice: local ids [0, T) (dummy = Ts when SLICED)
+        // local id of a label: slice members keep their offset, everything else goes to the dummy column
         auto local_type = [&](uint32_t t) -> uint32_t {
-            if (!SLICED) return t;   // labels are already in [0, T_all] with T_all = Ts the padding / unknown class
+            if (!SLICED) return t;   // labels are the sorted positions [0, Tc_all) themselves
             const uint32_t tl = t - (uint32_t)t0;
             return tl < (uint32_t)T ? tl : (uint32_t)Ts;
         };
@@ -705,7 +725,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             if (t < Tc) {
                 const int dA = mytot, dB = Stot - mytot;
                 float c12 = 0.0f, c2 = 0.0f;
-                if (t < T && dA != 0 && dB != 0) {
+                if (t < T && t0 + t != su && dA != 0 && dB != 0) {
                     const double r2 = __ddiv_rn(1.0, (double)dB);
                     c2 = __double2float_rn(r2);
                     c12 = __double2float_rn(__dadd_rn(__ddiv_rn(1.0, (double)dA), r2));
@@ -781,13 +801,15 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
         __syncthreads();
 
         // ---- phase 4: decode
-        for (int t = k; t < T; t += Kp) {
+        for (int ts = k; ts < T; ts += Kp) {
+            if (t0 + ts == su) continue;                 // the unknown-type class has no result
+            const int t = A.sorder[t0 + ts] - t0;        // (t0 + t) = type id of this sorted position
             const int32_t nk = A.class_cnt[t0 + t];
             const int32_t sizeb = (int32_t)(A.Nu - nk);
             float v, d;
             if (!(nk > 1 && sizeb > 1)) { v = __int_as_float(0x7fc00000); d = v; }
             else {
-                const uint32_t key = cb[t].best;
+                const uint32_t key = cb[ts].best;
                 v = (key <= 1u) ? 0.0f : __int_as_float((int)((key >> 1) | (((key & 1u) ^ 1u) << 31)));
                 d = dstat_of_f(v, nk, sizeb);
             }
@@ -821,35 +843,44 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
     class_table_geom(std::max<int64_t>(g.Nu, 1), &pl.shift, &pl.nb);
     pl.cum_smem = (g.Tc + 1 <= 1024) ? 1 : 0;
     const size_t smem_sm = (size_t)c->smem_per_sm, smem_cta_max = (size_t)c->smem_per_block_optin;
-    auto fixed = [&](int ts) { return (size_t)(ts + 1) * 16 + (size_t)pl.nb * 8 + (pl.cum_smem ? (size_t)(g.Tc + 1) * 4 : 0) + 64; };
+    // columns of the per-thread state: every class (T + 1) in one pass, or a slice of ts classes + the dummy column
+    auto fixed = [&](int cols) { return (size_t)cols * 16 + (size_t)pl.nb * 8 + (pl.cum_smem ? (size_t)(g.Tc + 1) * 4 : 0) + 64; };
     // threads per CTA when `ctas` CTAs share an SM (the per-CTA budget includes the 1 KB the driver reserves)
-    auto threads_for_n = [&](int ts, int ctas) {
-        const size_t f = fixed(ts);
-        const size_t budget = std::min(smem_cta_max, smem_sm / (size_t)ctas - 1024);
-        if (f + (size_t)(ts + 1) * 4 * 32 > budget) return 0;
-        const int kp = (int)std::min<size_t>(512, (budget - f) / ((size_t)(ts + 1) * 4));
+    // per-CTA budget: the SM's shared memory over the co-resident CTAs, minus the 1 KB the driver reserves per CTA and
+    // the kernel's few static variables
+    auto budget_for = [&](int ctas) { return std::min(smem_cta_max, smem_sm / (size_t)ctas - 1024) - 256; };
+    auto threads_for_n = [&](int cols, int ctas) {
+        const size_t f = fixed(cols);
+        const size_t budget = budget_for(ctas);
+        if (f + (size_t)cols * 4 * 32 > budget) return 0;
+        const int kp = (int)std::min<size_t>(512, (budget - f) / ((size_t)cols * 4));
         return (kp / 32) * 32;
     };
     // Two co-resident CTAs of half the size beat one large CTA at the same warp count (their serial phases 2 and 4
     // hide behind the other CTA's walks: 0.97 -> 0.87 ms on config B), so among the geometries with the most threads
     // per SM the one with more CTAs wins, down to 128 threads per CTA.
-    auto threads_for = [&](int ts) {
-        int best = threads_for_n(ts, 1), best_total = best;
+    int ctas_chosen = 1;
+    auto threads_for = [&](int cols) {
+        int best = threads_for_n(cols, 1), best_total = best;
+        ctas_chosen = 1;
         const int max_ctas = c->opt_null_ctas_per_sm > 0 ? c->opt_null_ctas_per_sm : 2;
         for (int n = 2; n <= max_ctas; n++) {
-            const int kp = threads_for_n(ts, n);
-            if (kp >= 128 && kp * n >= best_total) { best = kp; best_total = kp * n; }
+            const int kp = threads_for_n(cols, n);
+            if (kp >= 128 && kp * n >= best_total) { best = kp; best_total = kp * n; ctas_chosen = n; }
         }
         return best;
     };
-    int ts = std::max(g.T, 1), kp = threads_for(ts);
+    const int n_classes = g.T + 1;
+    int ts = g.T, cols = n_classes, kp = threads_for(cols);   // ts == T: not sliced
     const int min_kp = c->opt_null_min_threads > 0 ? c->opt_null_min_threads : 192;
     if (kp < min_kp) {
-        // slices of equal size, as few as give every slice at least 256 threads (or the maximum that fits)
+        // slices of equal size over the T + 1 classes, as few as give every slice at least 256 threads (or the
+        // maximum that fits); a slice has one more column, the dummy
         int n_slices = 2;
         for (;; n_slices++) {
-            ts = (int)div_up(g.T, n_slices);
-            kp = threads_for(ts);
+            ts = (int)div_up(n_classes, n_slices);
+            cols = ts + 1;
+            kp = threads_for(cols);
             if (kp >= 256 || ts == 1) break;
         }
         PCT_REQUIRE(kp >= 32, "shared memory too small for the null kernel's per-type state");
@@ -861,7 +892,15 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
     pl.Kp = kp;
     pl.Ts = ts;
     pl.seg = (int32_t)round_up(div_up(std::max<int64_t>(g.Nu, 1), kp), 4 * NF_PRE);
-    pl.smem = (size_t)(ts + 1) * kp * 4 + fixed(ts);
+    // region A of the class table (fine buckets for the classes narrower than a coarse bucket) takes what is left of
+    // the CTA's share of shared memory, up to 1024 entries
+    {
+        const size_t used = (size_t)cols * kp * 4 + fixed(cols);
+        const size_t budget = budget_for(ctas_chosen);
+        pl.nA_cap = (int32_t)std::min<size_t>(1024, budget > used ? (budget - used) / 8 : 0);
+        if (c->opt_null_fine_entries >= 0) pl.nA_cap = std::min(pl.nA_cap, c->opt_null_fine_entries);
+    }
+    pl.smem = (size_t)cols * kp * 4 + fixed(cols) + (size_t)pl.nA_cap * 8;
     int per_sm = (int)std::max<size_t>(1, smem_sm / (pl.smem + 1024));
     per_sm = std::min(per_sm, std::max(1, 2048 / kp));
     per_sm = std::min(per_sm, 4);
@@ -893,17 +932,26 @@ void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlan
     PCT_CUDA(cudaGetLastError());
 }
 
-// cum[] (+ the bucket table when nb > 0) of the type-sorted arrangement; needs class_cnt (k_gather_ranked).
-static size_t class_tab_cum_bytes(const EnrichGeom& g) { return (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16); }
-static size_t class_tab_sub_offset(const EnrichGeom& g, int32_t nb) { return class_tab_cum_bytes(g) + (size_t)round_up((int64_t)std::max(nb, 1) * 8, 16); }
+// Layout of c->cls_tab: cum[Tc + 1] | sorder[Tc] | ClassHdr | ctab[nA_cap + nb]; needs class_cnt (k_gather_ranked).
+struct ClassTabLayout { size_t sorder, hdr, ctab, bytes; };
+static ClassTabLayout class_tab_layout(const EnrichGeom& g, int32_t nb, int32_t nA_cap) {
+    ClassTabLayout l;
+    l.sorder = (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16);
+    l.hdr = l.sorder + (size_t)round_up((int64_t)g.Tc * 4, 16);
+    l.ctab = l.hdr + 16;
+    l.bytes = l.ctab + (size_t)(std::max(nb, 0) + std::max(nA_cap, 0)) * 8 + 64;
+    return l;
+}
 
-void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb) {
-    const size_t cum_bytes = class_tab_cum_bytes(g), sub_off = class_tab_sub_offset(g, nb);
-    c->cls_tab.reserve(sub_off + (size_t)std::max(nb, 1) * CT_NSUB * 8 + 64);
-    uint32_t* cum = c->cls_tab.as<uint32_t>();
-    uint2* ctab = reinterpret_cast<uint2*>(c->cls_tab.as<unsigned char>() + cum_bytes);
-    uint2* sub = reinterpret_cast<uint2*>(c->cls_tab.as<unsigned char>() + sub_off);
-    k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift, nb, cum, ctab, sub);
+void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb, int32_t nA_cap) {
+    const ClassTabLayout l = class_tab_layout(g, nb, nA_cap);
+    c->cls_tab.reserve(l.bytes);
+    unsigned char* base = c->cls_tab.as<unsigned char>();
+    c->cls_tab_nb = nb;
+    c->cls_tab_nA_cap = nA_cap;
+    k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift, nb, nA_cap,
+                                              reinterpret_cast<uint32_t*>(base), reinterpret_cast<int32_t*>(base + l.sorder),
+                                              reinterpret_cast<ClassHdr*>(base + l.hdr), reinterpret_cast<uint2*>(base + l.ctab));
     count_launch(c);
     PCT_CUDA(cudaGetLastError());
 }
@@ -913,14 +961,16 @@ void launch_labels_philox_rm(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, 
     FeistelParams fp;
     feistel_params(g, seed, rounds, &fp);
     const uint32_t* cum = c->cls_tab.as<uint32_t>();
+    const int32_t* sorder = reinterpret_cast<const int32_t*>(c->cls_tab.as<unsigned char>() +
+                                                             class_tab_layout(g, c->cls_tab_nb, c->cls_tab_nA_cap).sorder);
     for (int32_t p0 = 0; p0 < Pc; p0 += 32768) {
         const int32_t pc = std::min<int32_t>(32768, Pc - p0);
         dim3 grid((unsigned)div_up(g.Nu_pad, 256), (unsigned)pc);
         if (g.lab_bytes == 1)
-            k_labels_philox_rm<uint8_t><<<grid, 256, 0, c->stream>>>(g.Nu, g.Nu_pad, g.T, fp, perm_begin + p0, cum,
+            k_labels_philox_rm<uint8_t><<<grid, 256, 0, c->stream>>>(g.Nu, g.Nu_pad, g.T, fp, perm_begin + p0, cum, sorder,
                                                                      c->labels.as<uint8_t>() + (size_t)p0 * g.Nu_pad);
         else
-            k_labels_philox_rm<uint16_t><<<grid, 256, 0, c->stream>>>(g.Nu, g.Nu_pad, g.T, fp, perm_begin + p0, cum,
+            k_labels_philox_rm<uint16_t><<<grid, 256, 0, c->stream>>>(g.Nu, g.Nu_pad, g.T, fp, perm_begin + p0, cum, sorder,
                                                                       c->labels.as<uint16_t>() + (size_t)p0 * g.Nu_pad);
         count_launch(c);
     }
@@ -934,9 +984,11 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
     A.fxT4 = c->fxT.as<int4>();
     A.Sfx = c->Sfx.as<int>();
     A.class_cnt = c->class_cnt.as<int32_t>();
+    const ClassTabLayout l = class_tab_layout(g, pl.nb, pl.nA_cap);
     A.cum = c->cls_tab.as<uint32_t>();
-    A.ctab = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + class_tab_cum_bytes(g));
-    A.sub = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + class_tab_sub_offset(g, pl.nb));
+    A.sorder = reinterpret_cast<const int32_t*>(c->cls_tab.as<unsigned char>() + l.sorder);
+    A.hdr = reinterpret_cast<const ClassHdr*>(c->cls_tab.as<unsigned char>() + l.hdr);
+    A.ctab = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + l.ctab);
     const unsigned grid = (unsigned)std::min<int64_t>(Pc, (int64_t)pl.ctas_per_sm * c->num_sms);
     const int seg4 = pl.seg >> 2;
     c->labels.reserve((size_t)grid * seg4 * pl.Kp * pl.word_bytes + 64);
@@ -948,7 +1000,7 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
     A.null_d = c->null_d.as<float>();
     A.Nu = g.Nu;
     A.T_all = g.T; A.Ts = pl.Ts; A.seg = pl.seg; A.Pc = Pc; A.perm_begin = perm_begin;
-    A.P_stride = P_stride; A.p_off = p_off; A.nb = pl.nb; A.shift = pl.shift; A.cum_smem = pl.cum_smem;
+    A.P_stride = P_stride; A.p_off = p_off; A.nb = pl.nb; A.nA_cap = pl.nA_cap; A.shift = pl.shift; A.cum_smem = pl.cum_smem;
     feistel_params(g, seed, rounds, &A.fp);
     const bool sliced = pl.Ts < g.T;
 #define PCT_LAUNCH_NULL(LT, NR, SL)                                                          \

@@ -552,15 +552,19 @@ def test_fast_null_is_independent_of_the_kernel_geometry(ctx, oracle):
     outs = {}
     try:
         for name, opts in (("default", {}), ("64 threads", {P.OPT_NULL_THREADS: 64}), ("160 threads, 1 CTA/SM", {P.OPT_NULL_THREADS: 160, P.OPT_NULL_CTAS_PER_SM: 1}),
-                           ("sliced", {P.OPT_NULL_MIN_THREADS: 512, P.OPT_NULL_THREADS: 256}), ("no overlap", {P.OPT_OBS_OVERLAP: 0})):
-            for o in (P.OPT_NULL_THREADS, P.OPT_NULL_CTAS_PER_SM, P.OPT_NULL_MIN_THREADS):
+                           ("sliced", {P.OPT_NULL_MIN_THREADS: 512, P.OPT_NULL_THREADS: 256}), ("no overlap", {P.OPT_OBS_OVERLAP: 0}),
+                           # class table: no fine region (every small class resolved by walking the cumulative counts),
+                           # a fine region of 8 and of 100 entries
+                           ("coarse class table", {P.OPT_NULL_FINE_ENTRIES: 1}), ("8 fine entries", {P.OPT_NULL_FINE_ENTRIES: 9}),
+                           ("100 fine entries, sliced", {P.OPT_NULL_FINE_ENTRIES: 101, P.OPT_NULL_MIN_THREADS: 512, P.OPT_NULL_THREADS: 256})):
+            for o in (P.OPT_NULL_THREADS, P.OPT_NULL_CTAS_PER_SM, P.OPT_NULL_MIN_THREADS, P.OPT_NULL_FINE_ENTRIES):
                 ctx.set_option(o, 0)
             ctx.set_option(P.OPT_OBS_OVERLAP, 1)
             for o, v in opts.items():
                 ctx.set_option(o, v)
             outs[name] = ctx.enrich(s, order, lab, T, prm)
     finally:
-        for o in (P.OPT_NULL_THREADS, P.OPT_NULL_CTAS_PER_SM, P.OPT_NULL_MIN_THREADS):
+        for o in (P.OPT_NULL_THREADS, P.OPT_NULL_CTAS_PER_SM, P.OPT_NULL_MIN_THREADS, P.OPT_NULL_FINE_ENTRIES):
             ctx.set_option(o, 0)
         ctx.set_option(P.OPT_OBS_OVERLAP, 1)
     ref = outs["default"]

@@ -68,8 +68,13 @@ def _rank_main(rank, world, uid_q, res_q, n_perm):
         uid = uid_q.get(timeout=120)
     ctx.comm_init_rank(world, rank, uid)
     out, tm = _analysis(ctx, d, cfg, n_perm, PP.KS_FAST)
+    # the observed statistics are sharded by cell type: the a / b series of a type this rank did NOT walk (the other
+    # rank's first type) and of one it did
+    n_used = int(tm["n_used"])
+    other = (cfg.n_types + world - 1) // world * ((rank + 1) % world)
+    curves = {t: ctx.last_observed_curve(t, n_used) for t in (other, min(other + 1, cfg.n_types - 1), 0)}
     res_q.put((rank, out["null"], out["nullD"], out["results"], tm["gather_ms"], out["score"], out["n_genes_used"], out["kept"],
-               out["order"]))
+               out["order"], curves))
     ctx.close()
 
 
@@ -79,7 +84,8 @@ def test_two_rank_analysis_equals_single_gpu(ctx, small, n_perm):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cfg = small["cfg"]
-    ref, _ = _analysis(ctx, small, cfg, n_perm, P.KS_FAST)
+    ref, rtm = _analysis(ctx, small, cfg, n_perm, P.KS_FAST)
+    ref_curves = {t: ctx.last_observed_curve(t, int(rtm["n_used"])) for t in range(cfg.n_types)}
     sp = mp.get_context("spawn")
     uid_q, res_q = sp.Queue(), sp.Queue()
     procs = [sp.Process(target=_rank_main, args=(r, 2, uid_q, res_q, n_perm)) for r in range(2)]
@@ -89,7 +95,10 @@ def test_two_rank_analysis_equals_single_gpu(ctx, small, n_perm):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, null, nullD, res, gather_ms, score, used, kept, order in got:
+    for rank, null, nullD, res, gather_ms, score, used, kept, order, curves in got:
+        for t, (a, b) in curves.items():
+            assert_bits_equal_f32(a, ref_curves[t][0], f"rank {rank}: observed curve a of type {t}")
+            assert_bits_equal_f32(b, ref_curves[t][1], f"rank {rank}: observed curve b of type {t}")
         assert gather_ms > 0.0
         # stage 1 was sharded over the two ranks (every second tile of 256 cells each) and all-gathered
         assert np.array_equal(score.view(np.uint64), ref["score"].view(np.uint64)), f"rank {rank}: scores"
