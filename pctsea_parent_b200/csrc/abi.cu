@@ -245,7 +245,7 @@ void enrich_device(pctsea_ctx* c, int64_t N, const double* score_dev, const int3
     NullPlanFast plan;
     if (want_null && philox) {
         plan = plan_null_fast(c, g);
-        launch_class_tables(c, g, plan.shift, plan.nb, plan.nA_cap);
+        launch_class_tables(c, g, plan.shift, plan.tab_cap);
         if (fast) launch_null_fast_prepare(c, g, plan);
     }
     rec(c, EV_RANK);

@@ -142,7 +142,7 @@ struct pctsea_ctx {
     pctsea::DevBuf labels;                                      // EXACT null: [Pc][Nu_pad] permuted labels; fused null: per-CTA label scratch
     pctsea::DevBuf lab_ticket;                                  // permutation ticket counter of the fused null kernel
     pctsea::DevBuf cls_tab;                                     // size-sorted classes: cumulative counts, order, header, bucket table (null_fused.cu)
-    int32_t cls_tab_nb = 0, cls_tab_nA_cap = 0;                 // geometry cls_tab was last built for
+    int32_t cls_tab_cap = 0;                                    // table capacity cls_tab was last built for
     pctsea::DevBuf replay;                                      // [Pc][Nu] int32
     pctsea::DevBuf fxT;                                         // FAST mode: lane layout of the fixed-point scores
     pctsea::DevBuf null_ews, null_d;                            // [T][Pc]
@@ -262,7 +262,8 @@ struct NullPlanFast {
     int32_t Ts = 0;           // cell types per pass (== T unless sliced)
     int32_t ctas_per_sm = 1;
     int32_t nb = 0;           // coarse (region B) buckets of the class table
-    int32_t nA_cap = 0;       // capacity of its fine region A
+    int32_t nA_cap = 0;       // entries on top of nb that the CTA's shared memory has room for
+    int32_t tab_cap = 0;      // capacity of the class table = nb + nA_cap (its fine / coarse split is chosen on the device)
     int shift = 0;            // log2 of the coarse bucket width
     int cum_smem = 0;         // cumulative class counts held in shared memory
     int word_bytes = 4;       // bytes of one label word (4 positions)
@@ -270,7 +271,7 @@ struct NullPlanFast {
 };
 NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g);
 void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl);
-void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb, int32_t nA_cap);
+void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift_min, int32_t cap);
 void launch_labels_philox_rm(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, int32_t perm_begin, int32_t Pc, int rounds);
 void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& pl, uint64_t seed, int32_t perm_begin,
                        int32_t Pc, int rounds, int32_t P_stride, int32_t p_off);

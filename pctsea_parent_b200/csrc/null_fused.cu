@@ -191,8 +191,10 @@ __global__ void k_fx_transpose(const int* __restrict__ fx, int64_t Nu, int32_t s
 // long-tailed (config B's ranking: 100 types with a median of 87 cells next to buckets of 256 indices), and a bucket
 // that holds several boundaries needs more than that. Because the arrangement is sorted by size, all classes narrower
 // than a bucket sit in one short prefix [0, X) of the indices: that prefix gets its own, finer buckets (region A,
-// 2^shiftA indices each, as fine as the table's capacity allows), everything behind it the coarse ones (region B,
-// 2^shiftB indices, at most one boundary each by construction). Which region an index belongs to is one compare and
+// 2^shiftA indices each), everything behind it the coarse ones (region B, 2^shiftB indices, at most one boundary each
+// by construction). The host only fixes the table's capacity (what the CTA's shared memory has left); the split is
+// chosen on the device from the class sizes: the (shiftB, shiftA) that leaves the fewest indices in classes narrower
+// than a fine bucket. Which region an index belongs to is one compare and
 // two selects, no divergence. (Round 2's first form resolved the several-boundary buckets through a second-level
 // table in global memory: only 2 % of the indices took that path, but some lane of almost every warp did — 12 % of
 // the kernel's warp instructions.) A region-A bucket that still holds several boundaries (classes of a handful of
@@ -203,19 +205,41 @@ struct ClassHdr {     // written by k_class_tables, read by the kernels that use
     uint32_t X;       // indices below X use region A
     uint32_t shiftA;  // log2 of region A's bucket width
     uint32_t su;      // sorted position of the unknown-type class
-    uint32_t nA;      // region A entries in use (<= the capacity the tables were built for)
+    uint32_t nA;      // region A entries in use
+    uint32_t shiftB;  // log2 of region B's bucket width
+    uint32_t offB;    // first region B entry (region B is indexed by j >> shiftB over the whole ranking)
+    uint32_t pad0, pad1;
 };
 
 // Global loads with a cache policy. The kernel streams its fixed-point scores and parked labels through L1 (every
 // byte is used once per walk): the streams do not allocate there.
-__device__ __forceinline__ int4 ld_stream(const int4* p) {
+// The fixed-point scores (16 bytes per 4 positions, shared by every CTA and re-read in every walk of every
+// permutation) are asked to stay in L2 (evict-last policy): on a long ranking the per-CTA scratch streams are many
+// times the L2 and would otherwise push them out between two uses.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_stream_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ld_keep(const int4* p, uint64_t pol) {
     int4 v;
-    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {   // the CTA's own scratch: ordinary (coherent) load
     uint32_t v;
     asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint2 ld_stream(const uint2* p) {
@@ -246,22 +270,20 @@ __device__ __forceinline__ uint2 class_entry(const uint32_t* __restrict__ cum, u
     return e;
 }
 
-// One CTA: sorted order of the classes, their cumulative counts, the two-region bucket table.
-// ctab = [nA_cap region-A entries][nb region-B entries, indexed by j >> shiftB over the whole ranking].
+// One CTA: sorted order of the classes, their cumulative counts, the two-region bucket table of `cap` entries
+// (region A first, region B behind it).
 __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict__ class_cnt, int32_t Tc, int64_t Nu,
-                                                      int shiftB, int32_t nb, int32_t nA_cap, uint32_t* __restrict__ cum,
+                                                      int shift_min, int32_t cap, uint32_t* __restrict__ cum,
                                                       int32_t* __restrict__ sorder, ClassHdr* __restrict__ hdr,
                                                       uint2* __restrict__ ctab) {
     __shared__ uint32_t part[1024];
     __shared__ uint32_t s_buf[2048];   // class counts by id, later the cumulative counts, when they fit
-    __shared__ uint32_t s_small, s_X, s_shiftA, s_nA;
+    __shared__ uint32_t s_shiftA, s_nA, s_shiftB, s_offB;
     const bool fits = Tc + 1 <= 2048;
-    if (threadIdx.x == 0) s_small = 0u;
     if (fits) for (int c = threadIdx.x; c < Tc; c += 1024) s_buf[c] = (uint32_t)class_cnt[c];
     __syncthreads();
     // sorted position of a class = number of classes that come before it in (count, id) order; the unsorted counts
     // land in cum[1 ..] at their sorted positions
-    const uint32_t W = 1u << shiftB;
     for (int c = threadIdx.x; c < Tc; c += 1024) {
         const uint32_t mine = fits ? s_buf[c] : (uint32_t)class_cnt[c];
         uint32_t r = 0;
@@ -272,7 +294,6 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
         sorder[r] = c;
         cum[r + 1] = mine;
         if (c == Tc - 1) hdr->su = r;
-        if (mine < W) atomicAdd(&s_small, 1u);
     }
     __syncthreads();
     // inclusive scan of cum[1 .. Tc] in place (thread t owns a contiguous chunk)
@@ -299,25 +320,50 @@ __global__ void __launch_bounds__(1024) k_class_tables(const int32_t* __restrict
         cum = s_buf;
     }
     if (threadIdx.x == 0) {
-        // region A = [0, X): the classes narrower than a region-B bucket (they are the first s_small sorted
-        // positions), up to the next bucket boundary; as fine as nA_cap entries allow
-        const unsigned long long raw = cum[s_small];
-        unsigned long long X = (raw + W - 1) / W * W;
-        const unsigned long long cover = min(X, (unsigned long long)Nu);
-        uint32_t sA = 0;
-        while (nA_cap > 0 && ((cover + (1ull << sA) - 1) >> sA) > (unsigned long long)nA_cap) sA++;
-        if (nA_cap <= 0 || (int)sA >= shiftB || raw == 0) { X = 0; sA = 0; }   // no finer than region B: not worth a region
-        s_X = (uint32_t)min(X, 0xffffffffull);
-        s_shiftA = sA;
-        s_nA = X ? (uint32_t)((cover + (1ull << sA) - 1) >> sA) : 0u;
-        hdr->X = s_X; hdr->shiftA = sA; hdr->nA = s_nA;
+        // number of ranked cells in classes of fewer than w cells = cum[first sorted position whose class has >= w]
+        auto cells_below = [&](unsigned long long w) -> unsigned long long {
+            int lo = 0, hi = Tc;   // sorted by size: the first position with count >= w
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((unsigned long long)(cum[mid + 1] - cum[mid]) < w) lo = mid + 1; else hi = mid;
+            }
+            return cum[lo];
+        };
+        // Candidates: region B with buckets of 2^sB indices for the few sB that fit the capacity; what is left goes
+        // to region A = [0, X) (the classes narrower than a region-B bucket, up to the next bucket boundary), as
+        // fine as it can be. The cost of a candidate = the indices in classes narrower than a fine bucket (they
+        // are resolved by walking cum[]); fewest wins, ties to the smaller sB.
+        unsigned long long best_cost = ~0ull;
+        uint32_t bX = 0, bsA = 0, bnA = 0, bsB = (uint32_t)shift_min, boff = 0;
+        for (int sB = shift_min; sB <= shift_min + 5 && sB < 32; sB++) {
+            const unsigned long long W = 1ull << sB;
+            const long long nbB = (long long)(((unsigned long long)Nu + W - 1) >> sB);
+            const long long capA = (long long)cap - nbB;
+            if (capA < 0) continue;
+            const unsigned long long raw = cells_below(W);
+            unsigned long long X = (raw + W - 1) / W * W;
+            const unsigned long long cover = min(X, (unsigned long long)Nu);
+            uint32_t sA = 0;
+            while (capA > 0 && ((cover + (1ull << sA) - 1) >> sA) > (unsigned long long)capA) sA++;
+            unsigned long long cost;
+            uint32_t nA = 0;
+            if (capA <= 0 || (int)sA >= sB || raw == 0) { X = 0; sA = 0; cost = raw; }   // no finer than region B: no region A
+            else { nA = (uint32_t)((cover + (1ull << sA) - 1) >> sA); cost = cells_below(1ull << sA); }
+            if (cost < best_cost) {
+                best_cost = cost; bX = (uint32_t)min(X, 0xffffffffull); bsA = sA; bnA = nA; bsB = (uint32_t)sB;
+                boff = (uint32_t)(cap - nbB);
+            }
+            if (cost == 0) break;
+        }
+        s_shiftA = bsA; s_nA = bnA; s_shiftB = bsB; s_offB = boff;
+        hdr->X = bX; hdr->shiftA = bsA; hdr->nA = bnA; hdr->shiftB = bsB; hdr->offB = boff;
     }
     __syncthreads();
-    const uint32_t sA = s_shiftA, nA = s_nA;
-    for (int i = threadIdx.x; i < nA_cap; i += 1024)
+    const uint32_t sA = s_shiftA, nA = s_nA, sB = s_shiftB, offB = s_offB;
+    for (int i = threadIdx.x; i < (int)offB; i += 1024)
         ctab[i] = (uint32_t)i < nA ? class_entry(cum, (uint32_t)Tc, (long long)i << sA, 1ll << sA, Nu) : make_uint2(0xffffffffu, 1u);
-    for (int i = threadIdx.x; i < nb; i += 1024)
-        ctab[nA_cap + i] = class_entry(cum, (uint32_t)Tc, (long long)i << shiftB, 1ll << shiftB, Nu);
+    for (int i = threadIdx.x; i < cap - (int)offB; i += 1024)
+        ctab[offB + i] = class_entry(cum, (uint32_t)Tc, (long long)i << sB, 1ll << sB, Nu);
 }
 
 // Sorted positions (classes) of four indices. saddrA / saddrB = addresses of the two regions of the bucket table in
@@ -530,13 +576,14 @@ struct NullArgs {
     const uint32_t* cum;         // [Tc + 1] cumulative counts of the size-sorted classes
     const int32_t* sorder;       // [Tc] class id at every sorted position
     const ClassHdr* hdr;
-    const uint2* ctab;           // [nA_cap + nb]
+    const uint2* ctab;           // [tab_cap]
     void* scratch;               // [grid][seg4][Kp] label words
+    uint4* cstream;              // SLICED: [grid][seg + 4][Kp] compact records {class, score, prefix before, -} of the sparse slices
     int* ticket;
     float* null_ews;             // [T][P_stride]
     float* null_d;
     int64_t Nu;
-    int32_t T_all, Ts, seg, Pc, perm_begin, P_stride, p_off, nb, nA_cap, shift, cum_smem;
+    int32_t T_all, Ts, seg, Pc, perm_begin, P_stride, p_off, tab_cap, cum_smem;
     FeistelParams fp;
 };
 
@@ -545,8 +592,15 @@ struct NullArgs {
 // position su) has a column like every other class but zero constants, so it can never set a maximum; padding
 // positions carry it with zero scores.
 // SLICED: more classes than the per-thread shared-memory state can hold at once. The labels are then generated
-// in a pass of their own, and phases 1-4 run once per slice of Ts sorted positions on the parked labels, with every
-// other class mapped to the slice's dummy column (Ts), which takes the same read-modify-write but has zero constants.
+// in a pass of their own, and phases 1-4 run once per slice of Ts sorted positions, with every other class mapped to
+// the slice's dummy column (Ts), which takes the same read-modify-write but has zero constants. The classes are
+// sorted by size, so only the LAST slice is dense (it holds the largest classes, i.e. most positions: config D's
+// upper 150 of 301 classes own 89 % of the cells); it walks the parked labels of all positions. Every earlier slice
+// is sparse: the label pass appends a {class, score, prefix of all scores before the position} record for each of
+// their positions to a per-thread compact stream, and their phases 1 and 3 walk those records only — the work per
+// permutation is ~1.2 walks instead of one per slice. The parked labels serve the dense slice alone, so they are
+// parked as its LOCAL ids (members: offset in the slice; everything else: the dummy column), which always fit a
+// byte.
 template <typename LabT, int NR, bool SLICED>
 __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     typedef typename LaneWord<LabT>::type Word;
@@ -559,22 +613,25 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
     const int k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarp = Kp >> 5;
     int* numA = reinterpret_cast<int*>(smem_raw);                               // [Tc][Kp]
     TypeConst* cb = reinterpret_cast<TypeConst*>(numA + (size_t)Tc * Kp);       // [Tc]
-    uint2* ctab_s = reinterpret_cast<uint2*>(cb + Tc);                          // [nA_cap + nb]
-    uint32_t* cum_s = reinterpret_cast<uint32_t*>(ctab_s + A.nA_cap + A.nb);    // [T_all + 2] when it fits
+    uint2* ctab_s = reinterpret_cast<uint2*>(cb + Tc);                          // [tab_cap]
+    uint32_t* cum_s = reinterpret_cast<uint32_t*>(ctab_s + A.tab_cap);          // [T_all + 2] when it fits
     const uint32_t* cum = A.cum_smem ? cum_s : A.cum;
     const uint32_t cb_saddr = (uint32_t)__cvta_generic_to_shared(cb);
     const uint32_t ctab_saddr = (uint32_t)__cvta_generic_to_shared(ctab_s);
     const uint32_t col_saddr = (uint32_t)__cvta_generic_to_shared(numA) + 4u * (uint32_t)threadIdx.x;
     const uint32_t Kp4 = 4u * (uint32_t)blockDim.x;
-    for (int i = k; i < A.nA_cap + A.nb; i += Kp) ctab_s[i] = A.ctab[i];
-    const uint32_t ctabB_saddr = ctab_saddr + 8u * (uint32_t)A.nA_cap;
-    const uint32_t X = A.hdr->X, shiftA = A.hdr->shiftA, shiftB = (uint32_t)A.shift;
+    for (int i = k; i < A.tab_cap; i += Kp) ctab_s[i] = A.ctab[i];
+    const uint32_t ctabB_saddr = ctab_saddr + 8u * A.hdr->offB;
+    const uint32_t X = A.hdr->X, shiftA = A.hdr->shiftA, shiftB = A.hdr->shiftB;
     const int su = (int)A.hdr->su;
     if (A.cum_smem) for (int i = k; i < T_all + 2; i += Kp) cum_s[i] = A.cum[i];
     const int seg = A.seg;
     const uint32_t n = (uint32_t)A.Nu, a = A.fp.a, b = A.fp.b;
     Word* lab = reinterpret_cast<Word*>(A.scratch) + (size_t)blockIdx.x * (seg >> 2) * Kp + k;
+    uint4* cs = SLICED ? A.cstream + (size_t)blockIdx.x * (seg + 4) * Kp + k : nullptr;
+    const uint32_t dense0 = SLICED ? (uint32_t)((Tc_all - 1) / Ts * Ts) : 0u;   // first sorted position of the last (dense) slice
     const int4* fxp = A.fxT4 + k;
+    const uint64_t keep = l2_keep_policy();
     int* col = numA + k;   // this thread's private column: type t lives at col[t * Kp] (bank = k % 32 for every t)
     const uint32_t x0 = (uint32_t)k * (uint32_t)seg;
     const uint32_t L00 = x0 / b, R00 = x0 - L00 * b;
@@ -614,13 +671,16 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
 
         // ---- phase 1: labels of my segment + per-type segment sums (one shared-memory read-modify-write per
         // position, in program order). Four positions at a time: four independent round chains, no per-position tests.
+        uint32_t nrec = 0;   // SLICED: records in my compact stream
         {
+            int Srun = S0;       // SLICED: exact prefix of all scores before the current word
+            uint4* csw = cs;     // SLICED: next free record
             uint32_t L = L00, R = R00;
             uint32_t idx = 0;   // i4 * Kp: the same index addresses the label word and the score quad of (i4, k)
-            int4 fn = nw > 0 ? ld_stream(fxp) : make_int4(0, 0, 0, 0);
+            int4 fn = nw > 0 ? ld_keep(fxp, keep) : make_int4(0, 0, 0, 0);
             for (int i4 = 0; i4 < nw; i4++) {
                 const int4 fc = fn;
-                if (i4 + 1 < nw) fn = ld_stream(fxp + (idx + (uint32_t)Kp));
+                if (i4 + 1 < nw) fn = ld_keep(fxp + (idx + (uint32_t)Kp), keep);
                 const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
                 uint32_t y[4], cls[4];
                 if (i4 < nfull) {
@@ -665,30 +725,75 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                 if (!SLICED) {
                     int bq[4], aq[4];
                     rmw4(col_saddr, Kp4, cls, fq, bq, aq);
+                } else {
+                    int sb = Srun;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (cls[q] + 1u <= dense0 && i4 * 4 + q < nv) {   // a position of a sparse slice
+                            *csw = make_uint4(cls[q], (uint32_t)fq[q], (uint32_t)sb, 0u);
+                            csw += Kp;
+                            nrec++;
+                        }
+                        sb += fq[q];
+                        // parked for the dense slice: its local id, or the dummy column
+                        const uint32_t tl = cls[q] - dense0;
+                        cls[q] = tl < (uint32_t)(Tc_all - (int)dense0) ? tl : (uint32_t)Ts;
+                    }
+                    Srun = sb;
                 }
                 lab[idx] = LaneWord<LabT>::pack(cls);
                 idx += (uint32_t)Kp;
             }
             // pad my words to a whole number of NF_PRE groups (unknown class, zero scores): the second walk has no tail
-            const uint32_t dummy[4] = { (uint32_t)su, (uint32_t)su, (uint32_t)su, (uint32_t)su };
+            const uint32_t pad = SLICED ? (uint32_t)Ts : (uint32_t)su;   // zero scores on a column that cannot set a maximum
+            const uint32_t dummy[4] = { pad, pad, pad, pad };
             for (int i4 = nw; i4 < nwp; i4++) { lab[idx] = LaneWord<LabT>::pack(dummy); idx += (uint32_t)Kp; }
+            if (SLICED)   // whole groups of four records: the padding belongs to no slice (dummy column, zero score)
+                for (; nrec & 3u; nrec++) { *csw = make_uint4(0xffffffffu, 0u, 0u, 0u); csw += Kp; }
         }
 
       for (int t0 = 0; t0 < Tc_all; t0 += (SLICED ? Ts : Tc_all)) {   // one iteration unless SLICED
         const int T = SLICED ? min(Ts, Tc_all - t0) : Tc_all;   // classes of this slice: local ids [0, T) (dummy = Ts when SLICED)
         // local id of a label: slice members keep their offset, everything else goes to the dummy column
-        auto local_type = [&](uint32_t t) -> uint32_t {
-            if (!SLICED) return t;   // labels are the sorted positions [0, Tc_all) themselves
-            const uint32_t tl = t - (uint32_t)t0;
-            return tl < (uint32_t)T ? tl : (uint32_t)Ts;
+        // parked labels: the sorted positions themselves, or (SLICED) already the dense slice's local ids
+        auto local_type = [&](uint32_t t) -> uint32_t { return t; };
+        const bool sparse = SLICED && (uint32_t)t0 < dense0;
+        // four records of my compact stream -> local classes (members of this slice keep their offset, everything else
+        // goes to the dummy column), score, and the exact prefix before / after the position
+        auto load_records = [&](const uint4* p, uint4 (&rec)[4]) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) rec[u] = ld_stream(p + (size_t)u * Kp);
+        };
+        auto decode_records = [&](const uint4 (&rec)[4], uint32_t (&t)[4], int (&f)[4], int (&sb)[4], int (&sa)[4]) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t tl = rec[u].x - (uint32_t)t0;
+                t[u] = tl < (uint32_t)T ? tl : (uint32_t)Ts;
+                f[u] = (int)rec[u].y;
+                sb[u] = (int)rec[u].z;
+                sa[u] = sb[u] + f[u];
+            }
         };
         if (SLICED) {
             for (int t = 0; t < Tc; t++) col[t * Kp] = 0;
             for (int t = k; t < Tc; t += Kp) cb[t].best = 0u;
-            // phase 1 on the parked labels (each thread re-reads what it wrote itself: no barrier needed)
+            // phase 1 on the parked labels / the compact records (each thread re-reads what it wrote itself: no barrier needed)
+            if (sparse) {
+                uint4 rec[4], nxt[4];   // the next group's loads are in flight while this one is processed
+                if (nrec) load_records(cs, rec);
+                for (uint32_t r = 0; r < nrec; r += 4) {
+                    if (r + 4 < nrec) load_records(cs + (size_t)(r + 4) * Kp, nxt);
+                    uint32_t t[4];
+                    int f[4], sb[4], sa[4], bq[4], aq[4];
+                    decode_records(rec, t, f, sb, sa);
+                    rmw4(col_saddr, Kp4, t, f, bq, aq);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) rec[u] = nxt[u];
+                }
+            } else
             for (int i4 = 0; i4 < nw; i4++) {
                 const Word w = ld_stream(lab + (uint32_t)i4 * (uint32_t)Kp);
-                const int4 fc = ld_stream(fxp + (uint32_t)i4 * (uint32_t)Kp);
+                const int4 fc = ld_keep(fxp + (uint32_t)i4 * (uint32_t)Kp, keep);
                 const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
                 uint32_t t[4];
                 int bq[4], aq[4];
@@ -739,7 +844,42 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
 
         // ---- phase 3: suprema at hit / pre-hit positions. At the global position 0 the pre-hit candidate is
         // exactly 0 and cannot win.
-        {
+        if (sparse) {
+            uint4 rec[4], nxt[4];
+            if (nrec) load_records(cs, rec);
+            for (uint32_t r = 0; r < nrec; r += 4) {
+                if (r + 4 < nrec) load_records(cs + (size_t)(r + 4) * Kp, nxt);
+                uint32_t t[4];
+                int f[4], sb[4], sa[4], bq[4], aq[4];
+                decode_records(rec, t, f, sb, sa);
+#pragma unroll
+                for (int u = 0; u < 4; u++) rec[u] = nxt[u];
+                uint4 cq[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) cq[q] = lds128_volatile(cb_saddr + t[q] * 16u);
+                rmw4(col_saddr, Kp4, t, f, bq, aq);
+                float d0[4], d1[4];
+                bool rec = false;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {   // the same expressions as the dense walk below
+                    const float c12 = __uint_as_float(cq[q].x), c2 = __uint_as_float(cq[q].y), top = __uint_as_float(cq[q].w);
+                    d1[q] = __fmaf_rn(__int2float_rn(aq[q]), c12, -__fmul_rn(__int2float_rn(sa[q]), c2));
+                    d0[q] = __fmaf_rn(__int2float_rn(bq[q]), c12, -__fmul_rn(__int2float_rn(sb[q]), c2));
+                    rec = rec || (fabsf(d1[q]) >= top) || (fabsf(d0[q]) >= top);
+                }
+                if (rec) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t k1 = sup_key_fast(d1[q]), k0 = sup_key_fast(d0[q]);
+                        const uint32_t key = k0 > k1 ? k0 : k1;
+                        if (key > cq[q].z) {
+                            atomicMax(&cb[t[q]].best, key);
+                            atomicMax(&cb[t[q]].top, key >> 1);
+                        }
+                    }
+                }
+            }
+        } else {
             int S = S0;
             float Sf = __int2float_rn(S);
             Word wc[NF_PRE];   // register sets refilled in place: the loads run NF_PRE - 1 words ahead of their use
@@ -748,7 +888,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             uint32_t idx = 0;   // index of the group's first word
             if (nwp > 0) {
 #pragma unroll
-                for (int u = 0; u < NF_PRE; u++) { wc[u] = ld_stream(lab + (idx + u * Kpu)); fc[u] = ld_stream(fxp + (idx + u * Kpu)); }
+                for (int u = 0; u < NF_PRE; u++) { wc[u] = ld_stream(lab + (idx + u * Kpu)); fc[u] = ld_keep(fxp + (idx + u * Kpu), keep); }
             }
             for (int i4 = 0; i4 < nwp; i4 += NF_PRE) {
                 const bool more = i4 + NF_PRE < nwp;
@@ -757,7 +897,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                 for (int u = 0; u < NF_PRE; u++) {
                     const int fq[4] = { fc[u].x, fc[u].y, fc[u].z, fc[u].w };
                     const Word wcu = wc[u];
-                    if (more) { wc[u] = ld_stream(lab + (idx + u * Kpu)); fc[u] = ld_stream(fxp + (idx + u * Kpu)); }
+                    if (more) { wc[u] = ld_stream(lab + (idx + u * Kpu)); fc[u] = ld_keep(fxp + (idx + u * Kpu), keep); }
                     uint32_t t[4];
                     int bq[4], aq[4];
 #pragma unroll
@@ -845,6 +985,7 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
     const size_t smem_sm = (size_t)c->smem_per_sm, smem_cta_max = (size_t)c->smem_per_block_optin;
     // columns of the per-thread state: every class (T + 1) in one pass, or a slice of ts classes + the dummy column
     auto fixed = [&](int cols) { return (size_t)cols * 16 + (size_t)pl.nb * 8 + (pl.cum_smem ? (size_t)(g.Tc + 1) * 4 : 0) + 64; };
+    const int max_threads_sm = 65536 / 128;   // the kernel is compiled for up to 128 registers per thread
     // threads per CTA when `ctas` CTAs share an SM (the per-CTA budget includes the 1 KB the driver reserves)
     // per-CTA budget: the SM's shared memory over the co-resident CTAs, minus the 1 KB the driver reserves per CTA and
     // the kernel's few static variables
@@ -853,7 +994,7 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
         const size_t f = fixed(cols);
         const size_t budget = budget_for(ctas);
         if (f + (size_t)cols * 4 * 32 > budget) return 0;
-        const int kp = (int)std::min<size_t>(512, (budget - f) / ((size_t)cols * 4));
+        const int kp = (int)std::min<size_t>((size_t)(max_threads_sm / ctas), (budget - f) / ((size_t)cols * 4));
         return (kp / 32) * 32;
     };
     // Two co-resident CTAs of half the size beat one large CTA at the same warp count (their serial phases 2 and 4
@@ -876,13 +1017,20 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
     if (kp < min_kp) {
         // slices of equal size over the T + 1 classes, as few as give every slice at least 256 threads (or the
         // maximum that fits); a slice has one more column, the dummy
-        int n_slices = 2;
-        for (;; n_slices++) {
+        // Only the last slice is dense (the classes are sorted by size; the earlier slices walk their compact record
+        // streams), so more slices cost little and occupancy decides: the fewest slices that reach 480 threads per
+        // SM, else the geometry with the most.
+        int best_total = -1, best_ts = 1, best_cols = 2, best_kp = 0, best_ctas = 1;
+        for (int n_slices = 2;; n_slices++) {
             ts = (int)div_up(n_classes, n_slices);
             cols = ts + 1;
             kp = threads_for(cols);
-            if (kp >= 256 || ts == 1) break;
+            if (kp * ctas_chosen > best_total) {
+                best_total = kp * ctas_chosen; best_ts = ts; best_cols = cols; best_kp = kp; best_ctas = ctas_chosen;
+            }
+            if (best_total >= 480 || ts == 1 || n_slices >= 16) break;
         }
+        ts = best_ts; cols = best_cols; kp = best_kp; ctas_chosen = best_ctas;
         PCT_REQUIRE(kp >= 32, "shared memory too small for the null kernel's per-type state");
     }
     if (c->opt_null_threads > 0) kp = std::min(kp, (int)round_up(c->opt_null_threads, 32));
@@ -892,21 +1040,25 @@ NullPlanFast plan_null_fast(const pctsea_ctx* c, const EnrichGeom& g) {
     pl.Kp = kp;
     pl.Ts = ts;
     pl.seg = (int32_t)round_up(div_up(std::max<int64_t>(g.Nu, 1), kp), 4 * NF_PRE);
-    // region A of the class table (fine buckets for the classes narrower than a coarse bucket) takes what is left of
-    // the CTA's share of shared memory, up to 1024 entries
+    // The class table takes what is left of the CTA's share of shared memory on top of the nb coarse entries the
+    // geometry was sized with, up to 1024 more; how the capacity is split between fine and coarse buckets is decided
+    // on the device from the class sizes (k_class_tables).
     {
         const size_t used = (size_t)cols * kp * 4 + fixed(cols);
         const size_t budget = budget_for(ctas_chosen);
-        pl.nA_cap = (int32_t)std::min<size_t>(1024, budget > used ? (budget - used) / 8 : 0);
-        if (c->opt_null_fine_entries >= 0) pl.nA_cap = std::min(pl.nA_cap, c->opt_null_fine_entries);
+        int32_t extra = (int32_t)std::min<size_t>(1024, budget > used ? (budget - used) / 8 : 0);
+        if (c->opt_null_fine_entries >= 0) extra = std::min(extra, c->opt_null_fine_entries);
+        pl.nA_cap = extra;
     }
+    pl.tab_cap = pl.nb + pl.nA_cap;
     pl.smem = (size_t)cols * kp * 4 + fixed(cols) + (size_t)pl.nA_cap * 8;
     int per_sm = (int)std::max<size_t>(1, smem_sm / (pl.smem + 1024));
     per_sm = std::min(per_sm, std::max(1, 2048 / kp));
     per_sm = std::min(per_sm, 4);
     if (c->opt_null_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_null_ctas_per_sm);
     pl.ctas_per_sm = per_sm;
-    pl.word_bytes = 4 * g.lab_bytes;
+    // parked labels: sorted positions (one pass, at most T) or the dense slice's local ids (at most ts)
+    pl.word_bytes = (ts < g.T ? ts : g.T) <= 255 ? 4 : 8;
     return pl;
 }
 
@@ -934,22 +1086,21 @@ void launch_null_fast_prepare(pctsea_ctx* c, const EnrichGeom& g, const NullPlan
 
 // Layout of c->cls_tab: cum[Tc + 1] | sorder[Tc] | ClassHdr | ctab[nA_cap + nb]; needs class_cnt (k_gather_ranked).
 struct ClassTabLayout { size_t sorder, hdr, ctab, bytes; };
-static ClassTabLayout class_tab_layout(const EnrichGeom& g, int32_t nb, int32_t nA_cap) {
+static ClassTabLayout class_tab_layout(const EnrichGeom& g, int32_t cap) {
     ClassTabLayout l;
     l.sorder = (size_t)round_up((int64_t)(g.Tc + 1) * 4, 16);
     l.hdr = l.sorder + (size_t)round_up((int64_t)g.Tc * 4, 16);
-    l.ctab = l.hdr + 16;
-    l.bytes = l.ctab + (size_t)(std::max(nb, 0) + std::max(nA_cap, 0)) * 8 + 64;
+    l.ctab = l.hdr + 32;
+    l.bytes = l.ctab + (size_t)std::max(cap, 0) * 8 + 64;
     return l;
 }
 
-void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift, int32_t nb, int32_t nA_cap) {
-    const ClassTabLayout l = class_tab_layout(g, nb, nA_cap);
+void launch_class_tables(pctsea_ctx* c, const EnrichGeom& g, int shift_min, int32_t cap) {
+    const ClassTabLayout l = class_tab_layout(g, cap);
     c->cls_tab.reserve(l.bytes);
     unsigned char* base = c->cls_tab.as<unsigned char>();
-    c->cls_tab_nb = nb;
-    c->cls_tab_nA_cap = nA_cap;
-    k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift, nb, nA_cap,
+    c->cls_tab_cap = cap;
+    k_class_tables<<<1, 1024, 0, c->stream>>>(c->class_cnt.as<int32_t>(), g.Tc, g.Nu, shift_min, cap,
                                               reinterpret_cast<uint32_t*>(base), reinterpret_cast<int32_t*>(base + l.sorder),
                                               reinterpret_cast<ClassHdr*>(base + l.hdr), reinterpret_cast<uint2*>(base + l.ctab));
     count_launch(c);
@@ -962,7 +1113,7 @@ void launch_labels_philox_rm(pctsea_ctx* c, const EnrichGeom& g, uint64_t seed, 
     feistel_params(g, seed, rounds, &fp);
     const uint32_t* cum = c->cls_tab.as<uint32_t>();
     const int32_t* sorder = reinterpret_cast<const int32_t*>(c->cls_tab.as<unsigned char>() +
-                                                             class_tab_layout(g, c->cls_tab_nb, c->cls_tab_nA_cap).sorder);
+                                                             class_tab_layout(g, c->cls_tab_cap).sorder);
     for (int32_t p0 = 0; p0 < Pc; p0 += 32768) {
         const int32_t pc = std::min<int32_t>(32768, Pc - p0);
         dim3 grid((unsigned)div_up(g.Nu_pad, 256), (unsigned)pc);
@@ -984,15 +1135,19 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
     A.fxT4 = c->fxT.as<int4>();
     A.Sfx = c->Sfx.as<int>();
     A.class_cnt = c->class_cnt.as<int32_t>();
-    const ClassTabLayout l = class_tab_layout(g, pl.nb, pl.nA_cap);
+    const ClassTabLayout l = class_tab_layout(g, pl.tab_cap);
     A.cum = c->cls_tab.as<uint32_t>();
     A.sorder = reinterpret_cast<const int32_t*>(c->cls_tab.as<unsigned char>() + l.sorder);
     A.hdr = reinterpret_cast<const ClassHdr*>(c->cls_tab.as<unsigned char>() + l.hdr);
     A.ctab = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + l.ctab);
     const unsigned grid = (unsigned)std::min<int64_t>(Pc, (int64_t)pl.ctas_per_sm * c->num_sms);
     const int seg4 = pl.seg >> 2;
-    c->labels.reserve((size_t)grid * seg4 * pl.Kp * pl.word_bytes + 64);
+    const bool sliced = pl.Ts < g.T;
+    const size_t lab_bytes = (size_t)round_up((int64_t)((size_t)grid * seg4 * pl.Kp * pl.word_bytes), 256);
+    const size_t cs_bytes = sliced ? (size_t)grid * (pl.seg + 4) * pl.Kp * sizeof(uint4) : 0;
+    c->labels.reserve(lab_bytes + cs_bytes + 64);
     A.scratch = c->labels.p;
+    A.cstream = sliced ? reinterpret_cast<uint4*>(c->labels.as<unsigned char>() + lab_bytes) : nullptr;
     c->lab_ticket.reserve(64);
     PCT_CUDA(cudaMemsetAsync(c->lab_ticket.p, 0, 4, c->stream));
     A.ticket = c->lab_ticket.as<int>();
@@ -1000,9 +1155,8 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
     A.null_d = c->null_d.as<float>();
     A.Nu = g.Nu;
     A.T_all = g.T; A.Ts = pl.Ts; A.seg = pl.seg; A.Pc = Pc; A.perm_begin = perm_begin;
-    A.P_stride = P_stride; A.p_off = p_off; A.nb = pl.nb; A.nA_cap = pl.nA_cap; A.shift = pl.shift; A.cum_smem = pl.cum_smem;
+    A.P_stride = P_stride; A.p_off = p_off; A.tab_cap = pl.tab_cap; A.cum_smem = pl.cum_smem;
     feistel_params(g, seed, rounds, &A.fp);
-    const bool sliced = pl.Ts < g.T;
 #define PCT_LAUNCH_NULL(LT, NR, SL)                                                          \
     do {                                                                                     \
         ensure_dyn_smem(c, k_null_fused<LT, NR, SL>, pl.smem);                               \
@@ -1013,7 +1167,7 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
         if (rounds == PCTSEA_DEFAULT_FEISTEL_ROUNDS) PCT_LAUNCH_NULL(LT, PCTSEA_DEFAULT_FEISTEL_ROUNDS, SL); \
         else PCT_LAUNCH_NULL(LT, 0, SL);                                                     \
     } while (0)
-    if (g.lab_bytes == 2) { if (sliced) PCT_LAUNCH_NULL_R(uint16_t, true); else PCT_LAUNCH_NULL_R(uint16_t, false); }
+    if (pl.word_bytes == 8) { if (sliced) PCT_LAUNCH_NULL_R(uint16_t, true); else PCT_LAUNCH_NULL_R(uint16_t, false); }
     else                  { if (sliced) PCT_LAUNCH_NULL_R(uint8_t, true); else PCT_LAUNCH_NULL_R(uint8_t, false); }
 #undef PCT_LAUNCH_NULL_R
 #undef PCT_LAUNCH_NULL
