@@ -11,10 +11,12 @@
 //
 //   cells are grouped by 32 (group = warp, lane = cell). For every (group, gene):
 //     mo(group, gene) = { mask: bit l set iff the group's cell l has a non-zero of this gene,
-//                         off : number of non-zeros of the group in lower-numbered genes }
-//   stored in tiles of 8 groups, gene-major inside a tile (see gm_row_offset),
-//   gval[grp_base[group] + off + popc(mask & lanes below l)] = that cell's value: the group's non-zeros in
-//   (gene, cell) order. Size: 8 B * G * N/32 (config B 3.75 GB, D 15 GB) + 4 B * nnz.
+//                         off : position of the group's first value of this gene among the values of its TILE }
+//   stored in tiles of 8 groups (= the warps of one scoring CTA), gene-major inside a tile (see gm_row_offset),
+//   gval[tile_base + off + popc(mask & lanes below l)] = that cell's value: the tile's non-zeros in
+//   (gene, group, cell) order, so that the values of one gene for the 256 cells of a CTA are ONE contiguous run
+//   (~13 values on config B) instead of eight runs of ~1.6 values in eight different sectors.
+//   Size: 8 B * G * N/32 (config B 3.75 GB, D 15 GB) + 4 B * nnz.
 //
 // Scoring a list: one warp per group walks the list's genes, sorted by gene, in chunks of 32; the chunk's 32 masks
 // are bit-transposed so that each lane holds the set of the chunk's genes its own cell expresses and pops them in
@@ -49,21 +51,18 @@ __host__ __device__ __forceinline__ size_t gm_row_offset(int64_t grp, int32_t G)
     return (size_t)(grp / GM_TILE) * (size_t)G * GM_TILE + (size_t)(grp % GM_TILE);
 }
 
-// ---- build: one CTA per group of 32 cells; the genes go through shared memory in ranges of Gs (one pass for
-// matrices of up to ~51 k genes, more passes over the group's rows for larger gene sets) ------------------------
-__global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                                                  const float* __restrict__ val, const int32_t* __restrict__ slot_cell,
-                                                  const int64_t* __restrict__ grp_base, int32_t G, int32_t Gs,
-                                                  uint2* __restrict__ mo, float* __restrict__ gval) {
+// ---- build, three kernels. k_gm_masks: one CTA per group of 32 cells; the genes go through shared memory in ranges of
+// Gs (one pass for matrices of up to ~51 k genes, more passes over the group's rows for larger gene sets) and the
+// {mask, -} entries are written. k_gm_offsets: one CTA per tile turns the eight groups' value counts of every gene into
+// positions inside the tile's value array. k_gm_values: one CTA per group copies the values to their positions. ------
+__global__ void __launch_bounds__(256) k_gm_masks(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                  const int32_t* __restrict__ slot_cell, int32_t G, int32_t Gs,
+                                                  uint2* __restrict__ mo) {
     extern __shared__ unsigned s_mask[];   // [Gs]
-    __shared__ int s_part[256];
-    __shared__ unsigned s_run;             // values of the group in the gene ranges already done
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t grp = blockIdx.x;
     const int32_t* cells = slot_cell + grp * 32;   // the group's cells (-1 = empty slot)
     uint2* row = mo + gm_row_offset(grp, G);       // entry of gene g: row[g * GM_TILE]
-    const int64_t base = grp_base[grp];
-    if (tid == 0) s_run = 0u;
     for (int32_t r0 = 0; r0 < G; r0 += Gs) {
         const int32_t r1 = min(r0 + Gs, G), ng = r1 - r0;
         for (int g = tid; g < ng; g += blockDim.x) s_mask[g] = 0u;
@@ -78,41 +77,70 @@ __global__ void __launch_bounds__(256) k_gm_build(const int64_t* __restrict__ ro
             }
         }
         __syncthreads();
-        // exclusive prefix of popc(mask) over the range: contiguous chunk per thread + block scan of the chunk sums
-        const int chunk = (ng + blockDim.x - 1) / blockDim.x;
-        const int g0 = min(tid * chunk, ng), g1 = min(g0 + chunk, ng);
-        int sum = 0;
-        for (int g = g0; g < g1; g++) sum += __popc(s_mask[g]);
-        s_part[tid] = sum;
+        for (int g = tid; g < ng; g += blockDim.x) row[(size_t)(r0 + g) * GM_TILE] = make_uint2(s_mask[g], 0u);
         __syncthreads();
-        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
-            const int v = tid >= o ? s_part[tid - o] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gm_offsets(int64_t n_groups, int32_t G, uint2* __restrict__ mo) {
+    __shared__ unsigned s_scan[256];
+    __shared__ unsigned s_carry;
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    uint2* base = mo + (size_t)tile * (size_t)G * GM_TILE;
+    const int live = (int)min((long long)GM_TILE, (long long)(n_groups - tile * GM_TILE));   // groups of the last tile that exist
+    if (tid == 0) s_carry = 0u;
+    __syncthreads();
+    for (int32_t g0 = 0; g0 < G; g0 += 256) {
+        const int32_t g = g0 + tid;
+        unsigned cnt[GM_TILE], tot = 0;
+#pragma unroll
+        for (int w = 0; w < GM_TILE; w++) {
+            unsigned m = 0u;
+            if (g < G && w < live) m = base[(size_t)g * GM_TILE + w].x;
+            cnt[w] = __popc(m);
+            tot += cnt[w];
+        }
+        s_scan[tid] = tot;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const unsigned v = tid >= o ? s_scan[tid - o] : 0u;
             __syncthreads();
-            s_part[tid] += v;
+            s_scan[tid] += v;
             __syncthreads();
         }
-        unsigned run = s_run + (unsigned)(s_part[tid] - sum);
-        for (int g = g0; g < g1; g++) {
-            const unsigned m = s_mask[g];
-            row[(size_t)(r0 + g) * GM_TILE] = make_uint2(m, run);
-            run += __popc(m);
-        }
-        __syncthreads();   // the CTA's own global writes are visible to all of its threads from here
-        for (int ci = warp; ci < 32; ci += nwarps) {
-            const int32_t cl = cells[ci];
-            if (cl < 0) continue;
-            const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
-            const unsigned below = (1u << ci) - 1u;
-            for (int64_t k = b + lane; k < e; k += 32) {
-                const int32_t g = col[k];
-                if (g < r0 || g >= r1) continue;
-                const uint2 x = row[(size_t)g * GM_TILE];
-                gval[base + x.y + __popc(x.x & below)] = val[k];
+        unsigned run = s_carry + s_scan[tid] - tot;   // values of the tile in lower genes
+        if (g < G) {
+#pragma unroll
+            for (int w = 0; w < GM_TILE; w++) {
+                if (w < live) base[(size_t)g * GM_TILE + w].y = run;
+                run += cnt[w];
             }
         }
         __syncthreads();
-        if (tid == blockDim.x - 1) s_run += (unsigned)s_part[tid];
+        if (tid == 255) s_carry += s_scan[255];
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gm_values(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                   const float* __restrict__ val, const int32_t* __restrict__ slot_cell,
+                                                   const int64_t* __restrict__ grp_base, int32_t G,
+                                                   const uint2* __restrict__ mo, float* __restrict__ gval) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t grp = blockIdx.x;
+    const int32_t* cells = slot_cell + grp * 32;
+    const uint2* row = mo + gm_row_offset(grp, G);
+    const int64_t base = grp_base[grp];   // first value of the group's TILE
+    for (int ci = warp; ci < 32; ci += nwarps) {
+        const int32_t cl = cells[ci];
+        if (cl < 0) continue;
+        const int64_t b = row_ptr[cl], e = row_ptr[cl + 1];
+        const unsigned below = (1u << ci) - 1u;
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const uint2 x = row[(size_t)col[k] * GM_TILE];
+            gval[base + x.y + __popc(x.x & below)] = val[k];
+        }
     }
 }
 
@@ -160,7 +188,7 @@ struct GmArgs {
     const uint2* mo;
     const float* gval;
     const int32_t* slot_cell;   // [n_groups * 32] cell of every (group, lane) slot, -1 = empty
-    const int64_t* grp_base;    // [n_groups] first value of the group in gval
+    const int64_t* grp_base;    // [n_groups] first value of the group's tile in gval
     int64_t N, n_groups;
     int32_t G;
     const int32_t* gs_gene;
@@ -443,14 +471,22 @@ void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
     });
     // (Ordering the groups by decreasing size, so that the short ones fill the tail of the last wave, was measured
     // 12 % slower: the long groups then all run at the same time.)
+    // base[g] = first value of group g's tile (GM_TILE groups, the warps of one scoring CTA, share a value array)
     std::vector<int64_t> base((size_t)n_groups + 1, 0);
-    for (int64_t g = 0; g < n_groups; g++) {
-        int64_t cnt = 0;
-        for (int l = 0; l < 32; l++) {
-            const int32_t cl = slot[(size_t)g * 32 + l];
-            if (cl >= 0) cnt += rp[(size_t)cl + 1] - rp[cl];
+    {
+        int64_t run = 0, tile_start = 0;
+        for (int64_t g = 0; g < n_groups; g++) {
+            if (g % GM_TILE == 0) tile_start = run;
+            int64_t cnt = 0;
+            for (int l = 0; l < 32; l++) {
+                const int32_t cl = slot[(size_t)g * 32 + l];
+                if (cl >= 0) cnt += rp[(size_t)cl + 1] - rp[cl];
+            }
+            PCT_REQUIRE(run + cnt - tile_start < ((int64_t)1 << 32), "a tile of 256 cells holds 2^32 non-zeros or more");
+            base[(size_t)g] = tile_start;
+            run += cnt;
         }
-        base[(size_t)g + 1] = base[(size_t)g] + cnt;
+        base[(size_t)n_groups] = run;
     }
     uint2* mo = nullptr;
     float* gval = nullptr;
@@ -469,10 +505,12 @@ void build_gene_index(pctsea_ctx* c, pctsea_matrix* m) {
     }
     cudaError_t le = cudaMemcpyAsync(slot_dev, slot.data(), slot.size() * 4, cudaMemcpyHostToDevice, c->stream);
     if (le == cudaSuccess) le = cudaMemcpyAsync(base_dev, base.data(), base.size() * 8, cudaMemcpyHostToDevice, c->stream);
-    if (le == cudaSuccess) le = cudaFuncSetAttribute(k_gm_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (le == cudaSuccess) le = cudaFuncSetAttribute(k_gm_masks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (le == cudaSuccess) {
-        k_gm_build<<<(unsigned)n_groups, 256, smem, c->stream>>>(m->row_ptr, m->col, m->val, slot_dev, base_dev, G, Gs, mo, gval);
-        count_launch(c);
+        k_gm_masks<<<(unsigned)n_groups, 256, smem, c->stream>>>(m->row_ptr, m->col, slot_dev, G, Gs, mo);
+        k_gm_offsets<<<(unsigned)div_up(n_groups, GM_TILE), 256, 0, c->stream>>>(n_groups, G, mo);
+        k_gm_values<<<(unsigned)n_groups, 256, 0, c->stream>>>(m->row_ptr, m->col, m->val, slot_dev, base_dev, G, mo, gval);
+        count_launch(c, 3);
         le = cudaGetLastError();
     }
     if (le == cudaSuccess) le = cudaStreamSynchronize(c->stream);   // the host vectors above are the copy sources

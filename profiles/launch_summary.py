@@ -9,7 +9,7 @@ for row in csv.DictReader(lines):
     v = float(row["Metric Value"].replace(",", ""))
     v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(row["Metric Unit"], 1.0)
     agg.setdefault(row["Kernel Name"].split("(")[0][:70], []).append(v)
-LOAD = ("k_gm_build", "k_validate_csr", "k_validate_unique_cols")   # once per dataset (matrix load), not part of an analysis step
+LOAD = ("k_gm_build", "k_gm_masks", "k_gm_offsets", "k_gm_values", "k_validate_csr", "k_validate_unique_cols")   # once per dataset (matrix load), not part of an analysis step
 is_load = lambda k: any(n in k for n in LOAD)
 tot = sum(sum(v) for k, v in agg.items() if not is_load(k))
 print(f"{'us total':>12} {'n':>5} {'share':>7}  kernel   (cold-cache, serialised: compare shares; shares are of the analysis steps)")
