@@ -154,7 +154,7 @@ int         pctsea_get_timings(pctsea_ctx* ctx, pctsea_timings* out);
 #define PCTSEA_OPT_DEBUG_GAPS        9  /* 1: report idle gaps between the stages on stderr */
 #define PCTSEA_OPT_SHARD_SCORE      10  /* multi-GPU pctsea_analyze with the gene-major index: 1 (default) every rank scores
                                            1 / nranks of the cells and the scores are all-gathered; 0: every rank scores all */
-#define PCTSEA_OPT_OBS_CHAIN_MB     11  /* device memory for the observed accumulator history in MiB (0 = 1024): 8 bytes per
+#define PCTSEA_OPT_OBS_CHAIN_MB     11  /* device memory for the observed accumulator history in MiB (0 = 6144): 8 bytes per
                                            (ranked cell, type); the types go through it in slices when they do not fit */
 #define PCTSEA_OPT_NULL_FINE_ENTRIES 12 /* null kernel's class table: at most value - 1 fine entries for the small classes
                                            (0 = as many as fit the CTA's shared memory; 1 = none: every bucket coarse) */

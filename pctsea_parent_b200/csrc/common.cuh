@@ -111,7 +111,7 @@ struct pctsea_ctx {
     int opt_null_min_threads = 0;    // below this many threads per permutation the cell types are sliced (0 = 192)
     int opt_shard_observed = 1;      // multi-GPU analysis: observed statistics sharded by cell type over the ranks
     int opt_null_fine_entries = -1;  // cap on the fine (region A) entries of the null kernel's class table (-1 = what fits)
-    int opt_obs_chain_mb = 0;        // budget of the observed accumulator history in MiB (0 = 1024); more types than fit go in slices
+    int opt_obs_chain_mb = 0;        // budget of the observed accumulator history in MiB (0 = 6144); more types than fit go in slices
     int opt_shard_score = 1;         // multi-GPU analysis: stage 1 sharded over the ranks (0: every rank scores all cells)
     int opt_debug_gaps = 0;          // print a line to stderr when the stream sat idle between stages
     cudaStream_t stream = nullptr;

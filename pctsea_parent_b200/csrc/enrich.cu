@@ -240,7 +240,7 @@ __device__ __forceinline__ void block_scan2_sat(uint32_t& va, uint32_t& vb, uint
     }
     __syncthreads();
     if (warp > 0) { va = sat_add(va, scratch[warp - 1]); vb = sat_add(vb, scratch[32 + warp - 1]); }
-    __syncthreads();
+    // no trailing barrier: the caller passes at least one barrier before `scratch` is written again
 }
 
 constexpr int OBS_V = 4;                          // consecutive positions per thread and block step
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_chain(const double* __restr
                 }
             }
         }
-        __syncthreads();
+        if (first < OBS_STEP) __syncthreads();   // (uniform) the event below reads the accumulators written just above
         if (first < OBS_STEP && (first / OBS_V) == tid) {
             // the event position: the reference's own instruction sequence on the up-to-date accumulator
             const int v = first % OBS_V;
@@ -615,10 +615,11 @@ __global__ void k_obs_finish(const float2* __restrict__ chainT, const float* __r
 }
 
 // The accumulator history is kept for a slice of the cell types at a time: as many types as fit obs_chain_budget bytes
-// (1 GiB unless PCTSEA_OPT_OBS_CHAIN_MB says otherwise). Config B's 100 types x 219 530 cells are 176 MB and go in one
-// slice; an atlas-scale ranking (2 M cells x 300 types = 4.8 GB) takes five.
+// (6 GiB unless PCTSEA_OPT_OBS_CHAIN_MB says otherwise). Config B's 100 types x 219 530 cells are 176 MB and go in one
+// slice, and so does an atlas-scale ranking (2 M cells x 300 types = 4.8 GB): one launch of 300 chain CTAs keeps two or
+// three of them resident per SM (the walk is latency-bound: 15 ms in five slices of 64 types under a 1 GiB budget).
 static int32_t obs_types_per_slice(const pctsea_ctx* c, const EnrichGeom& g) {
-    const size_t budget = c->opt_obs_chain_mb > 0 ? (size_t)c->opt_obs_chain_mb << 20 : (size_t)1 << 30;
+    const size_t budget = c->opt_obs_chain_mb > 0 ? (size_t)c->opt_obs_chain_mb << 20 : (size_t)6 << 30;
     const size_t per_type = (size_t)std::max<int64_t>(g.Nu, 1) * sizeof(float2);
     return (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)std::max(g.T, 1), budget / per_type));
 }
