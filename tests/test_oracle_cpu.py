@@ -285,6 +285,29 @@ def test_feistel_permutation_is_a_bijection_and_global_indexed(oracle):
     assert np.array_equal(full[:, 3:7].view(np.uint32), part.view(np.uint32))
 
 
+def test_permuted_labels_are_the_size_sorted_arrangement_under_the_bijection(oracle):
+    """PHILOX mode (orc_perm_labels): position x carries the class at index pi(x) of the arrangement that lists the
+    T + 1 classes (unknown type last among the ids) in ascending order of their cell counts, ties by id — hand-built
+    here from the published bijection, so the arrangement's definition is pinned independently of the C code."""
+    T = 5
+    #           type:  0  1  2  3  4  unknown
+    counts = np.array([4, 0, 2, 4, 1, 2])
+    lab = np.repeat(np.array([0, 1, 2, 3, 4, -1], np.int32), counts)
+    rng = np.random.default_rng(5)
+    rng.shuffle(lab)                      # the observed order must not matter, only the multiset
+    # ascending (count, id): type 1 (0 cells), type 4 (1), type 2 (2), unknown = id 5 (2), type 0 (4), type 3 (4)
+    arrangement = np.array([4, 2, 2, -1, -1, 0, 0, 0, 0, 3, 3, 3, 3], np.int32)
+    for p in (0, 1, 7):
+        pi = oracle.feistel_perm(77, p, lab.size)
+        got = oracle.perm_labels(77, p, lab, T)
+        assert np.array_equal(got, arrangement[pi]), p
+        assert np.array_equal(np.sort(got), np.sort(lab))
+    # rows of the Feistel domain are a multiple of 4 positions long (the GPU generates four consecutive positions
+    # from one row): every residue class of pi's construction is still a bijection at awkward sizes
+    for n in (5, 13, 1023, 1025, 219_530):
+        assert np.array_equal(np.sort(oracle.feistel_perm(3, 2, n)), np.arange(n))
+
+
 def test_feistel_null_is_statistically_equivalent_to_jdk_shuffle(oracle):
     """north_star: PHILOX-mode nulls within a stated statistical tolerance of the reference's shuffle —
     per-type two-sample KS test at alpha = 0.001 with Bonferroni over the types, and p-values within
