@@ -26,6 +26,46 @@ def list_slice(n_lists: int, rank: int, world: int) -> Tuple[int, int]:
     return perm_slice(n_lists, rank, world)
 
 
+def analyze_batch_pooled(contexts, m, lists, sprm, min_score, n_types, nprm, **kw):
+    """Config E on one GPU through a pool of contexts, one host thread each — how the reference's web front-end runs
+    its analyses (an executor pool of PCTSEA instances, AnalyzeView.java:163, 747-766): list i goes to context
+    i mod len(contexts). The matrix is shared (read-only); every context has its own streams and workspaces, so one
+    list's latency-bound ranking and observed-statistics stages run beside another list's scoring (two contexts:
+    1.08 -> 0.84 ms per list on config B's matrix; three are slower again). Returns what Context.analyze_batch
+    returns, in list order; every list's results are bit-identical to a single-context call."""
+    import threading
+
+    import numpy as np
+    k = len(contexts)
+    if k == 1 or len(lists) < 2:
+        return contexts[0].analyze_batch(m, lists, sprm, min_score, n_types, nprm, **kw)
+    parts, errors = [None] * k, [None] * k
+
+    def work(j):
+        try:
+            if lists[j::k]:
+                parts[j] = contexts[j].analyze_batch(m, lists[j::k], sprm, min_score, n_types, nprm, **kw)
+        except BaseException as e:   # re-raised on the calling thread
+            errors[j] = e
+    threads = [threading.Thread(target=work, args=(j,)) for j in range(k)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    merged = {}
+    first = next(p for p in parts if p is not None)
+    for key, val in first.items():
+        arr = np.empty((len(lists),) + val.shape[1:], val.dtype)
+        for j in range(k):
+            if parts[j] is not None:
+                arr[j::k] = parts[j][key]
+        merged[key] = arr
+    return merged
+
+
 def gather_list_results(local: torch.Tensor, n_lists: int) -> torch.Tensor:
     """local: [lists of this rank][...] -> [n_lists][...] on every rank, in list order (uint8 views of the result
     structs travel as bytes)."""

@@ -804,6 +804,32 @@ def test_two_contexts_on_one_device(ctx, oracle):
         other.close()
 
 
+def test_pooled_contexts_share_one_matrix(ctx, small):
+    """Config E the way the reference's web front-end runs it (an executor pool of PCTSEA instances,
+    AnalyzeView.java:163): two contexts on one GPU, one host thread each, the SAME resident matrix, list i on context
+    i mod 2 (dist.analyze_batch_pooled). Every list's results equal the single-context batch bit for bit."""
+    from pctsea_parent_b200 import dist as pdist
+    d = small
+    cfg = d["cfg"]
+    m = _load(ctx, d)
+    m.set_labels(d["label"], cfg.n_types)
+    m.build_gene_index()
+    sprm = P.ScoreParams(0, 4, 0.2, 1, P.JITTER_PHILOX, 77)
+    nprm = ctx.null_params(16, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=9, min_pass=100)
+    lists = [tuple(t.numpy() for t in synth.make_list(cfg, "cpu", s)) for s in range(7)]
+    ref = ctx.analyze_batch(m, lists, sprm, cfg.min_score, cfg.n_types, nprm, want_null=True)
+    other = P.Context(0)
+    try:
+        for _ in range(3):   # a few rounds: the interleaving of the two threads differs from run to run
+            out = pdist.analyze_batch_pooled([ctx, other], m, lists, sprm, cfg.min_score, cfg.n_types, nprm, want_null=True)
+            assert np.array_equal(out["n_pass"], ref["n_pass"]) and np.array_equal(out["status"], ref["status"])
+            assert out["results"].tobytes() == ref["results"].tobytes()
+            assert_bits_equal_f32(out["null"], ref["null"], "pooled null")
+    finally:
+        other.close()
+        m.free()
+
+
 @pytest.mark.parametrize("gene_major", [False, True])
 def test_analyze_batch_equals_single_analyses(ctx, oracle, small, gene_major):
     """BASELINE config E in miniature: many lists against one resident matrix. Every list's results are
