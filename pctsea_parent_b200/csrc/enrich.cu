@@ -612,6 +612,7 @@ __global__ void k_obs_finish(const float2* __restrict__ chainT, const float* __r
         r.sec_supX = (int32_t)(0xffffffffu - (uint32_t)(sk & 0xffffffffull)) + 1;
     }
     results[t] = r;
+    reinterpret_cast<int32_t*>(&results[t])[3] = 0;   // the struct's padding word: records compare equal as bytes
 }
 
 // The accumulator history is kept for a slice of the cell types at a time: as many types as fit obs_chain_budget bytes
