@@ -46,8 +46,9 @@ extern "C" {
 
 #define PCTSEA_PERM_REPLAY 0    /* consume uploaded permutation index arrays (validation) */
 #define PCTSEA_PERM_PHILOX 1    /* generated: position x of permutation p carries the class at index pi_p(x) of the
-                                   TYPE-SORTED arrangement of the ranked labels (types ascending, unknown-type cells
-                                   last); pi_p = keyed Feistel bijection of [0, n_used) with arithmetic round
+                                   SIZE-SORTED arrangement of the ranked labels (the n_types + 1 classes — the last one
+                                   the unknown-type cells — in ascending order of their cell counts, ties by id, each a
+                                   contiguous run); pi_p = keyed Feistel bijection of [0, n_used) with arithmetic round
                                    functions, one Philox4x32-10 key per round and permutation. A pure function of
                                    (seed, global permutation index, x): identical for any GPU count or slicing. */
 

@@ -119,7 +119,7 @@ def feistel_perm(seed: int, p: int, n: int, rounds: int = DEFAULT_FEISTEL_ROUNDS
 
 
 def perm_labels(seed: int, p: int, lab, T: int, rounds: int = DEFAULT_FEISTEL_ROUNDS) -> np.ndarray:
-    """Permuted labels of PHILOX mode: the type-sorted arrangement of `lab` read through the Feistel bijection of
+    """Permuted labels of PHILOX mode: the size-sorted arrangement of `lab` read through the Feistel bijection of
     permutation p (global index)."""
     lab = np.ascontiguousarray(lab, dtype=np.int32)
     out = np.empty(lab.size, dtype=np.int32)

@@ -675,7 +675,7 @@ void orc_null(int64_t Nu, const double* s, const int32_t* lab, int32_t T, int32_
             for (int64_t i = 0; i < Nu; i++) labp[i] = lab[idx[i]];
             if (replay_out) memcpy(replay_out + (size_t)p * (size_t)Nu, idx, (size_t)Nu * sizeof(int32_t));
         } else {
-            /* PHILOX mode permutes the type-sorted arrangement (orc_perm_labels); there is no index array to replay */
+            /* PHILOX mode permutes the size-sorted arrangement (orc_perm_labels); there is no index array to replay */
             orc_perm_labels(seed, (uint32_t)(perm_begin + p), Nu, lab, T, rounds, labp);
         }
         null_one_perm(Nu, s, labp, T, P, p, nthreads, null_ews, null_d);

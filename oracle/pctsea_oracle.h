@@ -48,7 +48,7 @@ double   orc_jitter_uniform(uint64_t seed, uint64_t cell, uint32_t vec, uint32_t
  * functions, one Philox-generated 32-bit key per round, keyed by (seed, p). */
 void     orc_feistel_perm(uint64_t seed, uint32_t p, int64_t n, int rounds, int32_t* perm_out);
 void     orc_feistel_keys(uint64_t seed, uint32_t p, int rounds, uint32_t* keys_out);
-/* Permuted labels of PHILOX mode: lab_perm_out[x] = class at index pi_p(x) of the type-sorted arrangement of
+/* Permuted labels of PHILOX mode: lab_perm_out[x] = class at index pi_p(x) of the size-sorted arrangement of
  * lab[0..Nu) (types 0..T-1 ascending, unknown-type cells (-1) last). */
 void     orc_set_mix_variant(int v);   /* profiles/feistel_mix_check.py only */
 void     orc_perm_labels(uint64_t seed, uint32_t p, int64_t Nu, const int32_t* lab, int32_t T, int rounds,

@@ -6,12 +6,13 @@
 //   a8  utils/parallel/EnrichmentWeigthedScoreParallel.java:104-227 evaluated once per (type, permutation)
 //
 // Permutation (PCTSEA_PERM_PHILOX): position x of permutation p carries the class at index pi_p(x) of the
-// TYPE-SORTED arrangement of the ranked labels (a uniform permutation of any fixed arrangement of the same multiset
-// is a uniform arrangement). pi_p is a keyed Feistel bijection of [0,Nu) on Z_a x Z_b (a = ceil(sqrt Nu),
-// b = ceil(Nu/a), cycle-walking for the < a out-of-range points) with ARITHMETIC round functions
-//   F(v, key, mod) = umulhi(mix(v * M1 + key), mod),   one 32-bit Philox4x32-10 key per round and permutation,
-// so it lives entirely in registers: no tables, no shared memory, and "class of index j" is a look-up in a coarse
-// bucket table of the T+1 cumulative class counts. The round that is applied LAST modifies the high digit (the one
+// SIZE-SORTED arrangement of the ranked labels (classes in ascending order of their cell counts; a uniform
+// permutation of any fixed arrangement of the same multiset is a uniform arrangement). pi_p is a keyed Feistel
+// bijection of [0,Nu) on Z_a x Z_b (a near sqrt Nu, b = ceil(Nu/a) rounded up to a multiple of 4, cycle-walking for
+// the few out-of-range points) with ARITHMETIC round functions
+//   F(v, key, mod) = umulhi(mix(v * M + key), mod), mix(t) = t * (t >> 16), one Philox4x32-10 key per round and permutation,
+// so it lives entirely in registers: no tables, and "class of index j" is a look-up in a two-region bucket table of the
+// T+1 cumulative class counts in shared memory. The round that is applied LAST modifies the high digit (the one
 // that decides the class); with the sorted arrangement the class of a position is a range test on that digit, which
 // exposes the unevenness of a random round FUNCTION after 3-4 rounds as a 2 % inflation of the null's standard
 // deviation (profiles/feistel_rounds_check.txt) — 5 rounds are the default, measured indistinguishable from

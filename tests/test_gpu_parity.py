@@ -1205,7 +1205,7 @@ def test_philox_null_matches_jdk_shuffle_null_at_config_B_size(ctx, oracle):
     """north_star: 'in the Philox mode [nulls] must be within a stated statistical tolerance (KS test on the null
     distributions)'. At config B's size (219 530 ranked cells, 100 cell types), 2000 permutations each, all on the GPU:
         A  REPLAY of java.util.Collections.shuffle index arrays (the reference's permutation source) + EXACT arithmetic
-        B  PHILOX (keyed Feistel on the type-sorted arrangement)                                    + EXACT arithmetic
+        B  PHILOX (keyed Feistel on the size-sorted arrangement)                                    + EXACT arithmetic
         C  PHILOX                                                                                    + FAST arithmetic
     Stated tolerance, per cell type with Bonferroni over the types: two-sample KS statistic below the alpha = 0.001
     critical value; the numbers of |ES| values of A and of B / C above the pooled 99th and 99.9th percentiles within
