@@ -665,10 +665,9 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
             if constexpr (NR > 0) feistel_rounds<NR>(keys, a, b, NR, L, R);
             else feistel_rounds<0>(s_keys, a, b, A.fp.rounds, L, R);
         };
-        if (!SLICED) {
-            for (int t = 0; t < Tc; t++) col[t * Kp] = 0;
-            for (int t = k; t < Tc; t += Kp) cb[t].best = 0u;
-        }
+        // (SLICED: the dense slice comes first and takes its segment sums from the label pass, like the one-pass form)
+        for (int t = 0; t < Tc; t++) col[t * Kp] = 0;
+        for (int t = k; t < Tc; t += Kp) cb[t].best = 0u;
 
         // ---- phase 1: labels of my segment + per-type segment sums (one shared-memory read-modify-write per
         // position, in program order). Four positions at a time: four independent round chains, no per-position tests.
@@ -741,6 +740,8 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                         cls[q] = tl < (uint32_t)(Tc_all - (int)dense0) ? tl : (uint32_t)Ts;
                     }
                     Srun = sb;
+                    int bq[4], aq[4];
+                    rmw4(col_saddr, Kp4, cls, fq, bq, aq);   // the dense slice's segment sums
                 }
                 lab[idx] = LaneWord<LabT>::pack(cls);
                 idx += (uint32_t)Kp;
@@ -753,7 +754,9 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                 for (; nrec & 3u; nrec++) { *csw = make_uint4(0xffffffffu, 0u, 0u, 0u); csw += Kp; }
         }
 
-      for (int t0 = 0; t0 < Tc_all; t0 += (SLICED ? Ts : Tc_all)) {   // one iteration unless SLICED
+      // one iteration unless SLICED; then the dense (last) slice first, the sparse ones behind it
+      for (int sl = 0, t0 = SLICED ? (int)dense0 : 0; t0 >= 0 && t0 < Tc_all;
+           sl++, t0 = SLICED ? ((sl - 1) * Ts < (int)dense0 ? (sl - 1) * Ts : -1) : Tc_all) {
         const int T = SLICED ? min(Ts, Tc_all - t0) : Tc_all;   // classes of this slice: local ids [0, T) (dummy = Ts when SLICED)
         // local id of a label: slice members keep their offset, everything else goes to the dummy column
         // parked labels: the sorted positions themselves, or (SLICED) already the dense slice's local ids
@@ -775,11 +778,11 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                 sa[u] = sb[u] + f[u];
             }
         };
-        if (SLICED) {
+        if (sparse) {
             for (int t = 0; t < Tc; t++) col[t * Kp] = 0;
             for (int t = k; t < Tc; t += Kp) cb[t].best = 0u;
-            // phase 1 on the parked labels / the compact records (each thread re-reads what it wrote itself: no barrier needed)
-            if (sparse) {
+            // phase 1 on the compact records (each thread re-reads what it wrote itself: no barrier needed)
+            {
                 uint4 rec[4], nxt[4];   // the next group's loads are in flight while this one is processed
                 if (nrec) load_records(cs, rec);
                 for (uint32_t r = 0; r < nrec; r += 4) {
@@ -791,16 +794,6 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) rec[u] = nxt[u];
                 }
-            } else
-            for (int i4 = 0; i4 < nw; i4++) {
-                const Word w = ld_stream(lab + (uint32_t)i4 * (uint32_t)Kp);
-                const int4 fc = ld_keep(fxp + (uint32_t)i4 * (uint32_t)Kp, keep);
-                const int fq[4] = { fc.x, fc.y, fc.z, fc.w };
-                uint32_t t[4];
-                int bq[4], aq[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) t[q] = local_type(LaneWord<LabT>::get(w, q));
-                rmw4(col_saddr, Kp4, t, fq, bq, aq);
             }
         }
         __syncthreads();
