@@ -28,8 +28,9 @@
 // reference's sequential SimpleRegression update (measured <= 1e-11).
 //
 // Roofline: the bytes this path must read are 8 B per (list gene, group) entry + the matched values (config B:
-// 0.15 GB + 0.7 GB useful, 2.06 GB of DRAM sectors measured), not the 6.5 GB CSR: it sits between instruction issue
-// (66 %) and the latency of the dependent entry -> value loads, not at the HBM roofline (profiles/README.md).
+// 0.15 GB + 0.7 GB useful, 1.31 GB of DRAM sectors measured — 2.06 GB while every group had its own value array),
+// not the 6.5 GB CSR: it sits between instruction issue (61 %) and the latency of the dependent entry -> value loads,
+// not at the HBM roofline (profiles/README.md).
 #include "common.cuh"
 
 #include <algorithm>
