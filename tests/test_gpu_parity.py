@@ -350,6 +350,45 @@ def test_null_philox_fast_matches_oracle_fast(ctx, oracle, n_used, T, Pn, simple
         assert_bits_equal_f32(ne[:, p], exp, f"fast null perm {p}")
 
 
+def _label_layouts():
+    rng = np.random.default_rng(17)
+    out = {}
+    out["37 cells, 5 types"] = (rng.integers(0, 5, 37).astype(np.int32), 5)
+    out["4 cells, 2 types"] = (np.array([0, 1, 1, 0], np.int32), 2)
+    out["one type owns every cell"] = (np.full(5000, 2, np.int32), 6)
+    lab = np.concatenate([np.arange(40), np.full(1400, 47), np.full(2000, 44), np.full(1560, -1)]).astype(np.int32)
+    out["forty one-cell types, two big ones, 31 % unknown"] = (rng.permutation(lab), 50)
+    w = 1.0 / np.arange(1, 121) ** 2
+    sizes = np.maximum(3, np.floor(w / w.sum() * (70_000 - 3 * 120)).astype(np.int64))
+    lab = np.repeat(np.arange(120, dtype=np.int32), sizes)[:70_000]
+    lab = np.concatenate([lab, np.zeros(70_000 - lab.size, np.int32)])
+    out["long tail: 120 types, sizes ~ 1 / k^2, floor 3"] = (rng.permutation(lab), 120)
+    lab = np.repeat(np.arange(400, dtype=np.int32), 25)
+    out["400 types of 25 cells (sliced, every class narrower than a bucket)"] = (rng.permutation(lab), 400)
+    return out
+
+
+@pytest.mark.parametrize("layout", list(_label_layouts()))
+def test_null_class_table_edge_cases(ctx, oracle, layout):
+    """The class of a permuted index comes from a two-region bucket table of the size-sorted classes whose split is
+    chosen on the device: label layouts that stress it (tiny rankings, empty and one-cell classes, a single class,
+    long tails, more tiny classes than table entries), FAST and EXACT arithmetic against the oracle."""
+    lab, T = _label_layouts()[layout]
+    n_used = lab.size
+    s = synth.synthetic_ranked(n_used, max(T, 2), seed=5)[0]
+    order = np.arange(n_used, dtype=np.int32)
+    Pn = 3
+    res, ne, nd = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_FAST, seed=13))
+    F = oracle.fast_frac_bits(s)
+    for p in range(Pn):
+        exp = oracle.ks_null_fast_one(s, oracle.perm_labels(13, p, lab, T), T, F)
+        assert_bits_equal_f32(ne[:, p], exp, f"{layout}: fast null perm {p}")
+    one, _ = oracle.null(s, lab, T, Pn, perm_mode=1, seed=13)
+    ex = ctx.enrich(s, order, lab, T, ctx.null_params(Pn, perm_mode=P.PERM_PHILOX, ks_mode=P.KS_EXACT, seed=13))[1]
+    assert_bits_equal_f32(ex, one, f"{layout}: exact null")
+    assert_results_equal(res, oracle.ks_observed(s, lab, T), OBSERVED_FIELDS, f"{layout}: observed")
+
+
 @pytest.mark.parametrize("rounds", [2, 4, 6, 9])
 @pytest.mark.parametrize("n_used,T", [(5000, 12), (9000, 300), (500, 4)])
 def test_null_philox_explicit_round_counts(ctx, oracle, rounds, n_used, T):
