@@ -758,9 +758,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
       for (int sl = 0, t0 = SLICED ? (int)dense0 : 0; t0 >= 0 && t0 < Tc_all;
            sl++, t0 = SLICED ? ((sl - 1) * Ts < (int)dense0 ? (sl - 1) * Ts : -1) : Tc_all) {
         const int T = SLICED ? min(Ts, Tc_all - t0) : Tc_all;   // classes of this slice: local ids [0, T) (dummy = Ts when SLICED)
-        // local id of a label: slice members keep their offset, everything else goes to the dummy column
-        // parked labels: the sorted positions themselves, or (SLICED) already the dense slice's local ids
-        auto local_type = [&](uint32_t t) -> uint32_t { return t; };
+        // (parked labels are column ids already: the sorted positions themselves, or the dense slice's local ids)
         const bool sparse = SLICED && (uint32_t)t0 < dense0;
         // four records of my compact stream -> local classes (members of this slice keep their offset, everything else
         // goes to the dummy column), score, and the exact prefix before / after the position
@@ -895,7 +893,7 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     uint32_t t[4];
                     int bq[4], aq[4];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) t[q] = local_type(LaneWord<LabT>::get(wcu, q));
+                    for (int q = 0; q < 4; q++) t[q] = LaneWord<LabT>::get(wcu, q);
                     // the constants and the current maximum of each type in one 16-byte read, issued together with
                     // the running-sum reads so that their latency hides behind each other
                     uint4 cq[4];
