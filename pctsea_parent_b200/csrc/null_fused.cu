@@ -1132,9 +1132,14 @@ void launch_null_fused(pctsea_ctx* c, const EnrichGeom& g, const NullPlanFast& p
     A.sorder = reinterpret_cast<const int32_t*>(c->cls_tab.as<unsigned char>() + l.sorder);
     A.hdr = reinterpret_cast<const ClassHdr*>(c->cls_tab.as<unsigned char>() + l.hdr);
     A.ctab = reinterpret_cast<const uint2*>(c->cls_tab.as<unsigned char>() + l.ctab);
-    const unsigned grid = (unsigned)std::min<int64_t>(Pc, (int64_t)pl.ctas_per_sm * c->num_sms);
     const int seg4 = pl.seg >> 2;
     const bool sliced = pl.Ts < g.T;
+    // One scratch row per resident CTA: the parked labels and, when the classes go in slices, the compact records
+    // (16 B per position at worst). The persistent grid shrinks when that would pass 24 GiB (a 2 M-cell, 300-type
+    // ranking takes 10 GB with all 296 CTAs; a 50 M-cell one would take 250 GB).
+    const size_t row_bytes = (size_t)seg4 * pl.Kp * pl.word_bytes + (sliced ? (size_t)(pl.seg + 4) * pl.Kp * sizeof(uint4) : 0);
+    const int64_t grid_cap = std::max<int64_t>(1, (int64_t)(((size_t)24 << 30) / std::max<size_t>(row_bytes, 1)));
+    const unsigned grid = (unsigned)std::min<int64_t>(std::min<int64_t>(Pc, (int64_t)pl.ctas_per_sm * c->num_sms), grid_cap);
     const size_t lab_bytes = (size_t)round_up((int64_t)((size_t)grid * seg4 * pl.Kp * pl.word_bytes), 256);
     const size_t cs_bytes = sliced ? (size_t)grid * (pl.seg + 4) * pl.Kp * sizeof(uint4) : 0;
     c->labels.reserve(lab_bytes + cs_bytes + 64);
