@@ -425,6 +425,24 @@ def test_struct_layouts_match_header():
     assert _lib.TYPE_RESULT_DTYPE.fields["norm_supX"][1] == 16 and _lib.TYPE_RESULT_DTYPE.fields["fdr"][1] == 48
 
 
+def test_option_and_mode_constants_match_header():
+    """Every PCTSEA_OPT_* / mode constant of include/pctsea_b200.h has the same value in the Python binding (and the
+    binding defines no option the header does not)."""
+    import re
+    import pctsea_parent_b200 as P
+    from pctsea_parent_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pctsea_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+PCTSEA_(\w+)\s+(-?\d+)\b", hdr)}
+    opts = {k[4:]: v for k, v in defs.items() if k.startswith("OPT_")}
+    assert len(opts) >= 13
+    for name, val in opts.items():
+        assert getattr(_lib, "OPT_" + name) == val, name
+        assert getattr(P, "OPT_" + name) == val, name
+    assert {k for k in dir(_lib) if k.startswith("OPT_")} == {"OPT_" + k for k in opts}
+    for name in ("PERM_REPLAY", "PERM_PHILOX", "KS_EXACT", "KS_FAST", "JITTER_NAN", "JITTER_PHILOX"):
+        assert getattr(P, name) == defs[name], name
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "pctsea_parent_b200")
     for dirpath, _, files in os.walk(pkg):
