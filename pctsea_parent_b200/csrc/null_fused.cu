@@ -547,15 +547,22 @@ __device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
 __device__ __forceinline__ void rmw4(uint32_t col_saddr, uint32_t stride_bytes, const uint32_t (&t)[4], const int (&f)[4],
                                      int (&bq)[4], int (&aq)[4]) {
     uint32_t ad[4];
+    int ld[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { ad[q] = col_saddr + t[q] * stride_bytes; bq[q] = lds_i32(ad[q]); }
-    aq[0] = bq[0] + f[0];
-    bq[1] = (t[1] == t[0]) ? aq[0] : bq[1];
-    aq[1] = bq[1] + f[1];
-    bq[2] = (t[2] == t[1]) ? aq[1] : ((t[2] == t[0]) ? aq[0] : bq[2]);
-    aq[2] = bq[2] + f[2];
-    bq[3] = (t[3] == t[2]) ? aq[2] : ((t[3] == t[1]) ? aq[1] : ((t[3] == t[0]) ? aq[0] : bq[3]));
-    aq[3] = bq[3] + f[3];
+    for (int q = 0; q < 4; q++) { ad[q] = col_saddr + t[q] * stride_bytes; ld[q] = lds_i32(ad[q]); }
+    // All four reads precede the stores, so a repeated type reads the same old value at each occurrence: the value
+    // before position q = what was read + the scores of the earlier positions of the same type. Those sums depend
+    // on the types and scores only and are ready before the shared-memory reads return (two dependent adds behind
+    // the read instead of a chain of selects and adds through all four positions).
+    const int s10 = (t[1] == t[0]) ? f[0] : 0;
+    const int s20 = (t[2] == t[0]) ? f[0] : 0, s21 = (t[2] == t[1]) ? f[1] : 0;
+    const int s30 = (t[3] == t[0]) ? f[0] : 0, s31 = (t[3] == t[1]) ? f[1] : 0, s32 = (t[3] == t[2]) ? f[2] : 0;
+    bq[0] = ld[0];
+    bq[1] = ld[1] + s10;
+    bq[2] = ld[2] + s20 + s21;
+    bq[3] = ld[3] + (s30 + s31) + s32;
+#pragma unroll
+    for (int q = 0; q < 4; q++) aq[q] = bq[q] + f[q];
 #pragma unroll
     for (int q = 0; q < 4; q++) sts_i32(ad[q], aq[q]);   // same address: the later store carries the later value
 }
