@@ -107,3 +107,35 @@ def test_list_slice_covers_everything():
         for w in (1, 2, 8):
             sl = [pdist.list_slice(n, r, w) for r in range(w)]
             assert sl[0][0] == 0 and sum(c for _, c in sl) == n
+
+
+def test_pooled_batch_merges_in_list_order_and_propagates_errors():
+    """dist.analyze_batch_pooled (config E through a pool of contexts, one host thread each): list i goes to context
+    i mod k, the per-list outputs come back in list order, an exception of one context reaches the caller. Host logic
+    only: the contexts are stand-ins (the GPU test runs real ones)."""
+    import numpy as np
+    import pytest
+    from pctsea_parent_b200 import dist as pdist
+
+    class Fake:
+        def __init__(self, tag, fail=False):
+            self.tag, self.fail, self.seen = tag, fail, []
+
+        def analyze_batch(self, m, lists, sprm, min_score, n_types, nprm, **kw):
+            if self.fail:
+                raise RuntimeError("boom")
+            self.seen.append([int(g[0]) for g, _ in lists])
+            ids = np.array([int(g[0]) for g, _ in lists])
+            return {"results": np.stack([np.full(n_types, 10 * i + self.tag) for i in ids]), "n_pass": ids + 1000,
+                    "status": np.zeros(len(lists), np.int32)}
+
+    lists = [(np.array([i], np.int32), np.ones(1, np.float32)) for i in range(7)]
+    a, b = Fake(1), Fake(2)
+    out = pdist.analyze_batch_pooled([a, b], None, lists, None, 0.0, 3, None)
+    assert a.seen == [[0, 2, 4, 6]] and b.seen == [[1, 3, 5]]
+    assert list(out["n_pass"]) == [1000 + i for i in range(7)]
+    assert [int(r[0]) for r in out["results"]] == [10 * i + (1 if i % 2 == 0 else 2) for i in range(7)]
+    one = pdist.analyze_batch_pooled([Fake(5)], None, lists, None, 0.0, 3, None)
+    assert list(one["n_pass"]) == [1000 + i for i in range(7)]
+    with pytest.raises(RuntimeError):
+        pdist.analyze_batch_pooled([Fake(1), Fake(2, fail=True)], None, lists, None, 0.0, 3, None)
