@@ -913,14 +913,21 @@ __global__ void __launch_bounds__(512, 1) k_null_fused(const NullArgs A) {
                     // keys and the shared-memory atomics sit behind one branch per group of four positions.
                     float d0[4], d1[4];
                     bool rec = false;
+                    // the prefixes of all scores after each of the four positions, each one add away from S (exact:
+                    // |S| <= sum |fx| < 2^31), so that the four conversions do not wait for each other
+                    const int p2 = fq[0] + fq[1];
+                    const int Sq[4] = { S + fq[0], S + p2, S + (p2 + fq[2]), S + (p2 + (fq[2] + fq[3])) };
+                    float Sfq[5];
+                    Sfq[0] = Sf;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) Sfq[q + 1] = __int2float_rn(Sq[q]);
+                    S = Sq[3];
+                    Sf = Sfq[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const float c12 = __uint_as_float(cq[q].x), c2 = __uint_as_float(cq[q].y), top = __uint_as_float(cq[q].w);
-                        const float Spf = Sf;
-                        S += fq[q];   // exact: |S| <= sum |fx| < 2^31
-                        Sf = __int2float_rn(S);
-                        d1[q] = __fmaf_rn(__int2float_rn(aq[q]), c12, -__fmul_rn(Sf, c2));
-                        d0[q] = __fmaf_rn(__int2float_rn(bq[q]), c12, -__fmul_rn(Spf, c2));
+                        d1[q] = __fmaf_rn(__int2float_rn(aq[q]), c12, -__fmul_rn(Sfq[q + 1], c2));
+                        d0[q] = __fmaf_rn(__int2float_rn(bq[q]), c12, -__fmul_rn(Sfq[q], c2));
                         rec = rec || (fabsf(d1[q]) >= top) || (fabsf(d0[q]) >= top);
                     }
                     if (rec) {
